@@ -1,0 +1,128 @@
+"""Import the UNMODIFIED reference (Jarvis73/PEMP) for oracle pinning — TEST INFRASTRUCTURE ONLY.
+
+Works only where ``/root/reference`` exists (the build container).  The GPU box
+never has it, so nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may
+call into this module; they use ``oracle/restate.py`` and the committed
+fixtures in ``tests/golden/`` that ``oracle/make_golden.py`` produced with this
+module.
+
+What it does
+------------
+* puts ``oracle/shims`` (``sacred``, ``dropblock``) and the reference root on
+  ``sys.path`` and imports ``networks.{pemp_stage1,pemp_stage2,baseline,panet,
+  pfenet}`` and ``core.metrics`` as they are;
+* builds *head-only* model instances: the class is instantiated without running
+  its ``__init__`` (which would build a ResNet and read checkpoint files), and
+  ``encoder`` is replaced by a stub that returns the feature tensor we supply.
+  Every line of the hot path (``forward`` after the encoder call, ``mpm``,
+  ``compute_similarity``, ``alignLoss``) is then the reference's own code;
+* for PFENet, whose prior block is inline in ``forward``
+  (``networks/pfenet.py:201-229``), executes exactly those source lines, read
+  from the reference file at run time, in a namespace holding our tensors.
+"""
+import importlib
+import inspect
+import os
+import sys
+import textwrap
+
+import torch
+import torch.nn as nn
+
+REF_ROOT = os.environ.get("PEMP_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "networks", "pemp_stage1.py"))
+
+
+def _ensure_path():
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}; use oracle/restate.py + tests/golden instead")
+    for p in (REF_ROOT, _SHIMS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def module(name):
+    """Import a reference module, e.g. ``module('networks.pemp_stage1')``."""
+    _ensure_path()
+    return importlib.import_module(name)
+
+
+class _EncoderStub(nn.Module):
+    """Returns a pre-computed feature map regardless of the image input."""
+
+    def __init__(self, features):
+        super().__init__()
+        self.features = features
+
+    def forward(self, _images):
+        return self.features
+
+
+def _bare(cls):
+    obj = cls.__new__(cls)
+    nn.Module.__init__(obj)
+    return obj
+
+
+def head_only(model, features=None, ctr=None):
+    """Head-only instance of a reference model.
+
+    model : 'pemp_stage1' | 'pemp_stage2' | 'baseline' | 'panet'
+    features : [B(S+Q), c, h, w] tensor the stub encoder returns
+    ctr : [c, 2p] meta-prototype parameter (PEMP) or None for the protos==0 branch
+    """
+    mod = module(f"networks.{model}")
+    obj = _bare(mod.ModelClass)
+    if features is not None:
+        obj.encoder = _EncoderStub(features)
+    if model.startswith("pemp"):
+        obj.ctr = None if ctr is None else nn.Parameter(ctr.clone(), requires_grad=False)
+    obj.eval()
+    return obj
+
+
+def net_config(model="pemp_stage2"):
+    """The Sacred `net` config dict the reference would inject (dist_scalar, protos, ...)."""
+    mod = module(f"networks.{model}")
+    return dict(mod.net_ingredient.cfg)
+
+
+def dummy_images(B, S, Q, H, W):
+    """1-channel zero images: the head only reads their shape (`pemp_stage1.py:136-140`)."""
+    return torch.zeros(B, S, 1, H, W), torch.zeros(B, Q, 1, H, W)
+
+
+def few_shot_metric(classes):
+    return module("core.metrics").FewShotMetric(classes)
+
+
+def weighted_gap(supp_feat, mask):
+    return module("networks.pfenet").Weighted_GAP(supp_feat, mask)
+
+
+def pfenet_prior(query_feat_4, final_supp_list, mask_list, query_feat_3_hw, query_feat_hw):
+    """Run `networks/pfenet.py` lines "corr_query_mask_list = []" .. "corr_query_mask = F.interpolate(...)"
+    (201-231 in the surveyed revision) verbatim on our tensors."""
+    pf = module("networks.pfenet")
+    src = inspect.getsource(pf.PFENet.forward).splitlines()
+    start = next(i for i, l in enumerate(src) if l.strip().startswith("corr_query_mask_list = []"))
+    stop = next(i for i, l in enumerate(src) if i > start and l.strip().startswith("if self.shot > 1"))
+    block = textwrap.dedent("\n".join(src[start:stop]))
+    h3, w3 = query_feat_3_hw
+    hq, wq = query_feat_hw
+    ns = {
+        "torch": torch,
+        "F": torch.nn.functional,
+        "query_feat_4": query_feat_4,
+        "final_supp_list": list(final_supp_list),
+        "mask_list": list(mask_list),
+        # only .size() of these two is read by the block
+        "query_feat_3": torch.empty(1, 1, h3, w3),
+        "query_feat": torch.empty(1, 1, hq, wq),
+    }
+    exec(compile(block, "<pfenet.py:prior-block>", "exec"), ns)
+    return ns["corr_query_mask"]

@@ -1,0 +1,161 @@
+"""Synthetic few-shot episodes with the reference's tensor contract.
+
+The reference feeds its models `(sup_img [B,S,3,H,W], sup_mask [B,S,2,H,W], qry_img [B,Q,3,H,W]),
+qry_msk [B,Q,H',W'], cls [B]` (`data_kits/pascal_voc.py:462-537`).  PASCAL / COCO are not available
+offline and the backbone is not the product, so episodes here are generated at the *head's* input:
+the encoder output `features [B(S+Q), c, h, w]` (`networks/pemp_stage1.py:139-144`) plus the masks.
+
+Features = noise * N(0,1) + amp * u_fg on pixels whose nearest-down-sampled mask is foreground and
++ amp * u_bg elsewhere (u_* random unit vectors per episode), which gives non-trivial masks
+(fg-IoU 0.76-0.86 through the reference stage-1 head).  Support masks are one
+axis-aligned rectangle per shot covering 10-60 % of the image, `stack(fg, 1-fg)` as
+`pascal_voc.py:209-210`; the query mask has an optional 2-pixel band of the ignore label 255
+around the object (exercises `core/metrics.py:16-18`).
+
+Episode `i` depends only on `(base_seed, i)` - never on the batch or rank it lands in - so a sharded
+run over R ranks sees exactly the episode set of a single-rank run.
+"""
+from dataclasses import dataclass
+
+import torch
+
+REFERENCE_SEED = 1234          # reference default seed, `entry/pemp_stage1.py:32`
+
+
+@dataclass(frozen=True)
+class EpisodeSpec:
+    shot: int = 5
+    query: int = 1
+    channels: int = 512
+    h: int = 51
+    w: int = 51
+    H: int = 401
+    W: int = 401
+    out_h: int = 401           # size of the query ground-truth mask (the reference up-samples to it)
+    out_w: int = 401
+    classes: int = 20          # PASCAL-5i: 20, COCO-20i: 80
+    cls_lo: int = 1            # validation label range of split 0 (`data_kits/datasets.py:99-102`)
+    cls_hi: int = 5
+    amp: float = 1.0
+    noise: float = 0.5
+    protos: int = 3
+    ignore_band: int = 2       # width of the 255 band in the query mask; 0 disables
+    stages: int = 2            # 2 -> also emit the stage-2 encoder output `feats2`
+
+
+def nearest_src_index(out_size, in_size):
+    """ATen nearest rule `min(floor(dst * float(in / out)), in - 1)` in float32 (`pemp_stage1.py:147`)."""
+    scale = torch.tensor(float(in_size), dtype=torch.float32) / torch.tensor(float(out_size), dtype=torch.float32)
+    src = torch.floor(torch.arange(out_size, dtype=torch.float32) * scale).to(torch.int64)
+    return src.clamp_max(in_size - 1)
+
+
+def _rect(gen, H, W):
+    """Random rectangle covering 10-60 % of H x W; returns (y0, y1, x0, x1)."""
+    frac = 0.10 + 0.50 * torch.rand((), generator=gen).item()
+    aspect = 0.5 + torch.rand((), generator=gen).item()            # height / width ratio in [0.5, 1.5]
+    area = frac * H * W
+    rh = int(min(H - 2, max(4, round((area * aspect) ** 0.5))))
+    rw = int(min(W - 2, max(4, round(area / rh))))
+    y0 = int(torch.randint(0, H - rh, (), generator=gen).item())
+    x0 = int(torch.randint(0, W - rw, (), generator=gen).item())
+    return y0, y0 + rh, x0, x0 + rw
+
+
+def _features(gen, spec, fg_low, u_fg, u_bg):
+    """[c, h, w] feature map for one image given its low-res foreground mask [h, w]."""
+    f = torch.randn(spec.channels, spec.h, spec.w, generator=gen) * spec.noise
+    f += spec.amp * (u_fg[:, None, None] * fg_low + u_bg[:, None, None] * (1.0 - fg_low))
+    return f
+
+
+def make_episode(spec: EpisodeSpec, index: int, base_seed: int = REFERENCE_SEED):
+    """One episode on the CPU.  Returns a dict of tensors:
+    feats1 [S+Q, c, h, w], feats2 (if spec.stages == 2), sup_mask [S, 2, H, W] float32,
+    qry_msk [Q, out_h, out_w] uint8 in {0, 1, 255}, cls (int)."""
+    gen = torch.Generator().manual_seed(base_seed * 1_000_003 + index)
+    c = spec.channels
+    u = torch.randn(2, c, generator=gen)
+    u = u / u.norm(dim=1, keepdim=True)
+    iy, ix = nearest_src_index(spec.h, spec.H), nearest_src_index(spec.w, spec.W)
+
+    sup_mask = torch.zeros(spec.shot, 2, spec.H, spec.W)
+    lows = []
+    for s in range(spec.shot):
+        y0, y1, x0, x1 = _rect(gen, spec.H, spec.W)
+        sup_mask[s, 0, y0:y1, x0:x1] = 1.0
+        sup_mask[s, 1] = 1.0 - sup_mask[s, 0]
+        lows.append(sup_mask[s, 0][iy][:, ix])
+
+    qry_msk = torch.zeros(spec.query, spec.out_h, spec.out_w, dtype=torch.uint8)
+    oy, ox = nearest_src_index(spec.h, spec.out_h), nearest_src_index(spec.w, spec.out_w)
+    for q in range(spec.query):
+        y0, y1, x0, x1 = _rect(gen, spec.out_h, spec.out_w)
+        if spec.ignore_band > 0:
+            b = spec.ignore_band
+            qry_msk[q, max(0, y0 - b):y1 + b, max(0, x0 - b):x1 + b] = 255
+        qry_msk[q, y0:y1, x0:x1] = 1
+        lows.append((qry_msk[q] == 1).float()[oy][:, ox])
+
+    out = {"sup_mask": sup_mask, "qry_msk": qry_msk,
+           "cls": int(torch.randint(spec.cls_lo, spec.cls_hi + 1, (), generator=gen).item())}
+    for stage in range(spec.stages):
+        out[f"feats{stage + 1}"] = torch.stack([_features(gen, spec, m, u[0], u[1]) for m in lows])
+    return out
+
+
+def make_batch(spec: EpisodeSpec, indices, base_seed: int = REFERENCE_SEED):
+    """Stack episodes into the reference's batch layout:
+    feats* [B(S+Q), c, h, w], sup_mask [B, S, 2, H, W], qry_msk [B, Q, out_h, out_w] uint8, cls [B] int64."""
+    eps = [make_episode(spec, int(i), base_seed) for i in indices]
+    batch = {
+        "sup_mask": torch.stack([e["sup_mask"] for e in eps]),
+        "qry_msk": torch.stack([e["qry_msk"] for e in eps]),
+        "cls": torch.tensor([e["cls"] for e in eps], dtype=torch.int64),
+    }
+    for stage in range(spec.stages):
+        k = f"feats{stage + 1}"
+        batch[k] = torch.cat([e[k] for e in eps], dim=0)
+    return batch
+
+
+def make_ctr(spec: EpisodeSpec, stage: int = 1, base_seed: int = REFERENCE_SEED):
+    """Meta-prototype parameter `ctr [c, 2p]`, initialised like `torch.rand` (`pemp_stage1.py:105`)."""
+    gen = torch.Generator().manual_seed(base_seed * 7919 + stage)
+    return torch.rand(spec.channels, 2 * spec.protos, generator=gen)
+
+
+def device_batch(spec: EpisodeSpec, B: int, device, seed: int = REFERENCE_SEED):
+    """Throughput-benchmark batch generated directly on `device` (same statistics as `make_batch`,
+    vectorised; not bit-identical to it).  Used only where inputs must already be resident in HBM."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    S, Q, c, h, w, H, W = spec.shot, spec.query, spec.channels, spec.h, spec.w, spec.H, spec.W
+    cpu = torch.Generator().manual_seed(seed)
+    sup_fg = torch.zeros(B, S, H, W)
+    qry = torch.zeros(B, Q, spec.out_h, spec.out_w, dtype=torch.uint8)
+    for b in range(B):
+        for s in range(S):
+            y0, y1, x0, x1 = _rect(cpu, H, W)
+            sup_fg[b, s, y0:y1, x0:x1] = 1.0
+        for q in range(Q):
+            y0, y1, x0, x1 = _rect(cpu, spec.out_h, spec.out_w)
+            if spec.ignore_band > 0:
+                k = spec.ignore_band
+                qry[b, q, max(0, y0 - k):y1 + k, max(0, x0 - k):x1 + k] = 255
+            qry[b, q, y0:y1, x0:x1] = 1
+    iy, ix = nearest_src_index(h, H), nearest_src_index(w, W)
+    oy, ox = nearest_src_index(h, spec.out_h), nearest_src_index(w, spec.out_w)
+    low = torch.cat([sup_fg[:, :, iy][:, :, :, ix], (qry == 1).float()[:, :, oy][:, :, :, ox]], dim=1)   # [B, S+Q, h, w]
+    low = low.to(device)
+    u = torch.randn(B, 2, c, generator=gen, device=device)
+    u = u / u.norm(dim=2, keepdim=True)
+    batch = {
+        "sup_mask": torch.stack((sup_fg, 1.0 - sup_fg), dim=2).to(device),
+        "qry_msk": qry.to(device),
+        "cls": torch.randint(spec.cls_lo, spec.cls_hi + 1, (B,), generator=cpu).to(device),
+    }
+    for stage in range(spec.stages):
+        f = torch.randn(B, S + Q, c, h, w, generator=gen, device=device) * spec.noise
+        f += spec.amp * (u[:, 0, None, :, None, None] * low[:, :, None] + u[:, 1, None, :, None, None] * (1.0 - low[:, :, None]))
+        batch[f"feats{stage + 1}"] = f.view(B * (S + Q), c, h, w)
+    return batch
