@@ -1,0 +1,141 @@
+// K7  PANet prototype-alignment reverse pass (alignLoss).
+//
+// replaces networks/panet.py:158-194:
+//   pred.argmax(1) -> query fg/bg masks -> masked average pooling of the QUERY features (eps 1e-5), mean over Q
+//   -> cosine of every SUPPORT feature map against those prototypes (x dist_scalar) -> bilinear up-sampling to
+//   (H, W) -> F.cross_entropy against sup_mask_fg.long() (mean over B*S*H*W, no ignore label).
+//
+// Built from the K1 pooling and K3 matching kernels plus two small kernels here: the argmax mask and a fused
+// "up-sample + 2-class log-softmax + NLL + block sum" that never writes the [BS, 2, H, W] logits.
+// Algorithmic bytes: (Q+S)*c*hw*4 + 2*hw*4 + S*H*W*4 per episode.
+#include "common.cuh"
+
+int pemp_pool_launch(const float* fts, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
+                     int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st);
+
+namespace {
+
+constexpr int kCeThreads = 256;
+
+// pred [N, 2, hw] -> mask [N, 2, hw]: plane 0 = (argmax == 1), plane 1 = (argmax == 0)
+__global__ void argmax_masks_kernel(const float* __restrict__ pred, float* __restrict__ mask, long long total, int hw) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long n = i / hw;
+    int x = static_cast<int>(i - n * hw);
+    float bgv = __ldg(pred + (n * 2 + 0) * hw + x), fgv = __ldg(pred + (n * 2 + 1) * hw + x);
+    float isfg = fgv > bgv ? 1.f : 0.f;
+    mask[(n * 2 + 0) * hw + x] = isfg;
+    mask[(n * 2 + 1) * hw + x] = 1.f - isfg;
+  }
+}
+
+// rev [N, 2, h, w] low-res reverse logits, label planes [N][H*W] floats -> partial[blockIdx] = sum of NLL
+__global__ void __launch_bounds__(kCeThreads)
+upsample_ce_kernel(const float* __restrict__ rev, const float* __restrict__ label, long long label_stride, long long total,
+                   int h, int w, int H, int W, float sy, float sx, float* __restrict__ partial) {
+  const long long HW = static_cast<long long>(H) * W;
+  const int hw = h * w;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long n = i / HW;
+    long long r = i - n * HW;
+    int Y = static_cast<int>(r / W), X = static_cast<int>(r - static_cast<long long>(Y) * W);
+    Lerp ly = lerp_coeff(Y, sy, h), lx = lerp_coeff(X, sx, w);
+    float v[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const float* p = rev + (n * 2 + ch) * hw;
+      float a = __ldg(p + ly.i0 * w + lx.i0), b = __ldg(p + ly.i0 * w + lx.i1);
+      float c = __ldg(p + ly.i1 * w + lx.i0), d = __ldg(p + ly.i1 * w + lx.i1);
+      v[ch] = lerp2(ly.l0, lerp2(lx.l0, a, lx.l1, b), ly.l1, lerp2(lx.l0, c, lx.l1, d));
+    }
+    const int lab = static_cast<int>(__ldg(label + n * label_stride + r));   // .long() truncation
+    const float m = fmaxf(v[0], v[1]);
+    const float lse = m + logf(expf(v[0] - m) + expf(v[1] - m));
+    acc += lse - (lab == 1 ? v[1] : v[0]);
+  }
+  __shared__ float part[kCeThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = threadIdx.x < kCeThreads / 32 ? part[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
+// single CTA: add the block partials in index order in double, divide by the element count
+__global__ void ce_finalize_kernel(const float* __restrict__ partial, int n, double count, float* __restrict__ loss) {
+  __shared__ double part[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(partial[i]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) t += part[i];
+    loss[0] = static_cast<float>(t / count);
+  }
+}
+
+struct Plan {
+  int ce_blocks;
+  size_t off_qmask, off_proto, off_rev, off_partial, off_pool, total;
+};
+Plan make_plan(int B, int S, int Q, int c, int h, int w, int H, int W) {
+  Plan p;
+  const size_t hw = static_cast<size_t>(h) * w;
+  long long total = static_cast<long long>(B) * S * H * W;
+  p.ce_blocks = static_cast<int>(llmin((total + kCeThreads - 1) / kCeThreads, 148LL * 16));
+  p.off_qmask = 0;
+  p.off_proto = align_up(static_cast<size_t>(B) * Q * 2 * hw * sizeof(float), 256);
+  p.off_rev = p.off_proto + align_up(static_cast<size_t>(B) * c * 2 * sizeof(float), 256);
+  p.off_partial = p.off_rev + align_up(static_cast<size_t>(B) * S * 2 * hw * sizeof(float), 256);
+  p.off_pool = p.off_partial + align_up(static_cast<size_t>(p.ce_blocks) * sizeof(float), 256);
+  p.total = p.off_pool + pemp_map_pool_workspace_bytes(B, Q, c, static_cast<int>(hw));
+  return p;
+}
+
+}  // namespace
+
+extern "C" size_t pemp_panet_align_workspace_bytes(int B, int S, int Q, int c, int h, int w, int H, int W) {
+  if (B <= 0 || S <= 0 || Q <= 0 || c <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
+  return make_plan(B, S, Q, c, h, w, H, W).total;
+}
+
+extern "C" int pemp_panet_align(const float* qry_fts, const float* pred, const float* sup_fts, const float* sup_mask_fg,
+                                long long mask_stride, int B, int S, int Q, int c, int h, int w, int H, int W,
+                                float scalar, float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(qry_fts && pred && sup_fts && sup_mask_fg && loss, PEMP_E_NULL);
+  PEMP_REQUIRE(B > 0 && S > 0 && Q > 0 && c > 0 && h > 0 && w > 0 && H > 0 && W > 0, PEMP_E_SHAPE);
+  Plan pl = make_plan(B, S, Q, c, h, w, H, W);
+  PEMP_REQUIRE(workspace && workspace_bytes >= pl.total, PEMP_E_WORKSPACE);
+  char* ws = static_cast<char*>(workspace);
+  float* qmask = reinterpret_cast<float*>(ws + pl.off_qmask);
+  float* fgp = reinterpret_cast<float*>(ws + pl.off_proto);
+  float* bgp = fgp + static_cast<size_t>(B) * c;
+  float* rev = reinterpret_cast<float*>(ws + pl.off_rev);
+  float* partial = reinterpret_cast<float*>(ws + pl.off_partial);
+  cudaStream_t st = as_stream(stream);
+  const int hw = h * w;
+
+  long long npx = static_cast<long long>(B) * Q * hw;
+  argmax_masks_kernel<<<static_cast<unsigned>(llmin((npx + 255) / 256, 148LL * 8)), 256, 0, st>>>(pred, qmask, npx, hw);
+  // query prototypes: "shots" of the pooling kernel are the Q queries of an episode (panet.py:181-186)
+  int rc = pemp_pool_launch(qry_fts, qmask, qmask + hw, 2LL * hw, B, Q, c, hw, 1e-5f, nullptr, fgp, bgp, ws + pl.off_pool,
+                            workspace_bytes - pl.off_pool, st);
+  if (rc != PEMP_OK) return rc;
+  // reverse matching: every support map against its episode's query prototypes (panet.py:189, b-major expansion)
+  rc = pemp_cosine_match(sup_fts, fgp, bgp, B * S, B, c, hw, 1, scalar, nullptr, rev, nullptr, stream);
+  if (rc != PEMP_OK) return rc;
+  long long total = static_cast<long long>(B) * S * H * W;
+  upsample_ce_kernel<<<pl.ce_blocks, kCeThreads, 0, st>>>(rev, sup_mask_fg, mask_stride, total, h, w, H, W,
+                                                          lerp_scale(h, H), lerp_scale(w, W), partial);
+  ce_finalize_kernel<<<1, 256, 0, st>>>(partial, pl.ce_blocks, static_cast<double>(total), loss);
+  return launch_status();
+}

@@ -1,0 +1,237 @@
+// Resampling kernels: K0 nearest mask down-sampling, K4 bilinear up-sampling + argmax, K5 nearest label
+// up-sampling, the stand-alone bilinear resize and the adjoint (transposed) bilinear operator of K6.
+// All are tiny next to the feature streams (K1-K3); they are written for coalesced stores.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ K0
+// in [planes, H, W] -> out [planes, h, w]; one thread per output element.  Reads are a strided gather
+// (every ~8th float of every ~8th row): 51 of 401 rows are touched, ~13 % of the mask bytes.
+__global__ void mask_nearest_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int H, int W,
+                                    int h, int w, float sy, float sx) {
+  long long total = static_cast<long long>(planes) * h * w;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int x = static_cast<int>(i % w);
+    long long t = i / w;
+    int y = static_cast<int>(t % h);
+    long long pl = t / h;
+    out[i] = __ldg(in + (pl * H + nearest_src(y, sy, H)) * W + nearest_src(x, sx, W));
+  }
+}
+
+extern "C" int pemp_mask_nearest(const float* in, int planes, int H, int W, int h, int w, float* out,
+                                 pemp_stream_t stream) {
+  PEMP_REQUIRE(in && out, PEMP_E_NULL);
+  PEMP_REQUIRE(planes > 0 && H > 0 && W > 0 && h > 0 && w > 0, PEMP_E_SHAPE);
+  long long total = static_cast<long long>(planes) * h * w;
+  int block = 256;
+  int grid = static_cast<int>(llmin((total + block - 1) / block, 148LL * 16));
+  // ATen computes the scale as float(in) / out (UpSample.h compute_scales_value with no user scale)
+  float sy = static_cast<float>(H) / static_cast<float>(h), sx = static_cast<float>(W) / static_cast<float>(w);
+  mask_nearest_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, planes, H, W, h, w, sy, sx);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+__global__ void nearest_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int planes, int h, int w,
+                                   int H, int W, float sy, float sx) {
+  long long total = static_cast<long long>(planes) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int X = static_cast<int>(i % W);
+    long long t = i / W;
+    int Y = static_cast<int>(t % H);
+    long long pl = t / H;
+    out[i] = __ldg(in + (pl * h + nearest_src(Y, sy, h)) * w + nearest_src(X, sx, w));
+  }
+}
+
+extern "C" int pemp_nearest_resize_i64(const int64_t* in, int planes, int h, int w, int H, int W, int64_t* out,
+                                       pemp_stream_t stream) {
+  PEMP_REQUIRE(in && out, PEMP_E_NULL);
+  PEMP_REQUIRE(planes > 0 && H > 0 && W > 0 && h > 0 && w > 0, PEMP_E_SHAPE);
+  long long total = static_cast<long long>(planes) * H * W;
+  int block = 256;
+  int grid = static_cast<int>(llmin((total + block - 1) / block, 148LL * 16));
+  float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
+  nearest_i64_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, planes, h, w, H, W, sy, sx);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// pred [N, 2, h, w] -> logits [N, 2, H, W] (optional), mask8 / mask64 [N, H, W] (optional).
+// One thread produces 4 consecutive outputs of the flattened [N*H*W] index space so the uint8 mask is
+// written with aligned 32-bit stores whatever W is (401 is odd).  The low-res map (2*h*w floats, 20.8 KB
+// at 51x51) stays in L1/L2; the kernel is bound by the mask / logits store.
+template <bool kLogits, bool kMask8, bool kMask64>
+__global__ void upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logits,
+                                       uint8_t* __restrict__ mask8, int64_t* __restrict__ mask64, long long total,
+                                       int h, int w, int H, int W, float sy, float sx) {
+  const long long HW = static_cast<long long>(H) * W;
+  const int hw = h * w;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q * 4 < total;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      long long i = q * 4 + e;
+      if (i >= total) break;
+      int X = static_cast<int>(i % W);
+      long long t = i / W;
+      int Y = static_cast<int>(t % H);
+      long long n = t / H;
+      Lerp ly = lerp_coeff(Y, sy, h), lx = lerp_coeff(X, sx, w);
+      const float* p0 = pred + n * 2 * hw;
+      float v[2];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float* p = p0 + ch * hw;
+        float a = __ldg(p + ly.i0 * w + lx.i0), b = __ldg(p + ly.i0 * w + lx.i1);
+        float c = __ldg(p + ly.i1 * w + lx.i0), d = __ldg(p + ly.i1 * w + lx.i1);
+        v[ch] = lerp2(ly.l0, lerp2(lx.l0, a, lx.l1, b), ly.l1, lerp2(lx.l0, c, lx.l1, d));
+      }
+      uint32_t m = v[1] > v[0] ? 1u : 0u;   // first index wins ties => background
+      packed |= m << (8 * e);
+      if (kLogits) {
+        long long o = n * 2 * HW + static_cast<long long>(Y) * W + X;
+        logits[o] = v[0];
+        logits[o + HW] = v[1];
+      }
+      if (kMask64) mask64[i] = static_cast<int64_t>(m);
+    }
+    if (kMask8) {
+      if (q * 4 + 3 < total) {
+        reinterpret_cast<uint32_t*>(mask8)[q] = packed;
+      } else {
+        for (int e = 0; q * 4 + e < total; ++e) mask8[q * 4 + e] = static_cast<uint8_t>(packed >> (8 * e));
+      }
+    }
+  }
+}
+
+extern "C" int pemp_upsample_argmax(const float* pred, int N, int h, int w, int H, int W, float* logits, uint8_t* mask8,
+                                    int64_t* mask64, pemp_stream_t stream) {
+  PEMP_REQUIRE(pred, PEMP_E_NULL);
+  PEMP_REQUIRE(logits || mask8 || mask64, PEMP_E_NULL);
+  PEMP_REQUIRE(N > 0 && H > 0 && W > 0 && h > 0 && w > 0, PEMP_E_SHAPE);
+  PEMP_REQUIRE((reinterpret_cast<uintptr_t>(mask8) & 3) == 0, PEMP_E_ALIGN);
+  long long total = static_cast<long long>(N) * H * W;
+  int block = 256;
+  int grid = static_cast<int>(llmin((total / 4 + block) / block, 148LL * 32));
+  float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
+  cudaStream_t st = as_stream(stream);
+#define PEMP_LAUNCH_UA(L, M8, M64)                                                                              \
+  upsample_argmax_kernel<L, M8, M64><<<grid, block, 0, st>>>(pred, logits, mask8, mask64, total, h, w, H, W, sy, sx)
+  int sel = (logits ? 4 : 0) | (mask8 ? 2 : 0) | (mask64 ? 1 : 0);
+  switch (sel) {
+    case 1: PEMP_LAUNCH_UA(false, false, true); break;
+    case 2: PEMP_LAUNCH_UA(false, true, false); break;
+    case 3: PEMP_LAUNCH_UA(false, true, true); break;
+    case 4: PEMP_LAUNCH_UA(true, false, false); break;
+    case 5: PEMP_LAUNCH_UA(true, false, true); break;
+    case 6: PEMP_LAUNCH_UA(true, true, false); break;
+    default: PEMP_LAUNCH_UA(true, true, true); break;
+  }
+#undef PEMP_LAUNCH_UA
+  return launch_status();
+}
+
+// single-plane bilinear resize with the same arithmetic (PFENet's mask resize, pfenet.py:191,205)
+__global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int h,
+                                       int w, int H, int W, float sy, float sx) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int X = static_cast<int>(i % W);
+    long long t = i / W;
+    int Y = static_cast<int>(t % H);
+    const float* p = in + (t / H) * h * w;
+    Lerp ly = lerp_coeff(Y, sy, h), lx = lerp_coeff(X, sx, w);
+    float a = __ldg(p + ly.i0 * w + lx.i0), b = __ldg(p + ly.i0 * w + lx.i1);
+    float c = __ldg(p + ly.i1 * w + lx.i0), d = __ldg(p + ly.i1 * w + lx.i1);
+    out[i] = lerp2(ly.l0, lerp2(lx.l0, a, lx.l1, b), ly.l1, lerp2(lx.l0, c, lx.l1, d));
+  }
+}
+
+extern "C" int pemp_bilinear_resize(const float* in, int planes, int h, int w, int H, int W, float* out,
+                                    pemp_stream_t stream) {
+  PEMP_REQUIRE(in && out, PEMP_E_NULL);
+  PEMP_REQUIRE(planes > 0 && H > 0 && W > 0 && h > 0 && w > 0, PEMP_E_SHAPE);
+  long long total = static_cast<long long>(planes) * H * W;
+  int block = 256;
+  int grid = static_cast<int>(llmin((total + block - 1) / block, 148LL * 32));
+  bilinear_resize_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, total, h, w, H, W, lerp_scale(h, H),
+                                                                lerp_scale(w, W));
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------- K6 adjoint
+// wt[y, x] = sum_{Y, X} m[Y, X] * a_y(Y) * b_x(X), where a_y(Y) is the weight the forward bilinear
+// operator (h -> H, align_corners) gives source row y for output row Y.  With it
+//   sum_{YX} m * (U f) == sum_{yx} f * wt      (baseline.py:100-110 without the 329 MB/shot up-sampled copy).
+// One CTA per (plane, low-res row y): stage 1 reduces the <= 2/scale contributing mask rows into a
+// weighted row r[X] in shared memory (coalesced reads of the mask), stage 2 applies the column weights.
+// msum[plane] (optional) accumulates the plain mask sum (the reference's denominator, exact for 0/1 masks).
+__global__ void bilinear_adjoint_kernel(const float* __restrict__ mask, float* __restrict__ wt, float* __restrict__ msum,
+                                        int H, int W, int h, int w, float sy, float sx) {
+  extern __shared__ float row[];   // [W]
+  const int y = blockIdx.x, pl = blockIdx.y;
+  const float* m = mask + static_cast<long long>(pl) * H * W;
+  // rows Y whose i0 or i1 equals y lie in [ (y-1)/sy, (y+1)/sy ]; widen by one for rounding
+  int Ylo = 0, Yhi = H - 1;
+  if (sy > 0.f) {
+    Ylo = max(0, static_cast<int>(floorf((y - 1) / sy)) - 1);
+    Yhi = min(H - 1, static_cast<int>(ceilf((y + 1) / sy)) + 1);
+  }
+  for (int X = threadIdx.x; X < W; X += blockDim.x) {
+    float acc = 0.f;
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+      Lerp l = lerp_coeff(Y, sy, h);
+      float wgt = (l.i0 == y ? l.l0 : 0.f) + (l.i1 == y ? l.l1 : 0.f);
+      if (wgt != 0.f) acc = fmaf(wgt, __ldg(m + static_cast<long long>(Y) * W + X), acc);
+    }
+    row[X] = acc;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    int Xlo = 0, Xhi = W - 1;
+    if (sx > 0.f) {
+      Xlo = max(0, static_cast<int>(floorf((x - 1) / sx)) - 1);
+      Xhi = min(W - 1, static_cast<int>(ceilf((x + 1) / sx)) + 1);
+    }
+    float acc = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      Lerp l = lerp_coeff(X, sx, w);
+      float wgt = (l.i0 == x ? l.l0 : 0.f) + (l.i1 == x ? l.l1 : 0.f);
+      if (wgt != 0.f) acc = fmaf(wgt, row[X], acc);
+    }
+    wt[(static_cast<long long>(pl) * h + y) * w + x] = acc;
+  }
+}
+
+// plain per-plane sum (deterministic: one CTA per plane, fixed reduction tree)
+__global__ void plane_sum_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  __shared__ float part[32];
+  const float* p = in + blockIdx.x * n;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += __ldg(p + i);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+extern "C" int pemp_bilinear_adjoint(const float* mask, int planes, int H, int W, int h, int w, float* wt, float* msum,
+                                     pemp_stream_t stream) {
+  PEMP_REQUIRE(mask && wt, PEMP_E_NULL);
+  PEMP_REQUIRE(planes > 0 && H > 0 && W > 0 && h > 0 && w > 0 && W <= 12000, PEMP_E_SHAPE);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(h, planes);
+  bilinear_adjoint_kernel<<<grid, 256, W * sizeof(float), st>>>(mask, wt, msum, H, W, h, w, lerp_scale(h, H),
+                                                                lerp_scale(w, W));
+  if (msum) plane_sum_kernel<<<planes, 1024, 0, st>>>(mask, msum, static_cast<long long>(H) * W);
+  return launch_status();
+}

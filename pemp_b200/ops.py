@@ -1,0 +1,323 @@
+"""Torch-tensor front end of the C ABI: argument validation, workspace and stream plumbing.
+
+Each function takes CUDA tensors, passes raw device pointers + the current stream to
+`libpemp_b200.so`, and returns freshly allocated CUDA tensors.  Nothing here computes on the host and
+nothing falls back to PyTorch ops.
+"""
+import torch
+
+from . import _cabi
+
+_launches = 0      # kernels launched through this module (bench.py's `gpu_launches` claim)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (pemp_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _mask_pair(fg, bg, n_img, hw):
+    """fg / bg may be two views of one [n_img, 2, hw] tensor (the K0 output) or separate [n_img, hw] tensors.
+    Returns (fg_ptr, bg_ptr, stride_in_floats, keepalive)."""
+    if fg.dim() != 2 or fg.shape != (n_img, hw):
+        raise ValueError(f"mask must be [{n_img}, {hw}], got {tuple(fg.shape)}")
+    if bg is not None and bg.shape != fg.shape:
+        raise ValueError("fg and bg masks differ in shape")
+    ok = fg.stride(1) == 1 and (bg is None or (bg.stride(1) == 1 and bg.stride(0) == fg.stride(0)))
+    if n_img > 1 and fg.stride(0) < hw:
+        ok = False
+    if not ok:
+        fg = fg.contiguous()
+        bg = None if bg is None else bg.contiguous()
+    stride = fg.stride(0) if n_img > 1 else hw
+    return fg.data_ptr(), (0 if bg is None else bg.data_ptr()), stride, (fg, bg)
+
+
+# ------------------------------------------------------------------------------------------------ K0
+def mask_nearest(mask, h, w):
+    """[..., H, W] float32 -> [..., h, w] (`F.interpolate(mode='nearest')`, pemp_stage1.py:147)."""
+    mask = _need(mask, torch.float32, "mask")
+    H, W = mask.shape[-2:]
+    planes = mask.numel() // (H * W)
+    out = torch.empty(*mask.shape[:-2], h, w, dtype=torch.float32, device=mask.device)
+    _cabi.check(_cabi.lib().pemp_mask_nearest(mask.data_ptr(), planes, H, W, h, w, out.data_ptr(), _stream()),
+                "pemp_mask_nearest")
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K1 / K8
+def map_pool_lowres(fts, fg, bg, B, S, eps=1e-5):
+    """fts [B*S, c, hw]; fg, bg [B*S, hw] -> (fg_proto [B, c], bg_proto [B, c])  (pemp_stage1.py:223-227)."""
+    fts = _need(fts, torch.float32, "fts")
+    n_img, c, hw = fts.shape
+    if n_img != B * S:
+        raise ValueError(f"fts has {n_img} images, expected B*S = {B * S}")
+    fg = _need_loose(fg, "fg")
+    bg = None if bg is None else _need_loose(bg, "bg")
+    fgp, bgp, stride, keep = _mask_pair(fg, bg, n_img, hw)
+    L = _cabi.lib()
+    ws = _ws(L.pemp_map_pool_workspace_bytes(B, S, c, hw), fts.device)
+    out_f = torch.empty(B, c, dtype=torch.float32, device=fts.device)
+    out_b = torch.empty(B, c, dtype=torch.float32, device=fts.device) if bg is not None else None
+    _cabi.check(L.pemp_map_pool_lowres(fts.data_ptr(), fgp, bgp, stride, B, S, c, hw, float(eps), out_f.data_ptr(),
+                                       _ptr(out_b), ws.data_ptr(), ws.numel(), _stream()), "pemp_map_pool_lowres")
+    _count(2)
+    del keep
+    return out_f, out_b
+
+
+def _need_loose(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (pemp_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def weighted_gap(supp_feat, mask):
+    """PFENet `Weighted_GAP(supp_feat [B,c,h,w], mask [B,1,h,w]) -> [B,c,1,1]` (pfenet.py:15-20)."""
+    supp_feat = _need(supp_feat, torch.float32, "supp_feat")
+    mask = _need(mask, torch.float32, "mask")
+    B, c, h, w = supp_feat.shape
+    if mask.numel() != B * h * w:
+        raise ValueError(f"mask must be [B,1,h,w] = [{B},1,{h},{w}], got {tuple(mask.shape)}")
+    L = _cabi.lib()
+    ws = _ws(L.pemp_map_pool_workspace_bytes(B, 1, c, h * w), supp_feat.device)
+    out = torch.empty(B, c, 1, 1, dtype=torch.float32, device=supp_feat.device)
+    _cabi.check(L.pemp_weighted_gap(supp_feat.data_ptr(), mask.data_ptr(), B, c, h * w, out.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _stream()), "pemp_weighted_gap")
+    _count(2)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K2
+def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
+    """fts [B*S, c, hw]; ctr [c, 2p]; fg, bg [B*S, hw] -> fg_proto [B,c,p], bg_proto [B,c,p], adaptive_p [B,c,2p]
+    (pemp_stage1.py:202-213, pemp_stage2.py:174-186)."""
+    fts = _need(fts, torch.float32, "fts")
+    ctr = _need(ctr, torch.float32, "ctr")
+    n_img, c, hw = fts.shape
+    if n_img != B * S:
+        raise ValueError(f"fts has {n_img} images, expected B*S = {B * S}")
+    if ctr.dim() != 2 or ctr.shape[0] != c or ctr.shape[1] % 2:
+        raise ValueError(f"ctr must be [c, 2p] with c = {c}, got {tuple(ctr.shape)}")
+    p = ctr.shape[1] // 2
+    fgp, bgp, stride, keep = _mask_pair(_need_loose(fg, "fg"), _need_loose(bg, "bg"), n_img, hw)
+    L = _cabi.lib()
+    ws = _ws(L.pemp_meta_proto_attn_workspace_bytes(B, S, c, hw, p), fts.device)
+    out_f = torch.empty(B, c, p, dtype=torch.float32, device=fts.device)
+    out_b = torch.empty(B, c, p, dtype=torch.float32, device=fts.device)
+    adaptive = torch.empty(B, c, 2 * p, dtype=torch.float32, device=fts.device) if want_adaptive else None
+    _cabi.check(L.pemp_meta_proto_attn(fts.data_ptr(), ctr.data_ptr(), fgp, bgp, stride, B, S, c, hw, p, float(eps),
+                                       out_f.data_ptr(), out_b.data_ptr(), _ptr(adaptive), ws.data_ptr(), ws.numel(),
+                                       _stream()), "pemp_meta_proto_attn")
+    _count(3 if p > 1 else 2)
+    del keep
+    return out_f, out_b, adaptive
+
+
+# ------------------------------------------------------------------------------------------------ K3
+def cosine_match(qry, fg_proto, bg_proto, scalar=20.0, want_sim=False, want_pred=True, want_response=False):
+    """qry [N, c, hw]; protos [Bp, c] or [Bp, c, P] -> dict(sim [N,2,P,hw], pred [N,2,hw], response [N,hw] int64)
+    (compute_similarity + max over prototypes, pemp_stage1.py:214-222,233-261)."""
+    qry = _need(qry, torch.float32, "qry")
+    fg_proto = _need(fg_proto, torch.float32, "fg_proto")
+    bg_proto = _need(bg_proto, torch.float32, "bg_proto")
+    N, c, hw = qry.shape
+    if fg_proto.shape != bg_proto.shape or fg_proto.shape[1] != c:
+        raise ValueError(f"prototypes must be [Bp, {c}(, P)], got {tuple(fg_proto.shape)} / {tuple(bg_proto.shape)}")
+    Bp = fg_proto.shape[0]
+    P = 1 if fg_proto.dim() == 2 else fg_proto.shape[2]
+    if N % Bp:
+        raise ValueError(f"{N} query maps cannot be split over {Bp} prototype sets")
+    dev = qry.device
+    sim = torch.empty(N, 2, P, hw, dtype=torch.float32, device=dev) if want_sim else None
+    pred = torch.empty(N, 2, hw, dtype=torch.float32, device=dev) if want_pred else None
+    resp = torch.empty(N, hw, dtype=torch.int64, device=dev) if want_response else None
+    _cabi.check(_cabi.lib().pemp_cosine_match(qry.data_ptr(), fg_proto.data_ptr(), bg_proto.data_ptr(), N, Bp, c, hw, P,
+                                              float(scalar), _ptr(sim), _ptr(pred), _ptr(resp), _stream()),
+                "pemp_cosine_match")
+    _count(1)
+    return {"sim": sim, "pred": pred, "response": resp}
+
+
+# ------------------------------------------------------------------------------------------------ K4 / K5
+def upsample_argmax(pred, out_hw, want_logits=False, want_mask8=True, want_mask64=False):
+    """pred [N, 2, h, w] -> dict(logits [N,2,H,W], mask8 [N,H,W] uint8, mask64 [N,H,W] int64)
+    (F.interpolate bilinear align_corners + argmax, pemp_stage1.py:157-162, entry/pemp_stage1.py:52)."""
+    pred = _need(pred, torch.float32, "pred")
+    N, two, h, w = pred.shape
+    if two != 2:
+        raise ValueError("pred must be [N, 2, h, w]")
+    H, W = int(out_hw[0]), int(out_hw[1])
+    dev = pred.device
+    logits = torch.empty(N, 2, H, W, dtype=torch.float32, device=dev) if want_logits else None
+    m8 = torch.empty(N, H, W, dtype=torch.uint8, device=dev) if want_mask8 else None
+    m64 = torch.empty(N, H, W, dtype=torch.int64, device=dev) if want_mask64 else None
+    _cabi.check(_cabi.lib().pemp_upsample_argmax(pred.data_ptr(), N, h, w, H, W, _ptr(logits), _ptr(m8), _ptr(m64),
+                                                 _stream()), "pemp_upsample_argmax")
+    _count(1)
+    return {"logits": logits, "mask8": m8, "mask64": m64}
+
+
+def bilinear_resize(x, out_hw):
+    """[..., h, w] float32 -> [..., H, W], bilinear align_corners=True (pfenet.py:191,205)."""
+    x = _need(x, torch.float32, "x")
+    h, w = x.shape[-2:]
+    H, W = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty(*x.shape[:-2], H, W, dtype=torch.float32, device=x.device)
+    _cabi.check(_cabi.lib().pemp_bilinear_resize(x.data_ptr(), x.numel() // (h * w), h, w, H, W, out.data_ptr(),
+                                                 _stream()), "pemp_bilinear_resize")
+    _count(1)
+    return out
+
+
+def nearest_resize_labels(lab, out_hw):
+    """[..., h, w] int64 -> [..., H, W] nearest (response map, pemp_stage1.py:158-159)."""
+    lab = _need(lab, torch.int64, "labels")
+    h, w = lab.shape[-2:]
+    H, W = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty(*lab.shape[:-2], H, W, dtype=torch.int64, device=lab.device)
+    _cabi.check(_cabi.lib().pemp_nearest_resize_i64(lab.data_ptr(), lab.numel() // (h * w), h, w, H, W, out.data_ptr(),
+                                                    _stream()), "pemp_nearest_resize_i64")
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K6
+def map_pool_fullres(fts, sup_mask, B, S, eps=1e-5):
+    """fts [B*S, c, h, w]; sup_mask [B*S, 2, H, W] -> (fg_proto [B,c], bg_proto [B,c])  (baseline.py:100-110)."""
+    fts = _need(fts, torch.float32, "fts")
+    sup_mask = _need(sup_mask, torch.float32, "sup_mask")
+    n_img, c, h, w = fts.shape
+    if n_img != B * S or sup_mask.shape[:2] != (n_img, 2):
+        raise ValueError(f"expected fts [{B * S},c,h,w] and sup_mask [{B * S},2,H,W]")
+    H, W = sup_mask.shape[-2:]
+    L = _cabi.lib()
+    ws = _ws(L.pemp_map_pool_fullres_workspace_bytes(B, S, c, h, w), fts.device)
+    out_f = torch.empty(B, c, dtype=torch.float32, device=fts.device)
+    out_b = torch.empty(B, c, dtype=torch.float32, device=fts.device)
+    _cabi.check(L.pemp_map_pool_fullres(fts.data_ptr(), sup_mask.data_ptr(), B, S, c, h, w, H, W, float(eps),
+                                        out_f.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "pemp_map_pool_fullres")
+    _count(4)
+    return out_f, out_b
+
+
+def bilinear_adjoint(mask, out_hw, want_sum=True):
+    """mask [..., H, W] -> (U^T mask [..., h, w], plane sums [...])."""
+    mask = _need(mask, torch.float32, "mask")
+    H, W = mask.shape[-2:]
+    h, w = int(out_hw[0]), int(out_hw[1])
+    planes = mask.numel() // (H * W)
+    wt = torch.empty(*mask.shape[:-2], h, w, dtype=torch.float32, device=mask.device)
+    ms = torch.empty(mask.shape[:-2], dtype=torch.float32, device=mask.device) if want_sum else None
+    _cabi.check(_cabi.lib().pemp_bilinear_adjoint(mask.data_ptr(), planes, H, W, h, w, wt.data_ptr(), _ptr(ms), _stream()),
+                "pemp_bilinear_adjoint")
+    _count(2 if want_sum else 1)
+    return wt, ms
+
+
+# ------------------------------------------------------------------------------------------------ K7
+def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
+    """`PANet.alignLoss(qry_fts [BQ,c,h,w], pred [BQ,2,h,w], sup_fts [BS,c,h,w], sup_mask_fg [BS,1,H,W], Q)`
+    -> 0-dim loss tensor (panet.py:158-194)."""
+    qry_fts = _need(qry_fts, torch.float32, "qry_fts")
+    pred = _need(pred, torch.float32, "pred")
+    sup_fts = _need(sup_fts, torch.float32, "sup_fts")
+    sup_mask_fg = _need_loose(sup_mask_fg, "sup_mask_fg")
+    BQ, c, h, w = qry_fts.shape
+    BS = sup_fts.shape[0]
+    if BQ % Q:
+        raise ValueError("qry_fts batch is not a multiple of Q")
+    B = BQ // Q
+    if BS % B:
+        raise ValueError("sup_fts batch is not a multiple of B")
+    S = BS // B
+    H, W = sup_mask_fg.shape[-2:]
+    m = sup_mask_fg.reshape(BS, H * W) if sup_mask_fg.dim() != 2 else sup_mask_fg
+    if m.stride(1) != 1 or (BS > 1 and m.stride(0) < H * W):
+        m = m.contiguous()
+    stride = m.stride(0) if BS > 1 else H * W
+    L = _cabi.lib()
+    ws = _ws(L.pemp_panet_align_workspace_bytes(B, S, Q, c, h, w, H, W), qry_fts.device)
+    loss = torch.empty((), dtype=torch.float32, device=qry_fts.device)
+    _cabi.check(L.pemp_panet_align(qry_fts.data_ptr(), pred.data_ptr(), sup_fts.data_ptr(), m.data_ptr(), stride, B, S, Q,
+                                   c, h, w, H, W, float(scalar), loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "pemp_panet_align")
+    _count(6)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------ K9
+PRIOR_BF16, PRIOR_FP32, PRIOR_BF16X3 = 0, 1, 2
+
+
+def prior_mask(q4, s4, smask, precision=PRIOR_FP32, want_rowmax=False):
+    """q4 [B, C, hq, wq]; s4 [S, B, C, hs, ws]; smask [S, B, hs, ws] (support mask at feature size)
+    -> prior [B, 1, hq, wq] (and rowmax [S, B, hq*wq])  (pfenet.py:201-231)."""
+    q4 = _need(q4, torch.float32, "q4")
+    s4 = _need(s4, torch.float32, "s4")
+    smask = _need(smask, torch.float32, "smask")
+    B, C, hq, wq = q4.shape
+    S = s4.shape[0]
+    hs, ws_ = s4.shape[-2:]
+    if s4.shape[:3] != (S, B, C) or smask.numel() != S * B * hs * ws_:
+        raise ValueError("expected s4 [S,B,C,h,w] and smask [S,B,h,w]")
+    L = _cabi.lib()
+    ws = _ws(L.pemp_prior_mask_workspace_bytes(B, S, C, hs * ws_, hq * wq, precision), q4.device)
+    prior = torch.empty(B, 1, hq, wq, dtype=torch.float32, device=q4.device)
+    rowmax = torch.empty(S, B, hq * wq, dtype=torch.float32, device=q4.device) if want_rowmax else None
+    _cabi.check(L.pemp_prior_mask(q4.data_ptr(), s4.data_ptr(), smask.data_ptr(), B, S, C, hs * ws_, hq * wq, precision,
+                                  prior.data_ptr(), _ptr(rowmax), ws.data_ptr(), ws.numel(), _stream()),
+                "pemp_prior_mask")
+    _count(4)
+    return (prior, rowmax) if want_rowmax else prior
+
+
+# ------------------------------------------------------------------------------------------------ K10
+def iou_hist(pred, ref, cls, stat):
+    """Accumulate `FewShotMetric.update` counts on the device.  pred, ref [N, ...] uint8 (same shape);
+    cls [N] int64; stat [(C+1), 3] int64 is updated in place (core/metrics.py:9-23)."""
+    pred = _need(pred, torch.uint8, "pred")
+    ref = _need(ref, torch.uint8, "ref")
+    cls = _need(cls, torch.int64, "cls")
+    stat = _need(stat, torch.int64, "stat")
+    N = pred.shape[0]
+    if ref.numel() != pred.numel() or cls.numel() != N:
+        raise ValueError("pred / ref / cls disagree in size")
+    if stat.dim() != 2 or stat.shape[1] != 3:
+        raise ValueError("stat must be [(classes+1), 3]")
+    _cabi.check(_cabi.lib().pemp_iou_hist(pred.data_ptr(), ref.data_ptr(), cls.data_ptr(), N, pred.numel() // N,
+                                          stat.shape[0] - 1, stat.data_ptr(), _stream()), "pemp_iou_hist")
+    _count(1)
+    return stat
