@@ -12,6 +12,11 @@
  *     and never synchronise; they are re-entrant and may be issued from several host threads;
  *   - return value: 0 = PEMP_OK, negative = PEMP_E_* argument error (nothing was launched), positive =
  *     the cudaError_t reported by the launch.  No exceptions, no abort, no output on stdout/stderr;
+ *   - feature tensors take an *episode stride*: image i of a [B*S, c, hw] operand lives at
+ *       base + (i / S) * episode_stride + (i % S) * c * hw        (floats),
+ *     so the support (or query) maps can be read in place from the encoder output
+ *     `features [B, S+Q, c, h, w]` (episode_stride = (S+Q)*c*hw, networks/pemp_stage1.py:141-144) without the
+ *     copy `features[:, :S].reshape(...)` makes for B > 1.  0 means dense (episode_stride = S*c*hw);
  *   - workspace: `pemp_<op>_workspace_bytes(...)` gives the scratch size for the same dimensions; pass a
  *     256-byte aligned device buffer of at least that size.
  */
@@ -56,7 +61,7 @@ int pemp_mask_nearest(const float* in, int planes, int H, int W, int h, int w, f
  * NULL (then bg_proto is ignored).  Outputs fg_proto / bg_proto [B, c] = mean over the S shots of
  * sum_x f*m / (sum_x m + eps).                                                                         */
 size_t pemp_map_pool_workspace_bytes(int B, int S, int c, int hw);
-int pemp_map_pool_lowres(const float* fts, const float* fg, const float* bg, long long mask_stride,
+int pemp_map_pool_lowres(const float* fts, long long fts_episode_stride, const float* fg, const float* bg, long long mask_stride,
                          int B, int S, int c, int hw, float eps,
                          float* fg_proto, float* bg_proto,
                          void* workspace, size_t workspace_bytes, pemp_stream_t stream);
@@ -74,7 +79,7 @@ int pemp_weighted_gap(const float* supp_feat, const float* mask, int B, int c, i
  * Outputs fg_proto, bg_proto [B, c, p] and (nullable) adaptive_p [B, c, 2p] (fg columns first,
  * pemp_stage2.py:185).  1 <= p <= 4.                                                                    */
 size_t pemp_meta_proto_attn_workspace_bytes(int B, int S, int c, int hw, int p);
-int pemp_meta_proto_attn(const float* fts, const float* ctr, const float* fg, const float* bg, long long mask_stride,
+int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg, const float* bg, long long mask_stride,
                          int B, int S, int c, int hw, int p, float eps,
                          float* fg_proto, float* bg_proto, float* adaptive_p,
                          void* workspace, size_t workspace_bytes, pemp_stream_t stream);
@@ -90,7 +95,7 @@ int pemp_meta_proto_attn(const float* fts, const float* ctr, const float* fg, co
  *   pred     [N, 2, hw]     max over the P prototypes of each class
  *   response [N, hw] int64  bg-argmax where bg wins, fg-argmax + 3 where fg wins (pemp_stage1.py:217-222)
  * 1 <= P <= 4.                                                                                          */
-int pemp_cosine_match(const float* qry, const float* fg_proto, const float* bg_proto,
+int pemp_cosine_match(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
                       int N, int Bp, int c, int hw, int P, float scalar,
                       float* sim, float* pred, int64_t* response, pemp_stream_t stream);
 
@@ -116,7 +121,7 @@ int pemp_nearest_resize_i64(const int64_t* in, int planes, int h, int w, int H, 
  * to a [B*S, 2, h, w] weight map, the features are read once at low resolution.
  * fts [B*S, c, h*w]; sup_mask [B*S, 2, H, W] (fg, bg) -> fg_proto, bg_proto [B, c].                     */
 size_t pemp_map_pool_fullres_workspace_bytes(int B, int S, int c, int h, int w);
-int pemp_map_pool_fullres(const float* fts, const float* sup_mask, int B, int S, int c, int h, int w, int H, int W,
+int pemp_map_pool_fullres(const float* fts, long long fts_episode_stride, const float* sup_mask, int B, int S, int c, int h, int w, int H, int W,
                           float eps, float* fg_proto, float* bg_proto,
                           void* workspace, size_t workspace_bytes, pemp_stream_t stream);
 /* the adjoint resampler on its own: mask [planes, H, W] -> wt [planes, h, w], msum [planes] (nullable) =
@@ -130,7 +135,8 @@ int pemp_bilinear_adjoint(const float* mask, int planes, int H, int W, int h, in
  * sup_mask_fg: plane i at sup_mask_fg + i*mask_stride, [H, W] floats used as class labels (long cast).
  * loss[0] = mean over B*S*H*W of -log_softmax(upsampled reverse logits)[label].                         */
 size_t pemp_panet_align_workspace_bytes(int B, int S, int Q, int c, int h, int w, int H, int W);
-int pemp_panet_align(const float* qry_fts, const float* pred, const float* sup_fts,
+int pemp_panet_align(const float* qry_fts, long long qry_episode_stride, const float* pred,
+                     const float* sup_fts, long long sup_episode_stride,
                      const float* sup_mask_fg, long long mask_stride,
                      int B, int S, int Q, int c, int h, int w, int H, int W, float scalar,
                      float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream);

@@ -19,19 +19,19 @@ SIGNATURES = {
     "pemp_check_device": (I, []),
     "pemp_mask_nearest": (I, [P, I, I, I, I, I, P, P]),
     "pemp_map_pool_workspace_bytes": (SZ, [I, I, I, I]),
-    "pemp_map_pool_lowres": (I, [P, P, P, LL, I, I, I, I, F, P, P, P, SZ, P]),
+    "pemp_map_pool_lowres": (I, [P, LL, P, P, LL, I, I, I, I, F, P, P, P, SZ, P]),
     "pemp_weighted_gap": (I, [P, P, I, I, I, P, P, SZ, P]),
     "pemp_meta_proto_attn_workspace_bytes": (SZ, [I, I, I, I, I]),
-    "pemp_meta_proto_attn": (I, [P, P, P, P, LL, I, I, I, I, I, F, P, P, P, P, SZ, P]),
-    "pemp_cosine_match": (I, [P, P, P, I, I, I, I, I, F, P, P, P, P]),
+    "pemp_meta_proto_attn": (I, [P, LL, P, P, P, LL, I, I, I, I, I, F, P, P, P, P, SZ, P]),
+    "pemp_cosine_match": (I, [P, LL, P, P, I, I, I, I, I, F, P, P, P, P]),
     "pemp_upsample_argmax": (I, [P, I, I, I, I, I, P, P, P, P]),
     "pemp_bilinear_resize": (I, [P, I, I, I, I, I, P, P]),
     "pemp_nearest_resize_i64": (I, [P, I, I, I, I, I, P, P]),
     "pemp_map_pool_fullres_workspace_bytes": (SZ, [I, I, I, I, I]),
-    "pemp_map_pool_fullres": (I, [P, P, I, I, I, I, I, I, I, F, P, P, P, SZ, P]),
+    "pemp_map_pool_fullres": (I, [P, LL, P, I, I, I, I, I, I, I, F, P, P, P, SZ, P]),
     "pemp_bilinear_adjoint": (I, [P, I, I, I, I, I, P, P, P]),
     "pemp_panet_align_workspace_bytes": (SZ, [I, I, I, I, I, I, I, I]),
-    "pemp_panet_align": (I, [P, P, P, P, LL, I, I, I, I, I, I, I, I, F, P, P, SZ, P]),
+    "pemp_panet_align": (I, [P, LL, P, P, LL, P, LL, I, I, I, I, I, I, I, I, F, P, P, SZ, P]),
     "pemp_prior_mask_workspace_bytes": (SZ, [I, I, I, I, I, I]),
     "pemp_prior_mask": (I, [P, P, P, I, I, I, I, I, I, P, P, P, SZ, P]),
     "pemp_iou_hist": (I, [P, P, P, I, LL, I, P, P]),

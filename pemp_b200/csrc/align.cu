@@ -10,7 +10,7 @@
 // Algorithmic bytes: (Q+S)*c*hw*4 + 2*hw*4 + S*H*W*4 per episode.
 #include "common.cuh"
 
-int pemp_pool_launch(const float* fts, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
+int pemp_pool_launch(const float* fts, long long ep_stride, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
                      int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, void* workspace,
                      size_t workspace_bytes, cudaStream_t st);
 
@@ -108,7 +108,8 @@ extern "C" size_t pemp_panet_align_workspace_bytes(int B, int S, int Q, int c, i
   return make_plan(B, S, Q, c, h, w, H, W).total;
 }
 
-extern "C" int pemp_panet_align(const float* qry_fts, const float* pred, const float* sup_fts, const float* sup_mask_fg,
+extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stride, const float* pred,
+                                const float* sup_fts, long long sup_episode_stride, const float* sup_mask_fg,
                                 long long mask_stride, int B, int S, int Q, int c, int h, int w, int H, int W,
                                 float scalar, float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
   PEMP_REQUIRE(qry_fts && pred && sup_fts && sup_mask_fg && loss, PEMP_E_NULL);
@@ -127,11 +128,11 @@ extern "C" int pemp_panet_align(const float* qry_fts, const float* pred, const f
   long long npx = static_cast<long long>(B) * Q * hw;
   argmax_masks_kernel<<<static_cast<unsigned>(llmin((npx + 255) / 256, 148LL * 8)), 256, 0, st>>>(pred, qmask, npx, hw);
   // query prototypes: "shots" of the pooling kernel are the Q queries of an episode (panet.py:181-186)
-  int rc = pemp_pool_launch(qry_fts, qmask, qmask + hw, 2LL * hw, B, Q, c, hw, 1e-5f, nullptr, fgp, bgp, ws + pl.off_pool,
+  int rc = pemp_pool_launch(qry_fts, qry_episode_stride, qmask, qmask + hw, 2LL * hw, B, Q, c, hw, 1e-5f, nullptr, fgp, bgp, ws + pl.off_pool,
                             workspace_bytes - pl.off_pool, st);
   if (rc != PEMP_OK) return rc;
   // reverse matching: every support map against its episode's query prototypes (panet.py:189, b-major expansion)
-  rc = pemp_cosine_match(sup_fts, fgp, bgp, B * S, B, c, hw, 1, scalar, nullptr, rev, nullptr, stream);
+  rc = pemp_cosine_match(sup_fts, sup_episode_stride, fgp, bgp, B * S, B, c, hw, 1, scalar, nullptr, rev, nullptr, stream);
   if (rc != PEMP_OK) return rc;
   long long total = static_cast<long long>(B) * S * H * W;
   upsample_ce_kernel<<<pl.ce_blocks, kCeThreads, 0, st>>>(rev, sup_mask_fg, mask_stride, total, h, w, H, W,

@@ -51,7 +51,7 @@ static inline float lerp_scale(int in_size, int out_size) {
   return out_size > 1 ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.0f;
 }
 // out = fma(l0, a, l1*b): the operand order ATen's kernels compile to (probed against torch 2.11 CPU,
-// bit exact; see oracle/restate.py:bilinear_upsample).
+// bit exact; the probe is recorded in DESIGN.md).
 __device__ __forceinline__ float lerp2(float l0, float a, float l1, float b) {
   return __fmaf_rn(l0, a, __fmul_rn(l1, b));
 }

@@ -23,7 +23,7 @@ constexpr float kCosEps = 1e-8f; // F.cosine_similarity eps
 
 template <int K>
 __global__ void __launch_bounds__(kWarps * 32)
-cosine_match_kernel(const float* __restrict__ qry, const float* __restrict__ fg_proto, const float* __restrict__ bg_proto,
+cosine_match_kernel(const float* __restrict__ qry, long long ep_stride, const float* __restrict__ fg_proto, const float* __restrict__ bg_proto,
                     int Qper, int c, int hw, float scalar, float* __restrict__ sim, float* __restrict__ pred,
                     int64_t* __restrict__ response) {
   constexpr int P = K / 2;
@@ -69,7 +69,7 @@ cosine_match_kernel(const float* __restrict__ qry, const float* __restrict__ fg_
 #pragma unroll
     for (int k = 0; k < K; ++k) dot[i][k] = 0.f;
   }
-  const float* base = qry + static_cast<long long>(n) * c * hw + x0;
+  const float* base = qry + b * ep_stride + static_cast<long long>(n - b * Qper) * c * hw + x0;
   bool ok[kPix];
 #pragma unroll
   for (int i = 0; i < kPix; ++i) ok[i] = x0 + lane + 32 * i < hw;
@@ -142,7 +142,7 @@ cosine_match_kernel(const float* __restrict__ qry, const float* __restrict__ fg_
 }
 
 template <int K>
-int launch(const float* qry, const float* fg, const float* bg, int N, int Bp, int c, int hw, float scalar, float* sim,
+int launch(const float* qry, long long ep_stride, const float* fg, const float* bg, int N, int Bp, int c, int hw, float scalar, float* sim,
            float* pred, int64_t* response, cudaStream_t st) {
   size_t smem = (static_cast<size_t>(c) * kMaxK + static_cast<size_t>(kWarps) * (1 + K) * kTile) * sizeof(float);
   if (smem > 200 * 1024) return PEMP_E_SHAPE;
@@ -150,13 +150,14 @@ int launch(const float* qry, const float* fg, const float* bg, int N, int Bp, in
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(static_cast<unsigned>((hw + kTile - 1) / kTile) * N);
-  cosine_match_kernel<K><<<grid, kWarps * 32, smem, st>>>(qry, fg, bg, N / Bp, c, hw, scalar, sim, pred, response);
+  cosine_match_kernel<K><<<grid, kWarps * 32, smem, st>>>(qry, ep_stride ? ep_stride : static_cast<long long>(N / Bp) * c * hw, fg, bg, N / Bp, c, hw, scalar,
+                                                          sim, pred, response);
   return launch_status();
 }
 
 }  // namespace
 
-extern "C" int pemp_cosine_match(const float* qry, const float* fg_proto, const float* bg_proto, int N, int Bp, int c,
+extern "C" int pemp_cosine_match(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto, int N, int Bp, int c,
                                  int hw, int P, float scalar, float* sim, float* pred, int64_t* response,
                                  pemp_stream_t stream) {
   PEMP_REQUIRE(qry && fg_proto && bg_proto, PEMP_E_NULL);
@@ -165,9 +166,9 @@ extern "C" int pemp_cosine_match(const float* qry, const float* fg_proto, const 
   PEMP_REQUIRE(P >= 1 && P <= 4, PEMP_E_SHAPE);
   cudaStream_t st = as_stream(stream);
   switch (P) {
-    case 1: return launch<2>(qry, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
-    case 2: return launch<4>(qry, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
-    case 3: return launch<6>(qry, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
-    default: return launch<8>(qry, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
+    case 1: return launch<2>(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
+    case 2: return launch<4>(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
+    case 3: return launch<6>(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
+    default: return launch<8>(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
   }
 }

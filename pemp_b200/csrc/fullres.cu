@@ -10,7 +10,7 @@
 // Algorithmic bytes per shot: c*h*w*4 + 2*H*W*4.
 #include "common.cuh"
 
-int pemp_pool_launch(const float* fts, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
+int pemp_pool_launch(const float* fts, long long ep_stride, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
                      int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, void* workspace,
                      size_t workspace_bytes, cudaStream_t st);
 
@@ -34,7 +34,7 @@ extern "C" size_t pemp_map_pool_fullres_workspace_bytes(int B, int S, int c, int
   return make_plan(B, S, c, h, w).total;
 }
 
-extern "C" int pemp_map_pool_fullres(const float* fts, const float* sup_mask, int B, int S, int c, int h, int w, int H,
+extern "C" int pemp_map_pool_fullres(const float* fts, long long fts_episode_stride, const float* sup_mask, int B, int S, int c, int h, int w, int H,
                                      int W, float eps, float* fg_proto, float* bg_proto, void* workspace,
                                      size_t workspace_bytes, pemp_stream_t stream) {
   PEMP_REQUIRE(fts && sup_mask && fg_proto && bg_proto, PEMP_E_NULL);
@@ -48,6 +48,6 @@ extern "C" int pemp_map_pool_fullres(const float* fts, const float* sup_mask, in
   int rc = pemp_bilinear_adjoint(sup_mask, planes, H, W, h, w, wt, msum, stream);
   if (rc != PEMP_OK) return rc;
   const int hw = h * w;
-  return pemp_pool_launch(fts, wt, wt + hw, 2LL * hw, B, S, c, hw, eps, msum, fg_proto, bg_proto, ws + pl.off_pool,
+  return pemp_pool_launch(fts, fts_episode_stride, wt, wt + hw, 2LL * hw, B, S, c, hw, eps, msum, fg_proto, bg_proto, ws + pl.off_pool,
                           workspace_bytes - pl.off_pool, as_stream(stream));
 }

@@ -76,7 +76,7 @@ __global__ void mpa_prepare_kernel(const float* __restrict__ ctr, int c, int P, 
 // ---- main kernel -------------------------------------------------------------------------------------
 template <int P, int NQ>
 __global__ void __launch_bounds__(kThreads, 2)
-mpa_kernel(const float* __restrict__ fts, const float* __restrict__ table_g, const float* __restrict__ konst_g,
+mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ table_g, const float* __restrict__ konst_g,
            const float* __restrict__ fg, const float* __restrict__ bg, long long mask_stride, int c, int hw,
            int tiles_per_split, float* __restrict__ part_num, float* __restrict__ part_den) {
   constexpr int ND = 2 * (P - 1);
@@ -100,7 +100,7 @@ mpa_kernel(const float* __restrict__ fts, const float* __restrict__ table_g, con
     if (tid < ND) konst[tid] = __ldg(konst_g + tid);
   }
 
-  const float* img_base = fts + static_cast<long long>(img) * c * hw;
+  const float* img_base = fts + (img / S) * ep_stride + static_cast<long long>(img % S) * c * hw;
   const float* fgp = fg + img * mask_stride;
   const float* bgp = bg + img * mask_stride;
   const int quads = c >> 2;
@@ -336,7 +336,7 @@ Plan make_plan(int B, int S, int c, int hw, int P) {
 }
 
 template <int P, int NQ>
-int launch(const float* fts, const float* ctr, const float* fg, const float* bg, long long mask_stride, int B, int S,
+int launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg, long long mask_stride, int B, int S,
            int c, int hw, float eps, float* fg_proto, float* bg_proto, float* adaptive_p, char* ws, const Plan& pl,
            cudaStream_t st) {
   constexpr int ND = 2 * (P - 1), NDP = P <= 3 ? 4 : 8;
@@ -352,7 +352,7 @@ int launch(const float* fts, const float* ctr, const float* fg, const float* bg,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pl.nsplit, static_cast<unsigned>(B) * S);
-  mpa_kernel<P, NQ><<<grid, kThreads, smem, st>>>(fts, table, konst, fg, bg, mask_stride, c, hw, pl.tiles_per_split, num,
+  mpa_kernel<P, NQ><<<grid, kThreads, smem, st>>>(fts, ep_stride ? ep_stride : static_cast<long long>(S) * c * hw, S, table, konst, fg, bg, mask_stride, c, hw, pl.tiles_per_split, num,
                                                   den);
   long long total = static_cast<long long>(B) * c * 2 * P;
   mpa_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(num, den, B, S, c, P, pl.nsplit, eps,
@@ -367,7 +367,7 @@ extern "C" size_t pemp_meta_proto_attn_workspace_bytes(int B, int S, int c, int 
   return make_plan(B, S, c, hw, p).total;
 }
 
-extern "C" int pemp_meta_proto_attn(const float* fts, const float* ctr, const float* fg, const float* bg,
+extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg, const float* bg,
                                     long long mask_stride, int B, int S, int c, int hw, int p, float eps, float* fg_proto,
                                     float* bg_proto, float* adaptive_p, void* workspace, size_t workspace_bytes,
                                     pemp_stream_t stream) {
@@ -381,8 +381,8 @@ extern "C" int pemp_meta_proto_attn(const float* fts, const float* ctr, const fl
   cudaStream_t st = as_stream(stream);
   const bool wide = c > 512;
 #define PEMP_MPA(PP)                                                                                                   \
-  return wide ? launch<PP, 2>(fts, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st) \
-              : launch<PP, 1>(fts, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st)
+  return wide ? launch<PP, 2>(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st) \
+              : launch<PP, 1>(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st)
   switch (p) {
     case 1: PEMP_MPA(1);
     case 2: PEMP_MPA(2);

@@ -27,7 +27,7 @@ __host__ __device__ inline int chunk_len(int hw) {
 
 template <bool kTwo>
 __global__ void __launch_bounds__(kWarps * 32)
-pool_partial_kernel(const float* __restrict__ fts, const float* __restrict__ fg, const float* __restrict__ bg,
+pool_partial_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ fg, const float* __restrict__ bg,
                     long long mask_stride, int c, int hw, float* __restrict__ part, float* __restrict__ den) {
   const int chunk = blockIdx.x, img = blockIdx.y, nchunks = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -57,7 +57,7 @@ pool_partial_kernel(const float* __restrict__ fts, const float* __restrict__ fg,
     }
   }
 
-  const float* base = fts + static_cast<long long>(img) * c * hw + x0 + lane;
+  const float* base = fts + (img / S) * ep_stride + static_cast<long long>(img % S) * c * hw + x0 + lane;
   float* out = part + (static_cast<long long>(img) * nchunks + chunk) * c * 2;
   for (int ch = warp * 2; ch < c; ch += kWarps * 2) {
     const bool two_rows = ch + 1 < c;
@@ -134,38 +134,39 @@ extern "C" size_t pemp_map_pool_workspace_bytes(int B, int S, int c, int hw) {
 }
 
 // shared with fullres.cu / align.cu
-int pemp_pool_launch(const float* fts, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
+int pemp_pool_launch(const float* fts, long long ep_stride, const float* fg, const float* bg, long long mask_stride, int B, int S, int c,
                      int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, void* workspace,
                      size_t workspace_bytes, cudaStream_t st) {
   PEMP_REQUIRE(fts && fg && fg_proto, PEMP_E_NULL);
   PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_map_pool_workspace_bytes(B, S, c, hw), PEMP_E_WORKSPACE);
+  if (ep_stride == 0) ep_stride = static_cast<long long>(S) * c * hw;
   const int n = chunk_count(hw);
   const size_t imgs = static_cast<size_t>(B) * S;
   float* part = static_cast<float*>(workspace);
   float* den = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(imgs * n * c * 2 * sizeof(float), 256));
   dim3 grid(n, static_cast<unsigned>(imgs));
   if (bg)
-    pool_partial_kernel<true><<<grid, kWarps * 32, 0, st>>>(fts, fg, bg, mask_stride, c, hw, part, den);
+    pool_partial_kernel<true><<<grid, kWarps * 32, 0, st>>>(fts, ep_stride, S, fg, bg, mask_stride, c, hw, part, den);
   else
-    pool_partial_kernel<false><<<grid, kWarps * 32, 0, st>>>(fts, fg, nullptr, mask_stride, c, hw, part, den);
+    pool_partial_kernel<false><<<grid, kWarps * 32, 0, st>>>(fts, ep_stride, S, fg, nullptr, mask_stride, c, hw, part, den);
   int total = B * c;
   pool_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, den, den_override, B, S, c, n, eps, fg_proto,
                                                             bg ? bg_proto : nullptr);
   return launch_status();
 }
 
-extern "C" int pemp_map_pool_lowres(const float* fts, const float* fg, const float* bg, long long mask_stride, int B,
+extern "C" int pemp_map_pool_lowres(const float* fts, long long fts_episode_stride, const float* fg, const float* bg, long long mask_stride, int B,
                                     int S, int c, int hw, float eps, float* fg_proto, float* bg_proto, void* workspace,
                                     size_t workspace_bytes, pemp_stream_t stream) {
   PEMP_REQUIRE(!bg || bg_proto, PEMP_E_NULL);
-  return pemp_pool_launch(fts, fg, bg, mask_stride, B, S, c, hw, eps, nullptr, fg_proto, bg_proto, workspace,
+  return pemp_pool_launch(fts, fts_episode_stride, fg, bg, mask_stride, B, S, c, hw, eps, nullptr, fg_proto, bg_proto, workspace,
                           workspace_bytes, as_stream(stream));
 }
 
 extern "C" int pemp_weighted_gap(const float* supp_feat, const float* mask, int B, int c, int hw, float* out,
                                  void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
   // Weighted_GAP (pfenet.py:15-20): avg_pool(f*m)*h*w / (avg_pool(m)*h*w + 0.0005) == sum(f*m)/(sum(m)+5e-4)
-  return pemp_pool_launch(supp_feat, mask, nullptr, hw, B, 1, c, hw, 0.0005f, nullptr, out, nullptr, workspace,
+  return pemp_pool_launch(supp_feat, 0, mask, nullptr, hw, B, 1, c, hw, 0.0005f, nullptr, out, nullptr, workspace,
                           workspace_bytes, as_stream(stream));
 }

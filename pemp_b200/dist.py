@@ -1,0 +1,49 @@
+"""Episode-level data parallelism: one process per GPU, episodes sharded by index, and a single
+all-reduce (sum, int64) of the `FewShotMetric` counts per evaluation round.  No data-path collective."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init(backend=None):
+    """Initialise torch.distributed from the torchrun environment (no-op for a single process)."""
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def shard_indices(n_episodes, rank, world, first=0):
+    """Episodes i with i = rank (mod world): the union over ranks is exactly range(first, first + n) for any
+    world size, so sharded and single-GPU runs see the same episode set."""
+    return list(range(first + rank, first + n_episodes, world))
+
+
+def all_reduce_stat(stat):
+    """stat [(C+1), 3] int64 tensor summed over ranks in place (exact: integer addition)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stat, op=dist.ReduceOp.SUM)
+    return stat
+
+
+def max_over_ranks(value, device):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

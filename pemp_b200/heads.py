@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's model-facing prototype-head API.
+
+Function names, argument order and return shapes follow the reference methods they replace, so they can be
+bound onto the reference classes unchanged (`pemp_b200.dropin.patch`) or used through the small stand-alone
+classes at the bottom.  Sacred-injected config values (`dist_scalar=20`, `protos=3`; `pemp_stage1.py:21-29`)
+are ordinary keyword defaults here.  Everything is forward-only (the reference evaluates under
+`torch.no_grad()`, `core/base_trainer.py:69`) and runs on CUDA tensors only.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+DIST_SCALAR = 20      # `net.dist_scalar`, pemp_stage1.py:23 / baseline.py:22 / panet.py:21
+
+
+# ------------------------------------------------------------------------------------------------------
+# PEMP stage 1 / stage 2
+# ------------------------------------------------------------------------------------------------------
+def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=DIST_SCALAR):
+    """`compute_similarity` of all four reference models (pemp_stage1.py:233-261, pemp_stage2.py:205-233,
+    baseline.py:121-149, panet.py:122-156).
+
+    fg_proto / bg_proto [B, c] with qry_fts [N, c, h, w]      -> [N, 2, h, w]
+    fg_proto / bg_proto [B, c, p] with qry_fts [N, c, 1, h, w] -> [N, 2, p, h, w]
+    Channel 0 is background, 1 foreground.  N may be a multiple of B (prototypes are expanded b-major,
+    panet.py:145-149)."""
+    if qry_fts.dim() == 5:                      # PEMP passes [N, c, 1, h, w] (pemp_stage1.py:196)
+        N, c, _, h, w = qry_fts.shape
+    else:
+        N, c, h, w = qry_fts.shape
+    out = ops.cosine_match(qry_fts.reshape(N, c, h * w), fg_proto, bg_proto, dist_scalar, want_sim=True, want_pred=False)
+    sim = out["sim"]                                              # [N, 2, P, hw]
+    if fg_proto.dim() == 2:
+        return sim.view(N, 2, h, w)
+    return sim.view(N, 2, fg_proto.shape[2], h, w)
+
+
+def mpm(self, sup_fts, qry_fts, sup_fg, sup_bg, ret_ind, protos=None):
+    """`PEMPStage1.mpm` / `PEMPStage2.mpm` (pemp_stage1.py:166-230, pemp_stage2.py:165-202).
+
+    sup_fts [B, S, c, h, w]; qry_fts [B, Q, c, h, w]; sup_fg / sup_bg [BS, h, w]
+    -> pred [BQ, 2, h, w]  or  (pred, response [BQ, h, w] int64) when `ret_ind` and the model has `ctr`.
+    Stage 2's side effect `self.adaptive_p [B, c, 2p]` (pemp_stage2.py:185) is kept."""
+    B, S, c, h, w = sup_fts.shape
+    Q = qry_fts.shape[1]
+    hw = h * w
+    sup, qry = sup_fts, qry_fts                     # 5-D episode views are read in place (episode stride)
+    fg, bg = sup_fg.reshape(B * S, hw), sup_bg.reshape(B * S, hw)
+    scalar = getattr(self, "dist_scalar", DIST_SCALAR)
+    ctr = getattr(self, "ctr", None)
+    if ctr is not None:
+        if protos is not None and protos * 2 != ctr.shape[1]:
+            raise ValueError(f"protos={protos} does not match ctr of shape {tuple(ctr.shape)}")
+        fg_proto, bg_proto, adaptive = ops.meta_proto_attn(sup, ctr.detach(), fg, bg, B, S, eps=1e-6)
+        if getattr(self, "_pemp_keep_adaptive", False):
+            self.adaptive_p = adaptive
+        out = ops.cosine_match(qry, fg_proto, bg_proto, scalar, want_pred=True, want_response=bool(ret_ind))
+        pred = out["pred"].view(B * Q, 2, h, w)
+        if ret_ind:
+            return pred, out["response"].view(B * Q, h, w)
+        return pred
+    fg_proto, bg_proto = ops.map_pool_lowres(sup, fg, bg, B, S, eps=1e-5)
+    return ops.cosine_match(qry, fg_proto, bg_proto, scalar)["pred"].view(B * Q, 2, h, w)
+
+
+def pemp_head(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False):
+    """Everything `PEMPStage1.forward` / `PEMPStage2.forward` do after the encoder call
+    (pemp_stage1.py:141-163, pemp_stage2.py:140-162): split, nearest mask down-sampling, `mpm`, bilinear
+    up-sampling.  features [B(S+Q), c, h, w]; sup_mask [B, S, 2, H, W]."""
+    _, c, h, w = features.shape
+    H, W = sup_mask.shape[-2:]
+    feats = features.view(B, S + Q, c, h, w)
+    low = ops.mask_nearest(sup_mask.reshape(B * S, 2, H, W), h, w)            # [BS, 2, h, w]
+    pred = mpm(self, feats[:, :S], feats[:, S:], low[:, 0], low[:, 1], ret_ind)
+    if out_shape is None:
+        out_shape = (H, W)
+    if ret_ind and isinstance(pred, tuple):
+        pred, response = pred
+        output = ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
+        return output, ops.nearest_resize_labels(response, out_shape)
+    return ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
+
+
+def pemp_stage1_forward(self, sup_img, sup_mask, qry_img, out_shape=None, ret_ind=False):
+    """Drop-in `PEMPStage1.forward` (pemp_stage1.py:112-163): stock encoder, B200 head."""
+    B, S, channel, H, W = sup_img.size()
+    Q = qry_img.size(1)
+    img_cat = torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), channel, H, W)
+    features = self.encoder(img_cat)
+    return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind)
+
+
+def pemp_stage2_forward(self, sup_img, sup_mask, qry_img, qry_prior, out_shape=None, ret_ind=False):
+    """Drop-in `PEMPStage2.forward` (pemp_stage2.py:104-162): 4-channel input assembly and the ResNetCM
+    encoder stay on PyTorch, the head runs on the B200 kernels."""
+    B, S, channel, H, W = sup_img.size()
+    Q = qry_img.size(1)
+    img_cat = torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), channel, H, W)
+    sup_prior = sup_mask[:, :, :1]
+    qry_prior = qry_prior.view(B, Q, *qry_prior.shape[-3:])
+    prior_cat = torch.cat((sup_prior, qry_prior.float()), dim=1).view(B * (S + Q), 1, H, W)
+    inputs = torch.cat((img_cat, prior_cat), dim=1)
+    features = self.encoder((inputs, prior_cat))
+    self._pemp_keep_adaptive = True
+    return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Baseline / PANet
+# ------------------------------------------------------------------------------------------------------
+def baseline_head(self, features, sup_mask, B, S, Q, out_shape=None, with_align=False):
+    """`Baseline.forward` / `PANet.forward` after the encoder (baseline.py:97-118, panet.py:96-119)."""
+    _, c, h, w = features.shape
+    H, W = sup_mask.shape[-2:]
+    feats = features.view(B, S + Q, c, h, w)
+    sup_fts, qry_fts = feats[:, :S], feats[:, S:]   # episode views, read in place
+    mask = sup_mask.reshape(B * S, 2, H, W)
+    fg_proto, bg_proto = ops.map_pool_fullres(sup_fts, mask, B, S, eps=1e-5)
+    scalar = getattr(self, "dist_scalar", DIST_SCALAR)
+    pred = ops.cosine_match(qry_fts, fg_proto, bg_proto, scalar)["pred"].view(B * Q, 2, h, w)
+    if out_shape is None:
+        out_shape = (H, W)
+    output = ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
+    if with_align:
+        return output, alignLoss(self, qry_fts, pred, sup_fts, mask[:, 0:1], Q)
+    return output
+
+
+def baseline_forward(self, sup_img, sup_mask, qry_img, out_shape=None):
+    B, S, C, H, W = sup_img.size()
+    Q = qry_img.size(1)
+    features = self.encoder(torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), C, H, W))
+    return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=False)
+
+
+def panet_forward(self, sup_img, sup_mask, qry_img, out_shape=None):
+    B, S, C, H, W = sup_img.size()
+    Q = qry_img.size(1)
+    features = self.encoder(torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), C, H, W))
+    return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=True)
+
+
+def alignLoss(self, qry_fts, pred, sup_fts, sup_mask_fg, Q):
+    """`PANet.alignLoss` (panet.py:158-194) -> 0-dim tensor.  Unlike the reference (whose `.view` on an
+    expanded tensor raises for B > 1 with S > 1) any B, S, Q combination works."""
+    return ops.panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, getattr(self, "dist_scalar", DIST_SCALAR))
+
+
+# ------------------------------------------------------------------------------------------------------
+# PFENet
+# ------------------------------------------------------------------------------------------------------
+def Weighted_GAP(supp_feat, mask):
+    """`networks.pfenet.Weighted_GAP` (pfenet.py:15-20): [B,c,h,w], [B,1,h,w] -> [B,c,1,1]."""
+    return ops.weighted_gap(supp_feat, mask)
+
+
+def prior_mask(query_feat_4, final_supp_list, mask_list, precision=ops.PRIOR_FP32):
+    """The prior block of `PFENet.forward` (pfenet.py:201-231) as one call.
+
+    query_feat_4 [B, C, sp, sp]; final_supp_list: S tensors [B, C, sp, sp]; mask_list: S binary masks
+    [B, 1, H, W] -> corr_query_mask [B, 1, sp, sp].  (The reference's two trailing `F.interpolate` calls
+    are identities because feat-3, feat-4 and `query_feat` share one spatial size)"""
+    sp_h, sp_w = query_feat_4.shape[-2:]
+    s4 = torch.stack(list(final_supp_list), dim=0)
+    masks = torch.stack(list(mask_list), dim=0)                                # [S, B, 1, H, W]
+    small = ops.bilinear_resize(masks, s4.shape[-2:])[:, :, 0]                 # [S, B, sp, sp]
+    prior = ops.prior_mask(query_feat_4, s4, small, precision)
+    return prior.view(query_feat_4.shape[0], 1, sp_h, sp_w)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Stand-alone modules (same parameters / state-dict keys as the reference heads)
+# ------------------------------------------------------------------------------------------------------
+class PEMPHead(nn.Module):
+    """Head of `PEMPStage1` / `PEMPStage2`: the only parameter is `ctr [c, 2p]` (state-dict key `ctr`,
+    pemp_stage1.py:104-107), so reference checkpoints load."""
+
+    def __init__(self, out_channels=512, protos=3, dist_scalar=DIST_SCALAR, keep_adaptive=False):
+        super().__init__()
+        self.dist_scalar = dist_scalar
+        self.ctr = nn.Parameter(torch.rand(out_channels, protos * 2), requires_grad=True) if protos > 0 else None
+        self._pemp_keep_adaptive = keep_adaptive
+
+    mpm = mpm
+    compute_similarity = compute_similarity
+
+    def forward(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False):
+        return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind)
+
+
+class BaselineHead(nn.Module):
+    def __init__(self, dist_scalar=DIST_SCALAR, align=False):
+        super().__init__()
+        self.dist_scalar = dist_scalar
+        self.align = align
+
+    compute_similarity = compute_similarity
+    alignLoss = alignLoss
+
+    def forward(self, features, sup_mask, B, S, Q, out_shape=None):
+        return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=self.align)

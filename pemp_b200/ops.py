@@ -42,6 +42,27 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+def _episodes(t, B, S, name):
+    """Feature operand of B*S images.  Accepts image-major [B*S, c, hw] / [B*S, c, h, w] or the 5-D episode
+    view [B, S, c, h, w] - typically a slice `features.view(B, S+Q, c, h, w)[:, :S]` of the encoder output,
+    which is read in place through the episode stride (no copy).  Returns (tensor, episode_stride, c, hw)."""
+    t = _need_loose(t, name)
+    if t.dim() == 5:
+        if t.shape[0] != B or t.shape[1] != S:
+            raise ValueError(f"{name} must be [B={B}, S={S}, c, h, w], got {tuple(t.shape)}")
+        c, h, w = t.shape[2:]
+        hw = h * w
+        inner_ok = t.stride(4) == 1 and t.stride(3) == w and t.stride(2) == hw and (S == 1 or t.stride(1) == c * hw)
+        if not inner_ok or (B > 1 and t.stride(0) < S * c * hw):
+            t = t.contiguous()
+        return t, (t.stride(0) if B > 1 else S * c * hw), c, hw
+    if t.dim() not in (3, 4) or t.shape[0] != B * S:
+        raise ValueError(f"{name} must be [B*S={B * S}, c, hw], [B*S, c, h, w] or [B, S, c, h, w], got {tuple(t.shape)}")
+    t = t if t.is_contiguous() else t.contiguous()
+    c = t.shape[1]
+    return t, S * c * (t.numel() // (B * S * c)), c, t.numel() // (B * S * c)
+
+
 def _mask_pair(fg, bg, n_img, hw):
     """fg / bg may be two views of one [n_img, 2, hw] tensor (the K0 output) or separate [n_img, hw] tensors.
     Returns (fg_ptr, bg_ptr, stride_in_floats, keepalive)."""
@@ -75,18 +96,16 @@ def mask_nearest(mask, h, w):
 # ------------------------------------------------------------------------------------------------ K1 / K8
 def map_pool_lowres(fts, fg, bg, B, S, eps=1e-5):
     """fts [B*S, c, hw]; fg, bg [B*S, hw] -> (fg_proto [B, c], bg_proto [B, c])  (pemp_stage1.py:223-227)."""
-    fts = _need(fts, torch.float32, "fts")
-    n_img, c, hw = fts.shape
-    if n_img != B * S:
-        raise ValueError(f"fts has {n_img} images, expected B*S = {B * S}")
-    fg = _need_loose(fg, "fg")
-    bg = None if bg is None else _need_loose(bg, "bg")
+    fts, ep, c, hw = _episodes(fts, B, S, "fts")
+    n_img = B * S
+    fg = _need_loose(fg, "fg").reshape(n_img, hw) if fg.dim() != 2 else _need_loose(fg, "fg")
+    bg = None if bg is None else (_need_loose(bg, "bg").reshape(n_img, hw) if bg.dim() != 2 else _need_loose(bg, "bg"))
     fgp, bgp, stride, keep = _mask_pair(fg, bg, n_img, hw)
     L = _cabi.lib()
     ws = _ws(L.pemp_map_pool_workspace_bytes(B, S, c, hw), fts.device)
     out_f = torch.empty(B, c, dtype=torch.float32, device=fts.device)
     out_b = torch.empty(B, c, dtype=torch.float32, device=fts.device) if bg is not None else None
-    _cabi.check(L.pemp_map_pool_lowres(fts.data_ptr(), fgp, bgp, stride, B, S, c, hw, float(eps), out_f.data_ptr(),
+    _cabi.check(L.pemp_map_pool_lowres(fts.data_ptr(), ep, fgp, bgp, stride, B, S, c, hw, float(eps), out_f.data_ptr(),
                                        _ptr(out_b), ws.data_ptr(), ws.numel(), _stream()), "pemp_map_pool_lowres")
     _count(2)
     del keep
@@ -123,21 +142,23 @@ def weighted_gap(supp_feat, mask):
 def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
     """fts [B*S, c, hw]; ctr [c, 2p]; fg, bg [B*S, hw] -> fg_proto [B,c,p], bg_proto [B,c,p], adaptive_p [B,c,2p]
     (pemp_stage1.py:202-213, pemp_stage2.py:174-186)."""
-    fts = _need(fts, torch.float32, "fts")
+    fts, ep, c, hw = _episodes(fts, B, S, "fts")
     ctr = _need(ctr, torch.float32, "ctr")
-    n_img, c, hw = fts.shape
-    if n_img != B * S:
-        raise ValueError(f"fts has {n_img} images, expected B*S = {B * S}")
+    n_img = B * S
     if ctr.dim() != 2 or ctr.shape[0] != c or ctr.shape[1] % 2:
         raise ValueError(f"ctr must be [c, 2p] with c = {c}, got {tuple(ctr.shape)}")
     p = ctr.shape[1] // 2
-    fgp, bgp, stride, keep = _mask_pair(_need_loose(fg, "fg"), _need_loose(bg, "bg"), n_img, hw)
+    fg = _need_loose(fg, "fg")
+    bg = _need_loose(bg, "bg")
+    fg = fg if fg.dim() == 2 else fg.reshape(n_img, hw)
+    bg = bg if bg.dim() == 2 else bg.reshape(n_img, hw)
+    fgp, bgp, stride, keep = _mask_pair(fg, bg, n_img, hw)
     L = _cabi.lib()
     ws = _ws(L.pemp_meta_proto_attn_workspace_bytes(B, S, c, hw, p), fts.device)
     out_f = torch.empty(B, c, p, dtype=torch.float32, device=fts.device)
     out_b = torch.empty(B, c, p, dtype=torch.float32, device=fts.device)
     adaptive = torch.empty(B, c, 2 * p, dtype=torch.float32, device=fts.device) if want_adaptive else None
-    _cabi.check(L.pemp_meta_proto_attn(fts.data_ptr(), ctr.data_ptr(), fgp, bgp, stride, B, S, c, hw, p, float(eps),
+    _cabi.check(L.pemp_meta_proto_attn(fts.data_ptr(), ep, ctr.data_ptr(), fgp, bgp, stride, B, S, c, hw, p, float(eps),
                                        out_f.data_ptr(), out_b.data_ptr(), _ptr(adaptive), ws.data_ptr(), ws.numel(),
                                        _stream()), "pemp_meta_proto_attn")
     _count(3 if p > 1 else 2)
@@ -147,23 +168,27 @@ def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
 
 # ------------------------------------------------------------------------------------------------ K3
 def cosine_match(qry, fg_proto, bg_proto, scalar=20.0, want_sim=False, want_pred=True, want_response=False):
-    """qry [N, c, hw]; protos [Bp, c] or [Bp, c, P] -> dict(sim [N,2,P,hw], pred [N,2,hw], response [N,hw] int64)
+    """qry [N, c, hw] / [N, c, h, w] or the episode view [Bp, Q, c, h, w]; protos [Bp, c] or [Bp, c, P]
+    -> dict(sim [N,2,P,hw], pred [N,2,hw], response [N,hw] int64)
     (compute_similarity + max over prototypes, pemp_stage1.py:214-222,233-261)."""
-    qry = _need(qry, torch.float32, "qry")
     fg_proto = _need(fg_proto, torch.float32, "fg_proto")
     bg_proto = _need(bg_proto, torch.float32, "bg_proto")
-    N, c, hw = qry.shape
-    if fg_proto.shape != bg_proto.shape or fg_proto.shape[1] != c:
-        raise ValueError(f"prototypes must be [Bp, {c}(, P)], got {tuple(fg_proto.shape)} / {tuple(bg_proto.shape)}")
+    if fg_proto.shape != bg_proto.shape or fg_proto.dim() not in (2, 3):
+        raise ValueError(f"prototypes must be [Bp, c(, P)], got {tuple(fg_proto.shape)} / {tuple(bg_proto.shape)}")
     Bp = fg_proto.shape[0]
     P = 1 if fg_proto.dim() == 2 else fg_proto.shape[2]
-    if N % Bp:
-        raise ValueError(f"{N} query maps cannot be split over {Bp} prototype sets")
+    n_maps = qry.shape[0] * qry.shape[1] if qry.dim() == 5 else qry.shape[0]
+    if n_maps % Bp:
+        raise ValueError(f"{n_maps} query maps cannot be split over {Bp} prototype sets")
+    qry, ep, c, hw = _episodes(qry, Bp, n_maps // Bp, "qry")
+    N = n_maps
+    if fg_proto.shape[1] != c:
+        raise ValueError(f"prototypes have {fg_proto.shape[1]} channels, query features {c}")
     dev = qry.device
     sim = torch.empty(N, 2, P, hw, dtype=torch.float32, device=dev) if want_sim else None
     pred = torch.empty(N, 2, hw, dtype=torch.float32, device=dev) if want_pred else None
     resp = torch.empty(N, hw, dtype=torch.int64, device=dev) if want_response else None
-    _cabi.check(_cabi.lib().pemp_cosine_match(qry.data_ptr(), fg_proto.data_ptr(), bg_proto.data_ptr(), N, Bp, c, hw, P,
+    _cabi.check(_cabi.lib().pemp_cosine_match(qry.data_ptr(), ep, fg_proto.data_ptr(), bg_proto.data_ptr(), N, Bp, c, hw, P,
                                               float(scalar), _ptr(sim), _ptr(pred), _ptr(resp), _stream()),
                 "pemp_cosine_match")
     _count(1)
@@ -216,17 +241,20 @@ def nearest_resize_labels(lab, out_hw):
 # ------------------------------------------------------------------------------------------------ K6
 def map_pool_fullres(fts, sup_mask, B, S, eps=1e-5):
     """fts [B*S, c, h, w]; sup_mask [B*S, 2, H, W] -> (fg_proto [B,c], bg_proto [B,c])  (baseline.py:100-110)."""
-    fts = _need(fts, torch.float32, "fts")
+    if fts.dim() not in (4, 5):
+        raise ValueError("fts must be [B*S, c, h, w] or [B, S, c, h, w]")
+    h, w = fts.shape[-2:]
+    fts, ep, c, _ = _episodes(fts, B, S, "fts")
     sup_mask = _need(sup_mask, torch.float32, "sup_mask")
-    n_img, c, h, w = fts.shape
-    if n_img != B * S or sup_mask.shape[:2] != (n_img, 2):
-        raise ValueError(f"expected fts [{B * S},c,h,w] and sup_mask [{B * S},2,H,W]")
+    n_img = B * S
+    if sup_mask.shape[:2] != (n_img, 2):
+        raise ValueError(f"expected sup_mask [{B * S},2,H,W], got {tuple(sup_mask.shape)}")
     H, W = sup_mask.shape[-2:]
     L = _cabi.lib()
     ws = _ws(L.pemp_map_pool_fullres_workspace_bytes(B, S, c, h, w), fts.device)
     out_f = torch.empty(B, c, dtype=torch.float32, device=fts.device)
     out_b = torch.empty(B, c, dtype=torch.float32, device=fts.device)
-    _cabi.check(L.pemp_map_pool_fullres(fts.data_ptr(), sup_mask.data_ptr(), B, S, c, h, w, H, W, float(eps),
+    _cabi.check(L.pemp_map_pool_fullres(fts.data_ptr(), ep, sup_mask.data_ptr(), B, S, c, h, w, H, W, float(eps),
                                         out_f.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                 "pemp_map_pool_fullres")
     _count(4)
@@ -251,18 +279,19 @@ def bilinear_adjoint(mask, out_hw, want_sum=True):
 def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
     """`PANet.alignLoss(qry_fts [BQ,c,h,w], pred [BQ,2,h,w], sup_fts [BS,c,h,w], sup_mask_fg [BS,1,H,W], Q)`
     -> 0-dim loss tensor (panet.py:158-194)."""
-    qry_fts = _need(qry_fts, torch.float32, "qry_fts")
     pred = _need(pred, torch.float32, "pred")
-    sup_fts = _need(sup_fts, torch.float32, "sup_fts")
     sup_mask_fg = _need_loose(sup_mask_fg, "sup_mask_fg")
-    BQ, c, h, w = qry_fts.shape
-    BS = sup_fts.shape[0]
+    h, w = qry_fts.shape[-2:]
+    BQ = qry_fts.shape[0] * qry_fts.shape[1] if qry_fts.dim() == 5 else qry_fts.shape[0]
+    BS = sup_fts.shape[0] * sup_fts.shape[1] if sup_fts.dim() == 5 else sup_fts.shape[0]
     if BQ % Q:
         raise ValueError("qry_fts batch is not a multiple of Q")
     B = BQ // Q
     if BS % B:
         raise ValueError("sup_fts batch is not a multiple of B")
     S = BS // B
+    qry_fts, qep, c, _ = _episodes(qry_fts, B, Q, "qry_fts")
+    sup_fts, sep, _, _ = _episodes(sup_fts, B, S, "sup_fts")
     H, W = sup_mask_fg.shape[-2:]
     m = sup_mask_fg.reshape(BS, H * W) if sup_mask_fg.dim() != 2 else sup_mask_fg
     if m.stride(1) != 1 or (BS > 1 and m.stride(0) < H * W):
@@ -271,7 +300,7 @@ def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
     L = _cabi.lib()
     ws = _ws(L.pemp_panet_align_workspace_bytes(B, S, Q, c, h, w, H, W), qry_fts.device)
     loss = torch.empty((), dtype=torch.float32, device=qry_fts.device)
-    _cabi.check(L.pemp_panet_align(qry_fts.data_ptr(), pred.data_ptr(), sup_fts.data_ptr(), m.data_ptr(), stride, B, S, Q,
+    _cabi.check(L.pemp_panet_align(qry_fts.data_ptr(), qep, pred.data_ptr(), sup_fts.data_ptr(), sep, m.data_ptr(), stride, B, S, Q,
                                    c, h, w, H, W, float(scalar), loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                 "pemp_panet_align")
     _count(6)

@@ -142,9 +142,14 @@ def test_meta_proto_attn(ops, B, S, c, hw, p):
     df, db, _ = O.meta_proto_attention(f.double(), fg.double(), bg.double(), ctr.double(), B, S, p)
     err_ours = max(nrel(of.cpu(), df), nrel(ob.cpu(), db))
     err_ref = max(nrel(rf, df), nrel(rb, db))
-    assert nrel(of.cpu(), rf) < TOL and nrel(ob.cpu(), rb) < TOL, (err_ours, err_ref)
-    assert nrel(oa.cpu(), ra) < TOL
-    assert err_ours <= max(2 * err_ref, 2e-6), (err_ours, err_ref)
+    # Gate: within 1e-5 of the reference's fp32 result - unless the reference's own fp32 evaluation is
+    # further than that from the exact value (|D| grows with c, and the softmax amplifies its rounding:
+    # 4.5e-5 at c=1024), in which case the distance to the reference may not exceed the reference's own error.
+    gate = max(TOL, 1.5 * err_ref)
+    assert nrel(of.cpu(), rf) < gate and nrel(ob.cpu(), rb) < gate, (err_ours, err_ref)
+    assert nrel(oa.cpu(), ra) < gate
+    # and we must be no further from the exact (float64) value than the reference is
+    assert err_ours <= max(1.0 * err_ref, 2e-6), (err_ours, err_ref)
 
 
 def test_meta_proto_attn_general_masks_golden(ops):
