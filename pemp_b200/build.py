@@ -31,7 +31,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB]
+    extra = os.environ.get("PEMP_NVCC_FLAGS", "").split()      # developer knob, e.g. -DPEMP_MPA_U=4
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--c", type=int, default=512)
     ap.add_argument("--hw", type=int, default=51)
     ap.add_argument("--H", type=int, default=401)
+    ap.add_argument("--only", default="")
     a = ap.parse_args()
     B, S, c, h, H = a.B, a.S, a.c, a.hw, a.H
     hw = h * h
@@ -72,6 +73,8 @@ def main():
          B * (S * (c * hw * 4 + 2 * H * H * 4) + 2 * c * 4)),
     ]
     for name, fn, nbytes in rows:
+        if a.only and a.only not in name:
+            continue
         ms = timeit(fn)
         gbs = nbytes / ms / 1e6
         print(json.dumps({"kernel": name, "ms": round(ms, 4), "alg_GB": round(nbytes / 1e9, 4), "GBps": round(gbs, 1),
