@@ -13,53 +13,79 @@
 // (|ctr_j|^2 - |ctr_0|^2), so phase A is 2(P-1) dot products per pixel against difference vectors that a
 // tiny prologue kernel prepares once per launch (in double).  This is both cheaper than the 2P squared
 // distances (|D| ~ 300 loses 1e-4 absolute in fp32; the differences are O(10)) and closer to the exact
-// result.  Phase B is the weighted sum; for a pixel whose group mask is zero the P products are skipped
-// (warp-uniform test), which halves the work for complementary fg/bg masks.
+// result.  Phase B is the weighted sum; pixels whose group mask is zero are skipped (warp-uniform pixel
+// lists), which halves the work for complementary fg/bg masks.
 //
-// Mapping.  grid = (pixel split, image).  A CTA walks tiles of 32 pixels.
-//   phase A  lane <-> pixel, warp <-> a quarter-of-channels stripe: four channel rows per step are loaded with
-//            coalesced 128-byte row segments, multiplied against the difference table (one broadcast
-//            128-bit smem load per row) and stored TRANSPOSED into shared memory as Ft[pixel][channel]
-//            (row stride c+4 floats => conflict-free 128-bit stores);
-//   softmax  64 threads turn the reduced dots into the 2P weights of each pixel;
-//   phase B  thread <-> 4 consecutive channels x half of the tile's pixels: one conflict-free 128-bit smem
-//            load per pixel feeds 4*P (or 8*P) FMAs into register accumulators that live for the whole CTA.
+// Mapping.  A *cluster* of CS CTAs (CS = 2 when the channel count allows) owns a tile of TW = 32*CS pixels
+// of one image; CTA r of the cluster owns the channels [r*c/CS, (r+1)*c/CS).  Per tile:
+//   phase A  lane <-> CS pixels (l, l+32), warp <-> a contiguous range of channel quads: four rows per step are
+//            loaded with coalesced row segments (TW*4 contiguous bytes per row), multiplied against the
+//            difference table (one 128-bit shared load per row, amortised over the lane's CS pixels) and
+//            stored TRANSPOSED into shared memory as Ft[pixel][channel] (row stride = 4*odd floats =>
+//            conflict-free 128-bit stores);
+//   exchange the per-CTA partial dots are reduced over warps into E[buffer][d][pixel]; the peer's E is read
+//            through distributed shared memory after one cluster barrier (double buffered, so one barrier
+//            per tile orders both the read-after-write and the later write-after-read);
+//   softmax  2*TW threads turn the dots into the 2P weights of each pixel (both CTAs, redundantly);
+//   phase B  thread <-> kQPT channel quads x one pixel group: conflict-free 128-bit shared loads of Ft feed
+//            4*P FMAs per quad into register accumulators that live for the whole CTA.
 // Partial numerators / denominators go to the workspace per (image, split); `mpa_finalize_kernel` adds the
 // splits in index order, divides, and averages the shots - deterministic, no atomics.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kTW = 32;          // pixels per tile
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxChannels = 1536;      // Ft[32][c+4] must fit the 227 KB of shared memory
+constexpr int kMaxChannels = 3072;     // per-CTA Ft[32*CS][c/CS + 4] must fit the 227 KB of shared memory
 
-// floats reserved for the transposed tile Ft[kTW][4*kQPT*tpp + 4]; the epilogue reuses it as fold[ng][kQPT*8*P][tpp]
 #ifndef PEMP_MPA_QPT
-#define PEMP_MPA_QPT 1
+#define PEMP_MPA_QPT 2
 #endif
-#ifndef PEMP_MPA_U
-#define PEMP_MPA_U 8
+#ifndef PEMP_MPA_LOADS
+#define PEMP_MPA_LOADS 64              // independent row loads in flight per lane in phase A (specialised shapes)
 #endif
-#ifndef PEMP_MPA_PF
-#define PEMP_MPA_PF 0
-#endif
-#ifndef PEMP_MPA_INTERLEAVE
-#define PEMP_MPA_INTERLEAVE 1
+#ifndef PEMP_MPA_LOADS_GENERIC
+#define PEMP_MPA_LOADS_GENERIC 32      // ... run-time shapes need registers for address arithmetic
 #endif
 #ifndef PEMP_MPA_WAVES
 #define PEMP_MPA_WAVES 4
 #endif
+#ifndef PEMP_MPA_CLUSTER
+#define PEMP_MPA_CLUSTER 2
+#endif
 constexpr int kQPT = PEMP_MPA_QPT;     // channel quads per phase-B thread
-__host__ __device__ inline int ft_floats(int c, int P) {
-  int need = ((c >> 2) + kQPT - 1) / kQPT, tpp = 32;
-  while (tpp < need) tpp <<= 1;
-  int tile = kTW * (4 * kQPT * tpp + 4), fold = kThreads * kQPT * 2 * 4 * P;
-  return tile > fold ? tile : fold;
-}
+
 __host__ __device__ inline int nd_of(int P) { return 2 * (P - 1); }          // dot products per pixel
 __host__ __device__ inline int ndp_of(int P) { return P <= 3 ? 4 : 8; }      // padded table row
+
+// threads per phase-B pixel group for cc channels: power of two >= 32 (a warp never straddles groups)
+__host__ __device__ inline int tpp_of(int cc) {
+  int need = ((cc >> 2) + kQPT - 1) / kQPT, t = 32;
+  while (t < need) t <<= 1;
+  return t;
+}
+
+struct Smem {            // offsets in floats
+  int ldf, ft, table, red, ex, wgt, total;
+};
+__host__ __device__ inline Smem smem_layout(int cc, int P, int CS) {
+  const int TW = 32 * CS, NDP = ndp_of(P), ND = nd_of(P);
+  Smem s;
+  s.ldf = 4 * kQPT * tpp_of(cc) + 4;                           // >= cc, = 4 * odd
+  int tile = TW * s.ldf, fold = kThreads * kQPT * 2 * 4 * P;   // the epilogue reuses Ft as fold[ng][kQPT*8*P][tpp]
+  s.ft = 0;
+  s.table = tile > fold ? tile : fold;
+  s.red = s.table + (ND ? cc * NDP : 0);
+  s.ex = s.red + (ND ? kWarps * NDP * TW : 0);
+  s.wgt = s.ex + (ND ? 2 * NDP * TW : 0);
+  s.total = s.wgt + 2 * TW * 4;
+  return s;
+}
 
 // ---- prologue: difference table ------------------------------------------------------------------
 // table[c][ndp]: column (g*(P-1) + j-1) = 2*(ctr[c, g*P+j] - ctr[c, g*P]);  konst[g*(P-1)+j-1] =
@@ -92,65 +118,67 @@ __global__ void mpa_prepare_kernel(const float* __restrict__ ctr, int c, int P, 
 }
 
 // ---- main kernel -------------------------------------------------------------------------------------
-// Phase-B thread layout for c channels (quads = c/4): each thread owns kQPT = 2 channel quads
-// {q, q + tpp} of one pixel group; tpp = threads per pixel group (power of two, >= 32 so a warp never
-// straddles groups), ng = kThreads / tpp pixel groups of ppg = kTW / ng pixels.
-__host__ __device__ inline int tpp_of(int c) {
-  int need = ((c >> 2) + kQPT - 1) / kQPT, t = 32;
-  while (t < need) t <<= 1;
-  return t;
-}
-
-template <int P>
+// HWT / CCT > 0 fix the pixel count and the per-CTA channel count at compile time (the PEMP shapes): every row
+// offset, shared-memory stride and trip count becomes an immediate, which removes about half of the
+// instructions of the generic version (address arithmetic).  SAFE = true clamps pixel indices per lane and is
+// used when the image is narrower than one tile; otherwise the last tile is shifted left to end at hw and the
+// pixels it shares with the previous tile get zero weight.
+template <int P, int CS, int HWT, int CCT, bool SAFE>
 __global__ void __launch_bounds__(kThreads, 2)
 mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ table_g,
            const float* __restrict__ konst_g, const float* __restrict__ fg, const float* __restrict__ bg,
-           long long mask_stride, int c, int hw, int tiles_per_split, float* __restrict__ part_num,
-           float* __restrict__ part_den) {
+           long long mask_stride, int c_rt, int hw_rt, float* __restrict__ part_num, float* __restrict__ part_den) {
   constexpr int ND = 2 * (P - 1);
   constexpr int NDP = P <= 3 ? 4 : 8;
   constexpr int K = 2 * P;
+  constexpr int TW = 32 * CS;                      // pixels per tile
+  constexpr int U = (HWT > 0 ? PEMP_MPA_LOADS : PEMP_MPA_LOADS_GENERIC) / (4 * CS);   // quads per load batch
   extern __shared__ __align__(16) float smem[];
-  const int tpp = tpp_of(c);
-  const int ldf = 4 * kQPT * tpp + 4;                             // Ft row stride: >= c, = 4 * odd  => conflict-free
-  float* Ft = smem;                                        // [kTW][ldf] (also the epilogue's fold buffer)
-  float* table = Ft + ft_floats(c, P);                     // [c][NDP]
-  float* red = table + (ND ? c * NDP : 0);                 // [kWarps][NDP][kTW]
-  float* wgt = red + (ND ? kWarps * NDP * kTW : 0);        // [2][kTW][4]   softmax * mask
+  const int hw = HWT > 0 ? HWT : hw_rt;
+  const int cc = CCT > 0 ? CCT : c_rt / CS;        // channels owned by this CTA
+  const int c = cc * CS;
+  const Smem L = smem_layout(cc, P, CS);
+  const int ldf = L.ldf;
+  float* Ft = smem + L.ft;                         // [TW][ldf]
+  float* table = smem + L.table;                   // [cc][NDP]      rows of this CTA's channels
+  float* red = smem + L.red;                       // [kWarps][NDP][TW]
+  float* ex = smem + L.ex;                         // [2][NDP][TW]   partial dots of this CTA (double buffered)
+  float* wgt = smem + L.wgt;                       // [2][TW][4]     softmax * mask
   __shared__ float konst[8];
-  __shared__ unsigned live_mask[2];                        // bit x set <=> group g has a non-zero weight at pixel x
+  __shared__ unsigned live_mask[2][CS];            // bit x set <=> group g has a non-zero weight at pixel x
+  __shared__ float den_part[2][CS][4];
 
-  const int split = blockIdx.x, img = blockIdx.y, nsplit = gridDim.x;
+  const int rank = CS > 1 ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+  const int split = blockIdx.x / CS, nsplit = gridDim.x / CS, img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ntiles = (hw + kTW - 1) / kTW;
-#if PEMP_MPA_INTERLEAVE
-  // CTA `split` of an image walks tiles split, split + nsplit, ...: the CTAs of one image (adjacent block ids, so
-  // co-resident) touch adjacent 128-byte pieces of every channel row at about the same time (DRAM page locality)
-  const int t_begin = 0, t_end = (ntiles - split + nsplit - 1) / nsplit;
-#define PEMP_TILE(t) (split + (t) * nsplit)
-#else
-  const int t_begin = split * tiles_per_split, t_end = min(ntiles, t_begin + tiles_per_split);
-#define PEMP_TILE(t) (t)
-#endif
-  const int quads = c >> 2;
+  const int ntiles = (hw + TW - 1) / TW;
+  // cluster `split` of an image walks tiles split, split + nsplit, ...: the clusters of one image (adjacent
+  // block ids, co-resident) touch adjacent pieces of every channel row at about the same time
+  const int my_tiles = split < ntiles ? (ntiles - split + nsplit - 1) / nsplit : 0;
+  const int ch0 = rank * cc;
+  const int quads = cc >> 2;
 
   if (ND) {
-    for (int i = tid; i < c * NDP; i += kThreads) table[i] = __ldg(table_g + i);
+    for (int i = tid; i < cc * NDP; i += kThreads) table[i] = __ldg(table_g + ch0 * NDP + i);
     if (tid < ND) konst[tid] = __ldg(konst_g + tid);
   }
-  // channels beyond c in the padded Ft rows are never written by phase A: clear them once
-  for (int i = tid; i < kTW * (ldf - c); i += kThreads) Ft[(i / (ldf - c)) * ldf + c + i % (ldf - c)] = 0.f;
+  // channels beyond cc in the padded Ft rows are never written by phase A: clear them once
+  for (int i = tid; i < TW * (ldf - cc); i += kThreads) Ft[(i / (ldf - cc)) * ldf + cc + i % (ldf - cc)] = 0.f;
 
-  const float* img_base = fts + (img / S) * ep_stride + static_cast<long long>(img % S) * c * hw;
+  const float* img_base = fts + (img / S) * ep_stride + (static_cast<long long>(img % S) * c + ch0) * hw;
   const float* fgp = fg + img * mask_stride;
   const float* bgp = bg + img * mask_stride;
+  const float* ex_peer = nullptr;
+  if (CS > 1) ex_peer = cg::this_cluster().map_shared_rank(ex, rank ^ 1);
 
-  // phase-A ownership: contiguous quads per warp
+  // phase-A ownership: qw contiguous quads per warp
   const int qw = (quads + kWarps - 1) / kWarps;
-  const int q_lo = warp * qw, q_hi = min(quads, q_lo + qw);
+  const int q_lo = warp * qw;
+  const int nq = max(0, min(quads - q_lo, qw));    // == qw for every warp when kWarps divides quads
   // phase-B ownership (tpp is a power of two)
+  const int tpp = tpp_of(cc);
   const int tpp_shift = 31 - __clz(tpp);
-  const int ng = kThreads >> tpp_shift, ppg = kTW / ng;
+  const int ng = kThreads >> tpp_shift, ppg = TW / ng;
   const int qb = tid & (tpp - 1), grp = tid >> tpp_shift;
   float acc[kQPT][2][4][P];                                // [quad slot][group][channel][prototype]
 #pragma unroll
@@ -161,104 +189,115 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
       for (int e = 0; e < 4; ++e)
 #pragma unroll
         for (int j = 0; j < P; ++j) acc[a][g][e][j] = 0.f;
-  float den[P];   // threads < 64: denominators of group tid/32, summed over this lane's pixels
+  float den[P];   // softmax threads: denominators of their group, summed over their pixels
 #pragma unroll
   for (int j = 0; j < P; ++j) den[j] = 0.f;
 
   __syncthreads();
 
-  // Software pipeline: the first kPF quads of a warp's share (all of it for c <= 512) are loaded one tile ahead
-  // into registers, so the row loads of tile t+1 are in flight while tile t is in its softmax / phase-B part.
-  constexpr int kPF = PEMP_MPA_PF;
-  float v[kPF ? kPF : 1][4];
-  auto prefetch = [&](int tile) {
-    const int xx = min(PEMP_TILE(tile) * kTW + lane, hw - 1);        // dead pixels read a valid address; their weights are zero
-    const float* prow = img_base + static_cast<long long>(q_lo * 4) * hw + xx;
+  for (int it = 0; it < my_tiles; ++it) {
+    const int x_nom = (split + it * nsplit) * TW;            // nominal first pixel of the tile
+    const int x0 = SAFE ? x_nom : min(x_nom, hw - TW);       // window actually loaded
+    const int buf = it & 1;
+
+    // ---------------- phase A: load, dot with the difference table, transpose into Ft ---------------
+    float pd[CS][NDP];
 #pragma unroll
-    for (int u = 0; u < kPF; ++u) {
-      if (q_lo + u < q_hi) {
+    for (int s = 0; s < CS; ++s)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          v[u][e] = __ldg(prow);
-          prow += hw;
+      for (int d = 0; d < NDP; ++d) pd[s][d] = 0.f;
+    int xoff[CS];                                            // SAFE: per-lane clamped pixel offsets
+#pragma unroll
+    for (int s = 0; s < CS; ++s) xoff[s] = SAFE ? min(x0 + lane + 32 * s, hw - 1) : x0 + lane + 32 * s;
+    // consecutive channel rows are one `hw` stride apart: one running pointer, immediate offsets inside a batch
+    const float* prow = img_base + static_cast<long long>(q_lo * 4) * hw + (SAFE ? 0 : xoff[0]);
+    float* fst = Ft + lane * ldf + q_lo * 4;
+    const float4* trow = reinterpret_cast<const float4*>(table + q_lo * 4 * NDP);
+    for (int i = 0; i < nq; i += U) {
+      float v[U][4][CS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i + u < nq) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int s = 0; s < CS; ++s)
+              v[u][e][s] = SAFE ? __ldg(prow + (u * 4 + e) * hw + xoff[s]) : __ldg(prow + (u * 4 + e) * hw + 32 * s);
         }
       }
-    }
-  };
-  if (t_begin < t_end) prefetch(t_begin);
-
-  for (int t = t_begin; t < t_end; ++t) {
-    const int x = PEMP_TILE(t) * kTW + lane;
-    const bool live = x < hw;
-    const int xc = live ? x : hw - 1;
-
-    // ---------------- phase A: dot with the difference table, transpose into Ft ----------------------
-    float pd[NDP];
 #pragma unroll
-    for (int d = 0; d < NDP; ++d) pd[d] = 0.f;
-    auto consume = [&](int qq, const float (&r)[4]) {
-      if (ND) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4* t4 = reinterpret_cast<const float4*>(table + (qq * 4 + e) * NDP);
-          float4 ta = t4[0];
-          pd[0] = fmaf(r[e], ta.x, pd[0]);
-          pd[1] = fmaf(r[e], ta.y, pd[1]);
-          if (ND > 2) {
-            pd[2] = fmaf(r[e], ta.z, pd[2]);
-            pd[3] = fmaf(r[e], ta.w, pd[3]);
-          }
-          if (ND > 4) {
-            float4 tb = t4[1];
-            pd[4] = fmaf(r[e], tb.x, pd[4]);
-            pd[5] = fmaf(r[e], tb.y, pd[5]);
-          }
-        }
-      }
-      *reinterpret_cast<float4*>(Ft + lane * ldf + qq * 4) = make_float4(r[0], r[1], r[2], r[3]);
-    };
-#pragma unroll
-    for (int u = 0; u < kPF; ++u)
-      if (q_lo + u < q_hi) consume(q_lo + u, v[u]);
-    // channels beyond the prefetched share (c > 128 * kPF): plain load-then-use, U quads at a time
-    constexpr int U = PEMP_MPA_U;
-    if (q_lo + kPF < q_hi) {
-      const float* prow = img_base + static_cast<long long>((q_lo + kPF) * 4) * hw + xc;
-      for (int q = q_lo + kPF; q < q_hi; q += U) {
-        float r[U][4];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (q + u < q_hi) {
+      for (int u = 0; u < U; ++u) {
+        if (i + u < nq) {
+          if (ND) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              r[u][e] = __ldg(prow);
-              prow += hw;
+              const float4 ta = trow[(u * 4 + e) * (NDP / 4)];
+              float4 tb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ND > 4) tb = trow[(u * 4 + e) * (NDP / 4) + 1];
+#pragma unroll
+              for (int s = 0; s < CS; ++s) {
+                pd[s][0] = fmaf(v[u][e][s], ta.x, pd[s][0]);
+                pd[s][1] = fmaf(v[u][e][s], ta.y, pd[s][1]);
+                if (ND > 2) {
+                  pd[s][2] = fmaf(v[u][e][s], ta.z, pd[s][2]);
+                  pd[s][3] = fmaf(v[u][e][s], ta.w, pd[s][3]);
+                }
+                if (ND > 4) {
+                  pd[s][4] = fmaf(v[u][e][s], tb.x, pd[s][4]);
+                  pd[s][5] = fmaf(v[u][e][s], tb.y, pd[s][5]);
+                }
+              }
             }
           }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (q + u < q_hi) consume(q + u, r[u]);
+          for (int s = 0; s < CS; ++s)
+            *reinterpret_cast<float4*>(fst + 32 * s * ldf + u * 4) =
+                make_float4(v[u][0][s], v[u][1][s], v[u][2][s], v[u][3][s]);
+        }
       }
+      prow += static_cast<long long>(U * 4) * hw;
+      fst += U * 4;
+      trow += U * 4 * (NDP / 4);
     }
     if (ND) {
 #pragma unroll
-      for (int d = 0; d < ND; ++d) red[(warp * NDP + d) * kTW + lane] = pd[d];
+      for (int s = 0; s < CS; ++s)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) red[(warp * NDP + d) * TW + lane + 32 * s] = pd[s][d];
     }
     __syncthreads();
 
-    // ---------------- softmax weights: threads 0..31 foreground group, 32..63 background group ----------
-    if (tid < 64) {
-      const int g = tid >> 5;
-      float m = live ? __ldg((g ? bgp : fgp) + x) : 0.f;
+    // ---------------- exchange: this CTA's dots over its channels -> ex[buf]; peer's via DSMEM --------
+    if (ND) {
+      for (int i = tid; i < ND * TW; i += kThreads) {
+        const int d = i / TW, x = i - d * TW;
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) s += red[(wv * NDP + d) * TW + x];
+        ex[(buf * NDP + d) * TW + x] = s;
+      }
+      if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+    }
+
+    // ---------------- softmax weights: threads [0, TW) foreground group, [TW, 2*TW) background group ----
+    if (tid < 2 * TW) {
+      const int g = tid / TW, xl = tid - g * TW, x = x0 + xl;
+      // pixels before x_nom were already handled by the previous tile of the shifted last window
+      const float m = (x < hw && x >= x_nom) ? __ldg((g ? bgp : fgp) + x) : 0.f;
       float e[P];
       e[0] = 0.f;
       float mx = 0.f;
 #pragma unroll
       for (int j = 1; j < P; ++j) {
-        float s = 0.f;
-        for (int wv = 0; wv < kWarps; ++wv) s += red[(wv * NDP + g * (P - 1) + j - 1) * kTW + lane];
-        e[j] = s + konst[g * (P - 1) + j - 1];
+        const int d = g * (P - 1) + j - 1;
+        float s;
+        if (CS > 1) {   // fixed order rank 0 + rank 1 on both CTAs => identical weights
+          const float mine = ex[(buf * NDP + d) * TW + xl], theirs = ex_peer[(buf * NDP + d) * TW + xl];
+          s = rank == 0 ? mine + theirs : theirs + mine;
+        } else {
+          s = ex[(buf * NDP + d) * TW + xl];
+        }
+        e[j] = s + konst[d];
         mx = fmaxf(mx, e[j]);
       }
       float sum = 0.f;
@@ -275,41 +314,44 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
         den[j] += w4[j];
         any |= w4[j] != 0.f;
       }
-      *reinterpret_cast<float4*>(wgt + (g * kTW + lane) * 4) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+      *reinterpret_cast<float4*>(wgt + (g * TW + xl) * 4) = make_float4(w4[0], w4[1], w4[2], w4[3]);
       const unsigned bal = __ballot_sync(kFull, any);
-      if (lane == 0) live_mask[g] = bal;
+      if (lane == 0) live_mask[g][xl >> 5] = bal;
     }
-    if (t + 1 < t_end) prefetch(t + 1);
     __syncthreads();
 
     // ---------------- phase B: out[c, k] += f[c, x] * A[k, x] over the pixels whose weights are non-zero
-    // (warp-uniform pixel lists from the two bit masks; two pixels per step for load/FMA overlap)
+    // (warp-uniform pixel lists from the bit masks; two pixels per step for load/FMA overlap)
+    const float* fcol = Ft + qb * 4;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      unsigned m = (live_mask[g] >> (grp * ppg)) & (ppg == 32 ? 0xffffffffu : ((1u << ppg) - 1u));
-      while (m) {
-        const int i0 = __ffs(m) - 1;
-        m &= m - 1;
-        const bool two = m != 0;
-        const int i1 = two ? __ffs(m) - 1 : i0;
-        m &= m - 1;
-        const int p0 = grp * ppg + i0, p1 = grp * ppg + i1;
-        const float4 w0 = *reinterpret_cast<const float4*>(wgt + (g * kTW + p0) * 4);
-        float4 w1 = *reinterpret_cast<const float4*>(wgt + (g * kTW + p1) * 4);
-        if (!two) w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
+      for (int pbase = grp * ppg; pbase < (grp + 1) * ppg; pbase += 32) {
+        const int nbits = min(32, (grp + 1) * ppg - pbase);
+        unsigned m = (live_mask[g][pbase >> 5] >> (pbase & 31)) & (nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u));
+        while (m) {
+          const int i0 = __ffs(m) - 1;
+          m &= m - 1;
+          const bool two = m != 0;
+          const int i1 = two ? __ffs(m) - 1 : i0;
+          m &= m - 1;
+          const int p0 = pbase + i0, p1 = pbase + i1;
+          const float4 w0 = *reinterpret_cast<const float4*>(wgt + (g * TW + p0) * 4);
+          float4 w1 = *reinterpret_cast<const float4*>(wgt + (g * TW + p1) * 4);
+          if (!two) w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int a = 0; a < kQPT; ++a) {
-          const float4 f0 = *reinterpret_cast<const float4*>(Ft + p0 * ldf + (qb + a * tpp) * 4);
-          const float4 f1 = *reinterpret_cast<const float4*>(Ft + p1 * ldf + (qb + a * tpp) * 4);
-          const float fa[4] = {f0.x, f0.y, f0.z, f0.w}, fb[4] = {f1.x, f1.y, f1.z, f1.w};
+          for (int a = 0; a < kQPT; ++a) {
+            const float4 f0 = *reinterpret_cast<const float4*>(fcol + p0 * ldf + a * tpp * 4);
+            const float4 f1 = *reinterpret_cast<const float4*>(fcol + p1 * ldf + a * tpp * 4);
+            const float fa[4] = {f0.x, f0.y, f0.z, f0.w}, fb[4] = {f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int j = 0; j < P; ++j) {
-              acc[a][g][e][j] = fmaf(fa[e], wa[j], acc[a][g][e][j]);
-              acc[a][g][e][j] = fmaf(fb[e], wb[j], acc[a][g][e][j]);
-            }
+              for (int j = 0; j < P; ++j) {
+                acc[a][g][e][j] = fmaf(fa[e], wa[j], acc[a][g][e][j]);
+                acc[a][g][e][j] = fmaf(fb[e], wb[j], acc[a][g][e][j]);
+              }
+          }
         }
       }
     }
@@ -317,7 +359,7 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
   }
 
   // ---------------- epilogue: fold the pixel groups (fixed order), write the partials ------------------
-  float* fold = Ft;   // reuse: [ng][2*2*4*P][tpp]
+  float* fold = Ft;   // reuse: [ng][kQPT*2*4*P][tpp]
   constexpr int kAcc = kQPT * 2 * 4 * P;
   {
     int o = 0;
@@ -330,9 +372,17 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
 #pragma unroll
           for (int j = 0; j < P; ++j) fold[(grp * kAcc + (o++)) * tpp + qb] = acc[a][g][e][j];
   }
+  if (tid < 2 * TW) {   // denominators: per-warp sums, combined below in warp order
+    const int g = tid / TW, w_in_g = (tid - g * TW) >> 5;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const float s = warp_sum(den[j]);
+      if (lane == 0) den_part[g][w_in_g][j] = s;
+    }
+  }
   __syncthreads();
   if (grp == 0) {
-    float* out = part_num + (static_cast<long long>(img) * nsplit + split) * c * K;
+    float* out = part_num + ((static_cast<long long>(img) * nsplit + split) * c + ch0) * K;
     int o = 0;
 #pragma unroll
     for (int a = 0; a < kQPT; ++a) {
@@ -350,14 +400,14 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
           }
     }
   }
-  if (tid < 64) {
-    const int g = tid >> 5;
+  if (rank == 0 && tid < K) {
+    const int g = tid / P, j = tid - g * P;
+    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-      float s = warp_sum(den[j]);
-      if (lane == 0) part_den[(static_cast<long long>(img) * nsplit + split) * K + g * P + j] = s;
-    }
+    for (int wv = 0; wv < CS; ++wv) s += den_part[g][wv][j];
+    part_den[(static_cast<long long>(img) * nsplit + split) * K + tid] = s;
   }
+  if (CS > 1) cg::this_cluster().sync();   // the peer may still be reading this CTA's `ex`
 }
 
 // one thread per (b, channel, k)
@@ -387,25 +437,22 @@ __global__ void mpa_finalize_kernel(const float* __restrict__ part_num, const fl
   if (adaptive_p) adaptive_p[(static_cast<long long>(b) * c + ch) * K + k] = v;
 }
 
-int pick_splits(int imgs, int ntiles) {
-  // aim for >= 4 waves of 3 CTAs/SM on 148 SMs, never more splits than tiles, at least 2 tiles per split
-  int want = (PEMP_MPA_WAVES * 148 * 2 + imgs - 1) / imgs;
-  int cap = ntiles / 2 > 0 ? ntiles / 2 : 1;
-  int n = want < cap ? want : cap;
-  return n < 1 ? 1 : n;
-}
-
 struct Plan {
-  int nsplit, tiles_per_split;
-  size_t off_table, off_konst, off_num, off_den, total;
+  int cs, nsplit;
+  size_t smem_bytes, off_table, off_konst, off_num, off_den, total;
 };
 Plan make_plan(int B, int S, int c, int hw, int P) {
   Plan p;
   const size_t imgs = static_cast<size_t>(B) * S;
-  const int ntiles = (hw + kTW - 1) / kTW;
-  p.nsplit = pick_splits(static_cast<int>(imgs), ntiles);
-  p.tiles_per_split = (ntiles + p.nsplit - 1) / p.nsplit;
-  p.nsplit = (ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  // CTA pairs need an even split of whole quads; otherwise one CTA owns all channels
+  p.cs = (PEMP_MPA_CLUSTER == 2 && c % 8 == 0 && c >= 64) ? 2 : 1;
+  const int ntiles = (hw + 32 * p.cs - 1) / (32 * p.cs);
+  // aim for PEMP_MPA_WAVES waves of 2 CTAs/SM on 148 SMs; at least 2 tiles per split
+  int want = static_cast<int>((PEMP_MPA_WAVES * 148 * 2 + imgs * p.cs - 1) / (imgs * p.cs));
+  int cap = ntiles / 2 > 0 ? ntiles / 2 : 1;
+  p.nsplit = want < cap ? want : cap;
+  if (p.nsplit < 1) p.nsplit = 1;
+  p.smem_bytes = static_cast<size_t>(smem_layout(c / p.cs, P, p.cs).total) * sizeof(float);
   p.off_table = 0;
   p.off_konst = align_up(static_cast<size_t>(c) * ndp_of(P) * sizeof(float), 256);
   p.off_num = p.off_konst + 256;
@@ -414,25 +461,36 @@ Plan make_plan(int B, int S, int c, int hw, int P) {
   return p;
 }
 
-template <int P>
-int launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg, long long mask_stride, int B, int S,
-           int c, int hw, float eps, float* fg_proto, float* bg_proto, float* adaptive_p, char* ws, const Plan& pl,
-           cudaStream_t st) {
-  constexpr int ND = 2 * (P - 1), NDP = P <= 3 ? 4 : 8;
+template <int P, int CS, int HWT, int CCT, bool SAFE>
+int launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
+           long long mask_stride, int B, int S, int c, int hw, float eps, float* fg_proto, float* bg_proto,
+           float* adaptive_p, char* ws, const Plan& pl, cudaStream_t st) {
+  constexpr int ND = 2 * (P - 1);
   float* table = reinterpret_cast<float*>(ws + pl.off_table);
   float* konst = reinterpret_cast<float*>(ws + pl.off_konst);
   float* num = reinterpret_cast<float*>(ws + pl.off_num);
   float* den = reinterpret_cast<float*>(ws + pl.off_den);
   if (ND) mpa_prepare_kernel<<<8, 256, 0, st>>>(ctr, c, P, table, konst);
-  size_t smem = (static_cast<size_t>(ft_floats(c, P)) + (ND ? static_cast<size_t>(c) * NDP + kWarps * NDP * kTW : 0) +
-                 2 * kTW * 4) * sizeof(float);
-  if (smem > 227 * 1024) return PEMP_E_SHAPE;
-  cudaError_t e = cudaFuncSetAttribute(mpa_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  if (pl.smem_bytes > 227 * 1024) return PEMP_E_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(mpa_kernel<P, CS, HWT, CCT, SAFE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(pl.smem_bytes));
   if (e != cudaSuccess) return static_cast<int>(e);
-  dim3 grid(pl.nsplit, static_cast<unsigned>(B) * S);
-  mpa_kernel<P><<<grid, kThreads, smem, st>>>(fts, ep_stride ? ep_stride : static_cast<long long>(S) * c * hw, S, table, konst, fg, bg, mask_stride, c, hw, pl.tiles_per_split, num,
-                                                  den);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(pl.nsplit) * CS, static_cast<unsigned>(B) * S);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(S) * c * hw;
+  e = cudaLaunchKernelEx(&cfg, mpa_kernel<P, CS, HWT, CCT, SAFE>, fts, eps_stride, S, static_cast<const float*>(table),
+                         static_cast<const float*>(konst), fg, bg, mask_stride, c, hw, num, den);
+  if (e != cudaSuccess) return static_cast<int>(e);
   long long total = static_cast<long long>(B) * c * 2 * P;
   mpa_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(num, den, B, S, c, P, pl.nsplit, eps,
                                                                                  fg_proto, bg_proto, adaptive_p);
@@ -446,25 +504,32 @@ extern "C" size_t pemp_meta_proto_attn_workspace_bytes(int B, int S, int c, int 
   return make_plan(B, S, c, hw, p).total;
 }
 
-extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg, const float* bg,
-                                    long long mask_stride, int B, int S, int c, int hw, int p, float eps, float* fg_proto,
-                                    float* bg_proto, float* adaptive_p, void* workspace, size_t workspace_bytes,
-                                    pemp_stream_t stream) {
+extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                                    const float* bg, long long mask_stride, int B, int S, int c, int hw, int p,
+                                    float eps, float* fg_proto, float* bg_proto, float* adaptive_p, void* workspace,
+                                    size_t workspace_bytes, pemp_stream_t stream) {
   PEMP_REQUIRE(fts && ctr && fg && bg && fg_proto && bg_proto, PEMP_E_NULL);
   PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
   PEMP_REQUIRE(p >= 1 && p <= 4 && c % 4 == 0 && c <= kMaxChannels, PEMP_E_SHAPE);
   Plan pl = make_plan(B, S, c, hw, p);
+  PEMP_REQUIRE(pl.smem_bytes <= 227 * 1024, PEMP_E_SHAPE);
   PEMP_REQUIRE(workspace && workspace_bytes >= pl.total, PEMP_E_WORKSPACE);
   PEMP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, PEMP_E_ALIGN);
   char* ws = static_cast<char*>(workspace);
   cudaStream_t st = as_stream(stream);
-#define PEMP_MPA(PP) \
-  return launch<PP>(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st)
+#define PEMP_MPA_ARGS fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st
+  const bool safe = hw < 32 * pl.cs;
+  // fully specialised PEMP shape: c = 512, 51 x 51 features, 3 prototypes per class
+  if (p == 3 && pl.cs == 2 && c == 512 && hw == 2601) return launch<3, 2, 2601, 256, false>(PEMP_MPA_ARGS);
+#define PEMP_MPA(PP)                                                                            \
+  return pl.cs == 2 ? (safe ? launch<PP, 2, 0, 0, true>(PEMP_MPA_ARGS) : launch<PP, 2, 0, 0, false>(PEMP_MPA_ARGS)) \
+                    : (safe ? launch<PP, 1, 0, 0, true>(PEMP_MPA_ARGS) : launch<PP, 1, 0, 0, false>(PEMP_MPA_ARGS))
   switch (p) {
     case 1: PEMP_MPA(1);
     case 2: PEMP_MPA(2);
     case 3: PEMP_MPA(3);
     default: PEMP_MPA(4);
   }
+#undef PEMP_MPA_ARGS
 #undef PEMP_MPA
 }
