@@ -12,7 +12,7 @@
 // All paths share the pre-pass (mask multiply + column norms) and the tail (min-max + shot mean) below.
 #include "common.cuh"
 
-int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, const float* nq, const float* ns, int B,
+int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, float* nq, float* ns, int B,
                          int S, int C, int hw_s, int hw_q, int precision, float* rowmax, char* ws, size_t ws_bytes,
                          cudaStream_t st);
 size_t pemp_prior_tc_workspace_bytes(int B, int S, int C, int hw_s, int hw_q, int precision);
@@ -22,19 +22,29 @@ namespace {
 constexpr float kEps = 1e-7f;   // cosine_eps, pfenet.py:202
 
 // x [planes][C][hw] (optionally times mask [planes][hw]) -> out [planes][hw] = sqrt(sum_c (x*m)^2)
+// block = 32 pixels x 8 channel phases: coalesced 128-byte row segments, 8-way split of the channel loop
 __global__ void col_norm_kernel(const float* __restrict__ x, const float* __restrict__ mask, int C, int hw,
                                 float* __restrict__ out) {
-  const int pl = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hw) return;
-  const float m = mask ? __ldg(mask + static_cast<long long>(pl) * hw + i) : 1.f;
-  const float* p = x + static_cast<long long>(pl) * C * hw + i;
+  __shared__ float part[8][32];
+  const int pl = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
+  const bool ok = i < hw;
+  const float m = (ok && mask) ? __ldg(mask + static_cast<long long>(pl) * hw + i) : 1.f;
+  const float* p = x + static_cast<long long>(pl) * C * hw + (ok ? i : 0);
   float s = 0.f;
-  for (int c = 0; c < C; ++c) {
-    float v = __ldg(p + static_cast<long long>(c) * hw) * m;
+#pragma unroll 8
+  for (int c = ty; c < C; c += 8) {
+    float v = ok ? __ldg(p + static_cast<long long>(c) * hw) * m : 0.f;
     s = fmaf(v, v, s);
   }
-  out[static_cast<long long>(pl) * hw + i] = sqrtf(s);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += part[r][tx];
+    out[static_cast<long long>(pl) * hw + i] = sqrtf(t);
+  }
 }
 
 // ---- fp32 path ----------------------------------------------------------------------------------------
@@ -200,9 +210,9 @@ extern "C" int pemp_prior_mask(const float* q4, const float* s4, const float* sm
   float* rowmax = rowmax_out ? rowmax_out : reinterpret_cast<float*>(ws + pl.off_rowmax);
   cudaStream_t st = as_stream(stream);
 
-  col_norm_kernel<<<dim3((hw_q + 127) / 128, B), 128, 0, st>>>(q4, nullptr, C, hw_q, nq);
-  col_norm_kernel<<<dim3((hw_s + 127) / 128, S * B), 128, 0, st>>>(s4, smask, C, hw_s, ns);
   if (precision == 1) {
+    col_norm_kernel<<<dim3((hw_q + 31) / 32, B), dim3(32, 8), 0, st>>>(q4, nullptr, C, hw_q, nq);
+    col_norm_kernel<<<dim3((hw_s + 31) / 32, S * B), dim3(32, 8), 0, st>>>(s4, smask, C, hw_s, ns);
     prior_fp32_kernel<<<dim3((hw_q + BM - 1) / BM, S * B), kGemmThreads, 0, st>>>(q4, s4, smask, nq, ns, B, C, hw_s, hw_q,
                                                                                 rowmax);
   } else {

@@ -1,10 +1,419 @@
-// K9 tensor-core path (tcgen05 / TMA / TMEM).  Placeholder entry points until the UMMA kernel lands: they
-// report PEMP_E_SHAPE so callers fail loudly rather than silently taking another path.
+// K9 tensor-core path: the PFENet prior contraction on tcgen05 (5th-gen tensor cores), TMA-fed, accumulators in
+// tensor memory, with the max over support pixels fused into the epilogue.
+//
+// replaces the per-shot `torch.bmm(tmp_supp, tmp_query) / (bmm(norms) + eps)` + `.max(1)` of
+// networks/pfenet.py:213-222 (cuBLAS SGEMM + a [B, HWs, HWq] matrix of 52 MB written and re-read per shot).
+//
+// Formulation.  A pre-pass turns the channel-major fp32 maps into K-major bf16 operands that are already
+// divided by their column norms (support also multiplied by its mask):
+//     A[i, :] = q[:, i] / |q[:, i]|          [HWq, C]   (M operand, one row per query pixel)
+//     B[j, :] = m_j s[:, j] / |m_j s[:, j]|   [HWs, C]   (N operand, one row per support pixel; 0 if masked out)
+// so the accumulator D = A B^T holds cosines and the epilogue is a running max over support pixels, one
+// TMEM lane (= query pixel) per thread.  The reference's `+ 1e-7` in the denominator is re-applied exactly
+// (factor 1 / (1 + eps / (|q_i| |s_j|))) on the rare inputs where it is not below fp32 resolution.
+// precision 0: single bf16 product.  precision 2: three products A_hi B_hi + A_hi B_lo + A_lo B_hi
+// (x = hi + lo, both bf16) accumulated into the same TMEM tile - fp32-grade results at 1/3 of the rate.
+//
+// Kernel.  grid = (M tiles of 128 query pixels, S*B).  6 warps: warp 0 = TMA producer (4-stage ring of
+// 128x64 A and 256x64 B tiles, SWIZZLE_128B), warp 1 = MMA issuer (one elected thread, UMMA 128x256x16,
+// two 256-column fp32 accumulators in TMEM so the epilogue of N tile t overlaps the MMAs of t+1), warps 2-5 =
+// epilogue (tcgen05.ld 32 lanes x 32 columns, FMNMX).  Synchronisation is mbarrier only.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
-size_t pemp_prior_tc_workspace_bytes(int, int, int, int, int, int) { return 0; }
+namespace {
 
-int pemp_prior_tc_launch(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int,
-                         int, float*, char*, size_t, cudaStream_t) {
-  return PEMP_E_SHAPE;
+constexpr int BM = 128, BN = 256, BK = 64;            // CTA tile; BK bf16 = 128 bytes = one swizzle row
+constexpr int kStages = 4;
+constexpr int kUmmaK = 16;
+constexpr int kThreadsTc = 192;
+constexpr uint32_t kBytesA = BM * BK * 2, kBytesB = BN * BK * 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr float kEps = 1e-7f;
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all tcgen05 ops issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major tile of [rows][64 bf16], 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);        // start address            bits [0, 14)
+  d |= static_cast<uint64_t>(0) << 16;                            // leading byte offset: unused for swizzled K-major
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // stride byte offset       bits [32, 46)
+  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                            // layout: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------- pre-pass
+// One block per (plane, strip of 32 pixels).  Pass 1: column norms sqrt(sum_c (x*m)^2) (also written to `norm`
+// for the epilogue / the eps test).  Pass 2: the same 32 x C strip (256 KB, still in L2) is transposed through
+// shared memory into K-major bf16 rows scaled by mask / norm (0 where the norm is 0):
+//   x [planes][C][hw] fp32 -> out [planes][nsel][hw][C] bf16;  nsel = 2 also emits lo = bf16(x*scale - hi).
+// Reads and writes are coalesced in both passes.
+__global__ void __launch_bounds__(256)
+prep_kmajor_kernel(const float* __restrict__ x, const float* __restrict__ mask, int C, int hw, int nsel,
+                   float* __restrict__ norm, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  __shared__ float part[8][32];
+  __shared__ float scale_s[32];
+  const int pl = blockIdx.y, i0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;                     // 32 x 8
+  const float* xp = x + static_cast<long long>(pl) * C * hw;
+  const int i = i0 + tx;
+  const bool ok = i < hw;
+  const float m = (ok && mask) ? __ldg(mask + static_cast<long long>(pl) * hw + i) : 1.f;
+  // ---- pass 1: norms
+  float acc = 0.f;
+  const float* col = xp + (ok ? i : 0);
+#pragma unroll 8
+  for (int c = ty; c < C; c += 8) {
+    float v = ok ? __ldg(col + static_cast<long long>(c) * hw) * m : 0.f;
+    acc = fmaf(v, v, acc);
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += part[r][tx];
+    const float n = sqrtf(s);
+    if (ok) norm[static_cast<long long>(pl) * hw + i] = n;
+    scale_s[tx] = n > 0.f ? m / n : 0.f;
+  }
+  __syncthreads();
+  // ---- pass 2: transpose + scale + convert
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int c = c0 + ty + 8 * r;
+      tile[ty + 8 * r][tx] = (c < C && ok) ? __ldg(col + static_cast<long long>(c) * hw) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int il = ty + 8 * r, ii = i0 + il, c = c0 + tx;
+      if (ii < hw && c < C) {
+        const float v = tile[tx][il] * scale_s[il];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const long long o = ((static_cast<long long>(pl) * nsel) * hw + ii) * C + c;
+        out[o] = hi;
+        if (nsel == 2) out[o + static_cast<long long>(hw) * C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// flag[0] = 1 if the reference's `+ eps` is visible in fp32 for some (i, j): eps / (min|q| * min|s|) > 2^-25
+__global__ void eps_flag_kernel(const float* __restrict__ nq, long long n_q, const float* __restrict__ ns, long long n_s,
+                                float* __restrict__ flag) {
+  __shared__ float red[2][32];
+  float mq = INFINITY, ms = INFINITY;
+  for (long long i = threadIdx.x; i < n_q; i += blockDim.x) { float v = nq[i]; if (v > 0.f) mq = fminf(mq, v); }
+  for (long long i = threadIdx.x; i < n_s; i += blockDim.x) { float v = ns[i]; if (v > 0.f) ms = fminf(ms, v); }
+  for (int o = 16; o > 0; o >>= 1) {
+    mq = fminf(mq, __shfl_xor_sync(kFull, mq, o));
+    ms = fminf(ms, __shfl_xor_sync(kFull, ms, o));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mq; red[1][threadIdx.x >> 5] = ms; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) { mq = fminf(mq, red[0][w]); ms = fminf(ms, red[1][w]); }
+    mq = fminf(red[0][0], mq);
+    ms = fminf(red[1][0], ms);
+    bool visible = isfinite(mq) && isfinite(ms) && (kEps / (mq * ms) > 2.98e-8f);
+    flag[0] = visible ? 1.f : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- GEMM
+struct __align__(1024) TcSmem {
+  uint8_t a[kStages][kBytesA];
+  uint8_t b[kStages][kBytesB];
+  float sn[2][BN];                 // 1 / |s_j| of the current N tile (eps-visible path only), double buffered
+  uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+// nsel = 1: one product per k-block.  nsel = 2: rows [0, hw) hold hi, [hw, 2hw) hold lo; three products.
+__global__ void __launch_bounds__(kThreadsTc, 1)
+prior_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const float* __restrict__ nq, const float* __restrict__ ns, const float* __restrict__ eps_flag, int B,
+                int C, int hw_s, int hw_q, int nsel, float* __restrict__ rowmax) {
+  extern __shared__ uint8_t raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sb = blockIdx.y, b = sb % B;
+  const int m0 = blockIdx.x * BM;
+  const int n_tiles = (hw_s + BN - 1) / BN;
+  const int k_blocks = (C + BK - 1) / BK;
+  const int passes = nsel == 2 ? 3 : 1;
+  const long long a_row0 = static_cast<long long>(b) * nsel * hw_q;      // rows of this batch element in A
+  const long long b_row0 = static_cast<long long>(sb) * nsel * hw_s;     // rows of this (shot, batch) in B
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sm.tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        for (int p = 0; p < passes; ++p) {
+          const int a_sel = p == 2 ? 1 : 0, b_sel = p == 1 ? 1 : 0;     // (hi,hi), (hi,lo), (lo,hi)
+          for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+            const int st = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&sm.empty[st], ph ^ 1);
+            mbar_expect_tx(&sm.full[st], kBytesA + kBytesB);
+            tma_load_2d(&map_a, &sm.full[st], sm.a[st], kb * BK, static_cast<int>(a_row0 + static_cast<long long>(a_sel) * hw_q + m0));
+            tma_load_2d(&map_b, &sm.full[st], sm.b[st], kb * BK,
+                        static_cast<int>(b_row0 + static_cast<long long>(b_sel) * hw_s + t * BN));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_ph = (t >> 1) & 1;
+        mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);                       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + acc * BN;
+        uint32_t first = 1;
+        for (int pk = 0; pk < passes * k_blocks; ++pk, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&sm.full[st], ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(sm.a[st])), db = make_smem_desc(smem_u32(sm.b[st]));
+#pragma unroll
+          for (int k = 0; k < BK / kUmmaK; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          umma_commit(&sm.empty[st]);                                     // smem stage reusable once these MMAs retire
+        }
+        umma_commit(&sm.acc_full[acc]);                                   // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue: running max over support pixels =====================
+    const int q = warp & 3;                                               // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                                        // query pixel within the M tile
+    const int i = m0 + row;
+    const bool eps_visible = __ldg(eps_flag) != 0.f;
+    const float a_i = (eps_visible && i < hw_q) ? kEps / fmaxf(__ldg(nq + static_cast<long long>(b) * hw_q + i), 1e-30f) : 0.f;
+    float best = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_ph = (t >> 1) & 1;
+      const int n0 = t * BN;
+      if (eps_visible) {   // stage 1/|s_j| of this tile for the epilogue warps (named barrier over the 128 epilogue threads)
+        const int e = threadIdx.x - 64;
+        for (int j = e; j < BN; j += 128) {
+          float v = n0 + j < hw_s ? __ldg(ns + static_cast<long long>(sb) * hw_s + n0 + j) : 0.f;
+          sm.sn[acc][j] = v > 0.f ? 1.f / v : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&sm.acc_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        if (n0 + cb * 32 >= hw_s) break;                                  // columns past the last support pixel
+        uint32_t r[32];
+        tmem_ld32(taddr + cb * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]);
+          if (eps_visible) v = v / (1.f + a_i * sm.sn[acc][cb * 32 + j]);
+          if (n0 + cb * 32 + j < hw_s) best = fmaxf(best, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.acc_empty[acc]);                     // 4 epilogue warps -> count 4
+    }
+    if (i < hw_q) rowmax[static_cast<long long>(sb) * hw_q + i] = best;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;     // immutable after first resolution; benign race (same value)
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rows x C bf16, row-major; box = box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
+int make_map(CUtensorMap* map, const void* base, long long rows, int C, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return PEMP_E_ARCH;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PEMP_OK : PEMP_E_SHAPE;
+}
+
+struct Plan {
+  int nsel;
+  size_t off_a, off_b, off_flag, total;
+};
+Plan make_plan(int B, int S, int C, int hw_s, int hw_q, int precision) {
+  Plan p;
+  p.nsel = precision == 2 ? 2 : 1;
+  p.off_a = 0;
+  p.off_b = align_up(static_cast<size_t>(B) * p.nsel * hw_q * C * 2, 1024);
+  p.off_flag = p.off_b + align_up(static_cast<size_t>(S) * B * p.nsel * hw_s * C * 2, 1024);
+  p.total = p.off_flag + 256;
+  return p;
+}
+
+}  // namespace
+
+size_t pemp_prior_tc_workspace_bytes(int B, int S, int C, int hw_s, int hw_q, int precision) {
+  return make_plan(B, S, C, hw_s, hw_q, precision).total + 1024;   // + slack to align the base to 1024
+}
+
+int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, float* nq, float* ns, int B,
+                         int S, int C, int hw_s, int hw_q, int precision, float* rowmax, char* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+  PEMP_REQUIRE(C % 8 == 0, PEMP_E_SHAPE);                       // 16-byte row pitch of the bf16 operands (TMA)
+  Plan pl = make_plan(B, S, C, hw_s, hw_q, precision);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
+  PEMP_REQUIRE(base + pl.total <= ws + ws_bytes, PEMP_E_WORKSPACE);
+  __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(base + pl.off_a);
+  __nv_bfloat16* bmat = reinterpret_cast<__nv_bfloat16*>(base + pl.off_b);
+  float* flag = reinterpret_cast<float*>(base + pl.off_flag);
+
+  dim3 tb(32, 8);   // norms + K-major bf16 operands in one pass per tensor
+  prep_kmajor_kernel<<<dim3((hw_q + 31) / 32, B), tb, 0, st>>>(q4, nullptr, C, hw_q, pl.nsel, nq, a);
+  prep_kmajor_kernel<<<dim3((hw_s + 31) / 32, S * B), tb, 0, st>>>(s4, smask, C, hw_s, pl.nsel, ns, bmat);
+  eps_flag_kernel<<<1, 1024, 0, st>>>(nq, static_cast<long long>(B) * hw_q, ns, static_cast<long long>(S) * B * hw_s, flag);
+
+  CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, a, static_cast<long long>(B) * pl.nsel * hw_q, C, BM);
+  if (rc != PEMP_OK) return rc;
+  rc = make_map(&map_b, bmat, static_cast<long long>(S) * B * pl.nsel * hw_s, C, BN);
+  if (rc != PEMP_OK) return rc;
+
+  const size_t smem = sizeof(TcSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid((hw_q + BM - 1) / BM, S * B);
+  prior_tc_kernel<<<grid, kThreadsTc, smem, st>>>(map_a, map_b, nq, ns, flag, B, C, hw_s, hw_q, pl.nsel, rowmax);
+  return launch_status();
 }

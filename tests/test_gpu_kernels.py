@@ -260,6 +260,38 @@ def test_prior_fp32_golden(ops, name):
     assert np.abs(prior.cpu().numpy() - g["prior"]).max() < TOL * max(1.0, amp)
 
 
+def _prior_case(B, S, C, sp, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    q4 = torch.relu(torch.randn(B, C, sp, sp, generator=g)) * scale
+    s4 = torch.relu(torch.randn(S, B, C, sp, sp, generator=g)) * scale
+    small = (torch.rand(S, B, sp, sp, generator=g) > 0.45).float()
+    small[0, 0, :2] = 0.5                                   # fractional mask values (non 8x image sizes)
+    ref = torch.stack([O.pfenet_rowmax(q4, s4[s], small[s][:, None]) for s in range(S)])
+    return q4, s4, small, ref
+
+
+# tolerances on the PRE-normalisation cosine maxima (values in [0, 1]); the min-max step amplifies them by
+# 1 / (max - min), reported by the test below.  bf16 x 1: one rounding of each operand (2^-9 relative each);
+# bf16 x 3 (hi/lo split): fp32-grade.
+@pytest.mark.parametrize("precision,tol", [(0, 3e-3), (2, 3e-5)])
+@pytest.mark.parametrize("B,S,C,sp", [(1, 2, 64, 13), (2, 1, 256, 27), (1, 1, 2048, 24), (1, 3, 136, 33)])
+def test_prior_tensor_core_paths(ops, precision, tol, B, S, C, sp):
+    q4, s4, small, ref = _prior_case(B, S, C, sp, seed=C + sp)
+    prior, rowmax = ops.prior_mask(cu(q4), cu(s4), cu(small), precision=precision, want_rowmax=True)
+    assert nrel(rowmax.cpu(), ref) < tol, nrel(rowmax.cpu(), ref)
+    p32, r32 = ops.prior_mask(cu(q4), cu(s4), cu(small), precision=ops.PRIOR_FP32, want_rowmax=True)
+    amp = float(1.0 / (ref.max(dim=2).values - ref.min(dim=2).values).min())
+    assert float((prior - p32).abs().max()) < 2 * tol * max(1.0, amp)
+
+
+def test_prior_tensor_core_eps_visible(ops):
+    """Tiny feature norms make the reference's `+ 1e-7` visible; the epilogue re-applies it exactly."""
+    q4, s4, small, ref = _prior_case(1, 2, 64, 13, seed=5, scale=1e-4)
+    _, rowmax = ops.prior_mask(cu(q4), cu(s4), cu(small), precision=2, want_rowmax=True)
+    assert float(ref.max()) < 0.9                                       # eps really matters here
+    assert nrel(rowmax.cpu(), ref) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ whole head
 def _run_head(ops, feats, sup_mask, ctr, B, S, Q, out_shape):
     _, c, h, w = feats.shape

@@ -72,6 +72,16 @@ def main():
         ("K6 map_pool_fullres", lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
          B * (S * (c * hw * 4 + 2 * H * H * 4) + 2 * c * 4)),
     ]
+    if not a.only or "K9" in a.only:
+        Bp, Sp, Cp, spx = 1, 5, 2048, 60
+        q4 = torch.relu(torch.randn(Bp, Cp, spx, spx, device=dev, generator=g))
+        s4 = torch.relu(torch.randn(Sp, Bp, Cp, spx, spx, device=dev, generator=g))
+        sm = (torch.rand(Sp, Bp, spx, spx, device=dev, generator=g) > 0.5).float()
+        flop = 2.0 * Cp * (Sp * spx * spx) * (spx * spx) * Bp
+        for prec, tag in ((0, "bf16"), (2, "bf16x3"), (1, "fp32")):
+            ms = timeit(lambda: ops.prior_mask(q4, s4, sm, precision=prec), iters=5, warm=2)
+            print(json.dumps({"kernel": f"K9 prior_mask {tag} (whole op incl. pre-pass + tail)", "ms": round(ms, 4),
+                              "alg_GFLOP": round(flop / 1e9, 1), "TFLOPs": round(flop / ms / 1e9, 1), "S": Sp, "C": Cp, "hw": spx * spx}))
     for name, fn, nbytes in rows:
         if a.only and a.only not in name:
             continue
