@@ -23,10 +23,10 @@
 //            difference table (one 128-bit shared load per row, amortised over the lane's CS pixels) and
 //            stored TRANSPOSED into shared memory as Ft[pixel][channel] (row stride = 4*odd floats =>
 //            conflict-free 128-bit stores);
-//   exchange the per-CTA partial dots are reduced over warps into E[buffer][d][pixel]; the peer's E is read
-//            through distributed shared memory after one cluster barrier (double buffered, so one barrier
-//            per tile orders both the read-after-write and the later write-after-read);
-//   softmax  2*TW threads turn the dots into the 2P weights of each pixel (both CTAs, redundantly);
+//   exchange + softmax: 2*TW threads, one per (class group, pixel), add the warps' partial dots in a fixed
+//            order, push the sums into the peer CTA's shared memory with `st.async` (which completes a
+//            transaction mbarrier there - no fence, so global loads in flight are not drained) and, once the
+//            peer's sums have landed, turn the dots into the 2P weights of each pixel (both CTAs, redundantly);
 //   phase B  thread <-> kQPT channel quads x one pixel group: conflict-free 128-bit shared loads of Ft feed
 //            4*P FMAs per quad into register accumulators that live for the whole CTA.
 // Partial numerators / denominators go to the workspace per (image, split); `mpa_finalize_kernel` adds the
@@ -38,6 +38,41 @@
 namespace cg = cooperative_groups;
 
 namespace {
+
+// ---- cluster handshake without fences ---------------------------------------------------------------------
+// `cluster.sync()` compiles to MEMBAR + barrier + CCTL.IVALL: the fence waits for every outstanding global load of
+// the thread, which serialises the register prefetch of the next tile behind the barrier.  The per-tile exchange of
+// the partial dots therefore uses `st.async` into the peer's shared memory, completing a transaction mbarrier there.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t local_addr, uint32_t peer_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(peer_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_local(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_local(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_local(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MPA_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MPA_DONE;\n"
+      "bra MPA_WAIT;\n"
+      "MPA_DONE:\n"
+      "}\n" ::"r"(smem_addr_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -58,7 +93,20 @@ constexpr int kMaxChannels = 3072;     // per-CTA Ft[32*CS][c/CS + 4] must fit t
 #ifndef PEMP_MPA_CLUSTER
 #define PEMP_MPA_CLUSTER 2
 #endif
+#ifndef PEMP_MPA_PREFETCH
+#define PEMP_MPA_PREFETCH 0
+#endif
 constexpr int kQPT = PEMP_MPA_QPT;     // channel quads per phase-B thread
+#ifdef PEMP_MPA_DEBUG_SKIP_B           // timing experiments only (results are wrong)
+constexpr bool kDebugSkipB = true;
+#else
+constexpr bool kDebugSkipB = false;
+#endif
+#ifdef PEMP_MPA_DEBUG_SKIP_DOTS
+constexpr bool kDebugSkipDots = true;
+#else
+constexpr bool kDebugSkipDots = false;
+#endif
 
 __host__ __device__ inline int nd_of(int P) { return 2 * (P - 1); }          // dot products per pixel
 __host__ __device__ inline int ndp_of(int P) { return P <= 3 ? 4 : 8; }      // padded table row
@@ -71,7 +119,7 @@ __host__ __device__ inline int tpp_of(int cc) {
 }
 
 struct Smem {            // offsets in floats
-  int ldf, ft, table, red, ex, wgt, total;
+  int ldf, ft, table, red, exin, wgt, total;
 };
 __host__ __device__ inline Smem smem_layout(int cc, int P, int CS) {
   const int TW = 32 * CS, NDP = ndp_of(P), ND = nd_of(P);
@@ -81,8 +129,8 @@ __host__ __device__ inline Smem smem_layout(int cc, int P, int CS) {
   s.ft = 0;
   s.table = tile > fold ? tile : fold;
   s.red = s.table + (ND ? cc * NDP : 0);
-  s.ex = s.red + (ND ? kWarps * NDP * TW : 0);
-  s.wgt = s.ex + (ND ? 2 * NDP * TW : 0);
+  s.exin = s.red + (ND ? kWarps * NDP * TW : 0);             // the peer's partial dots land here (st.async), [2][NDP][TW]
+  s.wgt = s.exin + ((ND && CS > 1) ? 2 * NDP * TW : 0);
   s.total = s.wgt + 2 * TW * 4;
   return s;
 }
@@ -123,7 +171,7 @@ __global__ void mpa_prepare_kernel(const float* __restrict__ ctr, int c, int P, 
 // instructions of the generic version (address arithmetic).  SAFE = true clamps pixel indices per lane and is
 // used when the image is narrower than one tile; otherwise the last tile is shifted left to end at hw and the
 // pixels it shares with the previous tile get zero weight.
-template <int P, int CS, int HWT, int CCT, bool SAFE>
+template <int P, int CS, int HWT, int CCT, bool SAFE, bool PF>
 __global__ void __launch_bounds__(kThreads, 2)
 mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ table_g,
            const float* __restrict__ konst_g, const float* __restrict__ fg, const float* __restrict__ bg,
@@ -142,11 +190,12 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
   float* Ft = smem + L.ft;                         // [TW][ldf]
   float* table = smem + L.table;                   // [cc][NDP]      rows of this CTA's channels
   float* red = smem + L.red;                       // [kWarps][NDP][TW]
-  float* ex = smem + L.ex;                         // [2][NDP][TW]   partial dots of this CTA (double buffered)
+  float* exin = smem + L.exin;                     // [2][NDP][TW]   partial dots of the peer CTA
   float* wgt = smem + L.wgt;                       // [2][TW][4]     softmax * mask
   __shared__ float konst[8];
   __shared__ unsigned live_mask[2][CS];            // bit x set <=> group g has a non-zero weight at pixel x
   __shared__ float den_part[2][CS][4];
+  __shared__ __align__(8) uint64_t xbar[2];        // transaction barriers of the two exchange buffers
 
   const int rank = CS > 1 ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
   const int split = blockIdx.x / CS, nsplit = gridDim.x / CS, img = blockIdx.y;
@@ -168,8 +217,17 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
   const float* img_base = fts + (img / S) * ep_stride + (static_cast<long long>(img % S) * c + ch0) * hw;
   const float* fgp = fg + img * mask_stride;
   const float* bgp = bg + img * mask_stride;
-  const float* ex_peer = nullptr;
-  if (CS > 1) ex_peer = cg::this_cluster().map_shared_rank(ex, rank ^ 1);
+  uint32_t peer_exin = 0, peer_xbar = 0;
+  if (CS > 1 && ND) {
+    if (tid == 0) {
+      mbar_init_local(&xbar[0], 1);
+      mbar_init_local(&xbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    peer_exin = map_to_peer(smem_addr_u32(exin), rank ^ 1);
+    peer_xbar = map_to_peer(smem_addr_u32(&xbar[0]), rank ^ 1);
+    cg::this_cluster().sync();                     // barriers initialised before any remote store can arrive
+  }
 
   // phase-A ownership: qw contiguous quads per warp
   const int qw = (quads + kWarps - 1) / kWarps;
@@ -195,6 +253,22 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
 
   __syncthreads();
 
+  // PF (specialised shapes, one load batch per tile): the row loads of tile it+1 are issued into registers as soon
+  // as tile it's values have been consumed, so they are in flight during the exchange / softmax / phase B of tile it.
+  float vpf[PF ? U : 1][4][CS];
+  auto issue_loads = [&](int tile_it) {
+    const int xn = (split + tile_it * nsplit) * TW;
+    const int xw = min(xn, hw - TW);
+    const float* pr = img_base + static_cast<long long>(q_lo * 4) * hw + xw + lane;
+#pragma unroll
+    for (int u = 0; u < (PF ? U : 0); ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int s2 = 0; s2 < CS; ++s2) vpf[u][e][s2] = __ldg(pr + (u * 4 + e) * hw + 32 * s2);
+  };
+  if (PF && my_tiles > 0) issue_loads(0);
+
   for (int it = 0; it < my_tiles; ++it) {
     const int x_nom = (split + it * nsplit) * TW;            // nominal first pixel of the tile
     const int x0 = SAFE ? x_nom : min(x_nom, hw - TW);       // window actually loaded
@@ -217,7 +291,12 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
       float v[U][4][CS];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (i + u < nq) {
+        if (PF) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int s = 0; s < CS; ++s) v[u][e][s] = vpf[u][e][s];
+        } else if (i + u < nq) {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
 #pragma unroll
@@ -228,7 +307,7 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (i + u < nq) {
-          if (ND) {
+          if (ND && !kDebugSkipDots) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 ta = trow[(u * 4 + e) * (NDP / 4)];
@@ -265,23 +344,28 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
 #pragma unroll
         for (int d = 0; d < ND; ++d) red[(warp * NDP + d) * TW + lane + 32 * s] = pd[s][d];
     }
+    if (PF && it + 1 < my_tiles) issue_loads(it + 1);
     __syncthreads();
 
-    // ---------------- exchange: this CTA's dots over its channels -> ex[buf]; peer's via DSMEM --------
-    if (ND) {
-      for (int i = tid; i < ND * TW; i += kThreads) {
-        const int d = i / TW, x = i - d * TW;
-        float s = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < kWarps; ++wv) s += red[(wv * NDP + d) * TW + x];
-        ex[(buf * NDP + d) * TW + x] = s;
-      }
-      if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
-    }
-
-    // ---------------- softmax weights: threads [0, TW) foreground group, [TW, 2*TW) background group ----
+    // ---------------- exchange + softmax: threads [0, TW) foreground group, [TW, 2*TW) background group ----
+    // Thread (g, xl) owns the P-1 dots of group g at pixel xl: it adds the warps' partials (fixed order), sends the
+    // sums to the peer CTA (st.async completes the peer's transaction barrier) and waits for the peer's sums.
     if (tid < 2 * TW) {
       const int g = tid / TW, xl = tid - g * TW, x = x0 + xl;
+      float mine[P > 1 ? P - 1 : 1];
+#pragma unroll
+      for (int j = 1; j < P; ++j) {
+        const int d = g * (P - 1) + j - 1;
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) s += red[(wv * NDP + d) * TW + xl];
+        mine[j - 1] = s;
+        if (CS > 1) st_async_f32(peer_exin + ((buf * NDP + d) * TW + xl) * 4, s, peer_xbar + buf * 8);
+      }
+      if (CS > 1 && ND) {
+        if (tid == 0) mbar_expect_tx_local(&xbar[buf], ND * TW * 4);              // arm this tile's incoming transfer
+        mbar_wait_local(&xbar[buf], (it >> 1) & 1);                               // the peer's dots have landed
+      }
       // pixels before x_nom were already handled by the previous tile of the shifted last window
       const float m = (x < hw && x >= x_nom) ? __ldg((g ? bgp : fgp) + x) : 0.f;
       float e[P];
@@ -290,12 +374,10 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
 #pragma unroll
       for (int j = 1; j < P; ++j) {
         const int d = g * (P - 1) + j - 1;
-        float s;
+        float s = mine[j - 1];
         if (CS > 1) {   // fixed order rank 0 + rank 1 on both CTAs => identical weights
-          const float mine = ex[(buf * NDP + d) * TW + xl], theirs = ex_peer[(buf * NDP + d) * TW + xl];
-          s = rank == 0 ? mine + theirs : theirs + mine;
-        } else {
-          s = ex[(buf * NDP + d) * TW + xl];
+          const float theirs = exin[(buf * NDP + d) * TW + xl];
+          s = rank == 0 ? s + theirs : theirs + s;
         }
         e[j] = s + konst[d];
         mx = fmaxf(mx, e[j]);
@@ -324,7 +406,7 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
     // (warp-uniform pixel lists from the bit masks; two pixels per step for load/FMA overlap)
     const float* fcol = Ft + qb * 4;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < (kDebugSkipB ? 0 : 2); ++g) {
       for (int pbase = grp * ppg; pbase < (grp + 1) * ppg; pbase += 32) {
         const int nbits = min(32, (grp + 1) * ppg - pbase);
         unsigned m = (live_mask[g][pbase >> 5] >> (pbase & 31)) & (nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u));
@@ -407,7 +489,7 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
     for (int wv = 0; wv < CS; ++wv) s += den_part[g][wv][j];
     part_den[(static_cast<long long>(img) * nsplit + split) * K + tid] = s;
   }
-  if (CS > 1) cg::this_cluster().sync();   // the peer may still be reading this CTA's `ex`
+  if (CS > 1) cg::this_cluster().sync();   // remote stores into the peer (and the peer's into us) have all landed
 }
 
 // one thread per (b, channel, k)
@@ -461,7 +543,7 @@ Plan make_plan(int B, int S, int c, int hw, int P) {
   return p;
 }
 
-template <int P, int CS, int HWT, int CCT, bool SAFE>
+template <int P, int CS, int HWT, int CCT, bool SAFE, bool PF>
 int launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
            long long mask_stride, int B, int S, int c, int hw, float eps, float* fg_proto, float* bg_proto,
            float* adaptive_p, char* ws, const Plan& pl, cudaStream_t st) {
@@ -472,7 +554,7 @@ int launch(const float* fts, long long ep_stride, const float* ctr, const float*
   float* den = reinterpret_cast<float*>(ws + pl.off_den);
   if (ND) mpa_prepare_kernel<<<8, 256, 0, st>>>(ctr, c, P, table, konst);
   if (pl.smem_bytes > 227 * 1024) return PEMP_E_SHAPE;
-  cudaError_t e = cudaFuncSetAttribute(mpa_kernel<P, CS, HWT, CCT, SAFE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(mpa_kernel<P, CS, HWT, CCT, SAFE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(pl.smem_bytes));
   if (e != cudaSuccess) return static_cast<int>(e);
   cudaLaunchConfig_t cfg = {};
@@ -488,7 +570,7 @@ int launch(const float* fts, long long ep_stride, const float* ctr, const float*
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(S) * c * hw;
-  e = cudaLaunchKernelEx(&cfg, mpa_kernel<P, CS, HWT, CCT, SAFE>, fts, eps_stride, S, static_cast<const float*>(table),
+  e = cudaLaunchKernelEx(&cfg, mpa_kernel<P, CS, HWT, CCT, SAFE, PF>, fts, eps_stride, S, static_cast<const float*>(table),
                          static_cast<const float*>(konst), fg, bg, mask_stride, c, hw, num, den);
   if (e != cudaSuccess) return static_cast<int>(e);
   long long total = static_cast<long long>(B) * c * 2 * P;
@@ -520,10 +602,10 @@ extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stri
 #define PEMP_MPA_ARGS fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st
   const bool safe = hw < 32 * pl.cs;
   // fully specialised PEMP shape: c = 512, 51 x 51 features, 3 prototypes per class
-  if (p == 3 && pl.cs == 2 && c == 512 && hw == 2601) return launch<3, 2, 2601, 256, false>(PEMP_MPA_ARGS);
+  if (p == 3 && pl.cs == 2 && c == 512 && hw == 2601) return launch<3, 2, 2601, 256, false, PEMP_MPA_PREFETCH != 0>(PEMP_MPA_ARGS);
 #define PEMP_MPA(PP)                                                                            \
-  return pl.cs == 2 ? (safe ? launch<PP, 2, 0, 0, true>(PEMP_MPA_ARGS) : launch<PP, 2, 0, 0, false>(PEMP_MPA_ARGS)) \
-                    : (safe ? launch<PP, 1, 0, 0, true>(PEMP_MPA_ARGS) : launch<PP, 1, 0, 0, false>(PEMP_MPA_ARGS))
+  return pl.cs == 2 ? (safe ? launch<PP, 2, 0, 0, true, false>(PEMP_MPA_ARGS) : launch<PP, 2, 0, 0, false, false>(PEMP_MPA_ARGS)) \
+                    : (safe ? launch<PP, 1, 0, 0, true, false>(PEMP_MPA_ARGS) : launch<PP, 1, 0, 0, false, false>(PEMP_MPA_ARGS))
   switch (p) {
     case 1: PEMP_MPA(1);
     case 2: PEMP_MPA(2);
