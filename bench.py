@@ -67,7 +67,7 @@ class ClockSampler:
         self.rows, self.proc, self.thread = [], None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -77,19 +77,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
+        return [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7]
+
+    def stop(self, t0, t1, extra=None):
+        """Samples taken inside [t0, t1] (the timed region); `extra` = (t0, t1) of an untimed load loop used when the
+        timed region was shorter than the sampling period."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        rows, where = self.window(t0, t1), "timed region"
+        if not rows and extra is not None:
+            rows, where = self.window(*extra), "untimed repeat of the timed loop (timed region shorter than the sampling period)"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
-                "samples": len(rows), "reasons": reasons}
+                "samples": len(rows), "sampled_during": where, "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -191,6 +198,7 @@ def run_ours(args):
     from pemp_b200.evaluator import KernelTimer, PEMPStage2Pipeline
 
     rank, local_rank, world = pdist.init()
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # started early: nvidia-smi needs ~0.5 s to emit
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _cabi.check(_cabi.lib().pemp_check_device(), "pemp_check_device")
@@ -221,7 +229,6 @@ def run_ours(args):
     torch.cuda.synchronize()
     pdist.barrier()
     timer = KernelTimer()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ops.launch_count()
     stat.zero_()
     torch.cuda.synchronize()
@@ -236,7 +243,17 @@ def run_ours(args):
     launches = ops.launch_count() - launches0
     pdist.barrier()
     ms_total = pdist.max_over_ranks(ev0.elapsed_time(ev1), dev)
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    extra = None
+    if t_wall1 - t_wall0 < 0.25:          # keep the GPU under the same load long enough for a few clock samples
+        scratch = torch.zeros_like(stat)
+        e0 = time.time()
+        while time.time() - e0 < 0.4:
+            for _ in range(10):
+                step(f1, f2, batch["sup_mask"], batch["qry_msk"], batch["cls"], scratch)
+            torch.cuda.synchronize()
+        extra = (e0, time.time())
+        pdist.barrier()
+    clocks = sampler.stop(t_wall0, t_wall1, extra) if sampler else None
     ms_per_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total / 1e3)
 
