@@ -83,6 +83,10 @@ int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const f
                          int B, int S, int c, int hw, int p, float eps,
                          float* fg_proto, float* bg_proto, float* adaptive_p,
                          void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+/* Diagnostic (tests only; process-wide, not thread-safe): K2 has a TMA-fed persistent kernel for c = 512, p = 3,
+ * hw >= 32 and a generic kernel for every other shape.  mode 1 forces the generic kernel so the two can be
+ * compared on the same input; mode 0 restores the automatic choice.  Returns the previous mode.         */
+int pemp_debug_mpa_path(int mode);
 
 /* ---- K3  cosine matching ----------------------------------------------------------------------------
  * replaces  compute_similarity() [+ .max(dim=2), response map]   networks/pemp_stage1.py:214-222,233-261,

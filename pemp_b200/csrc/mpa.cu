@@ -37,6 +37,18 @@
 
 namespace cg = cooperative_groups;
 
+// TMA-fed persistent fast path for c = 512, P = 3 (mpa_tma.cu); PEMP_E_ALIGN = "operand not describable, use the
+// generic kernel", nothing launched.
+int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
+                        long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
+                        float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st);
+size_t pemp_mpa_tma_workspace_bytes(int B, int S, int hw);
+#ifndef PEMP_MPA_TMA
+#define PEMP_MPA_TMA 1
+#endif
+static inline bool mpa_tma_shape(int c, int hw, int p) { return PEMP_MPA_TMA && c == 512 && p == 3 && hw >= 32; }
+static int g_mpa_path = 0;   // diagnostic switch, see pemp_debug_mpa_path
+
 namespace {
 
 // ---- cluster handshake without fences ---------------------------------------------------------------------
@@ -581,9 +593,20 @@ int launch(const float* fts, long long ep_stride, const float* ctr, const float*
 
 }  // namespace
 
+extern "C" int pemp_debug_mpa_path(int mode) {
+  const int old = g_mpa_path;
+  if (mode == 0 || mode == 1) g_mpa_path = mode;
+  return old;
+}
+
 extern "C" size_t pemp_meta_proto_attn_workspace_bytes(int B, int S, int c, int hw, int p) {
   if (B <= 0 || S <= 0 || c <= 0 || hw <= 0 || p < 1 || p > 4) return 0;
-  return make_plan(B, S, c, hw, p).total;
+  size_t n = make_plan(B, S, c, hw, p).total;
+  if (mpa_tma_shape(c, hw, p)) {
+    const size_t t = pemp_mpa_tma_workspace_bytes(B, S, hw);
+    if (t > n) n = t;
+  }
+  return n;
 }
 
 extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
@@ -595,10 +618,15 @@ extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stri
   PEMP_REQUIRE(p >= 1 && p <= 4 && c % 4 == 0 && c <= kMaxChannels, PEMP_E_SHAPE);
   Plan pl = make_plan(B, S, c, hw, p);
   PEMP_REQUIRE(pl.smem_bytes <= 227 * 1024, PEMP_E_SHAPE);
-  PEMP_REQUIRE(workspace && workspace_bytes >= pl.total, PEMP_E_WORKSPACE);
+  PEMP_REQUIRE(workspace && workspace_bytes >= pemp_meta_proto_attn_workspace_bytes(B, S, c, hw, p), PEMP_E_WORKSPACE);
   PEMP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, PEMP_E_ALIGN);
   char* ws = static_cast<char*>(workspace);
   cudaStream_t st = as_stream(stream);
+  if (mpa_tma_shape(c, hw, p) && g_mpa_path != 1) {
+    const int rc = pemp_mpa_tma_launch(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, hw, eps, fg_proto, bg_proto,
+                                       adaptive_p, ws, workspace_bytes, st);
+    if (rc != PEMP_E_ALIGN) return rc;
+  }
 #define PEMP_MPA_ARGS fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st
   const bool safe = hw < 32 * pl.cs;
   // fully specialised PEMP shape: c = 512, 51 x 51 features, 3 prototypes per class

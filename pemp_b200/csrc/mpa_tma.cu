@@ -1,0 +1,557 @@
+// K2 fast path: meta-prototype attention as a persistent, TMA-fed, warp-specialised kernel (c = 512, P = 3).
+//
+// Same arithmetic as `mpa_kernel` (mpa.cu; reference networks/pemp_stage1.py:202-213, pemp_stage2.py:174-186):
+//   dots   d[x, 0..3] = sum_c f[c, x] * table[c, 0..3]          (differences of squared distances, see mpa.cu)
+//   A[k,x] = softmax_j(dots of class group g) * mask_g[x]       k = g*3 + j
+//   num[c,k] += f[c,x] A[k,x],  den[k] += A[k,x]
+// but the features never pass through registers on their way in:
+//
+//  * The support maps are [.., c, hw] fp32 with hw = 2601, so a channel row starts at an arbitrary 4-byte phase and
+//    neither 128-bit loads nor a [c, hw] tensor map (row pitch 10404 B) are legal.  FOUR rows, however, are 16*hw
+//    bytes: the tensor map describes the episode as  [S*c/4 groups][4*hw floats]  (pitch 16*hw B) and a box of
+//    32 floats x 128 groups starting at inner coordinate  e*hw + x  holds pixels x.. of the channels 4g+e,
+//    g = 0..127.  A box origin must itself be 16-byte aligned (tools/probes/tma_unaligned_probe.cu: any other inner
+//    coordinate traps), so the origin is rounded down to a multiple of 4 floats: box column i of class e holds pixel
+//    x_nom + i - o_e with o_e = (e*hw + x_nom) & 3, and a tile advances by 28 pixels so that the 28 nominal pixels
+//    are inside the 32 columns of every class (+14 % shared-memory traffic, no extra DRAM traffic: the 4-column
+//    overlap is an L2 hit).  Four boxes (e = 0..3) are one 512-channel tile (64 KB); they land in shared memory as
+//    128-byte rows with the 128-byte swizzle.  Columns outside the image row (neighbouring rows' data, or zero fill
+//    past the tensor) get zero weight.
+//  * One CTA per SM, persistent: CTA b owns the flat tile range [T*b/G, T*(b+1)/G) of the launch (tiles of one image
+//    are consecutive), so it touches 2-3 images and the pipeline never drains between them.  Warp 16 (one elected
+//    lane) is the producer: an 11-slot ring of 16-KB boxes with a full / empty mbarrier per slot, i.e. up to 176 KB
+//    of loads in flight per SM without a single load instruction or staging register in the consumers.
+//  * Warps 0-15 are consumers.  Warp w = 4*e + cp only ever touches box e of a tile:
+//      phase A  rows [32cp, 32cp+32) of the box, lane <-> (row mod 4, 16-byte chunk): one conflict-free LDS.128 gives
+//               4 pixels of a channel, the (pre-duplicated) table row comes with two more, 8 packed FFMA2 accumulate
+//               4 pixels x 4 dots; a halving butterfly over the 4 row groups leaves each lane with the 4 dots of one
+//               pixel, stored to a per-warp partial array;
+//      one named barrier over the 16 consumer warps (the only CTA-wide synchronisation per tile);
+//      softmax  the warp adds the 16 partials of ITS 8 pixels (pixels [8cp, 8cp+8)), 16 lanes turn them into the
+//               3 + 3 weights of a pixel (x mask) - replicated in the four warps that share cp, which is cheaper than
+//               a second barrier;
+//      phase B  lane <-> rows {l, l+32, l+64, l+96} of box e (the swizzle makes the column read conflict-free):
+//               for each live (pixel pair, class group) 12 FFMA2 accumulate {even, odd} pixel partial sums of
+//               4 channels x 3 prototypes - 48 accumulator registers that live across the whole image.
+//    At an image boundary the four warps of a box fold their accumulators through the box they just consumed
+//    (fixed order cp = 0..3) and write one partial per (image, CTA); `mpa_tma_finalize_kernel` adds the partials of an
+//    image in CTA order, divides and averages the shots - deterministic, no float atomics.
+#include <cuda.h>
+
+#include "common.cuh"
+
+int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
+                        long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
+                        float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st);
+size_t pemp_mpa_tma_workspace_bytes(int B, int S, int hw);
+
+namespace {
+
+constexpr int kC = 512, kP = 3, kK = 6;
+constexpr int kTW = 32;                          // floats per box row (one 128-byte swizzle row)
+constexpr int kStep = 28;                        // pixels a tile advances: kTW - 4 + 1 alignments of slack, see header
+constexpr int kBoxRows = kC / 4;                 // 128 channel groups
+constexpr int kBoxFloats = kBoxRows * kTW;       // 4096
+constexpr uint32_t kBoxBytes = kBoxFloats * 4;   // 16 KB
+#ifndef PEMP_MPA_TMA_SLOTS
+#define PEMP_MPA_TMA_SLOTS 11
+#endif
+constexpr int kNB = PEMP_MPA_TMA_SLOTS;
+constexpr int kCons = 16;                        // consumer warps
+constexpr int kThreadsT = (kCons + 4) * 32;      // + one producer warpgroup (setmaxnreg works on whole warpgroups)
+constexpr int kRegsCons = 112, kRegsProd = 24;   // the CTA pool is the launch allocation (640 x 96): 512 x 112 + 128 x 24 fits
+constexpr int kMaxGrid = 148;
+constexpr int kPartLd = 40;                      // pixel pitch of a dot row in `part`: banks 8d + p are all distinct
+
+struct TmaSmem {
+  alignas(1024) float ring[kNB][kBoxFloats];
+  alignas(16) float table[kC * 8];               // tile-row order, each coefficient twice: {t0,t0,t1,t1,t2,t2,t3,t3}
+  alignas(16) float part[2][kCons][4 * kPartLd];  // [tile parity][warp][dot][pixel]
+  alignas(16) float wts[kCons][4 * 2 * 8];       // [warp][pixel pair][group][{w0e,w0o,w1e,w1o,w2e,w2o,-,-}]
+  alignas(8) uint64_t full[kNB];
+  alignas(8) uint64_t empty[kNB];
+  alignas(8) uint64_t part_bar[2];               // all 16 warps have written part[b]
+  float konst[4];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MPAT_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MPAT_DONE;\n"
+      "bra MPAT_WAIT;\n"
+      "MPAT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// CTA that owns flat tile t when CTA b owns [T*b/G, T*(b+1)/G)
+__host__ __device__ inline int owner_of(long long t, long long T, int G) { return static_cast<int>(((t + 1) * G - 1) / T); }
+
+// ---- prologue: duplicated difference table in tile-row order --------------------------------------------
+// tile row R = e*128 + g  <->  channel 4g + e;  table[R][2d], [2d+1] = 2*(ctr[ch, g'*P + j] - ctr[ch, g'*P]) with
+// d = g'*(P-1) + j-1;  konst[d] = -(|ctr_{g'P+j}|^2 - |ctr_{g'P}|^2) in double.
+__global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __restrict__ table, float* __restrict__ konst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC * 4; i += gridDim.x * blockDim.x) {
+    const int R = i >> 2, d = i & 3;
+    const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
+    const int g = d >> 1, j = (d & 1) + 1;
+    // exact difference, then one rounding of the product with 2 log2(e): the dots come out in log2 units
+    const float v = static_cast<float>(2.8853900817779268 * (static_cast<double>(ctr[ch * kK + g * kP + j]) - ctr[ch * kK + g * kP]));
+    table[R * 8 + 2 * d] = v;
+    table[R * 8 + 2 * d + 1] = v;
+  }
+  if (blockIdx.x == 0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 4) {
+      const int g = warp >> 1, j = (warp & 1) + 1;
+      double s = 0.0;
+      for (int ch = lane; ch < kC; ch += 32) {
+        const double a = ctr[ch * kK + g * kP + j], b = ctr[ch * kK + g * kP];
+        s += (a - b) * (a + b);
+      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+      if (lane == 0) konst[warp] = static_cast<float>(-s * 1.4426950408889634);
+    }
+  }
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__global__ void __launch_bounds__(kThreadsT, 1)
+mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_img, long long T,
+               const float* __restrict__ table_g, const float* __restrict__ konst_g, const float* __restrict__ fg,
+               const float* __restrict__ bg, long long mask_stride, int maxp, float* __restrict__ part_num,
+               float* __restrict__ part_den) {
+  extern __shared__ uint8_t smem_raw[];
+  TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const long long t0 = T * cta / G, t1 = T * (cta + 1) / G;
+
+  for (int i = tid; i < kC * 8 / 4; i += kThreadsT)
+    reinterpret_cast<float4*>(sm.table)[i] = __ldg(reinterpret_cast<const float4*>(table_g) + i);
+  if (tid < 4) sm.konst[tid] = __ldg(konst_g + tid);
+  if (tid == 0) {
+    for (int s = 0; s < kNB; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 4);
+    }
+    mbar_init(&sm.part_bar[0], kCons);
+    mbar_init(&sm.part_bar[1], kCons);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= kCons) {
+    // ============================ producer: one lane feeds the ring ============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+    if (warp == kCons && lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+      int slot = 0;
+      uint32_t par = 1;                               // a fresh barrier's "previous phase" counts as complete
+      int img = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(img) * nt_img);
+      int ep = img / S, s = img - ep * S;
+      for (long long t = t0; t < t1; ++t) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = (e * hw + tl * kStep) & ~3;   // box origins must be 16-byte aligned
+          mbar_wait(&sm.empty[slot], par);
+          mbar_expect_tx(&sm.full[slot], kBoxBytes);
+          tma_load_3d(&map, &sm.full[slot], sm.ring[slot], c0, s * kBoxRows, ep);
+          if (++slot == kNB) {
+            slot = 0;
+            par ^= 1;
+          }
+        }
+        if (++tl == nt_img) {
+          tl = 0;
+          ++img;
+          if (++s == S) {
+            s = 0;
+            ++ep;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================ consumers ============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCons));
+  const int e = warp >> 2, cp = warp & 3;
+  // phase-A lane roles
+  const int rg = lane >> 3, jc = lane & 7;
+  // softmax lane roles: box column 8cp + px8, dot d; even d owns class group d >> 1
+  const int px8 = lane >> 2, d_own = lane & 3, g_own = d_own >> 1;
+  const bool owner = (d_own & 1) == 0;
+  const float k0 = sm.konst[g_own * 2], k1 = sm.konst[g_own * 2 + 1];
+  float* const wts = sm.wts[warp];
+
+  float2 acc[4][2][kP];                               // [row slot][group][prototype] = {even, odd column} sums
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int j = 0; j < kP; ++j) acc[i][g][j] = make_float2(0.f, 0.f);
+  float den[kP] = {0.f, 0.f, 0.f};
+
+  // ---- phase A of one tile: dots of the 32 box columns over this warp's 32 rows -> part[buf][warp] ----
+  auto phase_a = [&](const float* box, int o, int buf) {
+    float2 pa[2][4];                                  // [column pair][dot]
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) pa[p][d] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = cp * 32 + i * 4 + rg;            // row inside the box; rl & 7 = ((i & 1) << 2) | rg
+      const float4 f = *reinterpret_cast<const float4*>(box + rl * kTW + ((jc ^ (((i & 1) << 2) | rg)) << 2));
+      const float4* trow = reinterpret_cast<const float4*>(sm.table + (e * kBoxRows + rl) * 8);
+      const float4 ta = trow[0], tb = trow[1];
+      const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
+      const float2 td[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w), make_float2(tb.x, tb.y),
+                            make_float2(tb.z, tb.w)};
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        pa[0][d] = ffma2(f01, td[d], pa[0][d]);
+        pa[1][d] = ffma2(f23, td[d], pa[1][d]);
+      }
+    }
+    // halving butterfly over the row groups (lane bits 4 and 3): lane (rg, jc) ends with column 4*jc + rg
+    const bool hi = (lane & 16) != 0, lo = (lane & 8) != 0;
+    const int p = 4 * jc + rg - o;                    // pixel (relative to x_nom) of that column
+    float* dst = &sm.part[buf][warp][p];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const float2 keep = hi ? pa[1][d] : pa[0][d], send = hi ? pa[0][d] : pa[1][d];
+      const float rx = keep.x + __shfl_xor_sync(kFull, send.x, 16);
+      const float ry = keep.y + __shfl_xor_sync(kFull, send.y, 16);
+      const float keep2 = lo ? ry : rx, send2 = lo ? rx : ry;
+      const float q = keep2 + __shfl_xor_sync(kFull, send2, 8);
+      if (p >= 0 && p < kStep) dst[d * kPartLd] = q;  // [dot][pixel], row pitch 40: conflict-free for writer and reader
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.part_bar[buf]);
+  };
+
+  // ---- weights of this warp's 8 box columns: add the 16 partials, softmax per class group, x mask ----
+  unsigned live = 0;
+  // mask value of this lane's (column, class group) for a tile; 0 for columns that are not pixels of the tile
+  auto mask_of = [&](int img, int x_nom, int o) {
+    const int p_own = cp * 8 + px8 - o;
+    const bool p_ok = p_own >= 0 && p_own < kStep && x_nom + p_own < hw;
+    return (owner && p_ok) ? __ldg((g_own ? bg : fg) + img * mask_stride + x_nom + p_own) : 0.f;
+  };
+  auto softmax = [&](float m, int o, int buf, uint32_t parity) {
+    const int p_own = cp * 8 + px8 - o;
+    mbar_wait(&sm.part_bar[buf], parity);
+    float s0 = 0.f, s1 = 0.f;
+    const int idx = d_own * kPartLd + (p_own >= 0 && p_own < kStep ? p_own : 0);
+#pragma unroll
+    for (int w2 = 0; w2 < kCons; w2 += 2) {
+      s0 += sm.part[buf][w2][idx];
+      s1 += sm.part[buf][w2 + 1][idx];
+    }
+    const float tot = s0 + s1;
+    const float tot_next = __shfl_down_sync(kFull, tot, 1);
+    float w[kP] = {0.f, 0.f, 0.f};
+    if (owner) {                                      // dots are in log2 units (the table carries log2 e); m = 0 kills
+                                                      // columns outside the tile
+      const float e1 = tot + k0, e2 = tot_next + k1;
+      const float mx = fmaxf(0.f, fmaxf(e1, e2));
+      const float x0e = exp2f(0.f - mx), x1e = exp2f(e1 - mx), x2e = exp2f(e2 - mx);
+      const float r = m / (x0e + x1e + x2e);
+      w[0] = x0e * r;
+      w[1] = x1e * r;
+      w[2] = x2e * r;
+#pragma unroll
+      for (int j = 0; j < kP; ++j) den[j] += w[j];
+      float* wp = wts + ((px8 >> 1) * 2 + g_own) * 8 + (px8 & 1);
+      wp[0] = w[0];
+      wp[2] = w[1];
+      wp[4] = w[2];
+    }
+    live = __ballot_sync(kFull, (w[0] != 0.f) | (w[1] != 0.f) | (w[2] != 0.f));
+    __syncwarp();
+  };
+
+  // ---- phase B: rows {l, l+32, l+64, l+96} of the box x this warp's 8 columns ----
+  // A class group is skipped when none of the 8 columns has a non-zero weight in it (one warp-uniform test per
+  // group: with complementary masks most 8-pixel runs are all-foreground or all-background).
+  auto phase_b = [&](const float* box) {
+    float4 f[2][4];
+#pragma unroll
+    for (int ck = 0; ck < 2; ++ck)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        f[ck][i] = *reinterpret_cast<const float4*>(box + (lane + 32 * i) * kTW + (((2 * cp + ck) ^ (lane & 7)) << 2));
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if ((live & (0x11111111u << (2 * g))) == 0) continue;
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        const float4 wa = *reinterpret_cast<const float4*>(wts + (pp * 2 + g) * 8);
+        const float2 wb = *reinterpret_cast<const float2*>(wts + (pp * 2 + g) * 8 + 4);
+        const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 fv = f[pp >> 1][i];
+          const float2 fp = (pp & 1) ? make_float2(fv.z, fv.w) : make_float2(fv.x, fv.y);
+          acc[i][g][0] = ffma2(fp, w0, acc[i][g][0]);
+          acc[i][g][1] = ffma2(fp, w1, acc[i][g][1]);
+          acc[i][g][2] = ffma2(fp, wb, acc[i][g][2]);
+        }
+      }
+    }
+  };
+
+  // Software pipeline: per iteration  A(t+1), B(t), softmax(t+1).  The partial-dot exchange of tile t+1 is armed
+  // (mbarrier arrive) before B(t) and consumed after it, so no warp waits for the slowest one.
+  const int ntl = static_cast<int>(t1 - t0);
+  if (ntl <= 0) return;
+  int slot = e;
+  uint32_t par = 0;
+  int img = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(img) * nt_img);
+  {
+    const int x_nom = tl * kStep, o = (e * hw + x_nom) & 3;
+    const float m = mask_of(img, x_nom, o);
+    mbar_wait(&sm.full[slot], par);
+    phase_a(sm.ring[slot], o, 0);
+    softmax(m, o, 0, 0);
+  }
+  for (int k = 0; k < ntl; ++k) {
+    const bool have_next = k + 1 < ntl;
+    const bool last_of_img = (tl == nt_img - 1) || !have_next;
+    // next tile
+    int slot_n = slot + 4;
+    uint32_t par_n = par;
+    if (slot_n >= kNB) {
+      slot_n -= kNB;
+      par_n ^= 1;
+    }
+    int tl_n = tl + 1, img_n = img;
+    if (tl_n == nt_img) {
+      tl_n = 0;
+      ++img_n;
+    }
+    const int o_n = (e * hw + tl_n * kStep) & 3, buf_n = (k + 1) & 1;
+    float m_n = 0.f;
+    if (have_next) {
+      m_n = mask_of(img_n, tl_n * kStep, o_n);
+      mbar_wait(&sm.full[slot_n], par_n);
+      phase_a(sm.ring[slot_n], o_n, buf_n);
+    }
+    phase_b(sm.ring[slot]);
+
+    if (!last_of_img) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[slot]);
+    } else {
+      // ---------------- image boundary: fold the four column-owning warps of this box, write the partial ----------
+      float* scratch = sm.ring[slot];                 // [3][24][32] numerators, then [4][8] denominators
+      // denominators: sum the owner lanes of each class group (lane bits 2..4), result on lanes 0 (fg) and 2 (bg)
+#pragma unroll
+      for (int j = 0; j < kP; ++j) {
+        den[j] += __shfl_xor_sync(kFull, den[j], 4);
+        den[j] += __shfl_xor_sync(kFull, den[j], 8);
+        den[j] += __shfl_xor_sync(kFull, den[j], 16);
+      }
+      named_bar(2 + e, 128);                          // all four warps are done reading the box
+      if (cp > 0) {
+        int o2 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < kP; ++j) scratch[((cp - 1) * 24 + (o2++)) * 32 + lane] = acc[i][g][j].x + acc[i][g][j].y;
+      }
+      if (lane == 0 || lane == 2) {
+#pragma unroll
+        for (int j = 0; j < kP; ++j) scratch[3 * 24 * 32 + cp * 8 + g_own * kP + j] = den[j];
+      }
+      named_bar(2 + e, 128);
+      if (cp == 0) {
+        const int slot_idx = cta - owner_of(static_cast<long long>(img) * nt_img, T, G);
+        float* out = part_num + (static_cast<long long>(img) * maxp + slot_idx) * (kC * kK);
+        int o2 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[kK];
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < kP; ++j) {
+              float a2 = acc[i][g][j].x + acc[i][g][j].y;
+#pragma unroll
+              for (int r = 0; r < 3; ++r) a2 += scratch[(r * 24 + o2) * 32 + lane];
+              ++o2;
+              v[g * kP + j] = a2;
+            }
+          float2* dst = reinterpret_cast<float2*>(out + (e * kBoxRows + lane + 32 * i) * kK);
+          dst[0] = make_float2(v[0], v[1]);
+          dst[1] = make_float2(v[2], v[3]);
+          dst[2] = make_float2(v[4], v[5]);
+        }
+        if (e == 0 && lane < kK) {
+          float sden = 0.f;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) sden += scratch[3 * 24 * 32 + r * 8 + lane];
+          part_den[(static_cast<long long>(img) * maxp + slot_idx) * 8 + lane] = sden;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // scratch writes before the slot's next TMA fill
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[slot]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int j = 0; j < kP; ++j) acc[i][g][j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < kP; ++j) den[j] = 0.f;
+    }
+
+    if (have_next) softmax(m_n, o_n, buf_n, ((k + 1) >> 1) & 1);
+    slot = slot_n;
+    par = par_n;
+    tl = tl_n;
+    img = img_n;
+  }
+}
+
+// one thread per (b, channel, k): add the partials of every shot in CTA order, divide, average the shots
+__global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, const float* __restrict__ part_den, int B,
+                                        int S, int nt_img, long long T, int G, int maxp, float eps,
+                                        float* __restrict__ fg_proto, float* __restrict__ bg_proto,
+                                        float* __restrict__ adaptive_p) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(B) * kC * kK) return;
+  const int k = static_cast<int>(i % kK);
+  const long long t = i / kK;
+  const int ch = static_cast<int>(t % kC), b = static_cast<int>(t / kC);
+  const int R = (ch & 3) * kBoxRows + (ch >> 2);
+  float accum = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const long long img = static_cast<long long>(b) * S + s;
+    const int n = owner_of(img * nt_img + nt_img - 1, T, G) - owner_of(img * nt_img, T, G) + 1;
+    float num = 0.f, den = 0.f;
+    for (int sp = 0; sp < n; ++sp) {
+      num += part_num[((img * maxp + sp) * kC + R) * kK + k];
+      den += part_den[(img * maxp + sp) * 8 + k];
+    }
+    accum += num / (den + eps);
+  }
+  const float v = accum / static_cast<float>(S);
+  const int g = k / kP, j = k - g * kP;
+  (g == 0 ? fg_proto : bg_proto)[(static_cast<long long>(b) * kC + ch) * kP + j] = v;
+  if (adaptive_p) adaptive_p[(static_cast<long long>(b) * kC + ch) * kK + k] = v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;     // immutable after first resolution; benign race (same value)
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmaPlan {
+  int G, nt_img, maxp;
+  long long T;
+  size_t off_table, off_konst, off_num, off_den, total;
+};
+TmaPlan make_tma_plan(int B, int S, int hw) {
+  TmaPlan p;
+  p.nt_img = (hw + kStep - 1) / kStep;
+  p.T = static_cast<long long>(B) * S * p.nt_img;
+  // one CTA per SM; a CTA wants at least a few tiles to amortise its prologue
+  long long g = p.T / 4;
+  p.G = static_cast<int>(g < 1 ? 1 : (g > kMaxGrid ? kMaxGrid : g));
+  // partial slots per image: an image's nt_img tiles are spread over at most this many consecutive CTAs
+  const long long per_cta = p.T / p.G;                // every CTA owns per_cta or per_cta + 1 tiles
+  p.maxp = static_cast<int>((p.nt_img + per_cta - 1) / per_cta) + 1;
+  const size_t imgs = static_cast<size_t>(B) * S;
+  p.off_table = 0;
+  p.off_konst = kC * 8 * sizeof(float);
+  p.off_num = p.off_konst + 256;
+  p.off_den = p.off_num + align_up(imgs * p.maxp * kC * kK * sizeof(float), 256);
+  p.total = p.off_den + align_up(imgs * p.maxp * 8 * sizeof(float), 256);
+  return p;
+}
+
+}  // namespace
+
+size_t pemp_mpa_tma_workspace_bytes(int B, int S, int hw) { return make_tma_plan(B, S, hw).total; }
+
+// Returns PEMP_E_ALIGN (nothing launched) when the operand cannot be described by a tensor map; the caller then
+// uses the generic kernel.
+int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
+                        long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
+                        float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st) {
+  const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(S) * kC * hw;
+  if ((reinterpret_cast<uintptr_t>(fts) & 15) != 0 || (eps_stride & 3) != 0 || hw < kTW) return PEMP_E_ALIGN;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return PEMP_E_ALIGN;
+  const TmaPlan pl = make_tma_plan(B, S, hw);
+  PEMP_REQUIRE(ws_bytes >= pl.total, PEMP_E_WORKSPACE);
+
+  CUtensorMap map;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(4) * hw, static_cast<cuuint64_t>(S) * kBoxRows, static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(16) * hw, static_cast<cuuint64_t>(eps_stride) * 4};
+  cuuint32_t box[3] = {kTW, kBoxRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(fts), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return PEMP_E_ALIGN;
+
+  float* table = reinterpret_cast<float*>(ws + pl.off_table);
+  float* konst = reinterpret_cast<float*>(ws + pl.off_konst);
+  float* num = reinterpret_cast<float*>(ws + pl.off_num);
+  float* den = reinterpret_cast<float*>(ws + pl.off_den);
+  mpa_tma_prepare_kernel<<<8, 256, 0, st>>>(ctr, table, konst);
+  const size_t smem = sizeof(TmaSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(mpa_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  mpa_tma_kernel<<<pl.G, kThreadsT, smem, st>>>(map, S, hw, pl.nt_img, pl.T, table, konst, fg, bg, mask_stride, pl.maxp,
+                                               num, den);
+  const long long total = static_cast<long long>(B) * kC * kK;
+  mpa_tma_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      num, den, B, S, pl.nt_img, pl.T, pl.G, pl.maxp, eps, fg_proto, bg_proto, adaptive_p);
+  return launch_status();
+}

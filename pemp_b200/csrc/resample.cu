@@ -64,46 +64,61 @@ extern "C" int pemp_nearest_resize_i64(const int64_t* in, int planes, int h, int
 // written with aligned 32-bit stores whatever W is (401 is odd).  The low-res map (2*h*w floats, 20.8 KB
 // at 51x51) stays in L1/L2; the kernel is bound by the mask / logits store.
 template <bool kLogits, bool kMask8, bool kMask64>
-__global__ void upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logits,
-                                       uint8_t* __restrict__ mask8, int64_t* __restrict__ mask64, long long total,
-                                       int h, int w, int H, int W, float sy, float sx) {
-  const long long HW = static_cast<long long>(H) * W;
+__global__ void __launch_bounds__(256)
+upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logits, uint8_t* __restrict__ mask8,
+                       int64_t* __restrict__ mask64, long long total, int h, int w, int H, int W, float sy, float sx) {
+  const int HW = H * W;
   const int hw = h * w;
-  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q * 4 < total;
+  const long long nquads = (total + 3) >> 2;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < nquads;
        q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // one 64-bit and one 32-bit division per four outputs; (Y, X) then advance incrementally
+    const long long i0 = q << 2;
+    int n = static_cast<int>(i0 / HW);
+    const int r0 = static_cast<int>(i0 - static_cast<long long>(n) * HW);
+    int Y = r0 / W, X = r0 - Y * W;
+    const float* p0 = pred + static_cast<long long>(n) * 2 * hw;
+    Lerp ly = lerp_coeff(Y, sy, h);
+    const float* rt = p0 + ly.i0 * w;          // top / bottom source rows of channel 0 (channel 1 is +hw)
+    const float* rb = p0 + ly.i1 * w;
     uint32_t packed = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      long long i = q * 4 + e;
-      if (i >= total) break;
-      int X = static_cast<int>(i % W);
-      long long t = i / W;
-      int Y = static_cast<int>(t % H);
-      long long n = t / H;
-      Lerp ly = lerp_coeff(Y, sy, h), lx = lerp_coeff(X, sx, w);
-      const float* p0 = pred + n * 2 * hw;
-      float v[2];
+      if (i0 + e < total) {
+        const Lerp lx = lerp_coeff(X, sx, w);
+        float v[2];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const float* p = p0 + ch * hw;
-        float a = __ldg(p + ly.i0 * w + lx.i0), b = __ldg(p + ly.i0 * w + lx.i1);
-        float c = __ldg(p + ly.i1 * w + lx.i0), d = __ldg(p + ly.i1 * w + lx.i1);
-        v[ch] = lerp2(ly.l0, lerp2(lx.l0, a, lx.l1, b), ly.l1, lerp2(lx.l0, c, lx.l1, d));
+        for (int ch = 0; ch < 2; ++ch) {
+          const float a = __ldg(rt + ch * hw + lx.i0), b = __ldg(rt + ch * hw + lx.i1);
+          const float c = __ldg(rb + ch * hw + lx.i0), d = __ldg(rb + ch * hw + lx.i1);
+          v[ch] = lerp2(ly.l0, lerp2(lx.l0, a, lx.l1, b), ly.l1, lerp2(lx.l0, c, lx.l1, d));
+        }
+        const uint32_t m = v[1] > v[0] ? 1u : 0u;   // first index wins ties => background
+        packed |= m << (8 * e);
+        if (kLogits) {
+          const long long o = static_cast<long long>(n) * 2 * HW + static_cast<long long>(Y) * W + X;
+          logits[o] = v[0];
+          logits[o + HW] = v[1];
+        }
+        if (kMask64) mask64[i0 + e] = static_cast<int64_t>(m);
+        if (++X == W) {                             // next output row (never crosses an image inside a quad
+          X = 0;                                    // unless H*W % 4 != 0: then (Y == H) wraps to the next image)
+          if (++Y == H) {
+            Y = 0;
+            ++n;
+            p0 += 2 * hw;
+          }
+          ly = lerp_coeff(Y, sy, h);
+          rt = p0 + ly.i0 * w;
+          rb = p0 + ly.i1 * w;
+        }
       }
-      uint32_t m = v[1] > v[0] ? 1u : 0u;   // first index wins ties => background
-      packed |= m << (8 * e);
-      if (kLogits) {
-        long long o = n * 2 * HW + static_cast<long long>(Y) * W + X;
-        logits[o] = v[0];
-        logits[o + HW] = v[1];
-      }
-      if (kMask64) mask64[i] = static_cast<int64_t>(m);
     }
     if (kMask8) {
-      if (q * 4 + 3 < total) {
+      if (i0 + 3 < total) {
         reinterpret_cast<uint32_t*>(mask8)[q] = packed;
       } else {
-        for (int e = 0; q * 4 + e < total; ++e) mask8[q * 4 + e] = static_cast<uint8_t>(packed >> (8 * e));
+        for (int e = 0; i0 + e < total; ++e) mask8[i0 + e] = static_cast<uint8_t>(packed >> (8 * e));
       }
     }
   }

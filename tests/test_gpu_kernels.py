@@ -129,7 +129,10 @@ def test_weighted_gap_golden(ops):
 
 # ------------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("B,S,c,hw,p", [(2, 2, 32, 169, 3), (1, 5, 40, 165, 3), (1, 1, 512, 2601, 3), (2, 1, 64, 100, 1),
-                                        (1, 2, 48, 333, 2), (1, 1, 24, 70, 4), (1, 1, 1024, 200, 3)])
+                                        (1, 2, 48, 333, 2), (1, 1, 24, 70, 4), (1, 1, 1024, 200, 3),
+                                        # the TMA-fed persistent kernel (c = 512, p = 3): images split over several CTAs,
+                                        # ragged last tile, exactly one tile, fewer tiles than CTAs
+                                        (3, 2, 512, 2601, 3), (2, 5, 512, 100, 3), (1, 1, 512, 32, 3), (5, 1, 512, 45, 3)])
 def test_meta_proto_attn(ops, B, S, c, hw, p):
     torch.manual_seed(6)
     f = torch.randn(B * S, c, hw) * 0.5
@@ -164,6 +167,35 @@ def test_meta_proto_attn_general_masks_golden(ops):
     f0, b0 = ops.map_pool_lowres(cu(sup.reshape(B * S, c, h * w)), cu(fg.view(B * S, -1)), cu(bg.view(B * S, -1)), B, S)
     out0 = ops.cosine_match(cu(qry.reshape(-1, c, h * w)), f0, b0, 20.0)
     assert nrel(out0["pred"].cpu().view(-1, 2, h, w).numpy(), g["map_pred"]) < TOL
+
+
+def test_meta_proto_attn_tma_vs_generic_kernel_full_size(ops):
+    """B = 8 five-shot episodes at the PEMP shape, read in place from a [B, S+Q, c, h, w] encoder output: the
+    TMA-fed kernel and the generic kernel (independent implementations) must agree to fp32 rounding."""
+    from pemp_b200 import _cabi
+    torch.manual_seed(11)
+    B, S, Q, c, h = 8, 5, 1, 512, 51
+    feats = cu(torch.randn(B, S + Q, c, h, h) * 0.5)
+    ctr = cu(torch.rand(c, 6))
+    fg = torch.zeros(B * S, h, h)
+    for i in range(B * S):
+        y0, x0 = i % 20, (3 * i) % 25
+        fg[i, y0:y0 + 12 + i % 17, x0:x0 + 9 + i % 23] = 1
+    fg = cu(fg.view(B * S, -1))
+    sup = feats[:, :S]
+    a = ops.meta_proto_attn(sup, ctr, fg, 1 - fg, B, S)
+    _cabi.lib().pemp_debug_mpa_path(1)
+    try:
+        b = ops.meta_proto_attn(sup, ctr, fg, 1 - fg, B, S)
+    finally:
+        _cabi.lib().pemp_debug_mpa_path(0)
+    for x, y in zip(a, b):
+        assert nrel(x.cpu(), y.cpu()) < 2e-6
+    # and against the restatement on one episode
+    e = 5
+    rf, rb, _ = O.meta_proto_attention(sup[e].reshape(S, c, h * h).cpu(), fg[e * S:(e + 1) * S].cpu(),
+                                       1 - fg[e * S:(e + 1) * S].cpu(), ctr.cpu(), 1, S, 3)
+    assert nrel(a[0][e:e + 1].cpu(), rf) < TOL and nrel(a[1][e:e + 1].cpu(), rb) < TOL
 
 
 def test_meta_proto_attn_run_to_run_deterministic(ops):
