@@ -7,7 +7,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpemp_b200.so")
+# PEMP_B200_LIB selects a variant build of the SAME library (kernel-tuning experiments); there is still no fallback
+LIB_PATH = os.environ.get("PEMP_B200_LIB") or os.path.join(_HERE, "libpemp_b200.so")
 _lib = None
 
 P, I, LL, F, SZ = c_void_p, c_int, c_longlong, c_float, c_size_t

@@ -53,9 +53,13 @@ constexpr int kStep = 28;                        // pixels a tile advances: kTW 
 constexpr int kBoxRows = kC / 4;                 // 128 channel groups
 constexpr int kBoxFloats = kBoxRows * kTW;       // 4096
 constexpr uint32_t kBoxBytes = kBoxFloats * 4;   // 16 KB
-#ifndef PEMP_MPA_TMA_SLOTS
-#define PEMP_MPA_TMA_SLOTS 11
+#ifndef PEMP_MPA_TMA_DUP
+#define PEMP_MPA_TMA_DUP 1                       // table rows as {t0,t0,t1,t1,t2,t2,t3,t3}: no MOVs to form FFMA2 operands
 #endif
+#ifndef PEMP_MPA_TMA_SLOTS
+#define PEMP_MPA_TMA_SLOTS (PEMP_MPA_TMA_DUP ? 11 : 12)
+#endif
+constexpr int kTD = PEMP_MPA_TMA_DUP ? 8 : 4;    // floats per table row
 constexpr int kNB = PEMP_MPA_TMA_SLOTS;
 constexpr int kCons = 16;                        // consumer warps
 constexpr int kThreadsT = (kCons + 4) * 32;      // + one producer warpgroup (setmaxnreg works on whole warpgroups)
@@ -65,7 +69,7 @@ constexpr int kPartLd = 40;                      // pixel pitch of a dot row in 
 
 struct TmaSmem {
   alignas(1024) float ring[kNB][kBoxFloats];
-  alignas(16) float table[kC * 8];               // tile-row order, each coefficient twice: {t0,t0,t1,t1,t2,t2,t3,t3}
+  alignas(16) float table[kC * kTD];             // tile-row order: coefficients of channel 4g + e at row e*128 + g
   alignas(16) float part[2][kCons][4 * kPartLd];  // [tile parity][warp][dot][pixel]
   alignas(16) float wts[kCons][4 * 2 * 8];       // [warp][pixel pair][group][{w0e,w0o,w1e,w1o,w2e,w2o,-,-}]
   alignas(8) uint64_t full[kNB];
@@ -89,12 +93,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "MPAT_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MPAT_DONE;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // %2: suspend-time hint, the thread sleeps
+      "@p bra MPAT_DONE;\n"                                            // in hardware instead of spinning
       "bra MPAT_WAIT;\n"
       "MPAT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
@@ -111,8 +115,8 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 // CTA that owns flat tile t when CTA b owns [T*b/G, T*(b+1)/G)
 __host__ __device__ inline int owner_of(long long t, long long T, int G) { return static_cast<int>(((t + 1) * G - 1) / T); }
 
-// ---- prologue: duplicated difference table in tile-row order --------------------------------------------
-// tile row R = e*128 + g  <->  channel 4g + e;  table[R][2d], [2d+1] = 2*(ctr[ch, g'*P + j] - ctr[ch, g'*P]) with
+// ---- prologue: difference table in tile-row order --------------------------------------------
+// tile row R = e*128 + g  <->  channel 4g + e;  table[R][d] = 2 log2(e) * (ctr[ch, g'*P + j] - ctr[ch, g'*P]) with
 // d = g'*(P-1) + j-1;  konst[d] = -(|ctr_{g'P+j}|^2 - |ctr_{g'P}|^2) in double.
 __global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __restrict__ table, float* __restrict__ konst) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC * 4; i += gridDim.x * blockDim.x) {
@@ -121,8 +125,12 @@ __global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __r
     const int g = d >> 1, j = (d & 1) + 1;
     // exact difference, then one rounding of the product with 2 log2(e): the dots come out in log2 units
     const float v = static_cast<float>(2.8853900817779268 * (static_cast<double>(ctr[ch * kK + g * kP + j]) - ctr[ch * kK + g * kP]));
-    table[R * 8 + 2 * d] = v;
-    table[R * 8 + 2 * d + 1] = v;
+    if (kTD == 8) {
+      table[R * 8 + 2 * d] = v;
+      table[R * 8 + 2 * d + 1] = v;
+    } else {
+      table[R * 4 + d] = v;
+    }
   }
   if (blockIdx.x == 0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,19 +148,32 @@ __global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __r
 }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kThreadsT, 1)
 mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_img, long long T,
                const float* __restrict__ table_g, const float* __restrict__ konst_g, const float* __restrict__ fg,
                const float* __restrict__ bg, long long mask_stride, int maxp, float* __restrict__ part_num,
                float* __restrict__ part_den) {
-  extern __shared__ uint8_t smem_raw[];
-  TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  // the dynamic shared window starts 1024-byte aligned (declared alignment; checked once below), so every address in
+  // `sm` is a compile-time offset and nothing has to be re-derived inside the tile loop
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const long long t0 = T * cta / G, t1 = T * (cta + 1) / G;
 
-  for (int i = tid; i < kC * 8 / 4; i += kThreadsT)
+  for (int i = tid; i < kC * kTD / 4; i += kThreadsT)
     reinterpret_cast<float4*>(sm.table)[i] = __ldg(reinterpret_cast<const float4*>(table_g) + i);
   if (tid < 4) sm.konst[tid] = __ldg(konst_g + tid);
   if (tid == 0) {
@@ -211,6 +232,16 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   const bool owner = (d_own & 1) == 0;
   const float k0 = sm.konst[g_own * 2], k1 = sm.konst[g_own * 2 + 1];
   float* const wts = sm.wts[warp];
+  // Per-lane offsets that never change.  They pass through an empty `asm volatile` so the compiler keeps them in
+  // registers instead of re-deriving them from %tid in every phase of every tile (measured: ~60 integer
+  // instructions per warp and tile).
+  int off_a = (cp * 32 + rg) * kTW + ((jc ^ rg) << 2);            // phase A, even i; odd i: ^ 16; row step i*128
+  int off_t = (e * kBoxRows + cp * 32 + rg) * kTD;                // table row of (i = 0)
+  int off_b = lane * kTW + (((2 * cp) ^ (lane & 7)) << 2);        // phase B, chunk 2cp; chunk 2cp+1: ^ 4; row step 32*i
+  int col_a = 4 * jc + rg;                                        // box column this lane holds after the butterfly
+  int col_s = cp * 8 + px8;                                       // box column of the softmax / phase-B role
+  const float* mask_ptr = (g_own ? bg : fg) + col_s;              // + img*mask_stride + x_nom - o
+  asm volatile("" : "+r"(off_a), "+r"(off_t), "+r"(off_b), "+r"(col_a), "+r"(col_s), "+l"(mask_ptr));
 
   float2 acc[4][2][kP];                               // [row slot][group][prototype] = {even, odd column} sums
 #pragma unroll
@@ -230,22 +261,32 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
       for (int d = 0; d < 4; ++d) pa[p][d] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int rl = cp * 32 + i * 4 + rg;            // row inside the box; rl & 7 = ((i & 1) << 2) | rg
-      const float4 f = *reinterpret_cast<const float4*>(box + rl * kTW + ((jc ^ (((i & 1) << 2) | rg)) << 2));
-      const float4* trow = reinterpret_cast<const float4*>(sm.table + (e * kBoxRows + rl) * 8);
-      const float4 ta = trow[0], tb = trow[1];
+      // row cp*32 + 4i + rg of the box; its swizzle phase is ((i & 1) << 2) | rg
+      const float4 f = *reinterpret_cast<const float4*>(box + (off_a ^ ((i & 1) << 4)) + i * 4 * kTW);
+      const float4* trow = reinterpret_cast<const float4*>(sm.table + off_t + i * 4 * kTD);
+      const float4 ta = trow[0];
       const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
-      const float2 td[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w), make_float2(tb.x, tb.y),
-                            make_float2(tb.z, tb.w)};
+      float2 td[4];
+      if (kTD == 8) {
+        const float4 tb = trow[1];
+        td[0] = make_float2(ta.x, ta.y), td[1] = make_float2(ta.z, ta.w);
+        td[2] = make_float2(tb.x, tb.y), td[3] = make_float2(tb.z, tb.w);
+      } else {
+        td[0] = make_float2(ta.x, ta.x), td[1] = make_float2(ta.y, ta.y);
+        td[2] = make_float2(ta.z, ta.z), td[3] = make_float2(ta.w, ta.w);
+      }
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         pa[0][d] = ffma2(f01, td[d], pa[0][d]);
         pa[1][d] = ffma2(f23, td[d], pa[1][d]);
       }
+#ifdef PEMP_TMA_DEBUG_SHORT_A                        // timing experiments only (results are wrong)
+      if (i == 0) break;
+#endif
     }
     // halving butterfly over the row groups (lane bits 4 and 3): lane (rg, jc) ends with column 4*jc + rg
     const bool hi = (lane & 16) != 0, lo = (lane & 8) != 0;
-    const int p = 4 * jc + rg - o;                    // pixel (relative to x_nom) of that column
+    const int p = col_a - o;                          // pixel (relative to x_nom) of that column
     float* dst = &sm.part[buf][warp][p];
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
@@ -264,13 +305,15 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   unsigned live = 0;
   // mask value of this lane's (column, class group) for a tile; 0 for columns that are not pixels of the tile
   auto mask_of = [&](int img, int x_nom, int o) {
-    const int p_own = cp * 8 + px8 - o;
+    const int p_own = col_s - o;
     const bool p_ok = p_own >= 0 && p_own < kStep && x_nom + p_own < hw;
-    return (owner && p_ok) ? __ldg((g_own ? bg : fg) + img * mask_stride + x_nom + p_own) : 0.f;
+    return (owner && p_ok) ? __ldg(mask_ptr + (img * mask_stride + (x_nom - o))) : 0.f;
   };
   auto softmax = [&](float m, int o, int buf, uint32_t parity) {
-    const int p_own = cp * 8 + px8 - o;
+    const int p_own = col_s - o;
+#ifndef PEMP_TMA_DEBUG_NO_EXCHANGE                   // timing experiments only (results are wrong)
     mbar_wait(&sm.part_bar[buf], parity);
+#endif
     float s0 = 0.f, s1 = 0.f;
     const int idx = d_own * kPartLd + (p_own >= 0 && p_own < kStep ? p_own : 0);
 #pragma unroll
@@ -285,8 +328,9 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
                                                       // columns outside the tile
       const float e1 = tot + k0, e2 = tot_next + k1;
       const float mx = fmaxf(0.f, fmaxf(e1, e2));
-      const float x0e = exp2f(0.f - mx), x1e = exp2f(e1 - mx), x2e = exp2f(e2 - mx);
-      const float r = m / (x0e + x1e + x2e);
+      // ex2.approx: 2 ulp, arguments <= 0; the sum is in [1, 3], rcp.approx is 1 ulp
+      const float x0e = ex2_approx(0.f - mx), x1e = ex2_approx(e1 - mx), x2e = ex2_approx(e2 - mx);
+      const float r = m * rcp_approx(x0e + x1e + x2e);
       w[0] = x0e * r;
       w[1] = x1e * r;
       w[2] = x2e * r;
@@ -305,12 +349,15 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   // A class group is skipped when none of the 8 columns has a non-zero weight in it (one warp-uniform test per
   // group: with complementary masks most 8-pixel runs are all-foreground or all-background).
   auto phase_b = [&](const float* box) {
+#ifdef PEMP_TMA_DEBUG_SKIP_B                         // timing experiments only (results are wrong)
+    return;
+#endif
     float4 f[2][4];
 #pragma unroll
     for (int ck = 0; ck < 2; ++ck)
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        f[ck][i] = *reinterpret_cast<const float4*>(box + (lane + 32 * i) * kTW + (((2 * cp + ck) ^ (lane & 7)) << 2));
+        f[ck][i] = *reinterpret_cast<const float4*>(box + (off_b ^ (ck << 2)) + 32 * i * kTW);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       if ((live & (0x11111111u << (2 * g))) == 0) continue;
@@ -507,7 +554,7 @@ TmaPlan make_tma_plan(int B, int S, int hw) {
   p.maxp = static_cast<int>((p.nt_img + per_cta - 1) / per_cta) + 1;
   const size_t imgs = static_cast<size_t>(B) * S;
   p.off_table = 0;
-  p.off_konst = kC * 8 * sizeof(float);
+  p.off_konst = kC * kTD * sizeof(float);
   p.off_num = p.off_konst + 256;
   p.off_den = p.off_num + align_up(imgs * p.maxp * kC * kK * sizeof(float), 256);
   p.total = p.off_den + align_up(imgs * p.maxp * 8 * sizeof(float), 256);
@@ -545,7 +592,7 @@ int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr,
   float* num = reinterpret_cast<float*>(ws + pl.off_num);
   float* den = reinterpret_cast<float*>(ws + pl.off_den);
   mpa_tma_prepare_kernel<<<8, 256, 0, st>>>(ctr, table, konst);
-  const size_t smem = sizeof(TmaSmem) + 1024;
+  const size_t smem = sizeof(TmaSmem);
   cudaError_t e = cudaFuncSetAttribute(mpa_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   mpa_tma_kernel<<<pl.G, kThreadsT, smem, st>>>(map, S, hw, pl.nt_img, pl.T, table, konst, fg, bg, mask_stride, pl.maxp,
