@@ -265,8 +265,8 @@ def run_ours(args):
     traffic = None      # dram read+write bytes per K2 launch from the committed ncu --set full capture of this shape
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"mpa_kernel:B{B}:S{S}:c{c}:hw{h * wd}")
-    roofline = {"kernel": "mpa_kernel (K2 meta_proto_attn)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        traffic = json.load(open(tpath)).get(f"mpa_tma_kernel:B{B}:S{S}:c{c}:hw{h * wd}")
+    roofline = {"kernel": "mpa_tma_kernel (+ prepare, finalize; K2 meta_proto_attn)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": how,
                 "algorithmic_bytes_per_launch": k2_bytes, "launch_ms": k2_ms, "launches_timed": timer.count(),
                 "share_of_step": k2_ms * (stages if stages == 2 else 1) / ms_per_step}
