@@ -124,6 +124,70 @@ upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logit
   }
 }
 
+// K4 fast path (uint8 mask only - the evaluator's case).  ATen evaluates the bilinear sample as
+//   v = fma(ly.l0, Hrow(i0, X), ly.l1 * Hrow(i1, X)),   Hrow(y, X) = fma(lx.l0, p[y][x0], lx.l1 * p[y][x1]),
+// so the horizontal pass of a source row can be computed ONCE and shared by every output row that uses it (8 output
+// rows per source row at 51 -> 401) without changing a single bit.  A CTA owns a band of kBandRows output rows of one
+// image: it first fills shared memory with Hrow for the few source rows the band touches (both channels), then each
+// thread produces aligned quads of the flattened output range of the band: 4 shared loads, 2 lerps and a compare per
+// pixel instead of 8 cached global loads and 6 lerps.  Quads that straddle the band boundary are written per byte.
+constexpr int kBandRows = 16, kBandMaxSrc = 8;
+__global__ void __launch_bounds__(256)
+upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict__ mask8, int h, int w, int H, int W,
+                            float sy, float sx, int bands) {
+  extern __shared__ float hrow[];                    // [nsrc][2][W]
+  const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
+  const int Y0 = band * kBandRows, Y1 = min(H, Y0 + kBandRows);
+  const int src0 = lerp_coeff(Y0, sy, h).i0, nsrc = lerp_coeff(Y1 - 1, sy, h).i1 - src0 + 1;
+  const int hw = h * w;
+  const float* p0 = pred + static_cast<long long>(n) * 2 * hw + src0 * w;
+  for (int X = threadIdx.x; X < W; X += blockDim.x) {
+    const Lerp lx = lerp_coeff(X, sx, w);
+    for (int r = 0; r < nsrc; ++r)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float* row = p0 + ch * hw + r * w;
+        hrow[(r * 2 + ch) * W + X] = lerp2(lx.l0, __ldg(row + lx.i0), lx.l1, __ldg(row + lx.i1));
+      }
+  }
+  __syncthreads();
+  const long long HW = static_cast<long long>(H) * W;
+  const long long base0 = n * HW + static_cast<long long>(Y0) * W, base1 = n * HW + static_cast<long long>(Y1) * W;
+  for (long long q = (base0 >> 2) + threadIdx.x; (q << 2) < base1; q += blockDim.x) {
+    const long long i0 = q << 2;
+    const long long first = i0 < base0 ? base0 : i0;          // first element of the quad inside the band
+    const int r0 = static_cast<int>(first - n * HW);
+    int Y = r0 / W, X = r0 - Y * W;
+    Lerp ly = lerp_coeff(Y, sy, h);
+    const float* rt = hrow + (ly.i0 - src0) * 2 * W;
+    const float* rb = hrow + (ly.i1 - src0) * 2 * W;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = i0 + e;
+      if (i >= first && i < base1) {
+        const float v0 = lerp2(ly.l0, rt[X], ly.l1, rb[X]);
+        const float v1 = lerp2(ly.l0, rt[W + X], ly.l1, rb[W + X]);
+        packed |= (v1 > v0 ? 1u : 0u) << (8 * e);   // first index wins ties => background
+        if (++X == W) {
+          X = 0;
+          ++Y;
+          ly = lerp_coeff(min(Y, H - 1), sy, h);
+          rt = hrow + (ly.i0 - src0) * 2 * W;
+          rb = hrow + (ly.i1 - src0) * 2 * W;
+        }
+      }
+    }
+    if (i0 >= base0 && i0 + 3 < base1) {
+      reinterpret_cast<uint32_t*>(mask8)[q] = packed;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i0 + e >= base0 && i0 + e < base1) mask8[i0 + e] = static_cast<uint8_t>(packed >> (8 * e));
+    }
+  }
+}
+
 extern "C" int pemp_upsample_argmax(const float* pred, int N, int h, int w, int H, int W, float* logits, uint8_t* mask8,
                                     int64_t* mask64, pemp_stream_t stream) {
   PEMP_REQUIRE(pred, PEMP_E_NULL);
@@ -135,6 +199,16 @@ extern "C" int pemp_upsample_argmax(const float* pred, int N, int h, int w, int 
   int grid = static_cast<int>(llmin((total / 4 + block) / block, 148LL * 32));
   float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
   cudaStream_t st = as_stream(stream);
+  if (mask8 && !logits && !mask64) {
+    // source rows one band can touch: floor((kBandRows - 1) * sy) + 3 (top row, its partner, rounding)
+    const int nsrc_max = static_cast<int>((kBandRows - 1) * sy) + 3;
+    const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
+    if (nsrc_max <= kBandMaxSrc && smem <= 48 * 1024) {
+      const int bands = (H + kBandRows - 1) / kBandRows;
+      upsample_argmax_band_kernel<<<static_cast<unsigned>(N) * bands, 256, smem, st>>>(pred, mask8, h, w, H, W, sy, sx, bands);
+      return launch_status();
+    }
+  }
 #define PEMP_LAUNCH_UA(L, M8, M64)                                                                              \
   upsample_argmax_kernel<L, M8, M64><<<grid, block, 0, st>>>(pred, logits, mask8, mask64, total, h, w, H, W, sy, sx)
   int sel = (logits ? 4 : 0) | (mask8 ? 2 : 0) | (mask64 ? 1 : 0);

@@ -34,7 +34,8 @@ def test_mask_nearest_bit_exact(ops, H, W, h, w):
     assert torch.equal(ops.mask_nearest(cu(x), h, w).cpu(), O.mask_nearest(x, h, w))
 
 
-@pytest.mark.parametrize("h,w,H,W", [(51, 51, 401, 401), (51, 51, 333, 500), (13, 13, 97, 97), (7, 9, 50, 41), (5, 5, 5, 5)])
+@pytest.mark.parametrize("h,w,H,W", [(51, 51, 401, 401), (51, 51, 333, 500), (13, 13, 97, 97), (7, 9, 50, 41), (5, 5, 5, 5),
+                                     (51, 51, 21, 23), (60, 60, 473, 473), (3, 4, 401, 7)])
 def test_upsample_argmax_bit_exact_given_same_input(ops, h, w, H, W):
     """K4 in isolation is bit exact: logits equal ATen's CPU bilinear bit for bit, hence the masks too."""
     torch.manual_seed(1)
@@ -47,6 +48,10 @@ def test_upsample_argmax_bit_exact_given_same_input(ops, h, w, H, W):
     # and against torch's own CUDA kernel (the path the reference actually runs on a GPU)
     aten = torch.nn.functional.interpolate(cu(pred), (H, W), mode="bilinear", align_corners=True)
     assert torch.equal(out["mask64"], aten.argmax(1))
+    # the uint8-only call takes the banded kernel (shared horizontal pass): same bits, also for N where the bands of
+    # consecutive images share 32-bit words of the mask
+    only8 = ops.upsample_argmax(cu(pred), (H, W), want_mask8=True)["mask8"]
+    assert torch.equal(only8, out["mask8"])
 
 
 def test_upsample_ties_go_to_background(ops):
