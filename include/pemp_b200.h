@@ -102,6 +102,9 @@ int pemp_debug_mpa_path(int mode);
 int pemp_cosine_match(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
                       int N, int Bp, int c, int hw, int P, float scalar,
                       float* sim, float* pred, int64_t* response, pemp_stream_t stream);
+/* Diagnostic (tests only), as pemp_debug_mpa_path: K3 has a TMA-fed persistent kernel for c = 512, P in {1, 3},
+ * hw >= 32; mode 1 forces the generic kernel, mode 0 restores the automatic choice.  Returns the previous mode. */
+int pemp_debug_cosine_path(int mode);
 
 /* ---- K4  bilinear up-sampling (align_corners=True) + 2-way argmax -----------------------------------
  * replaces  F.interpolate(pred, out_shape, 'bilinear', align_corners=True) and logits.argmax(1)

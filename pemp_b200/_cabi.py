@@ -24,6 +24,7 @@ SIGNATURES = {
     "pemp_weighted_gap": (I, [P, P, I, I, I, P, P, SZ, P]),
     "pemp_meta_proto_attn_workspace_bytes": (SZ, [I, I, I, I, I]),
     "pemp_debug_mpa_path": (I, [I]),
+    "pemp_debug_cosine_path": (I, [I]),
     "pemp_meta_proto_attn": (I, [P, LL, P, P, P, LL, I, I, I, I, I, F, P, P, P, P, SZ, P]),
     "pemp_cosine_match": (I, [P, LL, P, P, I, I, I, I, I, F, P, P, P, P]),
     "pemp_upsample_argmax": (I, [P, I, I, I, I, I, P, P, P, P]),

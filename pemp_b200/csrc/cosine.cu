@@ -13,10 +13,21 @@
 // combined across warps through shared memory in a fixed order (bit-reproducible run to run).
 #include "common.cuh"
 
+// TMA-fed persistent fast path for c = 512, P in {1, 3} (cosine_tma.cu); PEMP_E_ALIGN = not covered, nothing launched
+int pemp_cosine_tma_launch(const float* qry, long long ep_stride, const float* fg, const float* bg, int N, int Bp, int hw,
+                           int P, float scalar, float* sim, float* pred, int64_t* response, cudaStream_t st);
+#ifndef PEMP_COS_TMA
+#define PEMP_COS_TMA 1
+#endif
+static int g_cos_path = 0;   // diagnostic switch, see pemp_debug_cosine_path
+
 namespace {
 
 constexpr int kTile = 128;       // pixels per CTA
-constexpr int kWarps = 8;        // channel-splitting warps per CTA
+#ifndef PEMP_COS_WARPS
+#define PEMP_COS_WARPS 8
+#endif
+constexpr int kWarps = PEMP_COS_WARPS;        // channel-splitting warps per CTA
 constexpr int kPix = kTile / 32; // pixels per lane
 constexpr int kMaxK = 8;         // prototype vectors per image (2P), padded row of the smem table
 constexpr float kCosEps = 1e-8f; // F.cosine_similarity eps
@@ -76,7 +87,10 @@ cosine_match_kernel(const float* __restrict__ qry, long long ep_stride, const fl
 
   const int per = (c + kWarps - 1) / kWarps;
   const int c_begin = warp * per, c_end = min(c, c_begin + per);
-  constexpr int U = 4;   // channel rows in flight per warp
+#ifndef PEMP_COS_U
+#define PEMP_COS_U 4
+#endif
+  constexpr int U = PEMP_COS_U;   // channel rows in flight per warp
   for (int ch = c_begin; ch < c_end; ch += U) {
     float v[U][kPix];
 #pragma unroll
@@ -157,6 +171,12 @@ int launch(const float* qry, long long ep_stride, const float* fg, const float* 
 
 }  // namespace
 
+extern "C" int pemp_debug_cosine_path(int mode) {
+  const int old = g_cos_path;
+  if (mode == 0 || mode == 1) g_cos_path = mode;
+  return old;
+}
+
 extern "C" int pemp_cosine_match(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto, int N, int Bp, int c,
                                  int hw, int P, float scalar, float* sim, float* pred, int64_t* response,
                                  pemp_stream_t stream) {
@@ -165,6 +185,10 @@ extern "C" int pemp_cosine_match(const float* qry, long long qry_episode_stride,
   PEMP_REQUIRE(N > 0 && Bp > 0 && c > 0 && hw > 0 && N % Bp == 0, PEMP_E_SHAPE);
   PEMP_REQUIRE(P >= 1 && P <= 4, PEMP_E_SHAPE);
   cudaStream_t st = as_stream(stream);
+  if (PEMP_COS_TMA && c == 512 && g_cos_path != 1) {
+    const int rc = pemp_cosine_tma_launch(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, hw, P, scalar, sim, pred, response, st);
+    if (rc != PEMP_E_ALIGN) return rc;
+  }
   switch (P) {
     case 1: return launch<2>(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);
     case 2: return launch<4>(qry, qry_episode_stride, fg_proto, bg_proto, N, Bp, c, hw, scalar, sim, pred, response, st);

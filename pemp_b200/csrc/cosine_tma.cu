@@ -1,0 +1,352 @@
+// K3 fast path: cosine matching as a persistent, TMA-fed, warp-specialised kernel (c = 512; P = 3 or 1).
+//
+// Same arithmetic as `cosine_match_kernel` (cosine.cu; reference networks/pemp_stage1.py:214-222,233-261,
+// pemp_stage2.py:187-194,205-233, baseline.py:121-149, panet.py:122-156):
+//   s[k, x] = (sum_c q[c, x] * p^[c, k]) * (1 / max(|q[:, x]|, 1e-8)) * scalar,   p^ = p / max(|p|, 1e-8)
+//   pred[g, x] = max_j s[g*P + j, x]   (first maximum wins),  response = argmax index (+3 for foreground)
+//
+// Data path as in mpa_tma.cu: the query maps [.., c, hw] are described to TMA as [c/4 groups][4*hw floats]; a box of
+// 32 floats x 128 groups at the 16-byte aligned inner coordinate (e*hw + x_nom) & ~3 holds the channels 4g + e, its
+// column i is pixel x_nom + i - o_e; tiles advance by 28 pixels.  One CTA per SM owns a flat range of tiles; warp 16
+// feeds an 8-slot ring of 16-KB boxes (full / empty mbarriers).  Consumer warp w = 4e + cp reads rows [32cp, 32cp+32)
+// of box e: lane <-> (row mod 4, 16-byte chunk), one row-contiguous LDS.128 per 4 pixels of a channel, the channel's
+// normalised prototypes (each value twice, so they are FFMA2 operands as loaded) from shared memory, 2 + 2K packed
+// FFMA2 per load for |q|^2 and the K dots of 4 pixels.  The slot is released as soon as the warp has read it.  A
+// halving butterfly over the 4 row groups leaves each lane with the 1 + K sums of one pixel; they go to
+// part[buffer][warp][value][pixel] and the warp arrives on the buffer's mbarrier.  The NEXT iteration (after the next
+// tile's loads and FMAs, so nobody waits) adds the 16 partials in a fixed order - 14 warps, two pixels each,
+// lane <-> (pixel, half of the partials, value) - and finishes the pixel: norm, scale, max / argmax, stores.
+// Four exchange buffers: a warp rewrites part[b] only after it passed the exchange two tiles later, which every
+// warp reaches after its last read of part[b].
+//
+// The prototype table depends on the episode: the consumers (re)build it in shared memory - normalised, in tile-row
+// order - whenever the episode of the current image changes (at most twice per CTA at the bench shape).
+#include <cuda.h>
+
+#include "common.cuh"
+
+int pemp_cosine_tma_launch(const float* qry, long long ep_stride, const float* fg, const float* bg, int N, int Bp, int hw,
+                           int P, float scalar, float* sim, float* pred, int64_t* response, cudaStream_t st);
+
+namespace {
+
+constexpr int kC = 512;
+constexpr int kTW = 32;                          // floats per box row
+constexpr int kStep = 28;                        // pixels per tile
+constexpr int kBoxRows = kC / 4;
+constexpr int kBoxFloats = kBoxRows * kTW;
+constexpr uint32_t kBoxBytes = kBoxFloats * 4;
+constexpr int kNB = 8;                           // ring slots (consumers hold 4, 4 in flight)
+constexpr int kCons = 16;
+constexpr int kThreadsC = (kCons + 1) * 32;
+constexpr int kPB = 4;
+constexpr int kPLd = 33;                         // pixel pitch of a value row in `part` (banks value + pixel + 7*warp)
+constexpr int kMaxGrid = 148;
+constexpr float kCosEps = 1e-8f;
+
+template <int K>
+struct CosSmem {
+  static constexpr int TL = (2 * K + 3) / 4 * 4;  // floats per table row: {p0,p0,p1,p1,...}
+  alignas(1024) float ring[kNB][kBoxFloats];
+  alignas(16) float table[kC * TL];
+  alignas(16) float part[kPB][kCons][(1 + K) * kPLd]; // [buffer][warp][value][pixel], odd pitch: see finalize
+  alignas(16) float red[kCons][8];
+  alignas(8) uint64_t full[kNB];
+  alignas(8) uint64_t empty[kNB];
+  alignas(8) uint64_t part_bar[kPB];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "COST_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra COST_DONE;\n"
+      "bra COST_WAIT;\n"
+      "COST_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <int K>
+__global__ void __launch_bounds__(kThreadsC, 1)
+cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int nt_img, long long T,
+                  const float* __restrict__ fg_proto, const float* __restrict__ bg_proto, float scalar,
+                  float* __restrict__ sim, float* __restrict__ pred, int64_t* __restrict__ response) {
+  constexpr int P = K / 2, NV = 1 + K, TL = CosSmem<K>::TL;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  CosSmem<K>& sm = *reinterpret_cast<CosSmem<K>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const long long t0 = T * cta / G, t1 = T * (cta + 1) / G;
+  const int ntl = static_cast<int>(t1 - t0);
+
+  if (tid == 0) {
+    for (int s = 0; s < kNB; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 4);
+    }
+    for (int b = 0; b < kPB; ++b) mbar_init(&sm.part_bar[b], kCons);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (ntl <= 0) return;
+
+  if (warp == kCons) {
+    // ============================ producer ============================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+      int slot = 0;
+      uint32_t par = 1;
+      int n = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(n) * nt_img);
+      int ep = n / Qper, q = n - ep * Qper;
+      for (int k = 0; k < ntl; ++k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = (e * hw + tl * kStep) & ~3;
+          mbar_wait(&sm.empty[slot], par);
+          mbar_expect_tx(&sm.full[slot], kBoxBytes);
+          tma_load_3d(&map, &sm.full[slot], sm.ring[slot], c0, q * kBoxRows, ep);
+          if (++slot == kNB) {
+            slot = 0;
+            par ^= 1;
+          }
+        }
+        if (++tl == nt_img) {
+          tl = 0;
+          if (++q == Qper) {
+            q = 0;
+            ++ep;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================ consumers ============================
+  const int e = warp >> 2, cp = warp & 3;
+  const int rg = lane >> 3, jc = lane & 7;
+  int off_a = (cp * 32 + rg) * kTW + ((jc ^ rg) << 2);      // even i; odd i: ^ 16; row step i*128
+  int off_t = (e * kBoxRows + cp * 32 + rg) * TL;
+  int col_a = 4 * jc + rg;                                  // box column this lane holds after the butterfly
+  asm volatile("" : "+r"(off_a), "+r"(off_t), "+r"(col_a));
+  // finalize roles: warp w < 14 finishes pixels w and w + 14; lane = pixsel*16 + half*8 + value
+  const int f_val = lane & 7, f_half = (lane >> 3) & 1, f_pix = warp + 14 * (lane >> 4);
+  const bool f_active = warp < 14 && f_val < NV;
+
+  // ---- finish tile (n, x_nom) whose partial sums are in part[pb] ----
+  auto finalize = [&](int n, int x_nom, int pb, uint32_t parity) {
+    mbar_wait(&sm.part_bar[pb], parity);
+    float s = 0.f;
+    if (f_active) {
+      const float* src = &sm.part[pb][f_half * 8][f_val * kPLd + f_pix];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += src[i * NV * kPLd];
+    }
+    s += __shfl_xor_sync(kFull, s, 8);                       // both halves: lower 8 warps + upper 8 warps
+    const float nrm = __shfl_sync(kFull, s, lane & 16);      // value 0 of this pixel
+    const float qinv = 1.0f / fmaxf(sqrtf(nrm), kCosEps);
+    const float v = s * qinv * scalar;                       // values 1..K: similarity to prototype k = value - 1
+    const int x = x_nom + f_pix;
+    const bool ok = warp < 14 && f_half == 0 && x < hw;
+    if (sim && ok && f_val >= 1 && f_val <= K) {
+      const int k = f_val - 1, g = k / P, j = k - g * P;
+      sim[((static_cast<long long>(n) * 2 + g) * P + j) * hw + x] = v;
+    }
+    // max / argmax over the P members of each group on its first lane (values 1 + g*P); first maximum wins
+    float best = v;
+    int arg = 0;
+#pragma unroll
+    for (int j = 1; j < P; ++j) {
+      const float o = __shfl_down_sync(kFull, v, j);
+      if (o > best) {
+        best = o;
+        arg = j;
+      }
+    }
+    const float best_fg = __shfl_down_sync(kFull, best, P);  // seen from the background leader (value 1)
+    const int arg_fg = __shfl_down_sync(kFull, arg, P);
+    if (ok && (f_val == 1 || f_val == 1 + P)) {
+      const int g = f_val == 1 ? 0 : 1;
+      if (pred) pred[(static_cast<long long>(n) * 2 + g) * hw + x] = best;
+      if (response && g == 0) response[static_cast<long long>(n) * hw + x] = best_fg > best ? arg_fg + 3 : arg;
+    }
+  };
+
+  int slot = e;
+  uint32_t par = 0;
+  int n = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(n) * nt_img);
+  int cur_b = -1, n_prev = 0, x_prev = 0;
+  for (int k = 0; k < ntl; ++k) {
+    const int b = n / Qper;
+    if (b != cur_b) {
+      // ---------------- (re)build the normalised prototype table of episode b ----------------
+      cur_b = b;
+      named_bar(1, kCons * 32);                              // nobody reads the old table any more
+      const int R = tid, ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
+      float raw[K];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        raw[j] = __ldg(bg_proto + (static_cast<long long>(b) * kC + ch) * P + j);
+        raw[P + j] = __ldg(fg_proto + (static_cast<long long>(b) * kC + ch) * P + j);
+      }
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const float ss = warp_sum(raw[kk] * raw[kk]);
+        if (lane == 0) sm.red[warp][kk] = ss;
+      }
+      named_bar(1, kCons * 32);
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        float ss = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < kCons; ++w2) ss += sm.red[w2][kk];
+        const float v = raw[kk] * (1.0f / fmaxf(sqrtf(ss), kCosEps));
+        sm.table[R * TL + 2 * kk] = v;
+        sm.table[R * TL + 2 * kk + 1] = v;
+      }
+      named_bar(1, kCons * 32);
+    }
+    const int x_nom = tl * kStep;
+    const int o = (e * hw + x_nom) & 3;
+    const float* box = sm.ring[slot];
+    mbar_wait(&sm.full[slot], par);
+
+    float2 acc[2][NV];                                       // [column pair][|q|^2, K dots]
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+      for (int kk = 0; kk < NV; ++kk) acc[p2][kk] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 f = *reinterpret_cast<const float4*>(box + (off_a ^ ((i & 1) << 4)) + i * 4 * kTW);
+      const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
+      const float* trow = sm.table + off_t + i * 4 * TL;
+      acc[0][0] = ffma2(f01, f01, acc[0][0]);
+      acc[1][0] = ffma2(f23, f23, acc[1][0]);
+#pragma unroll
+      for (int kk = 0; kk < K; kk += 2) {
+        const float4 t4 = *reinterpret_cast<const float4*>(trow + 2 * kk);
+        const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
+        acc[0][1 + kk] = ffma2(f01, ta, acc[0][1 + kk]);
+        acc[1][1 + kk] = ffma2(f23, ta, acc[1][1 + kk]);
+        acc[0][2 + kk] = ffma2(f01, tb, acc[0][2 + kk]);
+        acc[1][2 + kk] = ffma2(f23, tb, acc[1][2 + kk]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[slot]);             // the box is not read again
+
+    // halving butterfly over the row groups (lane bits 4 and 3): lane (rg, jc) ends with column 4*jc + rg
+    {
+      const bool hi = (lane & 16) != 0, lo = (lane & 8) != 0;
+      const int p = col_a - o;
+      float* dst = &sm.part[k & (kPB - 1)][warp][p];
+#pragma unroll
+      for (int kk = 0; kk < NV; ++kk) {
+        const float2 keep = hi ? acc[1][kk] : acc[0][kk], send = hi ? acc[0][kk] : acc[1][kk];
+        const float rx = keep.x + __shfl_xor_sync(kFull, send.x, 16);
+        const float ry = keep.y + __shfl_xor_sync(kFull, send.y, 16);
+        const float keep2 = lo ? ry : rx, send2 = lo ? rx : ry;
+        const float q = keep2 + __shfl_xor_sync(kFull, send2, 8);
+        if (p >= 0 && p < kStep) dst[kk * kPLd] = q;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.part_bar[k & (kPB - 1)]);
+
+    if (k > 0) finalize(n_prev, x_prev, (k - 1) & (kPB - 1), ((k - 1) / kPB) & 1);
+    n_prev = n;
+    x_prev = x_nom;
+    slot += 4;
+    if (slot >= kNB) {
+      slot -= kNB;
+      par ^= 1;
+    }
+    if (++tl == nt_img) {
+      tl = 0;
+      ++n;
+    }
+  }
+  finalize(n_prev, x_prev, (ntl - 1) & (kPB - 1), ((ntl - 1) / kPB) & 1);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;     // immutable after first resolution; benign race (same value)
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <int K>
+int launch_tma(const CUtensorMap& map, int Qper, int hw, int nt_img, long long T, int G, const float* fg, const float* bg,
+               float scalar, float* sim, float* pred, int64_t* response, cudaStream_t st) {
+  const size_t smem = sizeof(CosSmem<K>);
+  cudaError_t e = cudaFuncSetAttribute(cosine_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cosine_tma_kernel<K><<<G, kThreadsC, smem, st>>>(map, Qper, hw, nt_img, T, fg, bg, scalar, sim, pred, response);
+  return launch_status();
+}
+
+}  // namespace
+
+// Returns PEMP_E_ALIGN (nothing launched) when the shape or the operand is not covered; the caller then uses the
+// generic kernel.
+int pemp_cosine_tma_launch(const float* qry, long long ep_stride, const float* fg, const float* bg, int N, int Bp, int hw,
+                           int P, float scalar, float* sim, float* pred, int64_t* response, cudaStream_t st) {
+  const int Qper = N / Bp;
+  const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(Qper) * kC * hw;
+  if ((P != 3 && P != 1) || hw < kTW || (reinterpret_cast<uintptr_t>(qry) & 15) != 0 || (eps_stride & 3) != 0) return PEMP_E_ALIGN;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return PEMP_E_ALIGN;
+  const int nt_img = (hw + kStep - 1) / kStep;
+  const long long T = static_cast<long long>(N) * nt_img;
+  long long g = T / 4;
+  const int G = static_cast<int>(g < 1 ? 1 : (g > kMaxGrid ? kMaxGrid : g));
+
+  CUtensorMap map;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(4) * hw, static_cast<cuuint64_t>(Qper) * kBoxRows, static_cast<cuuint64_t>(Bp)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(16) * hw, static_cast<cuuint64_t>(eps_stride) * 4};
+  cuuint32_t box[3] = {kTW, kBoxRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qry), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return PEMP_E_ALIGN;
+  return P == 3 ? launch_tma<6>(map, Qper, hw, nt_img, T, G, fg, bg, scalar, sim, pred, response, st)
+                : launch_tma<2>(map, Qper, hw, nt_img, T, G, fg, bg, scalar, sim, pred, response, st);
+}

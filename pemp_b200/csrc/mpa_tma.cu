@@ -118,7 +118,13 @@ __host__ __device__ inline int owner_of(long long t, long long T, int G) { retur
 // ---- prologue: difference table in tile-row order --------------------------------------------
 // tile row R = e*128 + g  <->  channel 4g + e;  table[R][d] = 2 log2(e) * (ctr[ch, g'*P + j] - ctr[ch, g'*P]) with
 // d = g'*(P-1) + j-1;  konst[d] = -(|ctr_{g'P+j}|^2 - |ctr_{g'P}|^2) in double.
-__global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __restrict__ table, float* __restrict__ konst) {
+__global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __restrict__ table, float* __restrict__ konst,
+                                       int* __restrict__ nparts, int imgs, int nt_img, long long T, int G) {
+  // partials an image ends up with = CTAs its tile range touches (64-bit divisions: done once here, not per output)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < imgs; i += gridDim.x * blockDim.x) {
+    const long long first = static_cast<long long>(i) * nt_img;
+    nparts[i] = owner_of(first + nt_img - 1, T, G) - owner_of(first, T, G) + 1;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC * 4; i += gridDim.x * blockDim.x) {
     const int R = i >> 2, d = i & 3;
     const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
@@ -495,8 +501,8 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
 }
 
 // one thread per (b, channel, k): add the partials of every shot in CTA order, divide, average the shots
-__global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, const float* __restrict__ part_den, int B,
-                                        int S, int nt_img, long long T, int G, int maxp, float eps,
+__global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, const float* __restrict__ part_den,
+                                        const int* __restrict__ nparts, int B, int S, int maxp, float eps,
                                         float* __restrict__ fg_proto, float* __restrict__ bg_proto,
                                         float* __restrict__ adaptive_p) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -508,7 +514,7 @@ __global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, cons
   float accum = 0.f;
   for (int s = 0; s < S; ++s) {
     const long long img = static_cast<long long>(b) * S + s;
-    const int n = owner_of(img * nt_img + nt_img - 1, T, G) - owner_of(img * nt_img, T, G) + 1;
+    const int n = __ldg(nparts + img);
     float num = 0.f, den = 0.f;
     for (int sp = 0; sp < n; ++sp) {
       num += part_num[((img * maxp + sp) * kC + R) * kK + k];
@@ -540,7 +546,7 @@ EncodeTiledFn encode_fn() {
 struct TmaPlan {
   int G, nt_img, maxp;
   long long T;
-  size_t off_table, off_konst, off_num, off_den, total;
+  size_t off_table, off_konst, off_nparts, off_num, off_den, total;
 };
 TmaPlan make_tma_plan(int B, int S, int hw) {
   TmaPlan p;
@@ -555,7 +561,8 @@ TmaPlan make_tma_plan(int B, int S, int hw) {
   const size_t imgs = static_cast<size_t>(B) * S;
   p.off_table = 0;
   p.off_konst = kC * kTD * sizeof(float);
-  p.off_num = p.off_konst + 256;
+  p.off_nparts = p.off_konst + 256;
+  p.off_num = p.off_nparts + align_up(imgs * sizeof(int), 256);
   p.off_den = p.off_num + align_up(imgs * p.maxp * kC * kK * sizeof(float), 256);
   p.total = p.off_den + align_up(imgs * p.maxp * 8 * sizeof(float), 256);
   return p;
@@ -591,7 +598,8 @@ int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr,
   float* konst = reinterpret_cast<float*>(ws + pl.off_konst);
   float* num = reinterpret_cast<float*>(ws + pl.off_num);
   float* den = reinterpret_cast<float*>(ws + pl.off_den);
-  mpa_tma_prepare_kernel<<<8, 256, 0, st>>>(ctr, table, konst);
+  int* nparts = reinterpret_cast<int*>(ws + pl.off_nparts);
+  mpa_tma_prepare_kernel<<<8, 256, 0, st>>>(ctr, table, konst, nparts, B * S, pl.nt_img, pl.T, pl.G);
   const size_t smem = sizeof(TmaSmem);
   cudaError_t e = cudaFuncSetAttribute(mpa_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -599,6 +607,6 @@ int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr,
                                                num, den);
   const long long total = static_cast<long long>(B) * kC * kK;
   mpa_tma_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      num, den, B, S, pl.nt_img, pl.T, pl.G, pl.maxp, eps, fg_proto, bg_proto, adaptive_p);
+      num, den, nparts, B, S, pl.maxp, eps, fg_proto, bg_proto, adaptive_p);
   return launch_status();
 }

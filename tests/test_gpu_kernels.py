@@ -70,7 +70,11 @@ def test_nearest_labels_and_bilinear_resize(ops):
 
 # ------------------------------------------------------------------------------------------------ K3
 @pytest.mark.parametrize("N,Bp,c,hw,P", [(2, 2, 32, 169, 3), (4, 2, 48, 130, 1), (3, 1, 64, 2601, 3), (2, 2, 512, 2601, 3),
-                                         (1, 1, 20, 7, 2), (2, 1, 36, 300, 4)])
+                                         (1, 1, 20, 7, 2), (2, 1, 36, 300, 4),
+                                         # the TMA-fed persistent kernel (c = 512, P in {1, 3}): several queries per episode,
+                                         # ragged last tile, exactly one tile, fewer tiles than CTAs, single prototype
+                                         (6, 3, 512, 2601, 3), (5, 5, 512, 100, 3), (1, 1, 512, 32, 3), (4, 2, 512, 2601, 1),
+                                         (3, 3, 512, 45, 1), (2, 1, 512, 300, 2)])
 def test_cosine_match(ops, N, Bp, c, hw, P):
     torch.manual_seed(3)
     q = torch.randn(N, c, hw)
@@ -87,6 +91,28 @@ def test_cosine_match(ops, N, Bp, c, hw, P):
     margin_p = (top2[:, :, 0] - top2[:, :, -1]).min(dim=1).values if P > 1 else torch.full((N, hw), 1.0)
     safe = ((pred[:, 0] - pred[:, 1]).abs() > 1e-4) & (margin_p > 1e-4)
     assert torch.equal(out["response"].cpu()[safe], resp[safe])
+
+
+def test_cosine_match_tma_vs_generic_kernel_full_size(ops):
+    """B = 8 episodes at the PEMP shape, queries read in place from a [B, S+Q, c, h, w] encoder output: the TMA-fed
+    kernel and the generic kernel (independent implementations) agree to fp32 rounding, response maps included."""
+    from pemp_b200 import _cabi
+    torch.manual_seed(12)
+    B, S, Q, c, h = 8, 5, 1, 512, 51
+    feats = cu(torch.randn(B, S + Q, c, h, h) * 0.5)
+    fg, bg = cu(torch.randn(B, c, 3)), cu(torch.randn(B, c, 3))
+    qry = feats[:, S:]
+    a = ops.cosine_match(qry, fg, bg, 20.0, want_sim=True, want_pred=True, want_response=True)
+    _cabi.lib().pemp_debug_cosine_path(1)
+    try:
+        b = ops.cosine_match(qry, fg, bg, 20.0, want_sim=True, want_pred=True, want_response=True)
+    finally:
+        _cabi.lib().pemp_debug_cosine_path(0)
+    assert nrel(a["sim"].cpu(), b["sim"].cpu()) < 2e-6 and nrel(a["pred"].cpu(), b["pred"].cpu()) < 2e-6
+    sim = b["sim"].cpu()
+    top2 = sim.topk(2, dim=2).values
+    safe = ((b["pred"][:, 0] - b["pred"][:, 1]).abs().cpu() > 1e-4) & ((top2[:, :, 0] - top2[:, :, 1]).min(dim=1).values > 1e-4)
+    assert torch.equal(a["response"].cpu()[safe], b["response"].cpu()[safe]) and safe.float().mean() > 0.9
 
 
 def test_cosine_zero_vectors(ops):
