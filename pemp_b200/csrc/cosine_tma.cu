@@ -100,7 +100,8 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   CosSmem<K>& sm = *reinterpret_cast<CosSmem<K>*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  asm volatile("" : "+r"(tid), "+r"(lane), "+r"(warp));      // keep them in registers (no S2R re-reads in the loop)
   const int G = gridDim.x, cta = blockIdx.x;
   const long long t0 = T * cta / G, t1 = T * (cta + 1) / G;
   const int ntl = static_cast<int>(t1 - t0);
@@ -202,9 +203,9 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
   int slot = e;
   uint32_t par = 0;
   int n = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(n) * nt_img);
+  int b = n / Qper, q_in_b = n - b * Qper;                    // episode of image n, tracked without divisions
   int cur_b = -1, n_prev = 0, x_prev = 0;
   for (int k = 0; k < ntl; ++k) {
-    const int b = n / Qper;
     if (b != cur_b) {
       // ---------------- (re)build the normalised prototype table of episode b ----------------
       cur_b = b;
@@ -292,6 +293,10 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
     if (++tl == nt_img) {
       tl = 0;
       ++n;
+      if (++q_in_b == Qper) {
+        q_in_b = 0;
+        ++b;
+      }
     }
   }
   finalize(n_prev, x_prev, (ntl - 1) & (kPB - 1), ((ntl - 1) / kPB) & 1);
