@@ -5,7 +5,7 @@
 //   networks/baseline.py:100-110, networks/panet.py:99-109       (329 MB / shot of temporaries at 401x401)
 //
 // Identity:  sum_{YX} m[Y,X] (U f)[Y,X] = sum_{yx} f[y,x] (U^T m)[y,x]  with U the bilinear operator.  The
-// mask (2*H*W floats per shot) is pushed through U^T once (resample.cu: bilinear_adjoint_kernel), then the
+// mask (2*H*W floats per shot) is pushed through U^T once (resample.cu: adjoint_rows_kernel), then the
 // features are pooled at low resolution by the K1 kernel with the exact mask sums as denominators.
 // Algorithmic bytes per shot: c*h*w*4 + 2*H*W*4.
 #include "common.cuh"
@@ -14,16 +14,21 @@ int pemp_pool_launch(const float* fts, long long ep_stride, const float* fg, con
                      int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, void* workspace,
                      size_t workspace_bytes, cudaStream_t st);
 
+size_t pemp_adjoint_scratch_bytes(int planes, int h, int w);
+int pemp_adjoint_launch(const float* mask, int planes, int H, int W, int h, int w, float* wt, float* msum, char* scratch,
+                        cudaStream_t st);
+
 namespace {
 struct Plan {
-  size_t off_wt, off_sum, off_pool, total;
+  size_t off_wt, off_sum, off_adj, off_pool, total;
 };
 Plan make_plan(int B, int S, int c, int h, int w) {
   Plan p;
   size_t planes = static_cast<size_t>(B) * S * 2;
   p.off_wt = 0;
   p.off_sum = align_up(planes * h * w * sizeof(float), 256);
-  p.off_pool = p.off_sum + align_up(planes * sizeof(float), 256);
+  p.off_adj = p.off_sum + align_up(planes * sizeof(float), 256);
+  p.off_pool = p.off_adj + pemp_adjoint_scratch_bytes(static_cast<int>(planes), h, w);
   p.total = p.off_pool + pemp_map_pool_workspace_bytes(B, S, c, h * w);
   return p;
 }
@@ -45,7 +50,7 @@ extern "C" int pemp_map_pool_fullres(const float* fts, long long fts_episode_str
   float* wt = reinterpret_cast<float*>(ws + pl.off_wt);
   float* msum = reinterpret_cast<float*>(ws + pl.off_sum);
   int planes = B * S * 2;
-  int rc = pemp_bilinear_adjoint(sup_mask, planes, H, W, h, w, wt, msum, stream);
+  int rc = pemp_adjoint_launch(sup_mask, planes, H, W, h, w, wt, msum, ws + pl.off_adj, as_stream(stream));
   if (rc != PEMP_OK) return rc;
   const int hw = h * w;
   return pemp_pool_launch(fts, fts_episode_stride, wt, wt + hw, 2LL * hw, B, S, c, hw, eps, msum, fg_proto, bg_proto, ws + pl.off_pool,

@@ -293,6 +293,21 @@ def test_baseline_panet_golden(ops, name):
         assert abs(float(loss) - float(g["align_loss"])) < 1e-5 * max(1.0, abs(float(g["align_loss"])))
 
 
+@pytest.mark.parametrize("B,S,c,h,w,H,W", [(2, 2, 24, 13, 13, 97, 97), (1, 3, 16, 9, 12, 50, 77), (1, 1, 8, 20, 20, 11, 15),
+                                           (1, 2, 512, 51, 51, 401, 401)])
+def test_map_pool_fullres_vs_restatement(ops, B, S, c, h, w, H, W):
+    """K6 through the single-read adjoint (also down-sampling shapes, where most low-res rows own no mask row):
+    prototypes equal the up-sample-then-pool restatement (baseline.py:100-110); soft masks included."""
+    torch.manual_seed(9)
+    f = torch.randn(B * S, c, h, w)
+    m = torch.rand(B * S, 1, H, W)
+    m = torch.where(m > 0.5, torch.ones_like(m), m * (m > 0.3))          # 0 / fractional / 1
+    mask = torch.cat((m, 1 - m), 1)
+    rf, rb = O.map_pool_fullres(f, mask, B, S)
+    of, ob = ops.map_pool_fullres(cu(f), cu(mask), B, S)
+    assert nrel(of.cpu(), rf) < TOL and nrel(ob.cpu(), rb) < TOL
+
+
 def test_bilinear_adjoint_identity(ops):
     """sum_YX m (U f) == sum_yx f (U^T m) and sum(U^T m) == sum(m)."""
     torch.manual_seed(8)
