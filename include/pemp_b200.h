@@ -170,6 +170,18 @@ int pemp_prior_mask(const float* q4, const float* s4, const float* smask,
 int pemp_iou_hist(const uint8_t* pred, const uint8_t* ref, const int64_t* cls, int N, long long npix,
                   int num_classes, int64_t* stat, pemp_stream_t stream);
 
+/* ---- K11 communication module of the Stage-2 backbones ("next" row) ------------------------------------
+ * replaces  ResNetCM.comm / VGG16CM.comm                         networks/backbones.py:208-222, 469-479
+ *   mask_out = max_pool2d(mask_in, 3, stride, 1);  p = x * mask_out;
+ *   feat = linear(cat(mean_hw(p).view(B, spq, c).mean(1), max_hw(p).view(B, spq, c).mean(1)));  out = feat broadcast
+ * x [N, c, h, w] with N = B*spq; mask_in [N, 1, Hm, Wm]; weight [n_out, 2c] and bias [n_out] (nullable) as in
+ * nn.Linear; outputs mask_out [N, 1, h, w] and out [N, n_out, h, w].  h, w must equal the pooled size
+ * floor((Hm + 2 - 3) / stride) + 1.                                                                      */
+size_t pemp_comm_workspace_bytes(int N, int c, int spq, int n_out);
+int pemp_comm_module(const float* x, const float* mask_in, int N, int c, int h, int w, int Hm, int Wm, int stride,
+                     int spq, const float* weight, const float* bias, int n_out, float* mask_out, float* out,
+                     void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ Every fixture stores the inputs (or the seed that regenerates them through
   pemp_full_*       same at the BASELINE shape (c=512, 51x51, 401x401); inputs regenerated from the seed
   baseline_*, panet_*   `Baseline.forward` / `PANet.forward` head + `alignLoss` (`baseline.py:97-118`, `panet.py:96-194`)
   pfenet_*          `Weighted_GAP` (`pfenet.py:15-20`) and the prior block (`pfenet.py:201-231`)
+  comm_*            `ResNetCM.comm` / `VGG16CM.comm` (`backbones.py:208-222, 469-479`)
   metric_*          `FewShotMetric` (`core/metrics.py`) on random masks and on the two episodes the
                     reference ships under `http/static/1005_pascal_1shot_pemp_stage2_s0/` (the only
                     known-answer vectors in the reference; `data.json:"acc"` is their Dice score)
@@ -195,6 +196,22 @@ def metric_cases():
           miou=mi, miou_mean=mm, biou=bi, biou_mean=bm)
 
 
+def comm_cases():
+    """`ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479), the "next" row of SURVEY 8f."""
+    g = torch.Generator().manual_seed(77)
+    for name, variant, (B, spq, c, h, Hm, stride, n) in (("comm_resnet_s2", "resnet", (2, 3, 24, 21, 41, 2, 2)),
+                                                        ("comm_resnet_s1", "resnet", (1, 2, 16, 26, 26, 1, 2)),
+                                                        ("comm_vgg_s2", "vgg", (2, 2, 32, 13, 26, 2, 3))):
+        N = B * spq
+        x = torch.randn(N, c, h, h, generator=g)
+        mask = (torch.rand(N, 1, Hm, Hm, generator=g) > 0.7).float()
+        mask[0] = 0                                                   # an image without any foreground
+        weight, bias = torch.randn(n, 2 * c, generator=g) * 0.1, torch.randn(n, generator=g)
+        feat, pooled = R.comm(variant, x, mask, weight, bias, spq, stride)
+        _save(name, x=_np(x), mask=_np(mask), weight=_np(weight), bias=_np(bias), spq=spq, stride=stride,
+              feat=_np(feat), pooled=_np(pooled))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -203,6 +220,7 @@ def main():
     baseline_panet_cases()
     pfenet_cases()
     metric_cases()
+    comm_cases()
 
 
 if __name__ == "__main__":

@@ -126,3 +126,17 @@ def pfenet_prior(query_feat_4, final_supp_list, mask_list, query_feat_3_hw, quer
     }
     exec(compile(block, "<pfenet.py:prior-block>", "exec"), ns)
     return ns["corr_query_mask"]
+
+
+def comm(variant, x, mask, weight, bias, spq, stride):
+    """Run the reference's own `ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479) on our tensors: the
+    method only needs `self.spq` and the nn.Linear it is handed."""
+    import types
+    bb = module("networks.backbones")
+    cls = {"resnet": bb.ResNetCM, "vgg": bb.VGG16CM}[variant]
+    linear = nn.Linear(weight.shape[1], weight.shape[0], bias=bias is not None)
+    with torch.no_grad():
+        linear.weight.copy_(weight)
+        if bias is not None:
+            linear.bias.copy_(bias)
+        return cls.comm(types.SimpleNamespace(spq=spq), x, mask, linear, stride=stride)

@@ -12,7 +12,8 @@ What is rebound:
   networks.panet.PANet            : forward, compute_similarity, alignLoss
   networks.pfenet                 : Weighted_GAP (module function) + `prior_mask` added to the module
   core.metrics                    : FewShotMetric (and the name imported into core.base_trainer)
-The encoders (`self.encoder`) are untouched: the backbone stays on stock PyTorch.
+  networks.backbones              : ResNetCM.comm, VGG16CM.comm (only with `patch(comm=True)`: the "next" row of SURVEY 8f)
+The encoders (`self.encoder`) are otherwise untouched: the backbone stays on stock PyTorch.
 """
 import importlib
 import sys
@@ -37,9 +38,14 @@ def _maybe(module_name):
         return None
 
 
-def patch(models=("pemp_stage1", "pemp_stage2", "baseline", "panet", "pfenet"), metric=True):
+def patch(models=("pemp_stage1", "pemp_stage2", "baseline", "panet", "pfenet"), metric=True, comm=False):
     if _saved:
         return
+    if comm:
+        bb = _maybe("networks.backbones")
+        for cls_name in ("ResNetCM", "VGG16CM"):
+            if bb is not None and hasattr(bb, cls_name):
+                _set(getattr(bb, cls_name), "comm", heads.comm)
     table = {
         "pemp_stage1": ("PEMPStage1", {"forward": heads.pemp_stage1_forward, "mpm": heads.mpm,
                                        "compute_similarity": heads.compute_similarity}),

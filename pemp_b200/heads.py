@@ -200,3 +200,13 @@ class BaselineHead(nn.Module):
 
     def forward(self, features, sup_mask, B, S, Q, out_shape=None):
         return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=self.align)
+
+
+# ----------------------------------------------------------------------------------------------
+# "next" row: communication module of the Stage-2 backbones
+# ----------------------------------------------------------------------------------------------
+
+def comm(self, x, mask, linear, stride=2):
+    """Drop-in for `ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479): same arguments (`linear` is the
+    nn.Linear the backbone passes), same returns `(feat [N, n, h, w], pooled mask [N, 1, h, w])`."""
+    return ops.comm_module(x, mask, linear.weight, linear.bias, self.spq, stride)

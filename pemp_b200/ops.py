@@ -138,6 +138,34 @@ def weighted_gap(supp_feat, mask):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ K11
+def comm_module(x, mask, weight, bias, spq, stride=2):
+    """`ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479): x [N,c,h,w], mask [N,1,Hm,Wm], nn.Linear
+    weight [n,2c] / bias [n] -> (feat broadcast [N,n,h,w], pooled mask [N,1,h,w])."""
+    x = _need(x, torch.float32, "x")
+    mask = _need(mask, torch.float32, "mask")
+    weight = _need(weight, torch.float32, "weight")
+    bias = None if bias is None else _need(bias, torch.float32, "bias")
+    N, c, h, w = x.shape
+    if mask.dim() != 4 or mask.shape[0] != N or mask.shape[1] != 1:
+        raise ValueError(f"mask must be [N={N}, 1, Hm, Wm], got {tuple(mask.shape)}")
+    Hm, Wm = mask.shape[-2:]
+    n_out = weight.shape[0]
+    if weight.dim() != 2 or weight.shape[1] != 2 * c:
+        raise ValueError(f"weight must be [n, 2c = {2 * c}], got {tuple(weight.shape)}")
+    if N % spq:
+        raise ValueError(f"N = {N} is not a multiple of spq = {spq}")
+    L = _cabi.lib()
+    ws = _ws(L.pemp_comm_workspace_bytes(N, c, spq, n_out), x.device)
+    mask_out = torch.empty(N, 1, h, w, dtype=torch.float32, device=x.device)
+    out = torch.empty(N, n_out, h, w, dtype=torch.float32, device=x.device)
+    _cabi.check(L.pemp_comm_module(x.data_ptr(), mask.data_ptr(), N, c, h, w, Hm, Wm, int(stride), int(spq), weight.data_ptr(),
+                                   _ptr(bias), n_out, mask_out.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "pemp_comm_module")
+    _count(4)
+    return out, mask_out
+
+
 # ------------------------------------------------------------------------------------------------ K2
 def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
     """fts [B*S, c, hw]; ctr [c, 2p]; fg, bg [B*S, hw] -> fg_proto [B,c,p], bg_proto [B,c,p], adaptive_p [B,c,2p]

@@ -444,3 +444,35 @@ def test_argument_errors(ops):
         ops.meta_proto_attn(cu(torch.zeros(1, 6, 10)), cu(torch.zeros(6, 6)), cu(torch.zeros(1, 10)), cu(torch.zeros(1, 10)), 1, 1)  # c % 4
     with pytest.raises(ValueError):
         ops.meta_proto_attn(cu(torch.zeros(1, 8, 10)), cu(torch.zeros(8, 10)), cu(torch.zeros(1, 10)), cu(torch.zeros(1, 10)), 1, 1)  # p = 5
+
+
+# ------------------------------------------------------------------------------------------------ K11
+@pytest.mark.parametrize("name", ["comm_resnet_s2", "comm_resnet_s1", "comm_vgg_s2"])
+def test_comm_module_golden(ops, name):
+    """Communication module of the Stage-2 backbones against the reference's own `comm` outputs."""
+    g = golden(name)
+    x, mask, weight, bias = (cu(torch.from_numpy(g[k])) for k in ("x", "mask", "weight", "bias"))
+    feat, pooled = ops.comm_module(x, mask, weight, bias, int(g["spq"]), int(g["stride"]))
+    assert torch.equal(pooled.cpu(), torch.from_numpy(g["pooled"]))          # max-pool: exact
+    assert feat.shape == g["feat"].shape and nrel(feat.cpu().numpy(), g["feat"]) < TOL
+
+
+@pytest.mark.parametrize("B,spq,c,h,Hm,stride", [(2, 6, 64, 101, 201, 2), (1, 6, 256, 101, 101, 1), (2, 2, 512, 51, 101, 2),
+                                                 (1, 1, 8, 3, 5, 2)])
+def test_comm_module_backbone_shapes(ops, B, spq, c, h, Hm, stride):
+    """The three call sites of ResNetCM.forward at 401 x 401 inputs (backbones.py:230-240) + a tiny ragged case."""
+    torch.manual_seed(13)
+    N = B * spq
+    x = torch.randn(N, c, h, h)
+    mask = (torch.rand(N, 1, Hm, Hm) > 0.8).float()
+    weight, bias = torch.randn(2, 2 * c) * 0.05, torch.randn(2)
+    rf, rm = O.comm_module(x, mask, weight, bias, spq, stride)
+    of, om = ops.comm_module(cu(x), cu(mask), cu(weight), cu(bias), spq, stride)
+    assert torch.equal(om.cpu(), rm)
+    assert nrel(of.cpu(), rf) < TOL
+    # the per-channel maxima are exact: feed a weight that picks one max channel
+    w1 = torch.zeros(1, 2 * c)
+    w1[0, c + 3 % c] = float(spq)
+    rf1, _ = O.comm_module(x, mask, w1, None, spq, stride)
+    of1, _ = ops.comm_module(cu(x), cu(mask), cu(w1), None, spq, stride)
+    assert nrel(of1.cpu(), rf1) < 1e-6

@@ -110,6 +110,15 @@ def test_weighted_gap():
     assert nrel(out.numpy(), g["out"]) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["comm_resnet_s2", "comm_resnet_s1", "comm_vgg_s2"])
+def test_comm_module_bit_exact(name):
+    """`ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479) through the restatement."""
+    g = golden(name)
+    feat, pooled = O.comm_module(*(torch.from_numpy(g[k]) for k in ("x", "mask", "weight", "bias")), int(g["spq"]), int(g["stride"]))
+    assert np.array_equal(pooled.numpy(), g["pooled"])
+    assert np.array_equal(feat.numpy(), g["feat"])
+
+
 def test_metric_known_answers():
     """The two episodes the reference ships (`http/static/.../{000_01,001_03}`): expected rows are the
     numbers in SURVEY 4 / BASELINE.md, and the Dice must round to `data.json:"acc"`."""

@@ -72,6 +72,16 @@ def main():
         ("K6 map_pool_fullres", lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
          B * (S * (c * hw * 4 + 2 * H * H * 4) + 2 * c * 4)),
     ]
+    if not a.only or "K11" in a.only:
+        # ResNetCM.comm call site 2 (backbones.py:235): x2 [B*6, 256, 101, 101], stride 1
+        Nc, cc, hc = 16 * 6, 256, 101
+        xc = torch.randn(Nc, cc, hc, hc, device=dev, generator=g)
+        mc = (torch.rand(Nc, 1, hc, hc, device=dev, generator=g) > 0.7).float()
+        wc, bc = torch.randn(2, 2 * cc, device=dev, generator=g), torch.randn(2, device=dev, generator=g)
+        ms = timeit(lambda: ops.comm_module(xc, mc, wc, bc, 6, 1))
+        nb = Nc * (cc * hc * hc + 2 * hc * hc + 2 * hc * hc) * 4
+        print(json.dumps({"kernel": "K11 comm_module (maxpool + pool + linear + expand)", "ms": round(ms, 4), "alg_GB": round(nb / 1e9, 4),
+                          "GBps": round(nb / ms / 1e6, 1), "frac_of_hbm_peak": round(nb / ms / 1e6 / pk, 3), "peak": how, "N": Nc, "c": cc, "hw": hc * hc}))
     if not a.only or "K9" in a.only:
         Bp, Sp, Cp, spx = 1, 5, 2048, 60
         q4 = torch.relu(torch.randn(Bp, Cp, spx, spx, device=dev, generator=g))
