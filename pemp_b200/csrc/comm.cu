@@ -9,7 +9,7 @@
 // once: algorithmic bytes = N*c*hw*4 + N*(Hm*Wm + hw)*4 + N*n*hw*4.
 //
 // Kernels: (a) 3x3 max-pool of the mask (-inf padding, as ATen); (b) one CTA per (image, channel chunk) stages
-// the pooled mask of its image in shared memory and its warps walk channel rows with coalesced loads, 8 independent
+// the pooled mask of its image in shared memory and its warps walk channel rows with coalesced loads, 16 independent
 // accumulators per lane for the sum and the max of x*mask'; (c) one CTA per episode: means over the spq images,
 // the n x 2c linear layer (fixed summation order) and (d) the broadcast store.
 #include <math_constants.h>
@@ -45,6 +45,13 @@ __global__ void comm_maxpool_kernel(const float* __restrict__ in, float* __restr
 }
 
 constexpr int kCommThreads = 256;
+#ifndef PEMP_COMM_U
+#define PEMP_COMM_U 16
+#endif
+#ifndef PEMP_COMM_CTAS_PER_SM
+#define PEMP_COMM_CTAS_PER_SM 8
+#endif
+constexpr int kCU = PEMP_COMM_U;   // independent loads per lane
 
 // stats[n][0][ch] = sum_x x*m / hw,  stats[n][1][ch] = max_x x*m.   kSmemMask: the image's mask is staged in smem.
 template <bool kSmemMask>
@@ -63,19 +70,19 @@ comm_pool_kernel(const float* __restrict__ x, const float* __restrict__ mask, in
   const float inv_hw = 1.0f / static_cast<float>(hw);
   for (int ch = c0 + warp; ch < c1; ch += kCommThreads / 32) {
     const float* row = x + (static_cast<long long>(n) * c + ch) * hw;
-    float s[8], mx[8];
+    float s[kCU], mx[kCU];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kCU; ++u) {
       s[u] = 0.f;
       mx[u] = -CUDART_INF_F;
     }
     int i = lane;
-    for (; i + 7 * 32 < hw; i += 8 * 32) {
-      float v[8];
+    for (; i + (kCU - 1) * 32 < hw; i += kCU * 32) {
+      float v[kCU];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(row + i + 32 * u);
+      for (int u = 0; u < kCU; ++u) v[u] = __ldg(row + i + 32 * u);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kCU; ++u) {
         const float p = v[u] * (kSmemMask ? mp[i + 32 * u] : __ldg(mp + i + 32 * u));
         s[u] += p;
         mx[u] = fmaxf(mx[u], p);
@@ -86,8 +93,12 @@ comm_pool_kernel(const float* __restrict__ x, const float* __restrict__ mask, in
       s[0] += p;
       mx[0] = fmaxf(mx[0], p);
     }
-    float st = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-    float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+    float st = 0.f, mt = -CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < kCU; ++u) {      // fixed order
+      st += s[u];
+      mt = fmaxf(mt, mx[u]);
+    }
     st = warp_sum(st);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(kFull, mt, o));
@@ -152,7 +163,7 @@ extern "C" int pemp_comm_module(const float* x, const float* mask_in, int N, int
   const long long npix = static_cast<long long>(N) * hw;
   comm_maxpool_kernel<<<static_cast<unsigned>(llmin((npix + 255) / 256, 148LL * 16)), 256, 0, st>>>(mask_in, mask_out, N, Hm, Wm, h, w, stride);
   // channel chunks: enough CTAs for ~4 per SM, at least 8 rows (one per warp) each
-  int chunks = (4 * 148 + N - 1) / N;
+  int chunks = (PEMP_COMM_CTAS_PER_SM * 148 + N - 1) / N;
   if (chunks > c / 8) chunks = c / 8;
   if (chunks < 1) chunks = 1;
   const int rows = (c + chunks - 1) / chunks;
