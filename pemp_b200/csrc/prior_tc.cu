@@ -127,13 +127,29 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // shared memory into K-major bf16 rows scaled by mask / norm (0 where the norm is 0):
 //   x [planes][C][hw] fp32 -> out [planes][nsel][hw][C] bf16;  nsel = 2 also emits lo = bf16(x*scale - hi).
 // Reads and writes are coalesced in both passes.
+// Both operands go through ONE launch (the query planes alone are 113 CTAs at 60 x 60 - less than one per SM):
+// blockIdx.y < planes_q selects the query operand, the rest the support operand.
+struct PrepOperand {
+  const float* x;
+  const float* mask;   // nullable
+  int hw;
+  float* norm;
+  __nv_bfloat16* out;
+};
 __global__ void __launch_bounds__(256)
-prep_kmajor_kernel(const float* __restrict__ x, const float* __restrict__ mask, int C, int hw, int nsel,
-                   float* __restrict__ norm, __nv_bfloat16* __restrict__ out) {
-  __shared__ float tile[32][33];
+prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel) {
+  __shared__ float tile[128][33];
   __shared__ float part[8][32];
   __shared__ float scale_s[32];
-  const int pl = blockIdx.y, i0 = blockIdx.x * 32;
+  const bool is_q = static_cast<int>(blockIdx.y) < planes_q;
+  const PrepOperand& op = is_q ? oq : os;
+  const float* __restrict__ x = op.x;
+  const float* __restrict__ mask = op.mask;
+  const int hw = op.hw;
+  float* __restrict__ norm = op.norm;
+  __nv_bfloat16* __restrict__ out = op.out;
+  const int pl = is_q ? blockIdx.y : blockIdx.y - planes_q, i0 = blockIdx.x * 32;
+  if (i0 >= hw) return;
   const int tx = threadIdx.x, ty = threadIdx.y;                     // 32 x 8
   const float* xp = x + static_cast<long long>(pl) * C * hw;
   const int i = i0 + tx;
@@ -158,23 +174,35 @@ prep_kmajor_kernel(const float* __restrict__ x, const float* __restrict__ mask, 
     scale_s[tx] = n > 0.f ? m / n : 0.f;
   }
   __syncthreads();
-  // ---- pass 2: transpose + scale + convert
-  for (int c0 = 0; c0 < C; c0 += 32) {
+  // ---- pass 2: transpose + scale + convert, 128 channels per step: 16 independent loads per thread, then each
+  // thread packs two channels of one pixel into a 4-byte store (a warp writes 128 contiguous bytes of a K-major row)
+  for (int c0 = 0; c0 < C; c0 += 128) {
+    float v[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int c = c0 + ty + 8 * r;
-      tile[ty + 8 * r][tx] = (c < C && ok) ? __ldg(col + static_cast<long long>(c) * hw) : 0.f;
+    for (int r = 0; r < 16; ++r) {
+      const int c = c0 + ty + 8 * r;
+      v[r] = (c < C && ok) ? __ldg(col + static_cast<long long>(c) * hw) : 0.f;
     }
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int il = ty + 8 * r, ii = i0 + il, c = c0 + tx;
-      if (ii < hw && c < C) {
-        const float v = tile[tx][il] * scale_s[il];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const long long o = ((static_cast<long long>(pl) * nsel) * hw + ii) * C + c;
-        out[o] = hi;
-        if (nsel == 2) out[o + static_cast<long long>(hw) * C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    for (int r = 0; r < 16; ++r) tile[ty + 8 * r][tx] = v[r];
+    __syncthreads();
+    // thread (tx, ty) -> channel pair c0 + 2*(tx + 32*q), pixel ty + 8*p
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int cl = 2 * (tx + 32 * q), c = c0 + cl;
+#pragma unroll
+      for (int pz = 0; pz < 4; ++pz) {
+        const int il = ty + 8 * pz, ii = i0 + il;
+        if (ii < hw && c < C) {                                     // C % 8 == 0: a pair never straddles the end
+          const float sc = scale_s[il];
+          const float a0 = tile[cl][il] * sc, a1 = tile[cl + 1][il] * sc;
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(a0, a1);
+          const long long o = ((static_cast<long long>(pl) * nsel) * hw + ii) * C + c;
+          *reinterpret_cast<__nv_bfloat162*>(out + o) = hi;
+          if (nsel == 2)
+            *reinterpret_cast<__nv_bfloat162*>(out + o + static_cast<long long>(hw) * C) =
+                __floats2bfloat162_rn(a0 - __low2float(hi), a1 - __high2float(hi));
+        }
       }
     }
     __syncthreads();
@@ -400,8 +428,9 @@ int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, f
   float* flag = reinterpret_cast<float*>(base + pl.off_flag);
 
   dim3 tb(32, 8);   // norms + K-major bf16 operands in one pass per tensor
-  prep_kmajor_kernel<<<dim3((hw_q + 31) / 32, B), tb, 0, st>>>(q4, nullptr, C, hw_q, pl.nsel, nq, a);
-  prep_kmajor_kernel<<<dim3((hw_s + 31) / 32, S * B), tb, 0, st>>>(s4, smask, C, hw_s, pl.nsel, ns, bmat);
+  const int hw_max = hw_q > hw_s ? hw_q : hw_s;
+  prep_kmajor_kernel<<<dim3((hw_max + 31) / 32, B + S * B), tb, 0, st>>>(PrepOperand{q4, nullptr, hw_q, nq, a},
+                                                                        PrepOperand{s4, smask, hw_s, ns, bmat}, B, C, pl.nsel);
   eps_flag_kernel<<<1, 1024, 0, st>>>(nq, static_cast<long long>(B) * hw_q, ns, static_cast<long long>(S) * B * hw_s, flag);
 
   CUtensorMap map_a, map_b;
