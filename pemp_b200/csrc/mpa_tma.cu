@@ -118,43 +118,10 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 // CTA that owns flat tile t when CTA b owns [T*b/G, T*(b+1)/G)
 __host__ __device__ inline int owner_of(long long t, long long T, int G) { return static_cast<int>(((t + 1) * G - 1) / T); }
 
-// ---- prologue: difference table in tile-row order --------------------------------------------
+// ---- difference table (built by every CTA in its prologue - 12 KB of `ctr` from L2 - instead of a separate launch) --
 // tile row R = e*128 + g  <->  channel 4g + e;  table[R][d] = 2 log2(e) * (ctr[ch, g'*P + j] - ctr[ch, g'*P]) with
-// d = g'*(P-1) + j-1;  konst[d] = -(|ctr_{g'P+j}|^2 - |ctr_{g'P}|^2) in double.
-__global__ void mpa_tma_prepare_kernel(const float* __restrict__ ctr, float* __restrict__ table, float* __restrict__ konst,
-                                       int* __restrict__ nparts, int imgs, int nt_img, long long T, int G) {
-  // partials an image ends up with = CTAs its tile range touches (64-bit divisions: done once here, not per output)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < imgs; i += gridDim.x * blockDim.x) {
-    const long long first = static_cast<long long>(i) * nt_img;
-    nparts[i] = owner_of(first + nt_img - 1, T, G) - owner_of(first, T, G) + 1;
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC * 4; i += gridDim.x * blockDim.x) {
-    const int R = i >> 2, d = i & 3;
-    const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
-    const int g = d >> 1, j = (d & 1) + 1;
-    // exact difference, then one rounding of the product with 2 log2(e): the dots come out in log2 units
-    const float v = static_cast<float>(2.8853900817779268 * (static_cast<double>(ctr[ch * kK + g * kP + j]) - ctr[ch * kK + g * kP]));
-    if (kTD == 8) {
-      table[R * 8 + 2 * d] = v;
-      table[R * 8 + 2 * d + 1] = v;
-    } else {
-      table[R * 4 + d] = v;
-    }
-  }
-  if (blockIdx.x == 0) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < 4) {
-      const int g = warp >> 1, j = (warp & 1) + 1;
-      double s = 0.0;
-      for (int ch = lane; ch < kC; ch += 32) {
-        const double a = ctr[ch * kK + g * kP + j], b = ctr[ch * kK + g * kP];
-        s += (a - b) * (a + b);
-      }
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-      if (lane == 0) konst[warp] = static_cast<float>(-s * 1.4426950408889634);
-    }
-  }
-}
+// d = g'*(P-1) + j-1 (each value twice when kTD == 8);  konst[d] = -log2(e) * (|ctr_{g'P+j}|^2 - |ctr_{g'P}|^2),
+// accumulated in double in a fixed order (identical in every CTA).
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -169,8 +136,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 __global__ void __launch_bounds__(kThreadsT, 1)
-mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_img, long long T,
-               const float* __restrict__ table_g, const float* __restrict__ konst_g, const float* __restrict__ fg,
+mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_img, long long T, int imgs,
+               const float* __restrict__ ctr, int* __restrict__ nparts, const float* __restrict__ fg,
                const float* __restrict__ bg, long long mask_stride, int maxp, float* __restrict__ part_num,
                float* __restrict__ part_den) {
   // the dynamic shared window starts 1024-byte aligned (declared alignment; checked once below), so every address in
@@ -182,9 +149,35 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   const int G = gridDim.x, cta = blockIdx.x;
   const long long t0 = T * cta / G, t1 = T * (cta + 1) / G;
 
-  for (int i = tid; i < kC * kTD / 4; i += kThreadsT)
-    reinterpret_cast<float4*>(sm.table)[i] = __ldg(reinterpret_cast<const float4*>(table_g) + i);
-  if (tid < 4) sm.konst[tid] = __ldg(konst_g + tid);
+  for (int i = tid; i < kC * 4; i += kThreadsT) {
+    const int R = i >> 2, d = i & 3;
+    const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
+    const int g = d >> 1, j = (d & 1) + 1;
+    // exact difference, then one rounding of the product with 2 log2(e): the dots come out in log2 units
+    const float v = static_cast<float>(2.8853900817779268 *
+                                       (static_cast<double>(__ldg(ctr + ch * kK + g * kP + j)) - __ldg(ctr + ch * kK + g * kP)));
+    if (kTD == 8) {
+      sm.table[R * 8 + 2 * d] = v;
+      sm.table[R * 8 + 2 * d + 1] = v;
+    } else {
+      sm.table[R * 4 + d] = v;
+    }
+  }
+  if (warp < 4) {
+    const int g = warp >> 1, j = (warp & 1) + 1;
+    double s = 0.0;
+    for (int ch = lane; ch < kC; ch += 32) {
+      const double a = __ldg(ctr + ch * kK + g * kP + j), b = __ldg(ctr + ch * kK + g * kP);
+      s += (a - b) * (a + b);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (lane == 0) sm.konst[warp] = static_cast<float>(-s * 1.4426950408889634);
+  }
+  // partials an image ends up with = CTAs its tile range touches (64-bit divisions: once per image, for the finalize)
+  for (int i = cta * kThreadsT + tid; i < imgs; i += G * kThreadsT) {
+    const long long first = static_cast<long long>(i) * nt_img;
+    nparts[i] = owner_of(first + nt_img - 1, T, G) - owner_of(first, T, G) + 1;
+  }
   if (tid == 0) {
     for (int s = 0; s < kNB; ++s) {
       mbar_init(&sm.full[s], 1);
@@ -597,16 +590,13 @@ int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return PEMP_E_ALIGN;
 
-  float* table = reinterpret_cast<float*>(ws + pl.off_table);
-  float* konst = reinterpret_cast<float*>(ws + pl.off_konst);
   float* num = reinterpret_cast<float*>(ws + pl.off_num);
   float* den = reinterpret_cast<float*>(ws + pl.off_den);
   int* nparts = reinterpret_cast<int*>(ws + pl.off_nparts);
-  mpa_tma_prepare_kernel<<<8, 256, 0, st>>>(ctr, table, konst, nparts, B * S, pl.nt_img, pl.T, pl.G);
   const size_t smem = sizeof(TmaSmem);
   cudaError_t e = cudaFuncSetAttribute(mpa_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  mpa_tma_kernel<<<pl.G, kThreadsT, smem, st>>>(map, S, hw, pl.nt_img, pl.T, table, konst, fg, bg, mask_stride, pl.maxp,
+  mpa_tma_kernel<<<pl.G, kThreadsT, smem, st>>>(map, S, hw, pl.nt_img, pl.T, B * S, ctr, nparts, fg, bg, mask_stride, pl.maxp,
                                                num, den);
   const long long total = static_cast<long long>(B) * kC * kK;
   mpa_tma_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(

@@ -189,7 +189,8 @@ def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
     _cabi.check(L.pemp_meta_proto_attn(fts.data_ptr(), ep, ctr.data_ptr(), fgp, bgp, stride, B, S, c, hw, p, float(eps),
                                        out_f.data_ptr(), out_b.data_ptr(), _ptr(adaptive), ws.data_ptr(), ws.numel(),
                                        _stream()), "pemp_meta_proto_attn")
-    _count(3 if p > 1 else 2)
+    # launches: TMA path (c = 512, p = 3, hw >= 32) = main + finalize; generic = prepare (p > 1) + main + finalize
+    _count(2 if (c == 512 and p == 3 and hw >= 32) or p == 1 else 3)
     del keep
     return out_f, out_b, adaptive
 

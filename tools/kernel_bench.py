@@ -71,6 +71,11 @@ def main():
         ("K10 iou_hist", lambda: ops.iou_hist(m8, ref, cls, stat), B * 2 * H * H),
         ("K6 map_pool_fullres", lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
          B * (S * (c * hw * 4 + 2 * H * H * 4) + 2 * c * 4)),
+        # PANet alignLoss (panet.py:158-194): query pooling + S cosine passes over the support maps + fused up-sample / CE
+        ("K7 panet_align", lambda: ops.panet_align(qry.view(B, c, h, h), pred, sup.view(B * S, c, h, h), fgfull, 1),
+         B * ((1 + S) * c * hw * 4 + 2 * hw * 4 + S * H * H * 4)),
+        ("K8 weighted_gap", lambda: ops.weighted_gap(sup.view(B * S, c, h, h), low[:, 0].reshape(B * S, 1, h, h)),
+         B * S * (c * hw + hw) * 4),
     ]
     if not a.only or "K11" in a.only:
         # ResNetCM.comm call site 2 (backbones.py:235): x2 [B*6, 256, 101, 101], stride 1
