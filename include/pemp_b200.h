@@ -105,6 +105,8 @@ int pemp_cosine_match(const float* qry, long long qry_episode_stride, const floa
 /* Diagnostic (tests only), as pemp_debug_mpa_path: K3 has a TMA-fed persistent kernel for c = 512, P in {1, 3},
  * hw >= 32; mode 1 forces the generic kernel, mode 0 restores the automatic choice.  Returns the previous mode. */
 int pemp_debug_cosine_path(int mode);
+/* The same switch for K1 / K6 / K7 / K8 (masked average pooling): TMA-fed kernel for c in {256, 512}, hw >= 32. */
+int pemp_debug_pool_path(int mode);
 
 /* ---- K4  bilinear up-sampling (align_corners=True) + 2-way argmax -----------------------------------
  * replaces  F.interpolate(pred, out_shape, 'bilinear', align_corners=True) and logits.argmax(1)

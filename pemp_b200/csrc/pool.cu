@@ -13,6 +13,16 @@
 // `pool_finalize_kernel` adds the chunks in index order (deterministic), divides and averages the shots.
 #include "common.cuh"
 
+// TMA-fed persistent fast path for c in {256, 512} (pool_tma.cu); PEMP_E_ALIGN = not covered, nothing launched
+int pemp_pool_tma_launch(const float* fts, long long ep_stride, const float* fg, const float* bg, long long mask_stride, int B,
+                         int S, int c, int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, char* ws,
+                         size_t ws_bytes, cudaStream_t st);
+size_t pemp_pool_tma_workspace_bytes(int B, int S, int c, int hw);
+#ifndef PEMP_POOL_TMA
+#define PEMP_POOL_TMA 1
+#endif
+static int g_pool_path = 0;   // diagnostic switch, see pemp_debug_pool_path
+
 namespace {
 
 constexpr int kR = 16;        // max pixels per lane per chunk
@@ -130,7 +140,15 @@ __global__ void pool_finalize_kernel(const float* __restrict__ part, const float
 extern "C" size_t pemp_map_pool_workspace_bytes(int B, int S, int c, int hw) {
   if (B <= 0 || S <= 0 || c <= 0 || hw <= 0) return 0;
   size_t imgs = static_cast<size_t>(B) * S, n = chunk_count(hw);
-  return align_up(imgs * n * c * 2 * sizeof(float), 256) + align_up(imgs * n * 2 * sizeof(float), 256);
+  size_t generic = align_up(imgs * n * c * 2 * sizeof(float), 256) + align_up(imgs * n * 2 * sizeof(float), 256);
+  size_t tma = PEMP_POOL_TMA ? pemp_pool_tma_workspace_bytes(B, S, c, hw) : 0;
+  return generic > tma ? generic : tma;
+}
+
+extern "C" int pemp_debug_pool_path(int mode) {
+  const int old = g_pool_path;
+  if (mode == 0 || mode == 1) g_pool_path = mode;
+  return old;
 }
 
 // shared with fullres.cu / align.cu
@@ -141,6 +159,11 @@ int pemp_pool_launch(const float* fts, long long ep_stride, const float* fg, con
   PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_map_pool_workspace_bytes(B, S, c, hw), PEMP_E_WORKSPACE);
   if (ep_stride == 0) ep_stride = static_cast<long long>(S) * c * hw;
+  if (PEMP_POOL_TMA && g_pool_path != 1) {
+    const int rc = pemp_pool_tma_launch(fts, ep_stride, fg, bg, mask_stride, B, S, c, hw, eps, den_override, fg_proto, bg_proto,
+                                        static_cast<char*>(workspace), workspace_bytes, st);
+    if (rc != PEMP_E_ALIGN) return rc;
+  }
   const int n = chunk_count(hw);
   const size_t imgs = static_cast<size_t>(B) * S;
   float* part = static_cast<float*>(workspace);

@@ -126,7 +126,10 @@ def test_cosine_zero_vectors(ops):
 
 
 # ------------------------------------------------------------------------------------------------ K1 / K8
-@pytest.mark.parametrize("B,S,c,hw", [(2, 1, 32, 169), (1, 5, 48, 130), (2, 2, 512, 2601), (1, 1, 7, 33), (1, 3, 64, 5000)])
+@pytest.mark.parametrize("B,S,c,hw", [(2, 1, 32, 169), (1, 5, 48, 130), (2, 2, 512, 2601), (1, 1, 7, 33), (1, 3, 64, 5000),
+                                      # the TMA-fed persistent kernel (c in {256, 512}): images split over CTAs, ragged last tile,
+                                      # one tile, fewer tiles than CTAs, hw a multiple of 4 (all column offsets zero)
+                                      (3, 2, 512, 2601), (2, 5, 512, 100), (1, 1, 512, 32), (5, 1, 256, 45), (2, 3, 256, 3600)])
 def test_map_pool_lowres(ops, B, S, c, hw):
     torch.manual_seed(4)
     f = torch.randn(B * S, c, hw)
@@ -136,6 +139,29 @@ def test_map_pool_lowres(ops, B, S, c, hw):
     rf, rb = O.map_pool_lowres(f, fg, bg, B, S)
     of, ob = ops.map_pool_lowres(cu(f), cu(fg), cu(bg), B, S)
     assert nrel(of.cpu(), rf) < TOL and nrel(ob.cpu(), rb) < TOL
+
+
+def test_map_pool_tma_vs_generic_kernel_full_size(ops):
+    """B = 8 five-shot episodes at the PEMP shape, read in place from [B, S+Q, c, h, w], soft masks: the TMA-fed kernel
+    and the generic kernel agree to fp32 rounding; Weighted_GAP (one mask, c = 256) likewise."""
+    from pemp_b200 import _cabi
+    torch.manual_seed(14)
+    B, S, Q, c, h = 8, 5, 1, 512, 51
+    feats = cu(torch.randn(B, S + Q, c, h, h))
+    fg = cu(torch.rand(B * S, h * h) * (torch.rand(B * S, h * h) > 0.5))
+    bg = 1 - fg
+    gap_f, gap_m = cu(torch.randn(6, 256, 60, 60)), cu((torch.rand(6, 1, 60, 60) > 0.5).float())
+    a = ops.map_pool_lowres(feats[:, :S], fg, bg, B, S)
+    ga = ops.weighted_gap(gap_f, gap_m)
+    _cabi.lib().pemp_debug_pool_path(1)
+    try:
+        b = ops.map_pool_lowres(feats[:, :S], fg, bg, B, S)
+        gb = ops.weighted_gap(gap_f, gap_m)
+    finally:
+        _cabi.lib().pemp_debug_pool_path(0)
+    for x, y in zip(a, b):
+        assert nrel(x.cpu(), y.cpu()) < 2e-6
+    assert nrel(ga.cpu(), gb.cpu()) < 2e-6
 
 
 def test_map_pool_empty_mask_and_strided_masks(ops):
