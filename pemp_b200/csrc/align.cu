@@ -68,6 +68,57 @@ upsample_ce_kernel(const float* __restrict__ rev, const float* __restrict__ labe
   }
 }
 
+// Banded version (same idea as upsample_argmax_band_kernel in resample.cu): the bilinear sample is
+// fma(ly.l0, Hrow(i0, X), ly.l1 * Hrow(i1, X)) with Hrow(y, X) = fma(lx.l0, p[y][x0], lx.l1 * p[y][x1]); a CTA owns a band
+// of kCeBand output rows of one image, computes Hrow once for the few source rows the band touches (both channels) and
+// then needs 4 shared loads, 2 lerps, one exp and one log per pixel:  lse - v_label = max + log(1 + exp(-|v0 - v1|)) -
+// v_label.  The label rows of a band are one contiguous, coalesced range.  partial[image * bands + band].
+constexpr int kCeBand = 16, kCeMaxSrc = 8;
+__global__ void __launch_bounds__(kCeThreads)
+upsample_ce_band_kernel(const float* __restrict__ rev, const float* __restrict__ label, long long label_stride, int h, int w,
+                        int H, int W, float sy, float sx, int bands, float* __restrict__ partial) {
+  extern __shared__ float hrow[];                    // [nsrc][2][W]
+  const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
+  const int Y0 = band * kCeBand, Y1 = min(H, Y0 + kCeBand);
+  const int src0 = lerp_coeff(Y0, sy, h).i0, nsrc = lerp_coeff(Y1 - 1, sy, h).i1 - src0 + 1;
+  const int hw = h * w;
+  const float* p0 = rev + static_cast<long long>(n) * 2 * hw + src0 * w;
+  for (int X = threadIdx.x; X < W; X += blockDim.x) {
+    const Lerp lx = lerp_coeff(X, sx, w);
+    for (int r = 0; r < nsrc; ++r)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float* row = p0 + ch * hw + r * w;
+        hrow[(r * 2 + ch) * W + X] = lerp2(lx.l0, __ldg(row + lx.i0), lx.l1, __ldg(row + lx.i1));
+      }
+  }
+  __syncthreads();
+  const float* lab = label + n * label_stride;
+  float acc = 0.f;
+  for (int Y = Y0; Y < Y1; ++Y) {
+    const Lerp ly = lerp_coeff(Y, sy, h);
+    const float* rt = hrow + (ly.i0 - src0) * 2 * W;
+    const float* rb = hrow + (ly.i1 - src0) * 2 * W;
+    const float* lrow = lab + static_cast<long long>(Y) * W;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) {
+      const float v0 = lerp2(ly.l0, rt[X], ly.l1, rb[X]);
+      const float v1 = lerp2(ly.l0, rt[W + X], ly.l1, rb[W + X]);
+      const int lb = static_cast<int>(__ldg(lrow + X));                       // .long() truncation
+      const float m = fmaxf(v0, v1);
+      acc += (m + logf(1.0f + expf(-fabsf(v0 - v1)))) - (lb == 1 ? v1 : v0);
+    }
+  }
+  __shared__ float part[kCeThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s2 = threadIdx.x < kCeThreads / 32 ? part[threadIdx.x] : 0.f;
+    s2 = warp_sum(s2);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s2;
+  }
+}
+
 // single CTA: add the block partials in index order in double, divide by the element count
 __global__ void ce_finalize_kernel(const float* __restrict__ partial, int n, double count, float* __restrict__ loss) {
   __shared__ double part[32];
@@ -92,6 +143,8 @@ Plan make_plan(int B, int S, int Q, int c, int h, int w, int H, int W) {
   const size_t hw = static_cast<size_t>(h) * w;
   long long total = static_cast<long long>(B) * S * H * W;
   p.ce_blocks = static_cast<int>(llmin((total + kCeThreads - 1) / kCeThreads, 148LL * 16));
+  const long long band_blocks = static_cast<long long>(B) * S * ((H + kCeBand - 1) / kCeBand);
+  if (band_blocks > p.ce_blocks) p.ce_blocks = static_cast<int>(band_blocks);   // the banded kernel writes one partial per band
   p.off_qmask = 0;
   p.off_proto = align_up(static_cast<size_t>(B) * Q * 2 * hw * sizeof(float), 256);
   p.off_rev = p.off_proto + align_up(static_cast<size_t>(B) * c * 2 * sizeof(float), 256);
@@ -135,8 +188,18 @@ extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stri
   rc = pemp_cosine_match(sup_fts, sup_episode_stride, fgp, bgp, B * S, B, c, hw, 1, scalar, nullptr, rev, nullptr, stream);
   if (rc != PEMP_OK) return rc;
   long long total = static_cast<long long>(B) * S * H * W;
-  upsample_ce_kernel<<<pl.ce_blocks, kCeThreads, 0, st>>>(rev, sup_mask_fg, mask_stride, total, h, w, H, W,
-                                                          lerp_scale(h, H), lerp_scale(w, W), partial);
-  ce_finalize_kernel<<<1, 256, 0, st>>>(partial, pl.ce_blocks, static_cast<double>(total), loss);
+  const float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
+  const int nsrc_max = static_cast<int>((kCeBand - 1) * sy) + 3;
+  const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
+  int nparts;
+  if (nsrc_max <= kCeMaxSrc && smem <= 48 * 1024) {
+    const int bands = (H + kCeBand - 1) / kCeBand;
+    nparts = B * S * bands;
+    upsample_ce_band_kernel<<<nparts, kCeThreads, smem, st>>>(rev, sup_mask_fg, mask_stride, h, w, H, W, sy, sx, bands, partial);
+  } else {
+    nparts = static_cast<int>(llmin((total + kCeThreads - 1) / kCeThreads, 148LL * 16));
+    upsample_ce_kernel<<<nparts, kCeThreads, 0, st>>>(rev, sup_mask_fg, mask_stride, total, h, w, H, W, sy, sx, partial);
+  }
+  ce_finalize_kernel<<<1, 256, 0, st>>>(partial, nparts, static_cast<double>(total), loss);
   return launch_status();
 }
