@@ -351,6 +351,10 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, the image default)
+    # goes to stdout too, so keep NCCL at WARN unless the caller asked for more
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference(args)
     else:
