@@ -1,6 +1,6 @@
 """Build variant libraries of libpemp_b200.so with extra -D flags on one source file (kernel experiments).
-    python tools/build_variants.py mpa_tma.cu name1:-DX=1,-DY name2:-DZ ...   -> build/variants/libpemp_<name>.so
-They are copied to gpurun_variants/ so that they travel to the GPU box; run with PEMP_B200_LIB=<path>."""
+    python tools/build_variants.py mpa_tma.cu name1:-DX=1,-DY name2:-DZ ...   -> variants/libpemp_<name>.so
+variants/ is git-ignored but travels to the GPU box; run with PEMP_B200_LIB=<path>."""
 import os
 import sys
 from concurrent.futures import ThreadPoolExecutor
