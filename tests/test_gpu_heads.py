@@ -191,3 +191,48 @@ def test_episode_view_equals_dense_copy():
     m1 = ops.map_pool_lowres(feats[:, :S], fg, 1 - fg, B, S)
     m2 = ops.map_pool_lowres(feats[:, :S].reshape(B * S, c, h * w), fg, 1 - fg, B, S)
     assert torch.equal(m1[0], m2[0]) and torch.equal(m1[1], m2[1])
+
+
+def test_bench_size_properties_of_the_stage2_pipeline():
+    """BASELINE size (64 five-shot episodes per step, c = 512, 51 x 51, 401 x 401) through properties that do not need the
+    oracle: (1) the batch holds every episode twice (b and b + 32), in different CTAs / tile ranges of the persistent
+    kernels - prototypes, masks and counts of the two copies must agree; (2) the count table of the full batch equals
+    the sum of the tables of its two halves run separately (different launch shapes), bit for bit; (3) rows 1.. of the
+    table only contain the classes present."""
+    from pemp_b200 import ops
+    from pemp_b200.evaluator import PEMPStage2Pipeline
+    spec = E.EpisodeSpec()
+    B, S, Q, c, h, w = 64, spec.shot, spec.query, spec.channels, spec.h, spec.w
+    half = E.device_batch(spec, B // 2, "cuda", seed=4321)
+    rep = lambda t: torch.cat((t, t), dim=0).contiguous()
+    f1 = rep(half["feats1"].view(B // 2, S + Q, c, h, w))
+    f2 = rep(half["feats2"].view(B // 2, S + Q, c, h, w))
+    sup_mask, qry_msk, cls = rep(half["sup_mask"]), rep(half["qry_msk"]), rep(half["cls"])
+    ctr1, ctr2 = E.make_ctr(spec, 1).cuda(), E.make_ctr(spec, 2).cuda()
+    pipe = PEMPStage2Pipeline(ctr1, ctr2, spec.classes)
+
+    def run(sl):
+        stat = torch.zeros(spec.classes + 1, 3, dtype=torch.int64, device="cuda")
+        prior, mask = pipe.step(f1[sl, :S], f1[sl, S:], f2[sl, :S], f2[sl, S:], sup_mask[sl], qry_msk[sl], cls[sl], stat)
+        return prior, mask, stat
+
+    prior, mask, stat = run(slice(0, B))
+    # (1) the two copies of every episode
+    low = ops.mask_nearest(sup_mask.view(B * S, 2, spec.H, spec.W), h, w).view(B * S, 2, h * w)
+    fgp, bgp, _ = ops.meta_proto_attn(f2[:, :S], ctr2, low[:, 0], low[:, 1], B, S)
+    assert nrel(fgp[:32].cpu(), fgp[32:].cpu()) < 2e-6 and nrel(bgp[:32].cpu(), bgp[32:].cpu()) < 2e-6
+    flips = int((mask[:32] != mask[32:]).sum()) + int((prior[:32] != prior[32:]).sum())
+    assert flips <= 8, flips                        # pixels decided by less than the fp32 summation-order noise
+    # (2) additivity across launch shapes
+    _, m_a, s_a = run(slice(0, 32))
+    _, m_b, s_b = run(slice(32, 64))
+    assert int((torch.cat((m_a, m_b)) != mask).sum()) <= 8
+    if torch.equal(torch.cat((m_a, m_b)), mask):
+        assert torch.equal(s_a + s_b, stat)
+    # the table is exactly what the masks say (recount on the host with the reference's NumPy formulas)
+    ref = O.few_shot_stat(mask.cpu().numpy(), qry_msk.cpu().numpy(), cls.cpu().numpy(), spec.classes)
+    assert np.array_equal(stat.cpu().numpy(), ref)
+    # (3) only the classes present have counts
+    present = set(int(v) for v in cls.tolist())
+    rows = stat.cpu().numpy()
+    assert all((rows[k] == 0).all() for k in range(1, spec.classes + 1) if k not in present)
