@@ -66,7 +66,8 @@ constexpr int kTD = PEMP_MPA_TMA_DUP ? 8 : 4;    // floats per table row
 constexpr int kNB = PEMP_MPA_TMA_SLOTS;
 constexpr int kCons = 16;                        // consumer warps
 constexpr int kThreadsT = (kCons + 4) * 32;      // + one producer warpgroup (setmaxnreg works on whole warpgroups)
-constexpr int kRegsCons = 112, kRegsProd = 24;   // the CTA pool is the launch allocation (640 x 96): 512 x 112 + 128 x 24 fits
+constexpr int kRegsCons = 112, kRegsProd = 32;   // the CTA pool is the launch allocation (640 x 96) = 512 x 112 + 128 x 32
+constexpr int kWPairs = 20;                      // column pairs per weight array: pixels -4 .. 35 of a tile (zero padded)
 constexpr int kMaxGrid = 148;
 constexpr int kPartLd = 40;                      // pixel pitch of a dot row in `part`: banks 8d + p are all distinct
 
@@ -74,10 +75,15 @@ struct TmaSmem {
   alignas(1024) float ring[kNB][kBoxFloats];
   alignas(16) float table[kC * kTD];             // tile-row order: coefficients of channel 4g + e at row e*128 + g
   alignas(16) float part[2][kCons][4 * kPartLd];  // [tile parity][warp][dot][pixel]
-  alignas(16) float wts[kCons][4 * 2 * 8];       // [warp][pixel pair][group][{w0e,w0o,w1e,w1o,w2e,w2o,-,-}]
+  // weights of a tile, written by the two softmax warps: [tile parity][pairing][group][pixel pair]
+  // [{w0a,w0b,w1a,w1b,w2a,w2b,-,-}]; pairing 0 pairs pixels (2q-4, 2q-3), pairing 1 pixels (2q-3, 2q-2), so a consumer
+  // finds its column pair (columns 2i, 2i+1 = pixels 2i-o, 2i+1-o) as one aligned 32-byte record whatever o is
+  alignas(16) float wpx[2][2][2][kWPairs * 8];
+  unsigned wlive[2][2];                          // bit (pixel + 4) set <=> the pixel has a non-zero weight in the group
   alignas(8) uint64_t full[kNB];
   alignas(8) uint64_t empty[kNB];
   alignas(8) uint64_t part_bar[2];               // all 16 warps have written part[b]
+  alignas(8) uint64_t wts_bar[2];                // both softmax warps have written wpx[b] / wlive[b]
   float konst[4];
 };
 
@@ -178,6 +184,7 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
     const long long first = static_cast<long long>(i) * nt_img;
     nparts[i] = owner_of(first + nt_img - 1, T, G) - owner_of(first, T, G) + 1;
   }
+  for (int i = tid; i < 2 * 2 * 2 * kWPairs * 8; i += kThreadsT) (&sm.wpx[0][0][0][0])[i] = 0.f;   // padding stays 0
   if (tid == 0) {
     for (int s = 0; s < kNB; ++s) {
       mbar_init(&sm.full[s], 1);
@@ -185,6 +192,8 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
     }
     mbar_init(&sm.part_bar[0], kCons);
     mbar_init(&sm.part_bar[1], kCons);
+    mbar_init(&sm.wts_bar[0], 2);
+    mbar_init(&sm.wts_bar[1], 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -220,6 +229,68 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
           }
         }
       }
+    } else if (warp == kCons + 1 || warp == kCons + 2) {
+      // ============================ softmax warps: one per class group ============================
+      // lane <-> pixel of the tile.  The warp waits for the 16 partial dot sets of a tile, adds them in a fixed order,
+      // turns them into the 3 weights of its group (x mask) and publishes them in both pair alignments, together with
+      // the live-pixel bit mask; it also owns the denominators of its group.  The consumers never compute a weight.
+      const int g = warp - kCons - 1;
+      const float k0 = sm.konst[g * 2], k1 = sm.konst[g * 2 + 1];
+      const float* mrow = g ? bg : fg;
+      const int pl = lane < kStep ? lane : kStep - 1;             // clamped pixel for addressing
+      const int P = lane + 4;
+      float den[kP] = {0.f, 0.f, 0.f};
+      int img = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(img) * nt_img);
+      const int ntl = static_cast<int>(t1 - t0);
+      for (int k = 0; k < ntl; ++k) {
+        const int buf = k & 1, x_nom = tl * kStep;
+        const bool valid = lane < kStep && x_nom + lane < hw;
+        const float m = valid ? __ldg(mrow + (img * mask_stride + x_nom + lane)) : 0.f;
+        mbar_wait(&sm.part_bar[buf], (k >> 1) & 1);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const float* pr = &sm.part[buf][0][2 * g * kPartLd + pl];
+#pragma unroll
+        for (int w2 = 0; w2 < kCons; w2 += 2) {
+          s0 += pr[w2 * 4 * kPartLd];
+          s1 += pr[(w2 + 1) * 4 * kPartLd];
+          s2 += pr[w2 * 4 * kPartLd + kPartLd];
+          s3 += pr[(w2 + 1) * 4 * kPartLd + kPartLd];
+        }
+        // dots are in log2 units (the table carries log2 e); m = 0 kills pixels outside the tile / image
+        const float e1 = (s0 + s1) + k0, e2 = (s2 + s3) + k1;
+        const float mx = fmaxf(0.f, fmaxf(e1, e2));
+        // ex2.approx: 2 ulp, arguments <= 0; the sum is in [1, 3], rcp.approx is 1 ulp
+        const float x0e = ex2_approx(0.f - mx), x1e = ex2_approx(e1 - mx), x2e = ex2_approx(e2 - mx);
+        const float r = m * rcp_approx(x0e + x1e + x2e);
+        const float w[kP] = {x0e * r, x1e * r, x2e * r};
+        if (lane < kStep) {
+          float* wa = &sm.wpx[buf][0][g][(P >> 1) * 8 + (P & 1)];
+          float* wb = &sm.wpx[buf][1][g][((P - 1) >> 1) * 8 + ((P - 1) & 1)];
+#pragma unroll
+          for (int j = 0; j < kP; ++j) {
+            den[j] += w[j];
+            wa[2 * j] = w[j];
+            wb[2 * j] = w[j];
+          }
+        }
+        const unsigned lv = __ballot_sync(kFull, lane < kStep && ((w[0] != 0.f) | (w[1] != 0.f) | (w[2] != 0.f)));
+        if (lane == 0) sm.wlive[buf][g] = lv << 4;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.wts_bar[buf]);
+        if (tl == nt_img - 1 || k + 1 == ntl) {                    // image boundary: this CTA's denominators of the image
+          const int slot_idx = cta - owner_of(static_cast<long long>(img) * nt_img, T, G);
+#pragma unroll
+          for (int j = 0; j < kP; ++j) {
+            const float d = warp_sum(den[j]);
+            if (lane == 0) part_den[(static_cast<long long>(img) * maxp + slot_idx) * 8 + g * kP + j] = d;
+            den[j] = 0.f;
+          }
+        }
+        if (++tl == nt_img) {
+          tl = 0;
+          ++img;
+        }
+      }
     }
     return;
   }
@@ -229,11 +300,6 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   const int e = warp >> 2, cp = warp & 3;
   // phase-A lane roles
   const int rg = lane >> 3, jc = lane & 7;
-  // softmax lane roles: box column 8cp + px8, dot d; even d owns class group d >> 1
-  const int px8 = lane >> 2, d_own = lane & 3, g_own = d_own >> 1;
-  const bool owner = (d_own & 1) == 0;
-  const float k0 = sm.konst[g_own * 2], k1 = sm.konst[g_own * 2 + 1];
-  float* const wts = sm.wts[warp];
   // Per-lane offsets that never change.  They pass through an empty `asm volatile` so the compiler keeps them in
   // registers instead of re-deriving them from %tid in every phase of every tile (measured: ~60 integer
   // instructions per warp and tile).
@@ -241,9 +307,7 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   int off_t = (e * kBoxRows + cp * 32 + rg) * kTD;                // table row of (i = 0)
   int off_b = lane * kTW + (((2 * cp) ^ (lane & 7)) << 2);        // phase B, chunk 2cp; chunk 2cp+1: ^ 4; row step 32*i
   int col_a = 4 * jc + rg;                                        // box column this lane holds after the butterfly
-  int col_s = cp * 8 + px8;                                       // box column of the softmax / phase-B role
-  const float* mask_ptr = (g_own ? bg : fg) + col_s;              // + img*mask_stride + x_nom - o
-  asm volatile("" : "+r"(off_a), "+r"(off_t), "+r"(off_b), "+r"(col_a), "+r"(col_s), "+l"(mask_ptr));
+  asm volatile("" : "+r"(off_a), "+r"(off_t), "+r"(off_b), "+r"(col_a));
 
   float2 acc[4][2][kP];                               // [row slot][group][prototype] = {even, odd column} sums
 #pragma unroll
@@ -252,7 +316,6 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
     for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int j = 0; j < kP; ++j) acc[i][g][j] = make_float2(0.f, 0.f);
-  float den[kP] = {0.f, 0.f, 0.f};
 
   // ---- phase A of one tile: dots of the 32 box columns over this warp's 32 rows -> part[buf][warp] ----
   auto phase_a = [&](const float* box, int o, int buf) {
@@ -303,57 +366,16 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
     if (lane == 0) mbar_arrive(&sm.part_bar[buf]);
   };
 
-  // ---- weights of this warp's 8 box columns: add the 16 partials, softmax per class group, x mask ----
-  unsigned live = 0;
-  // mask value of this lane's (column, class group) for a tile; 0 for columns that are not pixels of the tile
-  auto mask_of = [&](int img, int x_nom, int o) {
-    const int p_own = col_s - o;
-    const bool p_ok = p_own >= 0 && p_own < kStep && x_nom + p_own < hw;
-    return (owner && p_ok) ? __ldg(mask_ptr + (img * mask_stride + (x_nom - o))) : 0.f;
-  };
-  auto softmax = [&](float m, int o, int buf, uint32_t parity) {
-    const int p_own = col_s - o;
-#ifndef PEMP_TMA_DEBUG_NO_EXCHANGE                   // timing experiments only (results are wrong)
-    mbar_wait(&sm.part_bar[buf], parity);
-#endif
-    float s0 = 0.f, s1 = 0.f;
-    const int idx = d_own * kPartLd + (p_own >= 0 && p_own < kStep ? p_own : 0);
-#pragma unroll
-    for (int w2 = 0; w2 < kCons; w2 += 2) {
-      s0 += sm.part[buf][w2][idx];
-      s1 += sm.part[buf][w2 + 1][idx];
-    }
-    const float tot = s0 + s1;
-    const float tot_next = __shfl_down_sync(kFull, tot, 1);
-    float w[kP] = {0.f, 0.f, 0.f};
-    if (owner) {                                      // dots are in log2 units (the table carries log2 e); m = 0 kills
-                                                      // columns outside the tile
-      const float e1 = tot + k0, e2 = tot_next + k1;
-      const float mx = fmaxf(0.f, fmaxf(e1, e2));
-      // ex2.approx: 2 ulp, arguments <= 0; the sum is in [1, 3], rcp.approx is 1 ulp
-      const float x0e = ex2_approx(0.f - mx), x1e = ex2_approx(e1 - mx), x2e = ex2_approx(e2 - mx);
-      const float r = m * rcp_approx(x0e + x1e + x2e);
-      w[0] = x0e * r;
-      w[1] = x1e * r;
-      w[2] = x2e * r;
-#pragma unroll
-      for (int j = 0; j < kP; ++j) den[j] += w[j];
-      float* wp = wts + ((px8 >> 1) * 2 + g_own) * 8 + (px8 & 1);
-      wp[0] = w[0];
-      wp[2] = w[1];
-      wp[4] = w[2];
-    }
-    live = __ballot_sync(kFull, (w[0] != 0.f) | (w[1] != 0.f) | (w[2] != 0.f));
-    __syncwarp();
-  };
-
   // ---- phase B: rows {l, l+32, l+64, l+96} of the box x this warp's 8 columns ----
   // A class group is skipped when none of the 8 columns has a non-zero weight in it (one warp-uniform test per
   // group: with complementary masks most 8-pixel runs are all-foreground or all-background).
-  auto phase_b = [&](const float* box) {
+  auto phase_b = [&](const float* box, int o, int buf) {
 #ifdef PEMP_TMA_DEBUG_SKIP_B                         // timing experiments only (results are wrong)
     return;
 #endif
+    // this warp's columns 8cp .. 8cp+7 are the pixels 8cp - o .. of the tile: bit (pixel + 4) of wlive, and the
+    // column pair 2i, 2i+1 is record ((8cp + 2i - o + 4) - (o & 1)) / 2 of pairing o & 1
+    const int sh = 8 * cp - o + 4;
     float4 f[2][4];
 #pragma unroll
     for (int ck = 0; ck < 2; ++ck)
@@ -362,11 +384,12 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
         f[ck][i] = *reinterpret_cast<const float4*>(box + (off_b ^ (ck << 2)) + 32 * i * kTW);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      if ((live & (0x11111111u << (2 * g))) == 0) continue;
+      if (((sm.wlive[buf][g] >> sh) & 0xffu) == 0) continue;
+      const float* wts = &sm.wpx[buf][o & 1][g][((sh - (o & 1)) >> 1) * 8];
 #pragma unroll
       for (int pp = 0; pp < 4; ++pp) {
-        const float4 wa = *reinterpret_cast<const float4*>(wts + (pp * 2 + g) * 8);
-        const float2 wb = *reinterpret_cast<const float2*>(wts + (pp * 2 + g) * 8 + 4);
+        const float4 wa = *reinterpret_cast<const float4*>(wts + pp * 8);
+        const float2 wb = *reinterpret_cast<const float2*>(wts + pp * 8 + 4);
         const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -380,20 +403,19 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
     }
   };
 
-  // Software pipeline: per iteration  A(t+1), B(t), softmax(t+1).  The partial-dot exchange of tile t+1 is armed
-  // (mbarrier arrive) before B(t) and consumed after it, so no warp waits for the slowest one.
+  // Software pipeline: per iteration  A(k+1), B(k).  The partial dots of tile k+1 are handed to the softmax warps
+  // (mbarrier arrive) before B(k); the weights of tile k were requested one B and one A earlier, so the wait on them is
+  // normally free.  Buffer reuse: the softmax warps write wpx[b] for tile k+2 only after all 16 arrivals of tile k+2,
+  // i.e. after every consumer finished B(k), the last reader of wpx[b]; a consumer rewrites part[b] in A(k+2), after its
+  // B(k), which waited for the weights of tile k and hence for the softmax warps' last read of part[b].
   const int ntl = static_cast<int>(t1 - t0);
   if (ntl <= 0) return;
   int slot = e;
   uint32_t par = 0;
   int img = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(img) * nt_img);
-  {
-    const int x_nom = tl * kStep, o = (e * hw + x_nom) & 3;
-    const float m = mask_of(img, x_nom, o);
-    mbar_wait(&sm.full[slot], par);
-    phase_a(sm.ring[slot], o, 0);
-    softmax(m, o, 0, 0);
-  }
+  int o = (e * hw + tl * kStep) & 3;
+  mbar_wait(&sm.full[slot], par);
+  phase_a(sm.ring[slot], o, 0);
   for (int k = 0; k < ntl; ++k) {
     const bool have_next = k + 1 < ntl;
     const bool last_of_img = (tl == nt_img - 1) || !have_next;
@@ -409,28 +431,20 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
       tl_n = 0;
       ++img_n;
     }
-    const int o_n = (e * hw + tl_n * kStep) & 3, buf_n = (k + 1) & 1;
-    float m_n = 0.f;
+    const int o_n = (e * hw + tl_n * kStep) & 3;
     if (have_next) {
-      m_n = mask_of(img_n, tl_n * kStep, o_n);
       mbar_wait(&sm.full[slot_n], par_n);
-      phase_a(sm.ring[slot_n], o_n, buf_n);
+      phase_a(sm.ring[slot_n], o_n, (k + 1) & 1);
     }
-    phase_b(sm.ring[slot]);
+    mbar_wait(&sm.wts_bar[k & 1], (k >> 1) & 1);
+    phase_b(sm.ring[slot], o, k & 1);
 
     if (!last_of_img) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[slot]);
     } else {
       // ---------------- image boundary: fold the four column-owning warps of this box, write the partial ----------
-      float* scratch = sm.ring[slot];                 // [3][24][32] numerators, then [4][8] denominators
-      // denominators: sum the owner lanes of each class group (lane bits 2..4), result on lanes 0 (fg) and 2 (bg)
-#pragma unroll
-      for (int j = 0; j < kP; ++j) {
-        den[j] += __shfl_xor_sync(kFull, den[j], 4);
-        den[j] += __shfl_xor_sync(kFull, den[j], 8);
-        den[j] += __shfl_xor_sync(kFull, den[j], 16);
-      }
+      float* scratch = sm.ring[slot];                 // [3][24][32] numerators
       named_bar(2 + e, 128);                          // all four warps are done reading the box
       if (cp > 0) {
         int o2 = 0;
@@ -440,10 +454,6 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
           for (int g = 0; g < 2; ++g)
 #pragma unroll
             for (int j = 0; j < kP; ++j) scratch[((cp - 1) * 24 + (o2++)) * 32 + lane] = acc[i][g][j].x + acc[i][g][j].y;
-      }
-      if (lane == 0 || lane == 2) {
-#pragma unroll
-        for (int j = 0; j < kP; ++j) scratch[3 * 24 * 32 + cp * 8 + g_own * kP + j] = den[j];
       }
       named_bar(2 + e, 128);
       if (cp == 0) {
@@ -468,12 +478,6 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
           dst[1] = make_float2(v[2], v[3]);
           dst[2] = make_float2(v[4], v[5]);
         }
-        if (e == 0 && lane < kK) {
-          float sden = 0.f;
-#pragma unroll
-          for (int r = 0; r < 4; ++r) sden += scratch[3 * 24 * 32 + r * 8 + lane];
-          part_den[(static_cast<long long>(img) * maxp + slot_idx) * 8 + lane] = sden;
-        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // scratch writes before the slot's next TMA fill
       __syncwarp();
@@ -484,11 +488,9 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
         for (int g = 0; g < 2; ++g)
 #pragma unroll
           for (int j = 0; j < kP; ++j) acc[i][g][j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < kP; ++j) den[j] = 0.f;
     }
 
-    if (have_next) softmax(m_n, o_n, buf_n, ((k + 1) >> 1) & 1);
+    o = o_n;
     slot = slot_n;
     par = par_n;
     tl = tl_n;
