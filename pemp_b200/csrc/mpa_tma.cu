@@ -21,18 +21,22 @@
 //    are consecutive), so it touches 2-3 images and the pipeline never drains between them.  Warp 16 (one elected
 //    lane) is the producer: an 11-slot ring of 16-KB boxes with a full / empty mbarrier per slot, i.e. up to 176 KB
 //    of loads in flight per SM without a single load instruction or staging register in the consumers.
-//  * Warps 0-15 are consumers.  Warp w = 4*e + cp only ever touches box e of a tile:
+//  * Warps 0-15 are consumers (112 registers each via setmaxnreg; the producer warpgroup gives registers back).
+//    Warp w = 4*e + cp only ever touches box e of a tile:
 //      phase A  rows [32cp, 32cp+32) of the box, lane <-> (row mod 4, 16-byte chunk): one conflict-free LDS.128 gives
 //               4 pixels of a channel, the (pre-duplicated) table row comes with two more, 8 packed FFMA2 accumulate
 //               4 pixels x 4 dots; a halving butterfly over the 4 row groups leaves each lane with the 4 dots of one
-//               pixel, stored to a per-warp partial array;
-//      one named barrier over the 16 consumer warps (the only CTA-wide synchronisation per tile);
-//      softmax  the warp adds the 16 partials of ITS 8 pixels (pixels [8cp, 8cp+8)), 16 lanes turn them into the
-//               3 + 3 weights of a pixel (x mask) - replicated in the four warps that share cp, which is cheaper than
-//               a second barrier;
+//               pixel, stored to part[tile parity][warp][dot][pixel]; the warp arrives on the buffer's mbarrier;
 //      phase B  lane <-> rows {l, l+32, l+64, l+96} of box e (the swizzle makes the column read conflict-free):
-//               for each live (pixel pair, class group) 12 FFMA2 accumulate {even, odd} pixel partial sums of
+//               for each live class group 12 FFMA2 per column pair accumulate {even, odd} column sums of
 //               4 channels x 3 prototypes - 48 accumulator registers that live across the whole image.
+//    Per iteration a consumer runs A(k+1), then B(k): the partial dots of tile k+1 are on their way to the softmax
+//    warps while it accumulates tile k, so nobody waits for the slowest warp.
+//  * Warps 17 and 18 (the producer's warpgroup) are the softmax warps, one per class group, lane <-> pixel of the tile:
+//    wait for the 16 partial dot sets, add them in a fixed order, exp2 / reciprocal (the table carries log2 e), x mask,
+//    and publish the 3 weights of every pixel in both column-pair alignments plus a bit mask of live pixels; they also
+//    own the group's denominators.  Consumers therefore never compute a weight (in the first version every consumer
+//    warp recomputed the weights of its 8 columns: 4 x redundant, 65 of 474 instructions per warp and tile).
 //    At an image boundary the four warps of a box fold their accumulators through the box they just consumed
 //    (fixed order cp = 0..3) and write one partial per (image, CTA); `mpa_tma_finalize_kernel` adds the partials of an
 //    image in CTA order, divides and averages the shots - deterministic, no float atomics.
