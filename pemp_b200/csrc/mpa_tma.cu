@@ -19,7 +19,7 @@
 //    past the tensor) get zero weight.
 //  * One CTA per SM, persistent: CTA b owns the flat tile range [T*b/G, T*(b+1)/G) of the launch (tiles of one image
 //    are consecutive), so it touches 2-3 images and the pipeline never drains between them.  Warp 16 (one elected
-//    lane) is the producer: an 11-slot ring of 16-KB boxes with a full / empty mbarrier per slot, i.e. up to 176 KB
+//    lane) is the producer: a 12-slot ring of 16-KB boxes with a full / empty mbarrier per slot, i.e. up to 192 KB
 //    of loads in flight per SM without a single load instruction or staging register in the consumers.
 //  * Warps 0-15 are consumers (112 registers each via setmaxnreg; the producer warpgroup gives registers back).
 //    Warp w = 4*e + cp only ever touches box e of a tile:
@@ -64,16 +64,23 @@ constexpr uint32_t kBoxBytes = kBoxFloats * 4;   // 16 KB
 #define PEMP_MPA_TMA_DUP 1                       // table rows as {t0,t0,t1,t1,t2,t2,t3,t3}: no MOVs to form FFMA2 operands
 #endif
 #ifndef PEMP_MPA_TMA_SLOTS
-#define PEMP_MPA_TMA_SLOTS (PEMP_MPA_TMA_DUP ? 11 : 12)
+#define PEMP_MPA_TMA_SLOTS 12                     // 3 tiles: two held by the consumers, one in flight (11 slots: -10 %)
 #endif
 constexpr int kTD = PEMP_MPA_TMA_DUP ? 8 : 4;    // floats per table row
 constexpr int kNB = PEMP_MPA_TMA_SLOTS;
 constexpr int kCons = 16;                        // consumer warps
 constexpr int kThreadsT = (kCons + 4) * 32;      // + one producer warpgroup (setmaxnreg works on whole warpgroups)
 constexpr int kRegsCons = 112, kRegsProd = 32;   // the CTA pool is the launch allocation (640 x 96) = 512 x 112 + 128 x 32
-constexpr int kWPairs = 20;                      // column pairs per weight array: pixels -4 .. 35 of a tile (zero padded)
+#ifndef PEMP_MPA_TMA_WPAIRS
+#define PEMP_MPA_TMA_WPAIRS 18
+#endif
+constexpr int kWPairs = PEMP_MPA_TMA_WPAIRS;                      // column pairs per weight array: pixels -4 .. 31 of a tile (zero padded)
 constexpr int kMaxGrid = 148;
-constexpr int kPartLd = 40;                      // pixel pitch of a dot row in `part`: banks 8d + p are all distinct
+#ifndef PEMP_MPA_TMA_PARTLD
+#define PEMP_MPA_TMA_PARTLD 28                    // = kStep: every byte counts, the 12th ring slot needs the room
+#endif
+constexpr int kPartLd = PEMP_MPA_TMA_PARTLD;     // pixel pitch of a dot row in `part` (>= 28; any pitch is conflict-free: a
+                                                 // warp instruction touches one dot row at 32 distinct pixels)
 
 struct TmaSmem {
   alignas(1024) float ring[kNB][kBoxFloats];
