@@ -264,6 +264,32 @@ def test_meta_proto_attn_run_to_run_deterministic(ops):
     assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+def test_tma_kernels_are_bitwise_repeatable_under_load(ops):
+    """compute-sanitizer is not available on the GPU pool, so hunt races the blunt way: the three persistent TMA kernels
+    (all 148 CTAs busy, several images per CTA, every mbarrier hand-off exercised thousands of times) must return
+    bit-identical results on 12 back-to-back runs while another stream keeps the SMs' shared memory and L2 busy."""
+    torch.manual_seed(21)
+    B, S, c, h = 16, 5, 512, 51
+    feats = cu(torch.randn(B, S + 1, c, h, h) * 0.5)
+    ctr = cu(torch.rand(c, 6))
+    fg = cu((torch.rand(B * S, h * h) > 0.55).float())
+    noise_stream = torch.cuda.Stream()
+    noise = cu(torch.randn(64, 512, 2601))
+    first = None
+    for it in range(12):
+        with torch.cuda.stream(noise_stream):
+            ops.map_pool_lowres(noise, fg[:64], 1 - fg[:64], 64, 1)        # competing persistent kernel
+        fgp, bgp, ad = ops.meta_proto_attn(feats[:, :S], ctr, fg, 1 - fg, B, S)
+        out = ops.cosine_match(feats[:, S:], fgp, bgp, 20.0, want_sim=True, want_response=True)
+        pf, pb = ops.map_pool_lowres(feats[:, :S], fg, 1 - fg, B, S)
+        cur = (fgp, bgp, ad, out["sim"], out["pred"], out["response"], pf, pb)
+        torch.cuda.synchronize()
+        if first is None:
+            first = [t.clone() for t in cur]
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(first, cur)), f"run {it} differs"
+
+
 # ------------------------------------------------------------------------------------------------ K10
 def test_iou_hist_known_answers(ops):
     """The two episodes the reference ships under http/static (the only known-answer vectors it has)."""
