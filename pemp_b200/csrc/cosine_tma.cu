@@ -8,16 +8,16 @@
 // Data path as in mpa_tma.cu: the query maps [.., c, hw] are described to TMA as [c/4 groups][4*hw floats]; a box of
 // 32 floats x 128 groups at the 16-byte aligned inner coordinate (e*hw + x_nom) & ~3 holds the channels 4g + e, its
 // column i is pixel x_nom + i - o_e; tiles advance by 28 pixels.  One CTA per SM owns a flat range of tiles; warp 16
-// feeds an 8-slot ring of 16-KB boxes (full / empty mbarriers).  Consumer warp w = 4e + cp reads rows [32cp, 32cp+32)
+// feeds an 11-slot ring of 16-KB boxes (full / empty mbarriers).  Consumer warp w = 4e + cp reads rows [32cp, 32cp+32)
 // of box e: lane <-> (row mod 4, 16-byte chunk), one row-contiguous LDS.128 per 4 pixels of a channel, the channel's
 // normalised prototypes (each value twice, so they are FFMA2 operands as loaded) from shared memory, 2 + 2K packed
 // FFMA2 per load for |q|^2 and the K dots of 4 pixels.  The slot is released as soon as the warp has read it.  A
 // halving butterfly over the 4 row groups leaves each lane with the 1 + K sums of one pixel; they go to
-// part[buffer][warp][value][pixel] and the warp arrives on the buffer's mbarrier.  The NEXT iteration (after the next
-// tile's loads and FMAs, so nobody waits) adds the 16 partials in a fixed order - 14 warps, two pixels each,
-// lane <-> (pixel, half of the partials, value) - and finishes the pixel: norm, scale, max / argmax, stores.
-// Four exchange buffers: a warp rewrites part[b] only after it passed the exchange two tiles later, which every
-// warp reaches after its last read of part[b].
+// part[buffer][warp][value][pixel] and the warp arrives on the buffer's mbarrier.  Two finishing warps (17, 18; 14
+// pixels each, lane <-> (pixel, half of the partials)) wait for that barrier, add the 16 partials in a fixed order, hand
+// the buffer back (second mbarrier) and finish the pixel: norm, scale, max / argmax, stores - so the 16 consumer warps
+// never leave their load / FFMA2 loop (in the first version they finished the previous tile themselves: 0.70 of the
+// HBM peak with an 8-slot ring and four exchange buffers, 0.80 now).
 //
 // The prototype table depends on the episode: the consumers (re)build it in shared memory - normalised, in tile-row
 // order - whenever the episode of the current image changes (at most twice per CTA at the bench shape).
@@ -36,11 +36,11 @@ constexpr int kStep = 28;                        // pixels per tile
 constexpr int kBoxRows = kC / 4;
 constexpr int kBoxFloats = kBoxRows * kTW;
 constexpr uint32_t kBoxBytes = kBoxFloats * 4;
-constexpr int kNB = 8;                           // ring slots (consumers hold 4, 4 in flight)
+constexpr int kNB = 11;                          // ring slots (the consumers hold 4, 7 in flight)
 constexpr int kCons = 16;
-constexpr int kThreadsC = (kCons + 1) * 32;
-constexpr int kPB = 4;
-constexpr int kPLd = 33;                         // pixel pitch of a value row in `part` (banks value + pixel + 7*warp)
+constexpr int kThreadsC = (kCons + 3) * 32;      // + producer warp + two finishing warps
+constexpr int kPB = 2;                           // exchange buffers (handed back by the finishing warps: free_bar)
+constexpr int kPLd = 29;                         // pixel pitch of a value row in `part`
 constexpr int kMaxGrid = 148;
 constexpr float kCosEps = 1e-8f;
 
@@ -53,7 +53,8 @@ struct CosSmem {
   alignas(16) float red[kCons][8];
   alignas(8) uint64_t full[kNB];
   alignas(8) uint64_t empty[kNB];
-  alignas(8) uint64_t part_bar[kPB];
+  alignas(8) uint64_t part_bar[kPB];               // all 16 consumer warps have written part[b]
+  alignas(8) uint64_t free_bar[kPB];               // both finishing warps have read part[b]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -111,7 +112,10 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 4);
     }
-    for (int b = 0; b < kPB; ++b) mbar_init(&sm.part_bar[b], kCons);
+    for (int b = 0; b < kPB; ++b) {
+      mbar_init(&sm.part_bar[b], kCons);
+      mbar_init(&sm.free_bar[b], 2);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -150,6 +154,64 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
     return;
   }
 
+  if (warp > kCons) {
+    // ============================ finishing warps ============================
+    // Warp 17 + hwp finishes pixels [14*hwp, 14*hwp + 14) of every tile: lane = pixel + 14*half adds the partial sums of
+    // the consumer warps [8*half, 8*half + 8) in index order, the two halves are combined (lower + upper, fixed), then
+    // lanes 0..13 do norm, scale, max / argmax over the P prototypes of each group (first maximum wins) and the stores.
+    const int hwp = warp - kCons - 1;
+    const int half = lane >= 14 ? 1 : 0, pix = 14 * hwp + (lane - 14 * half);
+    const bool act = lane < 28;
+    int n = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(n) * nt_img);
+    for (int k = 0; k < ntl; ++k) {
+      const int pb = k & (kPB - 1), x = tl * kStep + pix;
+      mbar_wait(&sm.part_bar[pb], (k / kPB) & 1);
+      float s[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) s[v] = 0.f;
+      if (act) {
+        const float* src = &sm.part[pb][half * 8][pix];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) s[v] += src[(i * NV + v) * kPLd];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.free_bar[pb]);          // part[pb] may be rewritten
+#pragma unroll
+      for (int v = 0; v < NV; ++v) s[v] += __shfl_down_sync(kFull, s[v], 14);   // lanes 0..13: lower + upper half
+      if (lane < 14 && x < hw) {
+        const float qinv = 1.0f / fmaxf(sqrtf(s[0]), kCosEps);
+        float best[2];
+        int arg[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          best[g] = -INFINITY;
+          arg[g] = 0;
+#pragma unroll
+          for (int j = 0; j < P; ++j) {
+            const float sv = s[1 + g * P + j] * qinv * scalar;
+            if (sim) sim[((static_cast<long long>(n) * 2 + g) * P + j) * hw + x] = sv;
+            if (sv > best[g]) {   // first maximum wins, as torch.max
+              best[g] = sv;
+              arg[g] = j;
+            }
+          }
+        }
+        if (pred) {
+          pred[(static_cast<long long>(n) * 2 + 0) * hw + x] = best[0];
+          pred[(static_cast<long long>(n) * 2 + 1) * hw + x] = best[1];
+        }
+        if (response) response[static_cast<long long>(n) * hw + x] = best[1] > best[0] ? arg[1] + 3 : arg[0];
+      }
+      if (++tl == nt_img) {
+        tl = 0;
+        ++n;
+      }
+    }
+    return;
+  }
+
   // ============================ consumers ============================
   const int e = warp >> 2, cp = warp & 3;
   const int rg = lane >> 3, jc = lane & 7;
@@ -157,54 +219,11 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
   int off_t = (e * kBoxRows + cp * 32 + rg) * TL;
   int col_a = 4 * jc + rg;                                  // box column this lane holds after the butterfly
   asm volatile("" : "+r"(off_a), "+r"(off_t), "+r"(col_a));
-  // finalize roles: warp w < 14 finishes pixels w and w + 14; lane = pixsel*16 + half*8 + value
-  const int f_val = lane & 7, f_half = (lane >> 3) & 1, f_pix = warp + 14 * (lane >> 4);
-  const bool f_active = warp < 14 && f_val < NV;
-
-  // ---- finish tile (n, x_nom) whose partial sums are in part[pb] ----
-  auto finalize = [&](int n, int x_nom, int pb, uint32_t parity) {
-    mbar_wait(&sm.part_bar[pb], parity);
-    float s = 0.f;
-    if (f_active) {
-      const float* src = &sm.part[pb][f_half * 8][f_val * kPLd + f_pix];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += src[i * NV * kPLd];
-    }
-    s += __shfl_xor_sync(kFull, s, 8);                       // both halves: lower 8 warps + upper 8 warps
-    const float nrm = __shfl_sync(kFull, s, lane & 16);      // value 0 of this pixel
-    const float qinv = 1.0f / fmaxf(sqrtf(nrm), kCosEps);
-    const float v = s * qinv * scalar;                       // values 1..K: similarity to prototype k = value - 1
-    const int x = x_nom + f_pix;
-    const bool ok = warp < 14 && f_half == 0 && x < hw;
-    if (sim && ok && f_val >= 1 && f_val <= K) {
-      const int k = f_val - 1, g = k / P, j = k - g * P;
-      sim[((static_cast<long long>(n) * 2 + g) * P + j) * hw + x] = v;
-    }
-    // max / argmax over the P members of each group on its first lane (values 1 + g*P); first maximum wins
-    float best = v;
-    int arg = 0;
-#pragma unroll
-    for (int j = 1; j < P; ++j) {
-      const float o = __shfl_down_sync(kFull, v, j);
-      if (o > best) {
-        best = o;
-        arg = j;
-      }
-    }
-    const float best_fg = __shfl_down_sync(kFull, best, P);  // seen from the background leader (value 1)
-    const int arg_fg = __shfl_down_sync(kFull, arg, P);
-    if (ok && (f_val == 1 || f_val == 1 + P)) {
-      const int g = f_val == 1 ? 0 : 1;
-      if (pred) pred[(static_cast<long long>(n) * 2 + g) * hw + x] = best;
-      if (response && g == 0) response[static_cast<long long>(n) * hw + x] = best_fg > best ? arg_fg + 3 : arg;
-    }
-  };
-
   int slot = e;
   uint32_t par = 0;
   int n = static_cast<int>(t0 / nt_img), tl = static_cast<int>(t0 - static_cast<long long>(n) * nt_img);
   int b = n / Qper, q_in_b = n - b * Qper;                    // episode of image n, tracked without divisions
-  int cur_b = -1, n_prev = 0, x_prev = 0;
+  int cur_b = -1;
   for (int k = 0; k < ntl; ++k) {
     if (b != cur_b) {
       // ---------------- (re)build the normalised prototype table of episode b ----------------
@@ -264,6 +283,8 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[slot]);             // the box is not read again
 
+    // the finishing warps must be done with the tile that used this exchange buffer last
+    if (k >= kPB) mbar_wait(&sm.free_bar[k & (kPB - 1)], ((k / kPB) + 1) & 1);
     // halving butterfly over the row groups (lane bits 4 and 3): lane (rg, jc) ends with column 4*jc + rg
     {
       const bool hi = (lane & 16) != 0, lo = (lane & 8) != 0;
@@ -282,9 +303,6 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.part_bar[k & (kPB - 1)]);
 
-    if (k > 0) finalize(n_prev, x_prev, (k - 1) & (kPB - 1), ((k - 1) / kPB) & 1);
-    n_prev = n;
-    x_prev = x_nom;
     slot += 4;
     if (slot >= kNB) {
       slot -= kNB;
@@ -299,7 +317,6 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
       }
     }
   }
-  finalize(n_prev, x_prev, (ntl - 1) & (kPB - 1), ((ntl - 1) / kPB) & 1);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
