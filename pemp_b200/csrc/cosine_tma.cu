@@ -8,7 +8,7 @@
 // Data path as in mpa_tma.cu: the query maps [.., c, hw] are described to TMA as [c/4 groups][4*hw floats]; a box of
 // 32 floats x 128 groups at the 16-byte aligned inner coordinate (e*hw + x_nom) & ~3 holds the channels 4g + e, its
 // column i is pixel x_nom + i - o_e; tiles advance by 28 pixels.  One CTA per SM owns a flat range of tiles; warp 16
-// feeds an 11-slot ring of 16-KB boxes (full / empty mbarriers).  Consumer warp w = 4e + cp reads rows [32cp, 32cp+32)
+// feeds an 8-slot ring of 16-KB boxes (full / empty mbarriers).  Consumer warp w = 4e + cp reads rows [32cp, 32cp+32)
 // of box e: lane <-> (row mod 4, 16-byte chunk), one row-contiguous LDS.128 per 4 pixels of a channel, the channel's
 // normalised prototypes (each value twice, so they are FFMA2 operands as loaded) from shared memory, 2 + 2K packed
 // FFMA2 per load for |q|^2 and the K dots of 4 pixels.  The slot is released as soon as the warp has read it.  A
@@ -17,7 +17,7 @@
 // pixels each, lane <-> (pixel, half of the partials)) wait for that barrier, add the 16 partials in a fixed order, hand
 // the buffer back (second mbarrier) and finish the pixel: norm, scale, max / argmax, stores - so the 16 consumer warps
 // never leave their load / FFMA2 loop (in the first version they finished the previous tile themselves: 0.70 of the
-// HBM peak with an 8-slot ring and four exchange buffers, 0.80 now).
+// HBM peak with four exchange buffers, 0.82 now).
 //
 // The prototype table depends on the episode: the consumers (re)build it in shared memory - normalised, in tile-row
 // order - whenever the episode of the current image changes (at most twice per CTA at the bench shape).
@@ -36,7 +36,17 @@ constexpr int kStep = 28;                        // pixels per tile
 constexpr int kBoxRows = kC / 4;
 constexpr int kBoxFloats = kBoxRows * kTW;
 constexpr uint32_t kBoxBytes = kBoxFloats * 4;
-constexpr int kNB = 11;                          // ring slots (the consumers hold 4, 7 in flight)
+#ifndef PEMP_COS_NB
+#define PEMP_COS_NB 8
+#endif
+constexpr int kNB = PEMP_COS_NB;                 // ring slots (the consumers hold 4, 4 in flight)
+// The ring must be a whole number of tiles (4 boxes): then slot s always carries the same channel class and the warp that
+// waits for use u+1 of a slot is the one that consumed use u.  With 10 or 11 slots a slot alternates between classes;
+// a warp of the other class can reach its parity wait for use u+1 before use u has even landed (boxes complete out of
+// order, and this kernel's consumers are usually waiting for data) - the parity test then passes on the phase BEFORE,
+// the warp reads a stale box and releases a slot it does not own: measured as `unspecified launch failure` within a
+// few hundred launches (8 slots: none; same throughput).
+static_assert(kNB % 4 == 0, "ring slots must be a multiple of the 4 boxes of a tile");
 constexpr int kCons = 16;
 constexpr int kThreadsC = (kCons + 3) * 32;      // + producer warp + two finishing warps
 constexpr int kPB = 2;                           // exchange buffers (handed back by the finishing warps: free_bar)

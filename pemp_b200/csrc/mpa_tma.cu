@@ -68,6 +68,9 @@ constexpr uint32_t kBoxBytes = kBoxFloats * 4;   // 16 KB
 #endif
 constexpr int kTD = PEMP_MPA_TMA_DUP ? 8 : 4;    // floats per table row
 constexpr int kNB = PEMP_MPA_TMA_SLOTS;
+// whole tiles only: a slot must always carry the same channel class, or a parity wait can pass on the phase before
+// (see cosine_tma.cu; the 11-slot builds of this kernel had that latent hazard)
+static_assert(kNB % 4 == 0, "ring slots must be a multiple of the 4 boxes of a tile");
 constexpr int kCons = 16;                        // consumer warps
 constexpr int kThreadsT = (kCons + 4) * 32;      // + one producer warpgroup (setmaxnreg works on whole warpgroups)
 constexpr int kRegsCons = 112, kRegsProd = 32;   // the CTA pool is the launch allocation (640 x 96) = 512 x 112 + 128 x 32

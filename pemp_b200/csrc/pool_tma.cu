@@ -38,6 +38,9 @@ struct PoolCfg {
   static constexpr uint32_t kBoxBytes = kBoxFloats * 4;
   static constexpr int kRL = kRows / 32;                    // row slots per lane
   static constexpr int kNB = C == 512 ? 12 : 16;            // ring slots (the consumers hold 4)
+  // whole tiles only: a slot always carries the same channel class, so the warp that waits for use u+1 of a slot is the
+  // one that consumed use u (otherwise a parity wait can pass on the phase before; see cosine_tma.cu)
+  static_assert(kNB % 4 == 0, "ring slots must be a multiple of the 4 boxes of a tile");
 };
 
 template <int C>
