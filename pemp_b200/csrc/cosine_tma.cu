@@ -21,9 +21,7 @@
 //
 // The prototype table depends on the episode: the consumers (re)build it in shared memory - normalised, in tile-row
 // order - whenever the episode of the current image changes (at most twice per CTA at the bench shape).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma_common.cuh"
 
 int pemp_cosine_tma_launch(const float* qry, long long ep_stride, const float* fg, const float* bg, int N, int Bp, int hw,
                            int P, float scalar, float* sim, float* pred, int64_t* response, cudaStream_t st);
@@ -67,40 +65,7 @@ struct CosSmem {
   alignas(8) uint64_t free_bar[kPB];               // both finishing warps have read part[b]
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "COST_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra COST_DONE;\n"
-      "bra COST_WAIT;\n"
-      "COST_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+using namespace pemp_tma;
 
 template <int K>
 __global__ void __launch_bounds__(kThreadsC, 1)
@@ -329,20 +294,6 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;     // immutable after first resolution; benign race (same value)
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 
 template <int K>
 int launch_tma(const CUtensorMap& map, int Qper, int hw, int nt_img, long long T, int G, const float* fg, const float* bg,
@@ -362,23 +313,13 @@ int pemp_cosine_tma_launch(const float* qry, long long ep_stride, const float* f
                            int P, float scalar, float* sim, float* pred, int64_t* response, cudaStream_t st) {
   const int Qper = N / Bp;
   const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(Qper) * kC * hw;
-  if ((P != 3 && P != 1) || hw < kTW || (reinterpret_cast<uintptr_t>(qry) & 15) != 0 || (eps_stride & 3) != 0) return PEMP_E_ALIGN;
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return PEMP_E_ALIGN;
+  if ((P != 3 && P != 1) || hw < kTW) return PEMP_E_ALIGN;
   const int nt_img = (hw + kStep - 1) / kStep;
   const long long T = static_cast<long long>(N) * nt_img;
   long long g = T / 4;
   const int G = static_cast<int>(g < 1 ? 1 : (g > kMaxGrid ? kMaxGrid : g));
-
   CUtensorMap map;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(4) * hw, static_cast<cuuint64_t>(Qper) * kBoxRows, static_cast<cuuint64_t>(Bp)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(16) * hw, static_cast<cuuint64_t>(eps_stride) * 4};
-  cuuint32_t box[3] = {kTW, kBoxRows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qry), dims, strides, box, estr,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return PEMP_E_ALIGN;
+  if (!make_rows4_map(&map, qry, Bp, Qper, kC, hw, eps_stride)) return PEMP_E_ALIGN;
   return P == 3 ? launch_tma<6>(map, Qper, hw, nt_img, T, G, fg, bg, scalar, sim, pred, response, st)
                 : launch_tma<2>(map, Qper, hw, nt_img, T, G, fg, bg, scalar, sim, pred, response, st);
 }

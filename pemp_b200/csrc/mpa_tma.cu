@@ -40,9 +40,7 @@
 //    At an image boundary the four warps of a box fold their accumulators through the box they just consumed
 //    (fixed order cp = 0..3) and write one partial per (image, CTA); `mpa_tma_finalize_kernel` adds the partials of an
 //    image in CTA order, divides and averages the shots - deterministic, no float atomics.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma_common.cuh"
 
 int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
                         long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
@@ -101,49 +99,7 @@ struct TmaSmem {
   float konst[4];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MPAT_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // %2: suspend-time hint, the thread sleeps
-      "@p bra MPAT_DONE;\n"                                            // in hardware instead of spinning
-      "bra MPAT_WAIT;\n"
-      "MPAT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// CTA that owns flat tile t when CTA b owns [T*b/G, T*(b+1)/G)
-__host__ __device__ inline int owner_of(long long t, long long T, int G) { return static_cast<int>(((t + 1) * G - 1) / T); }
-
-// ---- difference table (built by every CTA in its prologue - 12 KB of `ctr` from L2 - instead of a separate launch) --
-// tile row R = e*128 + g  <->  channel 4g + e;  table[R][d] = 2 log2(e) * (ctr[ch, g'*P + j] - ctr[ch, g'*P]) with
-// d = g'*(P-1) + j-1 (each value twice when kTD == 8);  konst[d] = -log2(e) * (|ctr_{g'P+j}|^2 - |ctr_{g'P}|^2),
-// accumulated in double in a fixed order (identical in every CTA).
-
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+using namespace pemp_tma;
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -540,20 +496,6 @@ __global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, cons
   if (adaptive_p) adaptive_p[(static_cast<long long>(b) * kC + ch) * kK + k] = v;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;     // immutable after first resolution; benign race (same value)
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 
 struct TmaPlan {
   int G, nt_img, maxp;
@@ -590,21 +532,11 @@ int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr,
                         long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
                         float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st) {
   const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(S) * kC * hw;
-  if ((reinterpret_cast<uintptr_t>(fts) & 15) != 0 || (eps_stride & 3) != 0 || hw < kTW) return PEMP_E_ALIGN;
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return PEMP_E_ALIGN;
+  if (hw < kTW) return PEMP_E_ALIGN;
   const TmaPlan pl = make_tma_plan(B, S, hw);
   PEMP_REQUIRE(ws_bytes >= pl.total, PEMP_E_WORKSPACE);
-
   CUtensorMap map;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(4) * hw, static_cast<cuuint64_t>(S) * kBoxRows, static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(16) * hw, static_cast<cuuint64_t>(eps_stride) * 4};
-  cuuint32_t box[3] = {kTW, kBoxRows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(fts), dims, strides, box, estr,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return PEMP_E_ALIGN;
+  if (!make_rows4_map(&map, fts, B, S, kC, hw, eps_stride)) return PEMP_E_ALIGN;
 
   float* num = reinterpret_cast<float*>(ws + pl.off_num);
   float* den = reinterpret_cast<float*>(ws + pl.off_den);

@@ -14,9 +14,7 @@
 // warp through 64 floats of shared memory.  At an image boundary the four warps of a box fold their sums through the
 // box they just consumed and write one partial per (image, CTA); the finalize kernel adds an image's partials in CTA
 // order, divides (optionally by caller-supplied denominators: K6) and averages the shots - deterministic.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma_common.cuh"
 
 int pemp_pool_tma_launch(const float* fts, long long ep_stride, const float* fg, const float* bg, long long mask_stride, int B,
                          int S, int c, int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, char* ws,
@@ -51,43 +49,8 @@ struct PoolSmem {
   alignas(8) uint64_t empty[PoolCfg<C>::kNB];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "POOLT_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra POOLT_DONE;\n"
-      "bra POOLT_WAIT;\n"
-      "POOLT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+using namespace pemp_tma;
 
-// CTA that owns flat tile t when CTA b owns [T*b/G, T*(b+1)/G)
-__host__ __device__ inline int owner_of(long long t, long long T, int G) { return static_cast<int>(((t + 1) * G - 1) / T); }
 
 template <int C, bool kTwo>
 __global__ void __launch_bounds__(kThreadsP, 1)
@@ -307,20 +270,6 @@ __global__ void pool_tma_finalize_kernel(const float* __restrict__ part_num, con
   if (bg_proto) bg_proto[i] = accb / static_cast<float>(S);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;     // immutable after first resolution; benign race (same value)
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 
 struct PoolPlan {
   int G, nt_img, maxp;
@@ -382,21 +331,11 @@ int pemp_pool_tma_launch(const float* fts, long long ep_stride, const float* fg,
                          int S, int c, int hw, float eps, const float* den_override, float* fg_proto, float* bg_proto, char* ws,
                          size_t ws_bytes, cudaStream_t st) {
   const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(S) * c * hw;
-  if ((c != 512 && c != 256) || hw < kTW || (reinterpret_cast<uintptr_t>(fts) & 15) != 0 || (eps_stride & 3) != 0) return PEMP_E_ALIGN;
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return PEMP_E_ALIGN;
+  if ((c != 512 && c != 256) || hw < kTW) return PEMP_E_ALIGN;
   const PoolPlan pl = make_pool_plan(B, S, c, hw);
   if (ws_bytes < pl.total) return PEMP_E_ALIGN;
-
   CUtensorMap map;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(4) * hw, static_cast<cuuint64_t>(S) * (c / 4), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(16) * hw, static_cast<cuuint64_t>(eps_stride) * 4};
-  cuuint32_t box[3] = {kTW, static_cast<cuuint32_t>(c / 4), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(fts), dims, strides, box, estr,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return PEMP_E_ALIGN;
+  if (!make_rows4_map(&map, fts, B, S, c, hw, eps_stride)) return PEMP_E_ALIGN;
   return c == 512 ? launch_pool<512>(map, pl, B, S, hw, fg, bg, mask_stride, eps, den_override, fg_proto, bg_proto, ws, st)
                   : launch_pool<256>(map, pl, B, S, hw, fg, bg, mask_stride, eps, den_override, fg_proto, bg_proto, ws, st);
 }
