@@ -131,7 +131,10 @@ upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logit
 // image: it first fills shared memory with Hrow for the few source rows the band touches (both channels), then each
 // thread produces aligned quads of the flattened output range of the band: 4 shared loads, 2 lerps and a compare per
 // pixel instead of 8 cached global loads and 6 lerps.  Quads that straddle the band boundary are written per byte.
-constexpr int kBandRows = 16, kBandMaxSrc = 8;
+#ifndef PEMP_K4_BAND
+#define PEMP_K4_BAND 16
+#endif
+constexpr int kBandRows = PEMP_K4_BAND, kBandMaxSrc = 8;
 __global__ void __launch_bounds__(256)
 upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict__ mask8, int h, int w, int H, int W,
                             float sy, float sx, int bands) {
