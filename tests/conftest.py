@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The tests bind the in-tree C-ABI library; build it once if this checkout has not been built yet (nvcc cross-
+    compiles without a GPU; the product itself never builds or falls back on its own)."""
+    from pemp_b200 import build as _build
+    if _build.stale():
+        _build.build()
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
