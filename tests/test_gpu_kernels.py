@@ -74,7 +74,7 @@ def test_nearest_labels_and_bilinear_resize(ops):
                                          # the TMA-fed persistent kernel (c = 512, P in {1, 3}): several queries per episode,
                                          # ragged last tile, exactly one tile, fewer tiles than CTAs, single prototype
                                          (6, 3, 512, 2601, 3), (5, 5, 512, 100, 3), (1, 1, 512, 32, 3), (4, 2, 512, 2601, 1),
-                                         (3, 3, 512, 45, 1), (2, 1, 512, 300, 2)])
+                                         (3, 3, 512, 45, 1), (2, 1, 512, 300, 2), (2, 2, 512, 20, 3), (3, 1, 512, 31, 1)])
 def test_cosine_match(ops, N, Bp, c, hw, P):
     torch.manual_seed(3)
     q = torch.randn(N, c, hw)
@@ -129,7 +129,8 @@ def test_cosine_zero_vectors(ops):
 @pytest.mark.parametrize("B,S,c,hw", [(2, 1, 32, 169), (1, 5, 48, 130), (2, 2, 512, 2601), (1, 1, 7, 33), (1, 3, 64, 5000),
                                       # the TMA-fed persistent kernel (c in {256, 512}): images split over CTAs, ragged last tile,
                                       # one tile, fewer tiles than CTAs, hw a multiple of 4 (all column offsets zero)
-                                      (3, 2, 512, 2601), (2, 5, 512, 100), (1, 1, 512, 32), (5, 1, 256, 45), (2, 3, 256, 3600)])
+                                      (3, 2, 512, 2601), (2, 5, 512, 100), (1, 1, 512, 32), (5, 1, 256, 45), (2, 3, 256, 3600),
+                                      (2, 2, 512, 20), (1, 3, 256, 31)])
 def test_map_pool_lowres(ops, B, S, c, hw):
     torch.manual_seed(4)
     f = torch.randn(B * S, c, hw)
@@ -189,7 +190,9 @@ def test_weighted_gap_golden(ops):
                                         (1, 2, 48, 333, 2), (1, 1, 24, 70, 4), (1, 1, 1024, 200, 3),
                                         # the TMA-fed persistent kernel (c = 512, p = 3): images split over several CTAs,
                                         # ragged last tile, exactly one tile, fewer tiles than CTAs
-                                        (3, 2, 512, 2601, 3), (2, 5, 512, 100, 3), (1, 1, 512, 32, 3), (5, 1, 512, 45, 3)])
+                                        (3, 2, 512, 2601, 3), (2, 5, 512, 100, 3), (1, 1, 512, 32, 3), (5, 1, 512, 45, 3),
+                                        # c = 512 but narrower than one TMA box: back to the generic kernel
+                                        (2, 2, 512, 20, 3), (1, 3, 512, 31, 3)])
 def test_meta_proto_attn(ops, B, S, c, hw, p):
     torch.manual_seed(6)
     f = torch.randn(B * S, c, hw) * 0.5
