@@ -22,7 +22,7 @@
 //    lane) is the producer: a 12-slot ring of 16-KB boxes with a full / empty mbarrier per slot, i.e. up to 192 KB
 //    of loads in flight per SM without a single load instruction or staging register in the consumers.
 //  * Warps 0-15 are consumers (112 registers each via setmaxnreg; the producer warpgroup gives registers back).
-//    Warp w = 4*e + cp only ever touches box e of a tile:
+//    Warp w = e + 4*cp (one channel class per warp scheduler) only ever touches box e of a tile:
 //      phase A  rows [32cp, 32cp+32) of the box, lane <-> (row mod 4, 16-byte chunk): one conflict-free LDS.128 gives
 //               4 pixels of a channel, the (pre-duplicated) table row comes with two more, 8 packed FFMA2 accumulate
 //               4 pixels x 4 dots; a halving butterfly over the 4 row groups leaves each lane with the 4 dots of one
