@@ -15,6 +15,12 @@
 
 #include "common.cuh"
 
+// L2 promotion of the box rows (128-byte pieces at a 16*hw-byte pitch).  Measured on K2 / K3 / K1 at the bench shapes:
+// 256 B 0.320 / 0.066 / 0.285 ms, 128 B and none 0.345 / 0.072 / 0.329 ms, 64 B 0.424 / 0.091 / 0.410 ms.
+#ifndef PEMP_TMA_L2PROMO
+#define PEMP_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+
 namespace pemp_tma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -83,7 +89,7 @@ static inline bool make_rows4_map(CUtensorMap* map, const float* base, int episo
   cuuint32_t box[3] = {32, static_cast<cuuint32_t>(c / 4), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, PEMP_TMA_L2PROMO,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
