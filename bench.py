@@ -219,8 +219,8 @@ def run_ours(args):
         else:
             H, W = sup_mask.shape[-2:]
             low = ops.mask_nearest(sup_mask.view(Bn * S, 2, H, W), h, wd).view(Bn * S, 2, h * wd)
-            m = pipe.stage2_mask(fa.view(Bn * (S + Q), c, h, wd), low, Bn, S, Q, tuple(qry_msk.shape[-2:]), timer)
-            ops.iou_hist(m, qry_msk.view(Bn * Q, -1), cls, st)
+            pipe.stage2_mask(fa.view(Bn * (S + Q), c, h, wd), low, Bn, S, Q, tuple(qry_msk.shape[-2:]), timer,
+                             hist=(qry_msk, cls, st))
         pdist.all_reduce_stat(st)
 
     # ---------------- value: device-resident inputs ------------------------------------------------------

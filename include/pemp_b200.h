@@ -171,6 +171,12 @@ int pemp_prior_mask(const float* q4, const float* s4, const float* smask,
  * episode, row cls[i] += foreground counts of episode i.  Integer atomics: order-independent, exact.     */
 int pemp_iou_hist(const uint8_t* pred, const uint8_t* ref, const int64_t* cls, int N, long long npix,
                   int num_classes, int64_t* stat, pemp_stream_t stream);
+/* K4 + K10 in one launch (what Evaluator.test_step + FewShotMetric.update do per batch, entry/pemp_stage2.py:63-65,
+ * core/metrics.py:9-23): up-sample pred [N,2,h,w] to (H,W), write the argmax mask8 [N,H,W] and accumulate the counts of
+ * (mask8, ref [N,H,W] uint8, cls [N]) into stat [(num_classes+1), 3].  mask8 and ref must be 4-byte aligned.          */
+int pemp_upsample_argmax_hist(const float* pred, int N, int h, int w, int H, int W, uint8_t* mask8,
+                              const uint8_t* ref, const int64_t* cls, int num_classes, int64_t* stat,
+                              pemp_stream_t stream);
 
 /* ---- K11 communication module of the Stage-2 backbones ("next" row) ------------------------------------
  * replaces  ResNetCM.comm / VGG16CM.comm                         networks/backbones.py:208-222, 469-479

@@ -23,6 +23,7 @@ SIGNATURES = {
     "pemp_map_pool_lowres": (I, [P, LL, P, P, LL, I, I, I, I, F, P, P, P, SZ, P]),
     "pemp_weighted_gap": (I, [P, P, I, I, I, P, P, SZ, P]),
     "pemp_meta_proto_attn_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "pemp_upsample_argmax_hist": (I, [P, I, I, I, I, I, P, P, P, I, P, P]),
     "pemp_comm_workspace_bytes": (SZ, [I, I, I, I]),
     "pemp_comm_module": (I, [P, P, I, I, I, I, I, I, I, I, P, P, I, P, P, P, SZ, P]),
     "pemp_debug_mpa_path": (I, [I]),

@@ -8,37 +8,15 @@
 // Roofline: HBM, 2 bytes per pixel.  One pass with 16-byte loads and byte-SIMD compares; counts are
 // integers, so the int64 atomics into `stat` are order independent and the result is exact.
 #include "common.cuh"
+#include "iou_count.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 
-struct Counts {
-  unsigned tp0, fp0, fn0, tp1, fp1, fn1;
-};
-
-__device__ __forceinline__ void count_word(uint32_t p, uint32_t r, Counts& k) {
-  // __vcmpeq4 gives 0xff per equal byte; popc / 8 = number of equal bytes (divided out at the end)
-  const uint32_t p0 = __vcmpeq4(p, 0x00000000u), p1 = __vcmpeq4(p, 0x01010101u);
-  const uint32_t r0 = __vcmpeq4(r, 0x00000000u), r1 = __vcmpeq4(r, 0x01010101u);
-  const uint32_t valid = ~__vcmpeq4(r, 0xffffffffu);
-  k.tp0 += __popc(p0 & r0);
-  k.fp0 += __popc(p0 & ~r0 & valid);
-  k.fn0 += __popc(~p0 & r0);
-  k.tp1 += __popc(p1 & r1);
-  k.fp1 += __popc(p1 & ~r1 & valid);
-  k.fn1 += __popc(~p1 & r1);
-}
-
-__device__ __forceinline__ void count_byte(uint8_t p, uint8_t r, Counts& k) {
-  const bool valid = r != 255;
-  k.tp0 += 8u * (p == 0 && r == 0);
-  k.fp0 += 8u * (p == 0 && r != 0 && valid);
-  k.fn0 += 8u * (p != 0 && r == 0);
-  k.tp1 += 8u * (p == 1 && r == 1);
-  k.fp1 += 8u * (p == 1 && r != 1 && valid);
-  k.fn1 += 8u * (p != 1 && r == 1);
-}
+using Counts = PempCounts;
+#define count_word pemp_count_word
+#define count_byte pemp_count_byte
 
 // grid = (chunks, N).  Each CTA handles a contiguous byte range of one episode.
 __global__ void __launch_bounds__(kThreads)

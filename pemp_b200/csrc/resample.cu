@@ -2,6 +2,7 @@
 // up-sampling, the stand-alone bilinear resize and the adjoint (transposed) bilinear operator of K6.
 // All are tiny next to the feature streams (K1-K3); they are written for coalesced stores.
 #include "common.cuh"
+#include "iou_count.cuh"
 
 // ------------------------------------------------------------------------------------------------ K0
 // in [planes, H, W] -> out [planes, h, w]; one thread per output element.  Reads are a strided gather
@@ -135,9 +136,13 @@ upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logit
 #define PEMP_K4_BAND 16
 #endif
 constexpr int kBandRows = PEMP_K4_BAND, kBandMaxSrc = 8;
+// kHist: the FewShotMetric counts of K10 (core/metrics.py:9-23) are taken from the mask bytes while they are still in
+// registers - one launch and one read of the mask fewer (pemp_upsample_argmax_hist).
+template <bool kHist>
 __global__ void __launch_bounds__(256)
 upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict__ mask8, int h, int w, int H, int W,
-                            float sy, float sx, int bands) {
+                            float sy, float sx, int bands, const uint8_t* __restrict__ ref, const int64_t* __restrict__ cls,
+                            int num_classes, unsigned long long* __restrict__ stat) {
   extern __shared__ float hrow[];                    // [nsrc][2][W]
   const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
   const int Y0 = band * kBandRows, Y1 = min(H, Y0 + kBandRows);
@@ -156,6 +161,7 @@ upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict_
   __syncthreads();
   const long long HW = static_cast<long long>(H) * W;
   const long long base0 = n * HW + static_cast<long long>(Y0) * W, base1 = n * HW + static_cast<long long>(Y1) * W;
+  PempCounts cnt = {0, 0, 0, 0, 0, 0};
   for (long long q = (base0 >> 2) + threadIdx.x; (q << 2) < base1; q += blockDim.x) {
     const long long i0 = q << 2;
     const long long first = i0 < base0 ? base0 : i0;          // first element of the quad inside the band
@@ -183,10 +189,37 @@ upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict_
     }
     if (i0 >= base0 && i0 + 3 < base1) {
       reinterpret_cast<uint32_t*>(mask8)[q] = packed;
+      if (kHist) pemp_count_word(packed, __ldg(reinterpret_cast<const uint32_t*>(ref) + q), cnt);
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (i0 + e >= base0 && i0 + e < base1) mask8[i0 + e] = static_cast<uint8_t>(packed >> (8 * e));
+        if (i0 + e >= base0 && i0 + e < base1) {
+          mask8[i0 + e] = static_cast<uint8_t>(packed >> (8 * e));
+          if (kHist) pemp_count_byte(static_cast<uint8_t>(packed >> (8 * e)), __ldg(ref + i0 + e), cnt);
+        }
+    }
+  }
+  if (kHist) {   // block reduction, then six integer atomics (order independent => exact)
+    __shared__ unsigned red[6][8];
+    unsigned v[6] = {cnt.tp0, cnt.fp0, cnt.fn0, cnt.tp1, cnt.fp1, cnt.fn1};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      unsigned sres = v[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sres += __shfl_xor_sync(kFull, sres, o);
+      if (lane == 0) red[k][warp] = sres;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      unsigned long long tot = 0;
+      for (int wv = 0; wv < 8; ++wv) tot += red[threadIdx.x][wv];
+      tot >>= 3;
+      if (tot) {
+        const int k = threadIdx.x;
+        const long long row = k < 3 ? 0 : cls[n];
+        if (row >= 0 && row <= num_classes) atomicAdd(stat + row * 3 + (k % 3), tot);
+      }
     }
   }
 }
@@ -208,7 +241,8 @@ extern "C" int pemp_upsample_argmax(const float* pred, int N, int h, int w, int 
     const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
     if (nsrc_max <= kBandMaxSrc && smem <= 48 * 1024) {
       const int bands = (H + kBandRows - 1) / kBandRows;
-      upsample_argmax_band_kernel<<<static_cast<unsigned>(N) * bands, 256, smem, st>>>(pred, mask8, h, w, H, W, sy, sx, bands);
+      upsample_argmax_band_kernel<false><<<static_cast<unsigned>(N) * bands, 256, smem, st>>>(pred, mask8, h, w, H, W, sy, sx, bands,
+                                                                                               nullptr, nullptr, 0, nullptr);
       return launch_status();
     }
   }
@@ -226,6 +260,28 @@ extern "C" int pemp_upsample_argmax(const float* pred, int N, int h, int w, int 
   }
 #undef PEMP_LAUNCH_UA
   return launch_status();
+}
+
+// K4 + K10 in one launch for the evaluator: uint8 masks and the FewShotMetric counts of (mask, ref, cls).
+// Falls back to the two separate kernels when the banded kernel does not cover the geometry.
+extern "C" int pemp_upsample_argmax_hist(const float* pred, int N, int h, int w, int H, int W, uint8_t* mask8,
+                                         const uint8_t* ref, const int64_t* cls, int num_classes, int64_t* stat,
+                                         pemp_stream_t stream) {
+  PEMP_REQUIRE(pred && mask8 && ref && cls && stat, PEMP_E_NULL);
+  PEMP_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && h > 0 && w > 0 && num_classes > 0, PEMP_E_SHAPE);
+  PEMP_REQUIRE((reinterpret_cast<uintptr_t>(mask8) & 3) == 0 && (reinterpret_cast<uintptr_t>(ref) & 3) == 0, PEMP_E_ALIGN);
+  const float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
+  const int nsrc_max = static_cast<int>((kBandRows - 1) * sy) + 3;
+  const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
+  if (nsrc_max <= kBandMaxSrc && smem <= 48 * 1024) {
+    const int bands = (H + kBandRows - 1) / kBandRows;
+    upsample_argmax_band_kernel<true><<<static_cast<unsigned>(N) * bands, 256, smem, as_stream(stream)>>>(
+        pred, mask8, h, w, H, W, sy, sx, bands, ref, cls, num_classes, reinterpret_cast<unsigned long long*>(stat));
+    return launch_status();
+  }
+  int rc = pemp_upsample_argmax(pred, N, h, w, H, W, nullptr, mask8, nullptr, stream);
+  if (rc != PEMP_OK) return rc;
+  return pemp_iou_hist(mask8, ref, cls, N, static_cast<long long>(H) * W, num_classes, stat, stream);
 }
 
 // single-plane bilinear resize with the same arithmetic (PFENet's mask resize, pfenet.py:191,205)

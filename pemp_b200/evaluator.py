@@ -43,21 +43,25 @@ class PEMPStage2Pipeline:
         self.classes = classes
         self.dist_scalar = dist_scalar
 
-    def _head(self, feats, low, ctr, B, S, Q, out_shape, timer):
+    def _head(self, feats, low, ctr, B, S, Q, out_shape, timer, hist=None):
         _, c, h, w = feats.shape
         f5 = feats.view(B, S + Q, c, h, w)
         sup, qry = f5[:, :S], f5[:, S:]               # read in place through the episode stride
         run = (lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S, want_adaptive=False))
         fgp, bgp, _ = timer.bracket(run) if timer is not None else run()
         pred = ops.cosine_match(qry, fgp, bgp, self.dist_scalar)["pred"].view(B * Q, 2, h, w)
+        if hist is not None:                          # (qry_msk, cls, stat): mask and FewShotMetric counts in one launch
+            ref, cls, stat = hist
+            return ops.upsample_argmax_hist(pred, out_shape, ref.view(B * Q, *out_shape),
+                                            cls.repeat_interleave(Q) if Q > 1 else cls, stat)
         return ops.upsample_argmax(pred, out_shape, want_mask8=True)["mask8"]
 
     def stage1_prior(self, feats1, low, B, S, Q, HW, timer=None):
         """-> qry_prior [BQ, H, W] uint8 (the reference builds an int64 [BQ,1,H,W] and `.float()`s it)."""
         return self._head(feats1, low, self.ctr1, B, S, Q, HW, timer)
 
-    def stage2_mask(self, feats2, low, B, S, Q, out_shape, timer=None):
-        return self._head(feats2, low, self.ctr2, B, S, Q, out_shape, timer)
+    def stage2_mask(self, feats2, low, B, S, Q, out_shape, timer=None, hist=None):
+        return self._head(feats2, low, self.ctr2, B, S, Q, out_shape, timer, hist)
 
     def step(self, sup_feats1, qry_feats1, sup_feats2, qry_feats2, sup_mask, qry_msk, cls, stat, timer=None):
         """One batch of episodes with support and query features stored separately:
@@ -75,6 +79,9 @@ class PEMPStage2Pipeline:
                                                                 want_adaptive=False))
             fgp, bgp, _ = timer.bracket(run) if timer is not None else run()
             pred = ops.cosine_match(qry, fgp, bgp, self.dist_scalar)["pred"].view(B * Q, 2, h, w)
-            out.append(ops.upsample_argmax(pred, shape, want_mask8=True)["mask8"])
-        ops.iou_hist(out[1], qry_msk.view(B * Q, -1), cls.repeat_interleave(Q) if Q > 1 else cls, stat)
+            if len(out) == 0:
+                out.append(ops.upsample_argmax(pred, shape, want_mask8=True)["mask8"])       # stage 1: the prior mask
+            else:                                                                             # stage 2: mask + counts, one launch
+                out.append(ops.upsample_argmax_hist(pred, shape, qry_msk.view(B * Q, *shape),
+                                                    cls.repeat_interleave(Q) if Q > 1 else cls, stat))
         return out[0], out[1]

@@ -363,6 +363,26 @@ def prior_mask(q4, s4, smask, precision=PRIOR_FP32, want_rowmax=False):
 
 
 # ------------------------------------------------------------------------------------------------ K10
+def upsample_argmax_hist(pred, out_hw, ref, cls, stat):
+    """K4 + K10 in one launch: pred [N,2,h,w] -> uint8 argmax mask [N,H,W] at `out_hw`, and the FewShotMetric counts of
+    (mask, ref [N,H,W] uint8, cls [N]) added to stat [(C+1),3] (entry/pemp_stage2.py:63-65, core/metrics.py:9-23)."""
+    pred = _need(pred, torch.float32, "pred")
+    ref = _need(ref, torch.uint8, "ref")
+    cls = _need(cls, torch.int64, "cls")
+    stat = _need(stat, torch.int64, "stat")
+    N, two, h, w = pred.shape
+    H, W = int(out_hw[0]), int(out_hw[1])
+    if two != 2 or ref.numel() != N * H * W or cls.numel() != N:
+        raise ValueError("pred must be [N,2,h,w], ref [N,H,W] at the output size, cls [N]")
+    if stat.dim() != 2 or stat.shape[1] != 3:
+        raise ValueError("stat must be [(classes+1), 3]")
+    m8 = torch.empty(N, H, W, dtype=torch.uint8, device=pred.device)
+    _cabi.check(_cabi.lib().pemp_upsample_argmax_hist(pred.data_ptr(), N, h, w, H, W, m8.data_ptr(), ref.data_ptr(), cls.data_ptr(),
+                                                      stat.shape[0] - 1, stat.data_ptr(), _stream()), "pemp_upsample_argmax_hist")
+    _count(1)
+    return m8
+
+
 def iou_hist(pred, ref, cls, stat):
     """Accumulate `FewShotMetric.update` counts on the device.  pred, ref [N, ...] uint8 (same shape);
     cls [N] int64; stat [(C+1), 3] int64 is updated in place (core/metrics.py:9-23)."""

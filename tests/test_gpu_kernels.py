@@ -353,6 +353,43 @@ def test_iou_hist_golden_random(ops):
     assert np.array_equal(stat.cpu().numpy(), g["stat"])
 
 
+@pytest.mark.parametrize("N,h,w,H,W", [(6, 51, 51, 401, 401), (3, 53, 53, 417, 417), (2, 13, 17, 57, 83), (1, 4, 4, 1, 7),
+                                        (4, 51, 51, 333, 500), (2, 3, 3, 401, 401)])
+def test_upsample_argmax_hist_equals_the_two_kernels_and_the_oracle(ops, N, h, w, H, W):
+    """K4 + K10 fused (banded kernel where it applies, the two launches otherwise): same mask bytes as K4, same counts
+    as K10 on them, and both equal to the oracle (entry/pemp_stage2.py:63-65, core/metrics.py:9-23)."""
+    rng = np.random.RandomState(N * H + w)
+    pred = torch.from_numpy(rng.randn(N, 2, h, w).astype(np.float32))
+    ref = rng.choice([0, 1, 255, 7], size=(N, H, W), p=[0.5, 0.4, 0.07, 0.03]).astype(np.uint8)
+    cls = rng.randint(1, 21, N)
+    stat = torch.zeros(21, 3, dtype=torch.int64, device="cuda")
+    m = ops.upsample_argmax_hist(cu(pred), (H, W), cu(torch.from_numpy(ref)), cu(torch.from_numpy(cls)), stat)
+    m = ops.upsample_argmax_hist(cu(pred), (H, W), cu(torch.from_numpy(ref)), cu(torch.from_numpy(cls)), stat)   # accumulates
+    two = ops.upsample_argmax(cu(pred), (H, W), want_mask8=True)["mask8"]
+    assert torch.equal(m, two)
+    stat2 = torch.zeros_like(stat)
+    ops.iou_hist(two, cu(torch.from_numpy(ref)), cu(torch.from_numpy(cls)), stat2)
+    assert torch.equal(stat, 2 * stat2)
+    o_mask = O.argmax2(O.bilinear_upsample(pred, H, W)).numpy().astype(np.uint8)
+    assert np.array_equal(m.cpu().numpy(), o_mask)
+    assert np.array_equal(stat.cpu().numpy(), 2 * O.few_shot_stat(o_mask, ref, cls, 20))
+
+
+def test_upsample_argmax_hist_rejects_bad_arguments(ops):
+    pred = torch.zeros(2, 2, 4, 4, device="cuda")
+    ref = torch.zeros(2, 9, 9, dtype=torch.uint8, device="cuda")
+    cls = torch.ones(2, dtype=torch.int64, device="cuda")
+    stat = torch.zeros(21, 3, dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError):
+        ops.upsample_argmax_hist(pred, (9, 9), ref[:1], cls, stat)
+    with pytest.raises(ValueError):
+        ops.upsample_argmax_hist(pred, (9, 9), ref, cls, stat[:, :2].contiguous())
+    with pytest.raises(ValueError):
+        ops.upsample_argmax_hist(pred, (9, 9), ref.float(), cls, stat)
+    with pytest.raises(ValueError):
+        ops.upsample_argmax_hist(pred.cpu(), (9, 9), ref, cls, stat)
+
+
 # ------------------------------------------------------------------------------------------------ K6 / K7
 @pytest.mark.parametrize("name", ["baseline_b2s1", "baseline_b1s3", "panet_b2s1", "panet_b1s3q2"])
 def test_baseline_panet_golden(ops, name):

@@ -69,6 +69,8 @@ def main():
         ("K3 cosine_match", lambda: ops.cosine_match(qry, fgp, bgp), B * (c * hw * 4 + c * 6 * 4 + 2 * hw * 4)),
         ("K4 upsample_argmax", lambda: ops.upsample_argmax(pred, (H, H)), B * (2 * hw * 4 + H * H)),
         ("K10 iou_hist", lambda: ops.iou_hist(m8, ref, cls, stat), B * 2 * H * H),
+        ("K4+K10 upsample_argmax_hist", lambda: ops.upsample_argmax_hist(pred, (H, H), ref.view(B, H, H), cls, stat),
+         B * (2 * hw * 4 + 2 * H * H)),
         ("K6 map_pool_fullres", lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
          B * (S * (c * hw * 4 + 2 * H * H * 4) + 2 * c * 4)),
         # PANet alignLoss (panet.py:158-194): query pooling + S cosine passes over the support maps + fused up-sample / CE
