@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="episodes per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     return ap.parse_args()
@@ -271,6 +272,30 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": k2_bytes, "launch_ms": k2_ms, "launches_timed": timer.count(),
                 "share_of_step": k2_ms * (stages if stages == 2 else 1) / ms_per_step}
 
+    # ---------------- the same step replayed from a CUDA graph (PEMPStage2Pipeline.capture) ---------------
+    graphed = None
+    if stages == 2 and not args.no_graph:
+        gstat = torch.zeros_like(stat)
+        g = pipe.capture(f1[:, :S], f1[:, S:], f2[:, :S], f2[:, S:], batch["sup_mask"], batch["qry_msk"], batch["cls"], gstat)
+        for _ in range(3):
+            g.replay()
+            pdist.all_reduce_stat(gstat)
+        torch.cuda.synchronize()
+        pdist.barrier()
+        gstat.zero_()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            g.replay()
+            pdist.all_reduce_stat(gstat)
+        g1.record()
+        torch.cuda.synchronize()
+        pdist.barrier()
+        ms_g = pdist.max_over_ranks(g0.elapsed_time(g1), dev)
+        graphed = {"value": B * world * args.steps / (ms_g / 1e3), "unit": "episodes/s", "ms_per_step": ms_g / args.steps,
+                   "kernels_per_graph": g.launches, "same_counts_as_eager": bool(torch.equal(gstat, stat))}
+        del g
+
     # ---------------- e2e: pinned host inputs, H2D + D2H inside the timed region -------------------------
     e2e = None
     if not args.no_e2e:
@@ -337,7 +362,7 @@ def run_ours(args):
     if rank == 0:
         out = {"metric": "episodes/sec of prototype head", "value": value, "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": config_of(args, spec, w, world), "clocks": clocks, "e2e": e2e,
+               "dtype": "f32", "data": "synthetic", "config": config_of(args, spec, w, world), "clocks": clocks, "e2e": e2e, "graphed": graphed,
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                "episode_roofline": {"algorithmic_MB_per_episode": (stages * (k2_bytes / B + Q * c * h * wd * 4 + 2 * h * wd * 4 + spec.H * spec.W)
                                                                   + 2 * spec.out_h * spec.out_w) / 1e6}}

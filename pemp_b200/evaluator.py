@@ -37,6 +37,38 @@ class KernelTimer:
         return len(self.pairs)
 
 
+class GraphedStep:
+    """`PEMPStage2Pipeline.step` captured once in a CUDA graph ("CUDA-graph the head").
+
+    The tensors given to `capture` are the graph's static buffers: write the next batch of features / masks / labels
+    into them (e.g. let the encoder produce into `out=`-style views of them, or `copy_`) and call `replay()`; `stat`
+    keeps accumulating, `prior` and `mask` are overwritten by every replay.  TMA descriptors, workspace addresses and
+    launch shapes are frozen in the graph, so the shapes are fixed for the life of the object."""
+
+    def __init__(self, pipe, args):
+        self.args = args
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        stat = args[7]
+        keep = stat.clone()
+        with torch.cuda.stream(side):                # warm-up outside the capture (function attributes, lazy module load)
+            pipe.step(*args)
+        cur.wait_stream(side)
+        n0 = ops.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.prior, self.mask = pipe.step(*args)
+        self.launches = ops.launch_count() - n0      # kernels recorded in the graph (capturing does not run them)
+        ops._count(-self.launches)
+        stat.copy_(keep)                             # the warm-up step must not be counted
+
+    def replay(self):
+        self.graph.replay()
+        ops._count(self.launches)
+        return self.prior, self.mask
+
+
 class PEMPStage2Pipeline:
     def __init__(self, ctr1, ctr2, classes=20, dist_scalar=20):
         self.ctr1, self.ctr2 = ctr1, ctr2
@@ -85,3 +117,7 @@ class PEMPStage2Pipeline:
                 out.append(ops.upsample_argmax_hist(pred, shape, qry_msk.view(B * Q, *shape),
                                                     cls.repeat_interleave(Q) if Q > 1 else cls, stat))
         return out[0], out[1]
+
+    def capture(self, sup_feats1, qry_feats1, sup_feats2, qry_feats2, sup_mask, qry_msk, cls, stat):
+        """-> GraphedStep replaying `step` on these (static) tensors with one graph launch instead of nine."""
+        return GraphedStep(self, (sup_feats1, qry_feats1, sup_feats2, qry_feats2, sup_mask, qry_msk, cls, stat))

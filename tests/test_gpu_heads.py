@@ -236,3 +236,41 @@ def test_bench_size_properties_of_the_stage2_pipeline():
     present = set(int(v) for v in cls.tolist())
     rows = stat.cpu().numpy()
     assert all((rows[k] == 0).all() for k in range(1, spec.classes + 1) if k not in present)
+
+
+@pytest.mark.parametrize("B,c", [(3, 64), (8, 512)])
+def test_graphed_step_replays_the_eager_step(B, c):
+    """SURVEY 8f row 1 ("CUDA-graph the head"): one graph launch replays the nine kernels of `step` on static buffers -
+    same masks and counts as the eager step, also after the buffers were refilled, and `stat` keeps accumulating."""
+    from pemp_b200 import ops
+    from pemp_b200.evaluator import PEMPStage2Pipeline
+    spec = E.EpisodeSpec(channels=c)
+    S, Q, h, w = spec.shot, spec.query, spec.h, spec.w
+    ctr1, ctr2 = E.make_ctr(spec, 1).cuda(), E.make_ctr(spec, 2).cuda()
+    pipe = PEMPStage2Pipeline(ctr1, ctr2, spec.classes)
+    batches = [E.device_batch(spec, B, "cuda", seed=900 + k) for k in range(3)]
+
+    def args_of(b, stat):
+        f1 = b["feats1"].view(B, S + Q, c, h, w)
+        f2 = b["feats2"].view(B, S + Q, c, h, w)
+        return f1[:, :S], f1[:, S:], f2[:, :S], f2[:, S:], b["sup_mask"], b["qry_msk"], b["cls"], stat
+
+    static = {k: v.clone() for k, v in batches[0].items() if torch.is_tensor(v)}
+    g_stat = torch.zeros(spec.classes + 1, 3, dtype=torch.int64, device="cuda")
+    g_stat[0, 0] = 7                                  # pre-existing counts survive the capture
+    graphed = pipe.capture(*args_of(static, g_stat))
+    per_step = 9 if c == 512 else 11                  # the generic K2 (c = 64) has a separate finalize launch per head
+    assert graphed.launches == per_step
+    assert int(g_stat[0, 0]) == 7 and int(g_stat.sum()) == 7      # neither warm-up nor capture counted anything
+    e_stat = torch.zeros_like(g_stat)
+    e_stat[0, 0] = 7
+    for b in batches:
+        for k in ("feats1", "feats2", "sup_mask", "qry_msk", "cls"):
+            static[k].copy_(b[k])
+        n0 = ops.launch_count()
+        prior, mask = graphed.replay()
+        assert ops.launch_count() - n0 == per_step
+        e_prior, e_mask = pipe.step(*args_of(b, e_stat))
+        assert torch.equal(prior, e_prior) and torch.equal(mask, e_mask)
+        assert torch.equal(g_stat, e_stat)
+    assert int(g_stat.sum()) > 7
