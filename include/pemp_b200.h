@@ -190,6 +190,29 @@ int pemp_comm_module(const float* x, const float* mask_in, int N, int c, int h, 
                      int spq, const float* weight, const float* bias, int n_out, float* mask_out, float* out,
                      void* workspace, size_t workspace_bytes, pemp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * K12  Training path: what autograd records for the head in entry/pemp_stage1.py:57-65.
+ * pemp_meta_proto_attn_train = pemp_meta_proto_attn (same kernels, same fg_proto / bg_proto) that also stores the
+ *   per-shot centres shot_centre [B*S, c, 2p] (foreground columns first) and denominators shot_den [B*S, 2p]
+ *   (sum of the attention + eps) for the backward.  Workspace: pemp_meta_proto_attn_workspace_bytes.
+ * pemp_meta_proto_attn_bwd: g_fg / g_bg [B, c, p] = gradient of fg_proto / bg_proto  ->  d_fts [B*S, c, hw] (dense),
+ *   d_ctr [c, 2p].  Masks are constants (no gradient), as in the reference.
+ * pemp_cosine_match_bwd: g_pred [N, 2, hw] = gradient of pred (after the max over prototypes; the arg-max is recomputed,
+ *   first maximum wins)  ->  d_qry [N, c, hw] (dense), d_fg / d_bg [Bp, c, P].  c <= 1024.                              */
+int pemp_meta_proto_attn_train(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                               const float* bg, long long mask_stride, int B, int S, int c, int hw, int p, float eps,
+                               float* fg_proto, float* bg_proto, float* shot_centre, float* shot_den, void* workspace,
+                               size_t workspace_bytes, pemp_stream_t stream);
+size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p);
+int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                             const float* bg, long long mask_stride, const float* shot_centre, const float* shot_den,
+                             const float* g_fg, const float* g_bg, int B, int S, int c, int hw, int p, float* d_fts,
+                             float* d_ctr, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P);
+int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
+                          const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
+                          float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

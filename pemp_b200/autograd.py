@@ -1,0 +1,77 @@
+"""Training path of the PEMP head: `torch.autograd.Function`s over the K2 / K3 kernels and their
+hand-written backward kernels (`csrc/train.cu`), so that `loss.backward()` of `entry/pemp_stage1.py:57-65` runs on them.
+
+    fg, bg = meta_proto_attn(sup_fts, ctr, sup_fg, sup_bg)          # pemp_stage1.py:202-213, grads to sup_fts and ctr
+    pred   = cosine_match(qry_fts, fg, bg, dist_scalar)             # pemp_stage1.py:214-215,233-261, grads to all three
+    loss   = F.cross_entropy(F.interpolate(pred, size, mode="bilinear", align_corners=True), target, ignore_index=255)
+
+Masks get no gradient (they are labels).  The up-sampling and the loss stay stock PyTorch, as in the reference.
+There is no CPU path: CUDA float32 tensors only.
+"""
+import torch
+
+from . import ops
+
+
+class _MetaProtoAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sup_fts, ctr, fg, bg, eps):
+        B, S = sup_fts.shape[:2]
+        fgp, bgp, saved = ops.meta_proto_attn_train(sup_fts, ctr, fg, bg, B, S, eps)
+        ctx.saved = saved
+        ctx.shape = tuple(sup_fts.shape)
+        return fgp, bgp
+
+    @staticmethod
+    def backward(ctx, g_fg, g_bg):
+        B, S = ctx.shape[:2]
+        zero = lambda g, like: torch.zeros(like, dtype=torch.float32, device=ctx.saved[0].device) if g is None else g.contiguous()
+        p = ctx.saved[2].shape[1] // 2
+        like = (B, ctx.shape[2], p)
+        d_fts, d_ctr = ops.meta_proto_attn_bwd(ctx.saved, zero(g_fg, like), zero(g_bg, like), B, S)
+        ctx.saved = None
+        return d_fts.view(ctx.shape), d_ctr, None, None, None
+
+
+class _CosineMatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qry_fts, fg_proto, bg_proto, scalar):
+        out = ops.cosine_match(qry_fts, fg_proto, bg_proto, scalar)["pred"]
+        ctx.save_for_backward(qry_fts, fg_proto, bg_proto)
+        ctx.scalar = scalar
+        return out
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        qry, fgp, bgp = ctx.saved_tensors
+        d_qry, d_fg, d_bg = ops.cosine_match_bwd(qry, fgp, bgp, g_pred.contiguous(), ctx.scalar)
+        return d_qry.view(qry.shape), d_fg, d_bg, None
+
+
+def meta_proto_attn(sup_fts, ctr, sup_fg, sup_bg, eps=1e-6):
+    """sup_fts [B, S, c, h, w] (may be a slice of the encoder output, read in place), ctr [c, 2p] (the module's
+    `self.ctr` viewed as [c, 2p]), sup_fg / sup_bg [B*S, h*w] -> fg_proto, bg_proto [B, c, p]; differentiable in
+    sup_fts and ctr."""
+    if sup_fts.dim() != 5:
+        raise ValueError("sup_fts must be [B, S, c, h, w]")
+    return _MetaProtoAttn.apply(sup_fts, ctr, sup_fg, sup_bg, eps)
+
+
+def cosine_match(qry_fts, fg_proto, bg_proto, scalar=20.0):
+    """qry_fts [B, Q, c, h, w]; prototypes [B, c, p] (or [B, c]) -> pred [B*Q, 2, h, w]; differentiable in all three."""
+    if qry_fts.dim() != 5:
+        raise ValueError("qry_fts must be [B, Q, c, h, w]")
+    B, Q, _, h, w = qry_fts.shape
+    return _CosineMatch.apply(qry_fts, fg_proto, bg_proto, scalar).view(B * Q, 2, h, w)
+
+
+def pemp_head_loss(features, sup_mask_low, ctr, B, S, Q, target, out_shape=None, scalar=20.0):
+    """One training step of the head as `entry/pemp_stage1.py:57-65` runs it: features [B*(S+Q), c, h, w] from the encoder,
+    sup_mask_low [B*S, 2, h*w] (K0 output), target [B*Q, H, W] int64 with 255 = ignore -> (loss, pred)."""
+    _, c, h, w = features.shape
+    f5 = features.view(B, S + Q, c, h, w)
+    fg, bg = meta_proto_attn(f5[:, :S], ctr, sup_mask_low[:, 0], sup_mask_low[:, 1])
+    pred = cosine_match(f5[:, S:], fg, bg, scalar)
+    size = tuple(target.shape[-2:]) if out_shape is None else tuple(out_shape)
+    logits = torch.nn.functional.interpolate(pred, size=size, mode="bilinear", align_corners=True)
+    return torch.nn.functional.cross_entropy(logits, target, ignore_index=255), pred

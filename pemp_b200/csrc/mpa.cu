@@ -41,7 +41,7 @@ namespace cg = cooperative_groups;
 // generic kernel", nothing launched.
 int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
                         long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
-                        float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st);
+                        float* adaptive_p, float* shot_centre, float* shot_den, char* ws, size_t ws_bytes, cudaStream_t st);
 size_t pemp_mpa_tma_workspace_bytes(int B, int S, int hw);
 #ifndef PEMP_MPA_TMA
 #define PEMP_MPA_TMA 1
@@ -507,7 +507,8 @@ mpa_kernel(const float* __restrict__ fts, long long ep_stride, int S, const floa
 // one thread per (b, channel, k)
 __global__ void mpa_finalize_kernel(const float* __restrict__ part_num, const float* __restrict__ part_den, int B, int S,
                                     int c, int P, int nsplit, float eps, float* __restrict__ fg_proto,
-                                    float* __restrict__ bg_proto, float* __restrict__ adaptive_p) {
+                                    float* __restrict__ bg_proto, float* __restrict__ adaptive_p,
+                                    float* __restrict__ shot_centre, float* __restrict__ shot_den) {
   const int K = 2 * P;
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(B) * c * K) return;
@@ -524,6 +525,10 @@ __global__ void mpa_finalize_kernel(const float* __restrict__ part_num, const fl
       den += part_den[(img * nsplit + sp) * K + k];
     }
     accum += num / (den + eps);
+    if (shot_centre) {      // training forward: per-shot centres [BS, c, 2P] and denominators [BS, 2P] for the backward
+      shot_centre[(img * c + ch) * K + k] = num / (den + eps);
+      if (ch == 0) shot_den[img * K + k] = den + eps;
+    }
   }
   float v = accum / static_cast<float>(S);
   int g = k / P, j = k - g * P;
@@ -558,7 +563,7 @@ Plan make_plan(int B, int S, int c, int hw, int P) {
 template <int P, int CS, int HWT, int CCT, bool SAFE, bool PF>
 int launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
            long long mask_stride, int B, int S, int c, int hw, float eps, float* fg_proto, float* bg_proto,
-           float* adaptive_p, char* ws, const Plan& pl, cudaStream_t st) {
+           float* adaptive_p, float* shot_centre, float* shot_den, char* ws, const Plan& pl, cudaStream_t st) {
   constexpr int ND = 2 * (P - 1);
   float* table = reinterpret_cast<float*>(ws + pl.off_table);
   float* konst = reinterpret_cast<float*>(ws + pl.off_konst);
@@ -587,7 +592,7 @@ int launch(const float* fts, long long ep_stride, const float* ctr, const float*
   if (e != cudaSuccess) return static_cast<int>(e);
   long long total = static_cast<long long>(B) * c * 2 * P;
   mpa_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(num, den, B, S, c, P, pl.nsplit, eps,
-                                                                                 fg_proto, bg_proto, adaptive_p);
+                                                                                 fg_proto, bg_proto, adaptive_p, shot_centre, shot_den);
   return launch_status();
 }
 
@@ -609,10 +614,10 @@ extern "C" size_t pemp_meta_proto_attn_workspace_bytes(int B, int S, int c, int 
   return n;
 }
 
-extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
-                                    const float* bg, long long mask_stride, int B, int S, int c, int hw, int p,
-                                    float eps, float* fg_proto, float* bg_proto, float* adaptive_p, void* workspace,
-                                    size_t workspace_bytes, pemp_stream_t stream) {
+static int mpa_entry(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                     const float* bg, long long mask_stride, int B, int S, int c, int hw, int p,
+                     float eps, float* fg_proto, float* bg_proto, float* adaptive_p, float* shot_centre, float* shot_den,
+                     void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
   PEMP_REQUIRE(fts && ctr && fg && bg && fg_proto && bg_proto, PEMP_E_NULL);
   PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
   PEMP_REQUIRE(p >= 1 && p <= 4 && c % 4 == 0 && c <= kMaxChannels, PEMP_E_SHAPE);
@@ -624,10 +629,11 @@ extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stri
   cudaStream_t st = as_stream(stream);
   if (mpa_tma_shape(c, hw, p) && g_mpa_path != 1) {
     const int rc = pemp_mpa_tma_launch(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, hw, eps, fg_proto, bg_proto,
-                                       adaptive_p, ws, workspace_bytes, st);
+                                       adaptive_p, shot_centre, shot_den, ws, workspace_bytes, st);
     if (rc != PEMP_E_ALIGN) return rc;
   }
-#define PEMP_MPA_ARGS fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, ws, pl, st
+#define PEMP_MPA_ARGS \
+  fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, eps, fg_proto, bg_proto, adaptive_p, shot_centre, shot_den, ws, pl, st
   const bool safe = hw < 32 * pl.cs;
   // fully specialised PEMP shape: c = 512, 51 x 51 features, 3 prototypes per class
   if (p == 3 && pl.cs == 2 && c == 512 && hw == 2601) return launch<3, 2, 2601, 256, false, PEMP_MPA_PREFETCH != 0>(PEMP_MPA_ARGS);
@@ -642,4 +648,23 @@ extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stri
   }
 #undef PEMP_MPA_ARGS
 #undef PEMP_MPA
+}
+
+extern "C" int pemp_meta_proto_attn(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                                    const float* bg, long long mask_stride, int B, int S, int c, int hw, int p,
+                                    float eps, float* fg_proto, float* bg_proto, float* adaptive_p, void* workspace,
+                                    size_t workspace_bytes, pemp_stream_t stream) {
+  return mpa_entry(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, p, eps, fg_proto, bg_proto, adaptive_p,
+                   nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+// Training forward: the same kernels, and the per-shot centres [BS, c, 2p] (fg columns first) and denominators
+// (sum of attention + eps) [BS, 2p] that pemp_meta_proto_attn_bwd needs.
+extern "C" int pemp_meta_proto_attn_train(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                                          const float* bg, long long mask_stride, int B, int S, int c, int hw, int p,
+                                          float eps, float* fg_proto, float* bg_proto, float* shot_centre, float* shot_den,
+                                          void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(shot_centre && shot_den, PEMP_E_NULL);
+  return mpa_entry(fts, fts_episode_stride, ctr, fg, bg, mask_stride, B, S, c, hw, p, eps, fg_proto, bg_proto, nullptr,
+                   shot_centre, shot_den, workspace, workspace_bytes, stream);
 }

@@ -44,7 +44,7 @@
 
 int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
                         long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
-                        float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st);
+                        float* adaptive_p, float* shot_centre, float* shot_den, char* ws, size_t ws_bytes, cudaStream_t st);
 size_t pemp_mpa_tma_workspace_bytes(int B, int S, int hw);
 
 namespace {
@@ -474,7 +474,8 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
 __global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, const float* __restrict__ part_den,
                                         const int* __restrict__ nparts, int B, int S, int maxp, float eps,
                                         float* __restrict__ fg_proto, float* __restrict__ bg_proto,
-                                        float* __restrict__ adaptive_p) {
+                                        float* __restrict__ adaptive_p, float* __restrict__ shot_centre,
+                                        float* __restrict__ shot_den) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(B) * kC * kK) return;
   const int k = static_cast<int>(i % kK);
@@ -491,6 +492,10 @@ __global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, cons
       den += part_den[(img * maxp + sp) * 8 + k];
     }
     accum += num / (den + eps);
+    if (shot_centre) {      // training forward (see mpa.cu)
+      shot_centre[(img * kC + ch) * kK + k] = num / (den + eps);
+      if (ch == 0) shot_den[img * kK + k] = den + eps;
+    }
   }
   const float v = accum / static_cast<float>(S);
   const int g = k / kP, j = k - g * kP;
@@ -532,7 +537,7 @@ size_t pemp_mpa_tma_workspace_bytes(int B, int S, int hw) { return make_tma_plan
 // uses the generic kernel.
 int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr, const float* fg, const float* bg,
                         long long mask_stride, int B, int S, int hw, float eps, float* fg_proto, float* bg_proto,
-                        float* adaptive_p, char* ws, size_t ws_bytes, cudaStream_t st) {
+                        float* adaptive_p, float* shot_centre, float* shot_den, char* ws, size_t ws_bytes, cudaStream_t st) {
   const long long eps_stride = ep_stride ? ep_stride : static_cast<long long>(S) * kC * hw;
   if (hw < kTW) return PEMP_E_ALIGN;
   const TmaPlan pl = make_tma_plan(B, S, hw);
@@ -550,6 +555,6 @@ int pemp_mpa_tma_launch(const float* fts, long long ep_stride, const float* ctr,
                                                num, den);
   const long long total = static_cast<long long>(B) * kC * kK;
   mpa_tma_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      num, den, nparts, B, S, pl.maxp, eps, fg_proto, bg_proto, adaptive_p);
+      num, den, nparts, B, S, pl.maxp, eps, fg_proto, bg_proto, adaptive_p, shot_centre, shot_den);
   return launch_status();
 }

@@ -1,0 +1,506 @@
+// K12  backward of the PEMP head for the training path.
+//
+// replaces what autograd records for                                   entry/pemp_stage1.py:57-65 (loss.backward())
+//   K3  compute_similarity + max over prototypes                      pemp_stage1.py:214-215, 233-261
+//   K2  meta-prototype attention                                      pemp_stage1.py:202-213
+// The reference's backward re-reads the [BS, c, 2P, hw] temporaries of the forward (4 x 32 MB per shot at the PEMP size).
+// Here each backward reads the feature map once and writes its gradient once: 2 * c * hw * 4 bytes per image.
+//
+// Both kernels share one skeleton.  A CTA owns a run of 32-pixel tiles of one image:
+//   load + phase A   lane = pixel, warp = channel subset: the tile goes to shared memory while the per-pixel dot products
+//                    with the [c, K] tables (prototypes / centres / gradient coefficients) accumulate in registers;
+//   pixel step       one warp: cross-warp sums, arg-max / softmax and their derivatives -> per-pixel coefficients;
+//   phase B1         lane = pixel: the gradient tile is a rank-2K combination of table rows (plus, for K3, the tile
+//                    itself) -> coalesced 128-byte stores;
+//   phase B2         thread = channel: the per-channel sums over pixels (gradients of prototypes / centres) accumulate in
+//                    registers across the CTA's tiles (tile rows are padded to 33 floats: conflict free both ways).
+// Per-CTA partial sums go to the workspace and a finalize kernel adds them in a fixed order (no float atomics).
+//
+// Math.  K3: sim_gk = scalar * (q . pn_gk) / max(|q|, eps), pred_g = max_k sim_gk (first maximum wins)
+//   dq  = sum_g gp_g * scalar * (pn_gk* / |q| - (q . pn_gk*) q / |q|^3)          (second term 0 when |q| < eps)
+//   dpn_gk = sum_x [k = k*] gp_g * scalar * q / |q|;   dproto = (dpn - pn (pn . dpn)) / |proto|   (dpn / eps if clamped)
+// K2: l_k = 2 f . ctr_k - |ctr_k|^2 (the |f|^2 term cancels in the softmax), sigma = softmax over the group,
+//   a_k = m_g sigma_k, centre_k = sum_x f a_k / den_k, den_k = sum_x a_k + eps, with A_k = g_centre_k / den_k:
+//   da_k = f . A_k - A_k . centre_k;  dl_k = sigma_k (m da_k - sum_j sigma_j m da_j)
+//   df = sum_k (a_k A_k + 2 dl_k ctr_k);   dctr_k = sum_x 2 dl_k f - ctr_k sum_x 2 dl_k
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBT = 256;           // threads per CTA
+constexpr int kBW = kBT / 32;      // warps
+constexpr int kLd = 33;            // padded tile row
+constexpr int kMaxCPT = 4;         // channels per thread in phase B2  =>  c <= 1024
+constexpr float kCosEps = 1e-8f;   // F.cosine_similarity's eps
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {   // scratch: kBW floats; every thread gets the sum
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kBW; ++w) s += scratch[w];
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------ K3 backward
+// pn [Bp][c][K] normalised prototypes (k < P: background, k >= P: foreground = the channel order of pred), nrm [Bp][K]
+__global__ void __launch_bounds__(kBT)
+proto_norm_kernel(const float* __restrict__ fg_proto, const float* __restrict__ bg_proto, int c, int P, float* __restrict__ pn,
+                  float* __restrict__ nrm) {
+  __shared__ float scratch[kBW];
+  const int b = blockIdx.x, K = 2 * P;
+  for (int k = 0; k < K; ++k) {
+    const float* src = (k < P ? bg_proto : fg_proto) + static_cast<long long>(b) * c * P + (k < P ? k : k - P);
+    float s = 0.f;
+    for (int ch = threadIdx.x; ch < c; ch += kBT) {
+      const float v = __ldg(src + static_cast<long long>(ch) * P);
+      s = fmaf(v, v, s);
+    }
+    const float n = sqrtf(block_sum(s, scratch));
+    const float inv = 1.0f / fmaxf(n, kCosEps);
+    for (int ch = threadIdx.x; ch < c; ch += kBT)
+      pn[(static_cast<long long>(b) * c + ch) * K + k] = __ldg(src + static_cast<long long>(ch) * P) * inv;
+    if (threadIdx.x == 0) nrm[b * K + k] = n;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBT, 2)
+cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, const float* __restrict__ pn,
+                  const float* __restrict__ g_pred, int c, int hw, int ntiles, float scalar, float* __restrict__ dq,
+                  float* __restrict__ part) {
+  constexpr int P = K / 2, NA = K + 1;
+  extern __shared__ float sm[];
+  float* tile = sm;                          // [c][33]
+  float* tab = tile + c * kLd;               // [c][K]
+  float* red = tab + c * K;                  // [kBW][NA][32]
+  float* sum = red + kBW * NA * 32;          // [NA][32]
+  float* wts = sum + NA * 32;                // [32][K]   phase-B2 weights
+  float* cg = wts + 32 * K;                  // [2][32]   coefficient of the selected prototype
+  float* tq = cg + 64;                       // [32]      coefficient of q
+  int* sel = reinterpret_cast<int*>(tq + 32);   // [2][32] selected table column
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.y, b = n / Q, qi = n - b * Q;
+  const float* src = qry + static_cast<long long>(b) * ep_stride + static_cast<long long>(qi) * c * hw;
+  for (int i = tid; i < c * K; i += kBT) tab[i] = __ldg(pn + static_cast<long long>(b) * c * K + i);
+  float accB[kMaxCPT][K];
+#pragma unroll
+  for (int i = 0; i < kMaxCPT; ++i)
+#pragma unroll
+    for (int k = 0; k < K; ++k) accB[i][k] = 0.f;
+  const int t0 = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
+  const int t1 = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
+  __syncthreads();
+  for (int t = t0; t < t1; ++t) {
+    const int x = t * 32 + lane;
+    const bool inb = x < hw;
+    float acc[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) acc[j] = 0.f;
+    for (int ch = warp; ch < c; ch += kBW) {
+      const float v = inb ? __ldg(src + static_cast<long long>(ch) * hw + x) : 0.f;
+      tile[ch * kLd + lane] = v;
+      acc[K] = fmaf(v, v, acc[K]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(v, tab[ch * K + k], acc[k]);
+    }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) red[(warp * NA + j) * 32 + lane] = acc[j];
+    __syncthreads();
+    for (int i = tid; i < NA * 32; i += kBT) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBW; ++w) s += red[w * NA * 32 + i];
+      sum[i] = s;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const float nq = sqrtf(sum[K * 32 + lane]);
+      const float invq = 1.0f / fmaxf(nq, kCosEps);
+      float tsum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        int best = 0;
+        float bv = sum[(g * P) * 32 + lane];
+#pragma unroll
+        for (int k = 1; k < P; ++k) {
+          const float v = sum[(g * P + k) * 32 + lane];
+          if (v > bv) {
+            bv = v;
+            best = k;
+          }
+        }
+        const float gp = inb ? __ldg(g_pred + (static_cast<long long>(n) * 2 + g) * hw + x) * scalar : 0.f;
+        const float co = gp * invq;
+        cg[g * 32 + lane] = co;
+        sel[g * 32 + lane] = g * P + best;
+        tsum = fmaf(gp, bv, tsum);
+#pragma unroll
+        for (int k = 0; k < P; ++k) wts[lane * K + g * P + k] = (k == best) ? co : 0.f;
+      }
+      tq[lane] = (nq < kCosEps) ? 0.f : tsum * invq * invq * invq;
+    }
+    __syncthreads();
+    {   // B1: dq tile
+      const float c0 = cg[lane], c1 = cg[32 + lane], tv = tq[lane];
+      const int s0 = sel[lane], s1 = sel[32 + lane];
+      float* dst = dq + static_cast<long long>(n) * c * hw + x;
+      for (int ch = warp; ch < c; ch += kBW) {
+        const float val = fmaf(c0, tab[ch * K + s0], fmaf(c1, tab[ch * K + s1], -tv * tile[ch * kLd + lane]));
+        if (inb) dst[static_cast<long long>(ch) * hw] = val;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxCPT; ++i) {   // B2: per-channel sums for the prototype gradients
+      const int ch = tid + i * kBT;
+      if (ch < c) {
+        for (int xx = 0; xx < 32; ++xx) {
+          const float v = tile[ch * kLd + xx];
+#pragma unroll
+          for (int k = 0; k < K; ++k) accB[i][k] = fmaf(wts[xx * K + k], v, accB[i][k]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* dstp = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * c * K;
+#pragma unroll
+  for (int i = 0; i < kMaxCPT; ++i) {
+    const int ch = tid + i * kBT;
+    if (ch < c) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) dstp[ch * K + k] = accB[i][k];
+    }
+  }
+}
+
+// one CTA per prototype set: add the partials of its Q query maps, then the backward of the normalisation
+__global__ void __launch_bounds__(kBT)
+cosine_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ pn, const float* __restrict__ nrm, int Q,
+                           int chunks, int c, int P, float* __restrict__ d_fg, float* __restrict__ d_bg) {
+  __shared__ float scratch[kBW];
+  const int b = blockIdx.x, K = 2 * P;
+  for (int k = 0; k < K; ++k) {
+    float d[kMaxCPT];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxCPT; ++i) {
+      const int ch = threadIdx.x + i * kBT;
+      d[i] = 0.f;
+      if (ch < c) {
+        for (int j = 0; j < Q * chunks; ++j)
+          d[i] += part[((static_cast<long long>(b) * Q * chunks + j) * c + ch) * K + k];
+        dot = fmaf(pn[(static_cast<long long>(b) * c + ch) * K + k], d[i], dot);
+      }
+    }
+    dot = block_sum(dot, scratch);
+    const float nv = nrm[b * K + k];
+    float* out = (k < P ? d_bg : d_fg) + static_cast<long long>(b) * c * P + (k < P ? k : k - P);
+#pragma unroll
+    for (int i = 0; i < kMaxCPT; ++i) {
+      const int ch = threadIdx.x + i * kBT;
+      if (ch < c) {
+        const float pv = pn[(static_cast<long long>(b) * c + ch) * K + k];
+        out[static_cast<long long>(ch) * P] = (nv < kCosEps) ? d[i] / kCosEps : (d[i] - pv * dot) / nv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2 backward
+// coef [BS][c][K] = g_centre / (S * den); beta [BS][2K] = { -sum_c coef * centre, |ctr_k|^2 }.   Columns k < P: foreground
+// group.  |ctr_k|^2 is a bias common to every pixel's logit, so it is summed in double (as the forward does).
+__global__ void __launch_bounds__(kBT)
+mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__ g_bg, const float* __restrict__ shot_centre,
+                       const float* __restrict__ shot_den, const float* __restrict__ ctr, int S, int c, int P,
+                       float* __restrict__ coef, float* __restrict__ beta) {
+  __shared__ float scratch[kBW];
+  const int n = blockIdx.x, b = n / S, K = 2 * P;
+  for (int k = 0; k < K; ++k) {
+    const float* g = (k < P ? g_fg : g_bg) + static_cast<long long>(b) * c * P + (k < P ? k : k - P);
+    const float inv = 1.0f / (static_cast<float>(S) * __ldg(shot_den + n * K + k));
+    float s = 0.f;
+    for (int ch = threadIdx.x; ch < c; ch += kBT) {
+      const float a = __ldg(g + static_cast<long long>(ch) * P) * inv;
+      coef[(static_cast<long long>(n) * c + ch) * K + k] = a;
+      s = fmaf(a, __ldg(shot_centre + (static_cast<long long>(n) * c + ch) * K + k), s);
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) beta[n * 2 * K + k] = -s;
+  }
+  if (threadIdx.x < K) {
+    double s2 = 0.0;
+    for (int ch = 0; ch < c; ++ch) {
+      const double v = static_cast<double>(__ldg(ctr + ch * K + threadIdx.x));
+      s2 = fma(v, v, s2);
+    }
+    beta[n * 2 * K + K + threadIdx.x] = static_cast<float>(s2);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBT, 2)
+mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ ctr,
+               const float* __restrict__ coef, const float* __restrict__ beta, const float* __restrict__ fg,
+               const float* __restrict__ bg, long long mask_stride, int c, int hw, int ntiles, float* __restrict__ dfts,
+               float* __restrict__ part) {
+  constexpr int P = K / 2, NA = 2 * K;
+  extern __shared__ float sm[];
+  float* tile = sm;                        // [c][33]
+  float* ctab = tile + c * kLd;            // [c][K]  centres
+  float* atab = ctab + c * K;              // [c][K]  gradient coefficients of this image
+  float* red = atab + c * K;               // [kBW][NA][32]
+  float* sum = red + kBW * NA * 32;        // [NA][32]
+  float* av = sum + NA * 32;               // [32][K]  a_k
+  float* dv = av + 32 * K;                 // [32][K]  2 dl_k
+  float* konst = dv + 32 * K;              // [K] |ctr_k|^2, [K] beta
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.y, b = n / S, si = n - b * S;
+  const float* src = fts + static_cast<long long>(b) * ep_stride + static_cast<long long>(si) * c * hw;
+  for (int i = tid; i < c * K; i += kBT) {
+    ctab[i] = __ldg(ctr + i);
+    atab[i] = __ldg(coef + static_cast<long long>(n) * c * K + i);
+  }
+  __syncthreads();
+  if (tid < K) {
+    konst[tid] = __ldg(beta + n * 2 * K + K + tid);
+    konst[K + tid] = __ldg(beta + n * 2 * K + tid);
+  }
+  float accB[kMaxCPT][K];
+#pragma unroll
+  for (int i = 0; i < kMaxCPT; ++i)
+#pragma unroll
+    for (int k = 0; k < K; ++k) accB[i][k] = 0.f;
+  float dsum = 0.f;
+  const int t0 = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
+  const int t1 = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
+  __syncthreads();
+  for (int t = t0; t < t1; ++t) {
+    const int x = t * 32 + lane;
+    const bool inb = x < hw;
+    float acc[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) acc[j] = 0.f;
+    for (int ch = warp; ch < c; ch += kBW) {
+      const float v = inb ? __ldg(src + static_cast<long long>(ch) * hw + x) : 0.f;
+      tile[ch * kLd + lane] = v;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        acc[k] = fmaf(v, ctab[ch * K + k], acc[k]);
+        acc[K + k] = fmaf(v, atab[ch * K + k], acc[K + k]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) red[(warp * NA + j) * 32 + lane] = acc[j];
+    __syncthreads();
+    for (int i = tid; i < NA * 32; i += kBT) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBW; ++w) s += red[w * NA * 32 + i];
+      sum[i] = s;
+    }
+    __syncthreads();
+    if (tid < 32) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float m = inb ? __ldg((g == 0 ? fg : bg) + static_cast<long long>(n) * mask_stride + x) : 0.f;
+        float l[P], mx = -CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          l[k] = fmaf(2.0f, sum[(g * P + k) * 32 + lane], -konst[g * P + k]);
+          mx = fmaxf(mx, l[k]);
+        }
+        float z = 0.f;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          l[k] = expf(l[k] - mx);
+          z += l[k];
+        }
+        const float iz = 1.0f / z;
+        float ds[P], dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          l[k] *= iz;                                                              // sigma_k
+          ds[k] = m * (sum[(K + g * P + k) * 32 + lane] + konst[K + g * P + k]);   // d sigma_k
+          dot = fmaf(l[k], ds[k], dot);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          av[lane * K + g * P + k] = m * l[k];
+          dv[lane * K + g * P + k] = 2.0f * l[k] * (ds[k] - dot);
+        }
+      }
+    }
+    __syncthreads();
+    {   // B1: df tile
+      float a[K], d[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        a[k] = av[lane * K + k];
+        d[k] = dv[lane * K + k];
+      }
+      float* dst = dfts + static_cast<long long>(n) * c * hw + x;
+      for (int ch = warp; ch < c; ch += kBW) {
+        float val = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) val = fmaf(a[k], atab[ch * K + k], fmaf(d[k], ctab[ch * K + k], val));
+        if (inb) dst[static_cast<long long>(ch) * hw] = val;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxCPT; ++i) {   // B2: sum_x 2 dl_k f
+      const int ch = tid + i * kBT;
+      if (ch < c) {
+        for (int xx = 0; xx < 32; ++xx) {
+          const float v = tile[ch * kLd + xx];
+#pragma unroll
+          for (int k = 0; k < K; ++k) accB[i][k] = fmaf(dv[xx * K + k], v, accB[i][k]);
+        }
+      }
+    }
+    if (tid < K) {
+      for (int xx = 0; xx < 32; ++xx) dsum += dv[xx * K + tid];
+    }
+    __syncthreads();
+  }
+  float* dstp = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * (c + 1) * K;
+#pragma unroll
+  for (int i = 0; i < kMaxCPT; ++i) {
+    const int ch = tid + i * kBT;
+    if (ch < c) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) dstp[ch * K + k] = accB[i][k];
+    }
+  }
+  if (tid < K) dstp[c * K + tid] = dsum;
+}
+
+// one thread per (channel, k): the partials of every image and chunk in index order (double accumulators)
+__global__ void mpa_bwd_finalize_kernel(const float* __restrict__ part, long long nparts, int c, int K, const float* __restrict__ ctr,
+                                        float* __restrict__ d_ctr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c * K) return;
+  const int k = i % K;
+  double s = 0.0, d = 0.0;
+  for (long long p = 0; p < nparts; ++p) {
+    const float* row = part + p * (c + 1) * K;
+    s += static_cast<double>(row[i]);
+    d += static_cast<double>(row[c * K + k]);
+  }
+  d_ctr[i] = static_cast<float>(s - static_cast<double>(__ldg(ctr + i)) * d);
+}
+
+struct BwdPlan {
+  int chunks, ntiles;
+};
+BwdPlan bwd_plan(int N, int hw) {
+  BwdPlan p;
+  p.ntiles = (hw + 31) / 32;
+  int want = (4 * 148 + N - 1) / N;          // ~2 waves of 2 CTAs per SM
+  p.chunks = want < 1 ? 1 : (want > p.ntiles ? p.ntiles : want);
+  return p;
+}
+size_t cos_smem(int c, int K) {
+  return (static_cast<size_t>(c) * kLd + static_cast<size_t>(c) * K + kBW * (K + 1) * 32 + (K + 1) * 32 + 32 * K + 64 + 32 + 64) * 4;
+}
+size_t mpa_smem(int c, int K) {
+  return (static_cast<size_t>(c) * kLd + 2 * static_cast<size_t>(c) * K + kBW * 2 * K * 32 + 2 * K * 32 + 2 * 32 * K + 2 * K) * 4;
+}
+
+template <int K>
+int launch_cos_bwd(const float* qry, long long ep, int Q, const float* pn, const float* g_pred, int N, int c, int hw,
+                   const BwdPlan& pl, float scalar, float* dq, float* part, cudaStream_t st) {
+  const size_t smem = cos_smem(c, K);
+  cudaError_t e = cudaFuncSetAttribute(cosine_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cosine_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(qry, ep, Q, pn, g_pred, c, hw, pl.ntiles, scalar, dq, part);
+  return PEMP_OK;
+}
+template <int K>
+int launch_mpa_bwd(const float* fts, long long ep, int S, const float* ctr, const float* coef, const float* beta, const float* fg,
+                   const float* bg, long long mask_stride, int N, int c, int hw, const BwdPlan& pl, float* dfts, float* part,
+                   cudaStream_t st) {
+  const size_t smem = mpa_smem(c, K);
+  cudaError_t e = cudaFuncSetAttribute(mpa_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  mpa_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, c, hw, pl.ntiles, dfts, part);
+  return PEMP_OK;
+}
+
+}  // namespace
+
+extern "C" size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P) {
+  if (N <= 0 || Bp <= 0 || c <= 0 || hw <= 0 || P < 1 || P > 4) return 0;
+  const BwdPlan pl = bwd_plan(N, hw);
+  const size_t K = 2 * P;
+  return align_up(static_cast<size_t>(Bp) * c * K * 4, 256) + align_up(static_cast<size_t>(Bp) * K * 4, 256) +
+         align_up(static_cast<size_t>(N) * pl.chunks * c * K * 4, 256);
+}
+
+extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
+                                     const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
+                                     float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(qry && fg_proto && bg_proto && g_pred && d_qry && d_fg && d_bg, PEMP_E_NULL);
+  PEMP_REQUIRE(N > 0 && N <= 65535 && Bp > 0 && c > 0 && hw > 0 && N % Bp == 0, PEMP_E_SHAPE);
+  PEMP_REQUIRE(P >= 1 && P <= 4 && c <= kMaxCPT * kBT && cos_smem(c, 2 * P) <= 227 * 1024, PEMP_E_SHAPE);
+  PEMP_REQUIRE(workspace && workspace_bytes >= pemp_cosine_match_bwd_workspace_bytes(N, Bp, c, hw, P), PEMP_E_WORKSPACE);
+  cudaStream_t st = as_stream(stream);
+  const BwdPlan pl = bwd_plan(N, hw);
+  const int K = 2 * P, Q = N / Bp;
+  char* ws = static_cast<char*>(workspace);
+  float* pn = reinterpret_cast<float*>(ws);
+  float* nrm = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(Bp) * c * K * 4, 256));
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(nrm) + align_up(static_cast<size_t>(Bp) * K * 4, 256));
+  const long long ep = qry_episode_stride ? qry_episode_stride : static_cast<long long>(Q) * c * hw;
+  proto_norm_kernel<<<Bp, kBT, 0, st>>>(fg_proto, bg_proto, c, P, pn, nrm);
+  int rc;
+  switch (P) {
+    case 1: rc = launch_cos_bwd<2>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
+    case 2: rc = launch_cos_bwd<4>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
+    case 3: rc = launch_cos_bwd<6>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
+    default: rc = launch_cos_bwd<8>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
+  }
+  if (rc != PEMP_OK) return rc;
+  cosine_bwd_finalize_kernel<<<Bp, kBT, 0, st>>>(part, pn, nrm, Q, pl.chunks, c, P, d_fg, d_bg);
+  return launch_status();
+}
+
+extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p) {
+  if (B <= 0 || S <= 0 || c <= 0 || hw <= 0 || p < 1 || p > 4) return 0;
+  const size_t N = static_cast<size_t>(B) * S, K = 2 * p;
+  const BwdPlan pl = bwd_plan(static_cast<int>(N), hw);
+  return align_up(N * c * K * 4, 256) + align_up(N * 2 * K * 4, 256) + align_up(N * pl.chunks * (c + 1) * K * 4, 256);
+}
+
+extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
+                                        const float* bg, long long mask_stride, const float* shot_centre, const float* shot_den,
+                                        const float* g_fg, const float* g_bg, int B, int S, int c, int hw, int p, float* d_fts,
+                                        float* d_ctr, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(fts && ctr && fg && bg && shot_centre && shot_den && g_fg && g_bg && d_fts && d_ctr, PEMP_E_NULL);
+  PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
+  PEMP_REQUIRE(p >= 1 && p <= 4 && c <= kMaxCPT * kBT && mpa_smem(c, 2 * p) <= 227 * 1024, PEMP_E_SHAPE);
+  PEMP_REQUIRE(workspace && workspace_bytes >= pemp_meta_proto_attn_bwd_workspace_bytes(B, S, c, hw, p), PEMP_E_WORKSPACE);
+  cudaStream_t st = as_stream(stream);
+  const int N = B * S, K = 2 * p;
+  const BwdPlan pl = bwd_plan(N, hw);
+  char* ws = static_cast<char*>(workspace);
+  float* coef = reinterpret_cast<float*>(ws);
+  float* beta = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(N) * c * K * 4, 256));
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(beta) + align_up(static_cast<size_t>(N) * 2 * K * 4, 256));
+  const long long ep = fts_episode_stride ? fts_episode_stride : static_cast<long long>(S) * c * hw;
+  mpa_bwd_prepare_kernel<<<N, kBT, 0, st>>>(g_fg, g_bg, shot_centre, shot_den, ctr, S, c, p, coef, beta);
+  int rc;
+  switch (p) {
+    case 1: rc = launch_mpa_bwd<2>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
+    case 2: rc = launch_mpa_bwd<4>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
+    case 3: rc = launch_mpa_bwd<6>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
+    default: rc = launch_mpa_bwd<8>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
+  }
+  if (rc != PEMP_OK) return rc;
+  mpa_bwd_finalize_kernel<<<(c * K + 255) / 256, 256, 0, st>>>(part, static_cast<long long>(N) * pl.chunks, c, K, ctr, d_ctr);
+  return launch_status();
+}

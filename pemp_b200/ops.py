@@ -399,3 +399,77 @@ def iou_hist(pred, ref, cls, stat):
                                           stat.shape[0] - 1, stat.data_ptr(), _stream()), "pemp_iou_hist")
     _count(1)
     return stat
+
+
+# ------------------------------------------------------------------------------------------------ K12 (training path)
+def meta_proto_attn_train(fts, ctr, fg, bg, B, S, eps=1e-6):
+    """K2 forward for training: -> (fg_proto [B,c,p], bg_proto [B,c,p], saved) where `saved` is what
+    `meta_proto_attn_bwd` needs (per-shot centres [BS,c,2p] and denominators [BS,2p])."""
+    fts, ep, c, hw = _episodes(fts, B, S, "fts")
+    ctr = _need(ctr, torch.float32, "ctr")
+    n_img = B * S
+    if ctr.dim() != 2 or ctr.shape[0] != c or ctr.shape[1] % 2:
+        raise ValueError(f"ctr must be [c, 2p] with c = {c}, got {tuple(ctr.shape)}")
+    p = ctr.shape[1] // 2
+    fg = _need_loose(fg, "fg").reshape(n_img, hw)
+    bg = _need_loose(bg, "bg").reshape(n_img, hw)
+    fgp, bgp, stride, keep = _mask_pair(fg, bg, n_img, hw)
+    L = _cabi.lib()
+    dev = fts.device
+    ws = _ws(L.pemp_meta_proto_attn_workspace_bytes(B, S, c, hw, p), dev)
+    out_f = torch.empty(B, c, p, dtype=torch.float32, device=dev)
+    out_b = torch.empty(B, c, p, dtype=torch.float32, device=dev)
+    centre = torch.empty(n_img, c, 2 * p, dtype=torch.float32, device=dev)
+    den = torch.empty(n_img, 2 * p, dtype=torch.float32, device=dev)
+    _cabi.check(L.pemp_meta_proto_attn_train(fts.data_ptr(), ep, ctr.data_ptr(), fgp, bgp, stride, B, S, c, hw, p, float(eps),
+                                             out_f.data_ptr(), out_b.data_ptr(), centre.data_ptr(), den.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream()), "pemp_meta_proto_attn_train")
+    _count(2 if (c == 512 and p == 3 and hw >= 32) or p == 1 else 3)
+    return out_f, out_b, (fts, ep, ctr, keep[0], keep[1] if keep[1] is not None else keep[0], centre, den)
+
+
+def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S):
+    """-> (d_fts [B*S, c, hw], d_ctr [c, 2p]) from the gradients of fg_proto / bg_proto [B, c, p]."""
+    fts, ep, ctr, fg, bg, centre, den = saved
+    c, p = ctr.shape[0], ctr.shape[1] // 2
+    hw = fg.shape[1]
+    g_fg = _need(g_fg, torch.float32, "g_fg")
+    g_bg = _need(g_bg, torch.float32, "g_bg")
+    if tuple(g_fg.shape) != (B, c, p) or tuple(g_bg.shape) != (B, c, p):
+        raise ValueError(f"gradients must be [{B}, {c}, {p}]")
+    fgp, bgp, stride, keep = _mask_pair(fg, bg, B * S, hw)
+    L = _cabi.lib()
+    dev = fts.device
+    ws = _ws(L.pemp_meta_proto_attn_bwd_workspace_bytes(B, S, c, hw, p), dev)
+    d_fts = torch.empty(B * S, c, hw, dtype=torch.float32, device=dev)
+    d_ctr = torch.empty(c, 2 * p, dtype=torch.float32, device=dev)
+    _cabi.check(L.pemp_meta_proto_attn_bwd(fts.data_ptr(), ep, ctr.data_ptr(), fgp, bgp, stride, centre.data_ptr(), den.data_ptr(),
+                                           g_fg.data_ptr(), g_bg.data_ptr(), B, S, c, hw, p, d_fts.data_ptr(), d_ctr.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream()), "pemp_meta_proto_attn_bwd")
+    _count(3)
+    del keep
+    return d_fts, d_ctr
+
+
+def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0):
+    """Backward of `cosine_match(...)["pred"]`: qry as in the forward, g_pred [N, 2, hw] -> (d_qry [N, c, hw],
+    d_fg, d_bg shaped like the prototypes)."""
+    fg_proto = _need(fg_proto, torch.float32, "fg_proto")
+    bg_proto = _need(bg_proto, torch.float32, "bg_proto")
+    g_pred = _need(g_pred, torch.float32, "g_pred")
+    Bp = fg_proto.shape[0]
+    P = 1 if fg_proto.dim() == 2 else fg_proto.shape[2]
+    n_maps = qry.shape[0] * qry.shape[1] if qry.dim() == 5 else qry.shape[0]
+    qry, ep, c, hw = _episodes(qry, Bp, n_maps // Bp, "qry")
+    if tuple(g_pred.shape) != (n_maps, 2, hw):
+        raise ValueError(f"g_pred must be [{n_maps}, 2, {hw}], got {tuple(g_pred.shape)}")
+    L = _cabi.lib()
+    dev = qry.device
+    ws = _ws(L.pemp_cosine_match_bwd_workspace_bytes(n_maps, Bp, c, hw, P), dev)
+    d_qry = torch.empty(n_maps, c, hw, dtype=torch.float32, device=dev)
+    d_fg, d_bg = torch.empty_like(fg_proto), torch.empty_like(bg_proto)
+    _cabi.check(L.pemp_cosine_match_bwd(qry.data_ptr(), ep, fg_proto.data_ptr(), bg_proto.data_ptr(), g_pred.data_ptr(), n_maps, Bp,
+                                        c, hw, P, float(scalar), d_qry.data_ptr(), d_fg.data_ptr(), d_bg.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream()), "pemp_cosine_match_bwd")
+    _count(3)
+    return d_qry, d_fg, d_bg

@@ -1,0 +1,162 @@
+"""K12: gradient parity of the training path.  The reference trains with autograd over the PyTorch ops of
+`pemp_stage1.py:202-261`; the oracle restates those ops in torch, so autograd over the ORACLE (float64) is the checker
+for the hand-written backward kernels.  Tolerance: 2e-5 of the largest gradient entry (fp32 kernels, float64 checker);
+where the op itself is ill conditioned in fp32 (soft-max over squared distances summed over >= 512 channels) the bar is
+the error of fp32 autograd over the same ops - i.e. of the reference's own training step - against the float64 result
+(`tools/probes/grad_error_probe.py`: 3-4e-5 for it, 0.4-2.5e-5 for the kernels)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import nrel
+from oracle import restate as O
+
+pytestmark = pytest.mark.gpu
+GTOL = 2e-5
+
+
+def _case(B, S, Q, c, h, w, P, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, S + Q, c, h, w, generator=g) * scale
+    ctr = torch.randn(c, 2 * P, generator=g) * 0.5 * scale
+    fg = (torch.rand(B * S, h * w, generator=g) > 0.6).float()
+    fg[0, : h * w // 3] = torch.rand(h * w // 3, generator=g)            # soft mask values are legal too
+    bg = 1.0 - fg
+    return feats, ctr, fg, bg
+
+
+@pytest.mark.parametrize("B,S,c,h,w,P", [(2, 2, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (2, 5, 512, 13, 13, 3),
+                                          (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (1, 3, 1024, 6, 7, 2)])
+def test_meta_proto_attn_backward_matches_autograd_of_the_oracle(B, S, c, h, w, P):
+    from pemp_b200 import autograd as A
+    feats, ctr, fg, bg = _case(B, S, 1, c, h, w, P, seed=c + h)
+    g = torch.Generator().manual_seed(7)
+    wf, wb = torch.randn(B, c, P, generator=g), torch.randn(B, c, P, generator=g)
+    # checker: float64 autograd over the oracle (and fp32 autograd over it = the reference's own arithmetic)
+    sup64 = feats[:, :S].double().reshape(B * S, c, h * w).requires_grad_(True)
+    ctr64 = ctr.double().requires_grad_(True)
+    of, ob, _ = O.meta_proto_attention(sup64, fg.double(), bg.double(), ctr64, B, S, P)
+    ((of * wf.double()).sum() + (ob * wb.double()).sum()).backward()
+    sup32 = feats[:, :S].reshape(B * S, c, h * w).clone().requires_grad_(True)
+    ctr32 = ctr.clone().requires_grad_(True)
+    of32, ob32, _ = O.meta_proto_attention(sup32, fg, bg, ctr32, B, S, P)
+    ((of32 * wf).sum() + (ob32 * wb).sum()).backward()
+    tol_f = max(GTOL, nrel(sup32.grad, sup64.grad.float()))
+    tol_c = max(GTOL, nrel(ctr32.grad, ctr64.grad.float()))
+    # kernels (the support features are a strided slice of the encoder output, read in place)
+    f_cu = feats.cuda().requires_grad_(True)
+    ctr_cu = ctr.cuda().requires_grad_(True)
+    kf, kb = A.meta_proto_attn(f_cu[:, :S], ctr_cu, fg.cuda(), bg.cuda())
+    assert nrel(kf.detach().cpu(), of.detach().float()) < 1e-5 and nrel(kb.detach().cpu(), ob.detach().float()) < 1e-5
+    ((kf * wf.cuda()).sum() + (kb * wb.cuda()).sum()).backward()
+    d_sup = f_cu.grad[:, :S].reshape(B * S, c, h * w).cpu()
+    assert float(f_cu.grad[:, S:].abs().max()) == 0.0
+    assert nrel(d_sup, sup64.grad.float()) <= tol_f
+    assert nrel(ctr_cu.grad.cpu(), ctr64.grad.float()) <= tol_c
+
+
+@pytest.mark.parametrize("B,Q,c,h,w,P", [(2, 1, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (2, 2, 512, 13, 13, 3),
+                                          (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (2, 1, 1024, 6, 7, 2)])
+def test_cosine_match_backward_matches_autograd_of_the_oracle(B, Q, c, h, w, P):
+    from pemp_b200 import autograd as A
+    g = torch.Generator().manual_seed(c + w)
+    qry = torch.randn(B, Q, c, h, w, generator=g)
+    shape = (B, c, P) if P > 1 else (B, c)
+    fgp, bgp = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    wgt = torch.randn(B * Q, 2, h, w, generator=g)
+    q64 = qry.double().reshape(B * Q, c, h * w).requires_grad_(True)
+    f64, b64 = fgp.double().requires_grad_(True), bgp.double().requires_grad_(True)
+    pred64, _ = O.reduce_over_protos(O.cosine_match(q64, f64, b64, 20.0))
+    (pred64 * wgt.double().view(B * Q, 2, h * w)).sum().backward()
+    q_cu = qry.cuda().requires_grad_(True)
+    f_cu, b_cu = fgp.cuda().requires_grad_(True), bgp.cuda().requires_grad_(True)
+    pred = A.cosine_match(q_cu, f_cu, b_cu, 20.0)
+    assert nrel(pred.detach().cpu().view(B * Q, 2, h * w), pred64.detach().float()) < 1e-5
+    (pred * wgt.cuda()).sum().backward()
+    assert nrel(q_cu.grad.cpu().view(B * Q, c, h * w), q64.grad.float()) < GTOL
+    assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
+    assert nrel(b_cu.grad.cpu(), b64.grad.float()) < GTOL
+
+
+def test_cosine_match_backward_with_tiny_vectors_uses_the_clamped_branch():
+    """|q| < eps and |proto| < eps: F.cosine_similarity clamps the norm, so the projection term of the gradient vanishes."""
+    from pemp_b200 import autograd as A
+    B, Q, c, h, w, P = 1, 1, 16, 4, 8, 3
+    g = torch.Generator().manual_seed(5)
+    qry = torch.randn(B, Q, c, h, w, generator=g)
+    qry[0, 0, :, 0, :3] = 0.0
+    qry[0, 0, :, 1, :2] *= 1e-12
+    fgp, bgp = torch.randn(B, c, P, generator=g), torch.randn(B, c, P, generator=g)
+    bgp[0, :, 1] = 0.0
+    wgt = torch.randn(B * Q, 2, h, w, generator=g)
+    q64 = qry.double().reshape(B * Q, c, h * w).requires_grad_(True)
+    f64, b64 = fgp.double().requires_grad_(True), bgp.double().requires_grad_(True)
+    pred64, _ = O.reduce_over_protos(O.cosine_match(q64, f64, b64, 20.0))
+    (pred64 * wgt.double().view(B * Q, 2, h * w)).sum().backward()
+    q_cu = qry.cuda().requires_grad_(True)
+    f_cu, b_cu = fgp.cuda().requires_grad_(True), bgp.cuda().requires_grad_(True)
+    (A.cosine_match(q_cu, f_cu, b_cu, 20.0) * wgt.cuda()).sum().backward()
+    live = torch.ones(h * w, dtype=torch.bool)
+    live[:3] = False                                      # exactly-zero q: sub-gradient of max/ties is implementation defined
+    assert nrel(q_cu.grad.cpu().view(c, h * w)[:, live], q64.grad.float()[0][:, live]) < GTOL
+    assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
+
+
+@pytest.mark.parametrize("B,S,Q,c,h,w,H,W", [(2, 2, 1, 64, 9, 9, 33, 33), (1, 5, 1, 512, 51, 51, 401, 401), (2, 1, 2, 128, 13, 11, 50, 41)])
+def test_head_loss_gradients_match_the_reference_training_step(B, S, Q, c, h, w, H, W):
+    """`entry/pemp_stage1.py:57-65`: loss = CE(up-sampled pred, query mask with 255 ignored); gradients reach the encoder
+    output (support and query halves) and the meta-prototype centres."""
+    from pemp_b200 import autograd as A
+    P = 3
+    feats, ctr, fg, bg = _case(B, S, Q, c, h, w, P, seed=11 + c)
+    g = torch.Generator().manual_seed(3)
+    target = torch.randint(0, 2, (B * Q, H, W), generator=g)
+    target[:, :2] = 255
+    low = torch.stack((fg, bg), dim=1)                                    # [BS, 2, hw]
+    # checker
+    f64 = feats.double().requires_grad_(True)
+    ctr64 = ctr.double().requires_grad_(True)
+    of, ob, _ = O.meta_proto_attention(f64[:, :S].reshape(B * S, c, h * w), fg.double(), bg.double(), ctr64, B, S, P)
+    p64, _ = O.reduce_over_protos(O.cosine_match(f64[:, S:].reshape(B * Q, c, h * w), of, ob, 20.0))
+    lg64 = torch.nn.functional.interpolate(p64.view(B * Q, 2, h, w), size=(H, W), mode="bilinear", align_corners=True)
+    loss64 = torch.nn.functional.cross_entropy(lg64, target, ignore_index=255)
+    loss64.backward()
+    f32 = feats.clone().requires_grad_(True)
+    ctr32 = ctr.clone().requires_grad_(True)
+    of32, ob32, _ = O.meta_proto_attention(f32[:, :S].reshape(B * S, c, h * w), fg, bg, ctr32, B, S, P)
+    p32, _ = O.reduce_over_protos(O.cosine_match(f32[:, S:].reshape(B * Q, c, h * w), of32, ob32, 20.0))
+    lg32 = torch.nn.functional.interpolate(p32.view(B * Q, 2, h, w), size=(H, W), mode="bilinear", align_corners=True)
+    torch.nn.functional.cross_entropy(lg32, target, ignore_index=255).backward()
+    tol_f = max(GTOL, nrel(f32.grad, f64.grad.float()))
+    tol_c = max(GTOL, nrel(ctr32.grad, ctr64.grad.float()))
+    # kernels
+    f_cu = feats.cuda().view(B * (S + Q), c, h, w).requires_grad_(True)
+    ctr_cu = ctr.cuda().requires_grad_(True)
+    loss, pred = A.pemp_head_loss(f_cu, low.cuda(), ctr_cu, B, S, Q, target.cuda())
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss64.detach())) < 1e-5 * max(1.0, abs(float(loss64.detach())))
+    assert nrel(f_cu.grad.cpu().view(B, S + Q, c, h, w), f64.grad.float()) <= tol_f
+    assert nrel(ctr_cu.grad.cpu(), ctr64.grad.float()) <= tol_c
+
+
+def test_backward_is_deterministic():
+    from pemp_b200 import autograd as A
+    B, S, Q, c, h, w, P = 2, 2, 1, 512, 21, 21, 3
+    feats, ctr, fg, bg = _case(B, S, Q, c, h, w, P, seed=2)
+    grads = []
+    for _ in range(2):
+        f_cu = feats.cuda().requires_grad_(True)
+        ctr_cu = ctr.cuda().requires_grad_(True)
+        kf, kb = A.meta_proto_attn(f_cu[:, :S], ctr_cu, fg.cuda(), bg.cuda())
+        A.cosine_match(f_cu[:, S:], kf, kb).square().sum().backward()
+        grads.append((f_cu.grad.clone(), ctr_cu.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+
+
+def test_training_ops_refuse_cpu_tensors():
+    from pemp_b200 import autograd as A
+    feats, ctr, fg, bg = _case(1, 1, 1, 16, 4, 4, 3, seed=1)
+    with pytest.raises(ValueError):
+        A.meta_proto_attn(feats[:, :1], ctr, fg, bg)
+    with pytest.raises(ValueError):
+        A.cosine_match(feats[:, 1:], torch.zeros(1, 16, 3), torch.zeros(1, 16, 3))
