@@ -195,10 +195,11 @@ int pemp_comm_module(const float* x, const float* mask_in, int N, int c, int h, 
  * pemp_meta_proto_attn_train = pemp_meta_proto_attn (same kernels, same fg_proto / bg_proto) that also stores the
  *   per-shot centres shot_centre [B*S, c, 2p] (foreground columns first) and denominators shot_den [B*S, 2p]
  *   (sum of the attention + eps) for the backward.  Workspace: pemp_meta_proto_attn_workspace_bytes.
- * pemp_meta_proto_attn_bwd: g_fg / g_bg [B, c, p] = gradient of fg_proto / bg_proto  ->  d_fts [B*S, c, hw] (dense),
- *   d_ctr [c, 2p].  Masks are constants (no gradient), as in the reference.
+ * pemp_meta_proto_attn_bwd: g_fg / g_bg [B, c, p] = gradient of fg_proto / bg_proto  ->  d_fts (image (b, s) at
+ *   d_fts + b * d_fts_episode_stride + s * c * hw; stride 0 = dense [B*S, c, hw] - a non-zero stride writes straight into
+ *   the support half of the gradient of the encoder output [B, S+Q, c, hw]), d_ctr [c, 2p].  Masks get no gradient.
  * pemp_cosine_match_bwd: g_pred [N, 2, hw] = gradient of pred (after the max over prototypes; the arg-max is recomputed,
- *   first maximum wins)  ->  d_qry [N, c, hw] (dense), d_fg / d_bg [Bp, c, P].  c <= 1024.                              */
+ *   first maximum wins)  ->  d_qry (same addressing with d_qry_episode_stride), d_fg / d_bg [Bp, c, P].  c <= 1024.   */
 int pemp_meta_proto_attn_train(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
                                const float* bg, long long mask_stride, int B, int S, int c, int hw, int p, float eps,
                                float* fg_proto, float* bg_proto, float* shot_centre, float* shot_den, void* workspace,
@@ -207,11 +208,20 @@ size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int
 int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
                              const float* bg, long long mask_stride, const float* shot_centre, const float* shot_den,
                              const float* g_fg, const float* g_bg, int B, int S, int c, int hw, int p, float* d_fts,
-                             float* d_ctr, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+                             long long d_fts_episode_stride, float* d_ctr, void* workspace, size_t workspace_bytes,
+                             pemp_stream_t stream);
 size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P);
 int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
                           const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
-                          float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+                          long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes,
+                          pemp_stream_t stream);
+
+/* K13  loss of the training step and its gradient (entry/pemp_stage1.py:51,57-60): mean cross entropy, 255 ignored, of the
+ * bilinear (align_corners) up-sampling of pred [N, 2, h, w] to the target [N, H, W] (int64, or uint8 when target_is_u8).
+ * loss [1]; d_pred [N, 2, h, w] = d loss / d pred (nullable: loss only).                                              */
+size_t pemp_upsample_ce_workspace_bytes(int N, int h, int w, int H, int W);
+int pemp_upsample_ce(const float* pred, const void* target, int target_is_u8, int N, int h, int w, int H, int W,
+                     float* loss, float* d_pred, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -26,9 +26,11 @@ SIGNATURES = {
     "pemp_upsample_argmax_hist": (I, [P, I, I, I, I, I, P, P, P, I, P, P]),
     "pemp_meta_proto_attn_train": (I, [P, LL, P, P, P, LL, I, I, I, I, I, F, P, P, P, P, P, SZ, P]),
     "pemp_meta_proto_attn_bwd_workspace_bytes": (SZ, [I, I, I, I, I]),
-    "pemp_meta_proto_attn_bwd": (I, [P, LL, P, P, P, LL, P, P, P, P, I, I, I, I, I, P, P, P, SZ, P]),
+    "pemp_meta_proto_attn_bwd": (I, [P, LL, P, P, P, LL, P, P, P, P, I, I, I, I, I, P, LL, P, P, SZ, P]),
     "pemp_cosine_match_bwd_workspace_bytes": (SZ, [I, I, I, I, I]),
-    "pemp_cosine_match_bwd": (I, [P, LL, P, P, P, I, I, I, I, I, F, P, P, P, P, SZ, P]),
+    "pemp_cosine_match_bwd": (I, [P, LL, P, P, P, I, I, I, I, I, F, P, LL, P, P, P, SZ, P]),
+    "pemp_upsample_ce_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "pemp_upsample_ce": (I, [P, P, I, I, I, I, I, I, P, P, P, SZ, P]),
     "pemp_comm_workspace_bytes": (SZ, [I, I, I, I]),
     "pemp_comm_module": (I, [P, P, I, I, I, I, I, I, I, I, P, P, I, P, P, P, SZ, P]),
     "pemp_debug_mpa_path": (I, [I]),

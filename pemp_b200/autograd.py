@@ -5,7 +5,8 @@ hand-written backward kernels (`csrc/train.cu`), so that `loss.backward()` of `e
     pred   = cosine_match(qry_fts, fg, bg, dist_scalar)             # pemp_stage1.py:214-215,233-261, grads to all three
     loss   = F.cross_entropy(F.interpolate(pred, size, mode="bilinear", align_corners=True), target, ignore_index=255)
 
-Masks get no gradient (they are labels).  The up-sampling and the loss stay stock PyTorch, as in the reference.
+Masks get no gradient (they are labels).  `upsample_ce` is the up-sampling + cross entropy of the last line as one op
+(K13: the full-size logits are never stored; the gradient comes out of the forward pass).
 There is no CPU path: CUDA float32 tensors only.
 """
 import torch
@@ -48,6 +49,61 @@ class _CosineMatch(torch.autograd.Function):
         return d_qry.view(qry.shape), d_fg, d_bg, None
 
 
+class _UpsampleCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        loss, d_pred = ops.upsample_ce(pred, target, want_grad=True)
+        ctx.save_for_backward(d_pred)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_pred,) = ctx.saved_tensors
+        return d_pred * g, None
+
+
+class _PempHead(torch.autograd.Function):
+    """K2 -> K3 on the encoder output [B, S+Q, c, h, w] as ONE autograd node: both backward kernels write straight into
+    the two halves of one gradient tensor (separate nodes would make autograd zero-fill, copy and add two full-size
+    tensors for the `[:, :S]` / `[:, S:]` slices - three extra passes over the largest tensor of the step)."""
+
+    @staticmethod
+    def forward(ctx, f5, ctr, fg, bg, S, scalar, eps):
+        B = f5.shape[0]
+        sup, qry = f5[:, :S], f5[:, S:]
+        fgp, bgp, saved = ops.meta_proto_attn_train(sup, ctr, fg, bg, B, S, eps)
+        pred = ops.cosine_match(qry, fgp, bgp, scalar)["pred"]
+        ctx.saved, ctx.protos, ctx.f5 = saved, (fgp, bgp), f5
+        ctx.S, ctx.scalar = S, scalar
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        f5, S = ctx.f5, ctx.S
+        B = f5.shape[0]
+        d_f5 = torch.empty(f5.shape, dtype=torch.float32, device=f5.device)
+        fgp, bgp = ctx.protos
+        _, d_fg, d_bg = ops.cosine_match_bwd(f5[:, S:], fgp, bgp, g_pred.contiguous(), ctx.scalar, out=d_f5[:, S:])
+        _, d_ctr = ops.meta_proto_attn_bwd(ctx.saved, d_fg, d_bg, B, S, out=d_f5[:, :S])
+        ctx.saved = ctx.protos = ctx.f5 = None
+        return d_f5, d_ctr, None, None, None, None, None
+
+
+def pemp_head(features, sup_mask_low, ctr, B, S, Q, scalar=20.0, eps=1e-6):
+    """features [B*(S+Q), c, h, w] (encoder output), sup_mask_low [B*S, 2, h*w], ctr [c, 2p] -> pred [B*Q, 2, h, w];
+    differentiable in features and ctr (`PEMPStage1.forward` in training mode, pemp_stage1.py:140-162 without the
+    up-sampling)."""
+    _, c, h, w = features.shape
+    f5 = features.view(B, S + Q, c, h, w)
+    return _PempHead.apply(f5, ctr, sup_mask_low[:, 0], sup_mask_low[:, 1], S, scalar, eps).view(B * Q, 2, h, w)
+
+
+def upsample_ce(pred, target):
+    """loss = CrossEntropyLoss(ignore_index=255)(F.interpolate(pred, target.shape[-2:], bilinear, align_corners=True),
+    target) in one pass, gradient included (K13)."""
+    return _UpsampleCE.apply(pred, target)
+
+
 def meta_proto_attn(sup_fts, ctr, sup_fg, sup_bg, eps=1e-6):
     """sup_fts [B, S, c, h, w] (may be a slice of the encoder output, read in place), ctr [c, 2p] (the module's
     `self.ctr` viewed as [c, 2p]), sup_fg / sup_bg [B*S, h*w] -> fg_proto, bg_proto [B, c, p]; differentiable in
@@ -68,10 +124,7 @@ def cosine_match(qry_fts, fg_proto, bg_proto, scalar=20.0):
 def pemp_head_loss(features, sup_mask_low, ctr, B, S, Q, target, out_shape=None, scalar=20.0):
     """One training step of the head as `entry/pemp_stage1.py:57-65` runs it: features [B*(S+Q), c, h, w] from the encoder,
     sup_mask_low [B*S, 2, h*w] (K0 output), target [B*Q, H, W] int64 with 255 = ignore -> (loss, pred)."""
-    _, c, h, w = features.shape
-    f5 = features.view(B, S + Q, c, h, w)
-    fg, bg = meta_proto_attn(f5[:, :S], ctr, sup_mask_low[:, 0], sup_mask_low[:, 1])
-    pred = cosine_match(f5[:, S:], fg, bg, scalar)
-    size = tuple(target.shape[-2:]) if out_shape is None else tuple(out_shape)
-    logits = torch.nn.functional.interpolate(pred, size=size, mode="bilinear", align_corners=True)
-    return torch.nn.functional.cross_entropy(logits, target, ignore_index=255), pred
+    pred = pemp_head(features, sup_mask_low, ctr, B, S, Q, scalar)
+    if out_shape is not None and tuple(out_shape) != tuple(target.shape[-2:]):
+        raise ValueError("the loss is taken at the size of the target")
+    return upsample_ce(pred, target), pred

@@ -29,10 +29,17 @@
 
 namespace {
 
-constexpr int kBT = 256;           // threads per CTA
-constexpr int kBW = kBT / 32;      // warps
-constexpr int kLd = 33;            // padded tile row
-constexpr int kMaxCPT = 4;         // channels per thread in phase B2  =>  c <= 1024
+#ifndef PEMP_BWD_THREADS
+#define PEMP_BWD_THREADS 256
+#endif
+#ifndef PEMP_BWD_UNROLL
+#define PEMP_BWD_UNROLL 8
+#endif
+constexpr int kBT = PEMP_BWD_THREADS;   // threads per CTA
+constexpr int kBW = kBT / 32;           // warps
+constexpr int kLd = 33;                 // padded tile row
+constexpr int kMaxCPT = 1024 / kBT;     // channels per thread in phase B2  =>  c <= 1024
+constexpr int kUn = PEMP_BWD_UNROLL;    // feature loads in flight per lane in phase A
 constexpr float kCosEps = 1e-8f;   // F.cosine_similarity's eps
 
 __device__ __forceinline__ float block_sum(float v, float* scratch) {   // scratch: kBW floats; every thread gets the sum
@@ -68,48 +75,87 @@ proto_norm_kernel(const float* __restrict__ fg_proto, const float* __restrict__ 
   }
 }
 
+// Table rows are K floats (K even => 8-byte aligned): a row is K/2 LDS.64 whose column pairs feed the packed FFMA2 (two
+// fp32 FMAs per issue slot) - the phases below are issue bound, not HBM bound, at K = 6.  (Rows padded to 8 floats would
+// be two LDS.128, but push the CTA past half of the SM's shared memory at c = 512.)
+template <int K>
+struct Pad {
+  static constexpr int KP = K;
+  static constexpr int H = KP / 2;
+};
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+template <int KP>
+__device__ __forceinline__ void load_row(const float* row, float2 (&r)[KP / 2]) {
+#pragma unroll
+  for (int j = 0; j < KP / 2; ++j) r[j] = reinterpret_cast<const float2*>(row)[j];
+}
+
 template <int K>
 __global__ void __launch_bounds__(kBT, 2)
 cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, const float* __restrict__ pn,
                   const float* __restrict__ g_pred, int c, int hw, int ntiles, float scalar, float* __restrict__ dq,
-                  float* __restrict__ part) {
-  constexpr int P = K / 2, NA = K + 1;
-  extern __shared__ float sm[];
-  float* tile = sm;                          // [c][33]
-  float* tab = tile + c * kLd;               // [c][K]
-  float* red = tab + c * K;                  // [kBW][NA][32]
+                  long long d_ep_stride, float* __restrict__ part) {
+  constexpr int P = K / 2, KP = Pad<K>::KP, H = Pad<K>::H, NA = KP + 1;
+  extern __shared__ __align__(16) float sm[];
+  float* tab = sm;                           // [c][KP]
+  float* wts = tab + c * KP;                 // [32][KP]  phase-B2 weights
+  float* tile = wts + 32 * KP;               // [c][33]
+  float* red = tile + c * kLd;               // [kBW][NA][32]
   float* sum = red + kBW * NA * 32;          // [NA][32]
-  float* wts = sum + NA * 32;                // [32][K]   phase-B2 weights
-  float* cg = wts + 32 * K;                  // [2][32]   coefficient of the selected prototype
+  float* cg = sum + NA * 32;                 // [2][32]   coefficient of the selected prototype
   float* tq = cg + 64;                       // [32]      coefficient of q
   int* sel = reinterpret_cast<int*>(tq + 32);   // [2][32] selected table column
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.y, b = n / Q, qi = n - b * Q;
   const float* src = qry + static_cast<long long>(b) * ep_stride + static_cast<long long>(qi) * c * hw;
-  for (int i = tid; i < c * K; i += kBT) tab[i] = __ldg(pn + static_cast<long long>(b) * c * K + i);
-  float accB[kMaxCPT][K];
+  for (int i = tid; i < c * KP; i += kBT) {
+    const int ch = i / KP, k = i - ch * KP;
+    tab[i] = k < K ? __ldg(pn + (static_cast<long long>(b) * c + ch) * K + k) : 0.f;
+  }
+  for (int i = tid; i < 32 * KP; i += kBT) wts[i] = 0.f;
+  float2 accB[kMaxCPT][H];
 #pragma unroll
   for (int i = 0; i < kMaxCPT; ++i)
 #pragma unroll
-    for (int k = 0; k < K; ++k) accB[i][k] = 0.f;
+    for (int k = 0; k < H; ++k) accB[i][k] = make_float2(0.f, 0.f);
   const int t0 = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
   const int t1 = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
   __syncthreads();
   for (int t = t0; t < t1; ++t) {
     const int x = t * 32 + lane;
     const bool inb = x < hw;
-    float acc[NA];
+    float2 acc[H];
+    float nacc = 0.f;
 #pragma unroll
-    for (int j = 0; j < NA; ++j) acc[j] = 0.f;
-    for (int ch = warp; ch < c; ch += kBW) {
-      const float v = inb ? __ldg(src + static_cast<long long>(ch) * hw + x) : 0.f;
-      tile[ch * kLd + lane] = v;
-      acc[K] = fmaf(v, v, acc[K]);
+    for (int j = 0; j < H; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int ch0 = warp; ch0 < c; ch0 += kBW * kUn) {
+      float vv[kUn];
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] = fmaf(v, tab[ch * K + k], acc[k]);
+      for (int u = 0; u < kUn; ++u) {
+        const int ch = ch0 + u * kBW;
+        vv[u] = (inb && ch < c) ? __ldg(src + static_cast<long long>(ch) * hw + x) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kUn; ++u) {
+        const int ch = ch0 + u * kBW;
+        if (ch < c) {
+          const float v = vv[u];
+          tile[ch * kLd + lane] = v;
+          nacc = fmaf(v, v, nacc);
+          float2 r[H];
+          load_row<KP>(tab + ch * KP, r);
+          const float2 v2 = make_float2(v, v);
+#pragma unroll
+          for (int j = 0; j < H; ++j) acc[j] = ffma2(v2, r[j], acc[j]);
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < NA; ++j) red[(warp * NA + j) * 32 + lane] = acc[j];
+    for (int j = 0; j < H; ++j) {
+      red[(warp * NA + 2 * j) * 32 + lane] = acc[j].x;
+      red[(warp * NA + 2 * j + 1) * 32 + lane] = acc[j].y;
+    }
+    red[(warp * NA + KP) * 32 + lane] = nacc;
     __syncthreads();
     for (int i = tid; i < NA * 32; i += kBT) {
       float s = 0.f;
@@ -119,7 +165,7 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
     }
     __syncthreads();
     if (tid < 32) {
-      const float nq = sqrtf(sum[K * 32 + lane]);
+      const float nq = sqrtf(sum[KP * 32 + lane]);
       const float invq = 1.0f / fmaxf(nq, kCosEps);
       float tsum = 0.f;
 #pragma unroll
@@ -140,17 +186,18 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
         sel[g * 32 + lane] = g * P + best;
         tsum = fmaf(gp, bv, tsum);
 #pragma unroll
-        for (int k = 0; k < P; ++k) wts[lane * K + g * P + k] = (k == best) ? co : 0.f;
+        for (int k = 0; k < P; ++k) wts[lane * KP + g * P + k] = (k == best) ? co : 0.f;
       }
       tq[lane] = (nq < kCosEps) ? 0.f : tsum * invq * invq * invq;
     }
     __syncthreads();
     {   // B1: dq tile
-      const float c0 = cg[lane], c1 = cg[32 + lane], tv = tq[lane];
+      const float c0 = cg[lane], c1 = cg[32 + lane], tv = -tq[lane];
       const int s0 = sel[lane], s1 = sel[32 + lane];
-      float* dst = dq + static_cast<long long>(n) * c * hw + x;
+      float* dst = dq + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(qi) * c * hw + x;
+#pragma unroll 4
       for (int ch = warp; ch < c; ch += kBW) {
-        const float val = fmaf(c0, tab[ch * K + s0], fmaf(c1, tab[ch * K + s1], -tv * tile[ch * kLd + lane]));
+        const float val = fmaf(c0, tab[ch * KP + s0], fmaf(c1, tab[ch * KP + s1], tv * tile[ch * kLd + lane]));
         if (inb) dst[static_cast<long long>(ch) * hw] = val;
       }
     }
@@ -158,10 +205,14 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
     for (int i = 0; i < kMaxCPT; ++i) {   // B2: per-channel sums for the prototype gradients
       const int ch = tid + i * kBT;
       if (ch < c) {
+#pragma unroll 4
         for (int xx = 0; xx < 32; ++xx) {
           const float v = tile[ch * kLd + xx];
+          float2 r[H];
+          load_row<KP>(wts + xx * KP, r);
+          const float2 v2 = make_float2(v, v);
 #pragma unroll
-          for (int k = 0; k < K; ++k) accB[i][k] = fmaf(wts[xx * K + k], v, accB[i][k]);
+          for (int k = 0; k < H; ++k) accB[i][k] = ffma2(r[k], v2, accB[i][k]);
         }
       }
     }
@@ -173,7 +224,7 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
     const int ch = tid + i * kBT;
     if (ch < c) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) dstp[ch * K + k] = accB[i][k];
+      for (int k = 0; k < K; ++k) dstp[ch * K + k] = (k & 1) ? accB[i][k / 2].y : accB[i][k / 2].x;
     }
   }
 }
@@ -247,34 +298,38 @@ __global__ void __launch_bounds__(kBT, 2)
 mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ ctr,
                const float* __restrict__ coef, const float* __restrict__ beta, const float* __restrict__ fg,
                const float* __restrict__ bg, long long mask_stride, int c, int hw, int ntiles, float* __restrict__ dfts,
-               float* __restrict__ part) {
-  constexpr int P = K / 2, NA = 2 * K;
-  extern __shared__ float sm[];
-  float* tile = sm;                        // [c][33]
-  float* ctab = tile + c * kLd;            // [c][K]  centres
-  float* atab = ctab + c * K;              // [c][K]  gradient coefficients of this image
-  float* red = atab + c * K;               // [kBW][NA][32]
+               long long d_ep_stride, float* __restrict__ part) {
+  constexpr int P = K / 2, KP = Pad<K>::KP, H = Pad<K>::H, NA = 2 * KP;
+  extern __shared__ __align__(16) float sm[];
+  float* ctab = sm;                        // [c][KP]  centres
+  float* atab = ctab + c * KP;             // [c][KP]  gradient coefficients of this image
+  float* av = atab + c * KP;               // [32][KP] a_k
+  float* dv = av + 32 * KP;                // [32][KP] 2 dl_k
+  float* tile = dv + 32 * KP;              // [c][33]
+  float* red = tile + c * kLd;             // [kBW][NA][32]
   float* sum = red + kBW * NA * 32;        // [NA][32]
-  float* av = sum + NA * 32;               // [32][K]  a_k
-  float* dv = av + 32 * K;                 // [32][K]  2 dl_k
-  float* konst = dv + 32 * K;              // [K] |ctr_k|^2, [K] beta
+  float* konst = sum + NA * 32;            // [K] |ctr_k|^2, [K] beta
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.y, b = n / S, si = n - b * S;
   const float* src = fts + static_cast<long long>(b) * ep_stride + static_cast<long long>(si) * c * hw;
-  for (int i = tid; i < c * K; i += kBT) {
-    ctab[i] = __ldg(ctr + i);
-    atab[i] = __ldg(coef + static_cast<long long>(n) * c * K + i);
+  for (int i = tid; i < c * KP; i += kBT) {
+    const int ch = i / KP, k = i - ch * KP;
+    ctab[i] = k < K ? __ldg(ctr + ch * K + k) : 0.f;
+    atab[i] = k < K ? __ldg(coef + (static_cast<long long>(n) * c + ch) * K + k) : 0.f;
   }
-  __syncthreads();
+  for (int i = tid; i < 32 * KP; i += kBT) {
+    av[i] = 0.f;
+    dv[i] = 0.f;
+  }
   if (tid < K) {
     konst[tid] = __ldg(beta + n * 2 * K + K + tid);
     konst[K + tid] = __ldg(beta + n * 2 * K + tid);
   }
-  float accB[kMaxCPT][K];
+  float2 accB[kMaxCPT][H];
 #pragma unroll
   for (int i = 0; i < kMaxCPT; ++i)
 #pragma unroll
-    for (int k = 0; k < K; ++k) accB[i][k] = 0.f;
+    for (int k = 0; k < H; ++k) accB[i][k] = make_float2(0.f, 0.f);
   float dsum = 0.f;
   const int t0 = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
   const int t1 = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
@@ -282,20 +337,41 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
   for (int t = t0; t < t1; ++t) {
     const int x = t * 32 + lane;
     const bool inb = x < hw;
-    float acc[NA];
+    float2 accC[H], accA[H];
 #pragma unroll
-    for (int j = 0; j < NA; ++j) acc[j] = 0.f;
-    for (int ch = warp; ch < c; ch += kBW) {
-      const float v = inb ? __ldg(src + static_cast<long long>(ch) * hw + x) : 0.f;
-      tile[ch * kLd + lane] = v;
+    for (int j = 0; j < H; ++j) accC[j] = accA[j] = make_float2(0.f, 0.f);
+    for (int ch0 = warp; ch0 < c; ch0 += kBW * kUn) {
+      float vv[kUn];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        acc[k] = fmaf(v, ctab[ch * K + k], acc[k]);
-        acc[K + k] = fmaf(v, atab[ch * K + k], acc[K + k]);
+      for (int u = 0; u < kUn; ++u) {
+        const int ch = ch0 + u * kBW;
+        vv[u] = (inb && ch < c) ? __ldg(src + static_cast<long long>(ch) * hw + x) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kUn; ++u) {
+        const int ch = ch0 + u * kBW;
+        if (ch < c) {
+          const float v = vv[u];
+          tile[ch * kLd + lane] = v;
+          float2 rc[H], ra[H];
+          load_row<KP>(ctab + ch * KP, rc);
+          load_row<KP>(atab + ch * KP, ra);
+          const float2 v2 = make_float2(v, v);
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            accC[j] = ffma2(v2, rc[j], accC[j]);
+            accA[j] = ffma2(v2, ra[j], accA[j]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < NA; ++j) red[(warp * NA + j) * 32 + lane] = acc[j];
+    for (int j = 0; j < H; ++j) {
+      red[(warp * NA + 2 * j) * 32 + lane] = accC[j].x;
+      red[(warp * NA + 2 * j + 1) * 32 + lane] = accC[j].y;
+      red[(warp * NA + KP + 2 * j) * 32 + lane] = accA[j].x;
+      red[(warp * NA + KP + 2 * j + 1) * 32 + lane] = accA[j].y;
+    }
     __syncthreads();
     for (int i = tid; i < NA * 32; i += kBT) {
       float s = 0.f;
@@ -324,30 +400,35 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
         float ds[P], dot = 0.f;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-          l[k] *= iz;                                                              // sigma_k
-          ds[k] = m * (sum[(K + g * P + k) * 32 + lane] + konst[K + g * P + k]);   // d sigma_k
+          l[k] *= iz;                                                                // sigma_k
+          ds[k] = m * (sum[(KP + g * P + k) * 32 + lane] + konst[K + g * P + k]);    // d sigma_k
           dot = fmaf(l[k], ds[k], dot);
         }
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-          av[lane * K + g * P + k] = m * l[k];
-          dv[lane * K + g * P + k] = 2.0f * l[k] * (ds[k] - dot);
+          av[lane * KP + g * P + k] = m * l[k];
+          dv[lane * KP + g * P + k] = 2.0f * l[k] * (ds[k] - dot);
         }
       }
     }
     __syncthreads();
-    {   // B1: df tile
-      float a[K], d[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        a[k] = av[lane * K + k];
-        d[k] = dv[lane * K + k];
-      }
-      float* dst = dfts + static_cast<long long>(n) * c * hw + x;
+    {   // B1: df tile = sum_k a_k A_k + 2 dl_k ctr_k
+      float2 a[H], d[H];
+      load_row<KP>(av + lane * KP, a);
+      load_row<KP>(dv + lane * KP, d);
+      float* dst = dfts + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(si) * c * hw + x;
+#pragma unroll 4
       for (int ch = warp; ch < c; ch += kBW) {
-        float val = 0.f;
+        float2 rc[H], ra[H];
+        load_row<KP>(ctab + ch * KP, rc);
+        load_row<KP>(atab + ch * KP, ra);
+        float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < K; ++k) val = fmaf(a[k], atab[ch * K + k], fmaf(d[k], ctab[ch * K + k], val));
+        for (int j = 0; j < H; ++j) {
+          v0 = ffma2(a[j], ra[j], v0);
+          v1 = ffma2(d[j], rc[j], v1);
+        }
+        const float val = (v0.x + v0.y) + (v1.x + v1.y);
         if (inb) dst[static_cast<long long>(ch) * hw] = val;
       }
     }
@@ -355,15 +436,19 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
     for (int i = 0; i < kMaxCPT; ++i) {   // B2: sum_x 2 dl_k f
       const int ch = tid + i * kBT;
       if (ch < c) {
+#pragma unroll 4
         for (int xx = 0; xx < 32; ++xx) {
           const float v = tile[ch * kLd + xx];
+          float2 r[H];
+          load_row<KP>(dv + xx * KP, r);
+          const float2 v2 = make_float2(v, v);
 #pragma unroll
-          for (int k = 0; k < K; ++k) accB[i][k] = fmaf(dv[xx * K + k], v, accB[i][k]);
+          for (int k = 0; k < H; ++k) accB[i][k] = ffma2(r[k], v2, accB[i][k]);
         }
       }
     }
     if (tid < K) {
-      for (int xx = 0; xx < 32; ++xx) dsum += dv[xx * K + tid];
+      for (int xx = 0; xx < 32; ++xx) dsum += dv[xx * KP + tid];
     }
     __syncthreads();
   }
@@ -373,25 +458,44 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
     const int ch = tid + i * kBT;
     if (ch < c) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) dstp[ch * K + k] = accB[i][k];
+      for (int k = 0; k < K; ++k) dstp[ch * K + k] = (k & 1) ? accB[i][k / 2].y : accB[i][k / 2].x;
     }
   }
   if (tid < K) dstp[c * K + tid] = dsum;
 }
 
-// one thread per (channel, k): the partials of every image and chunk in index order (double accumulators)
-__global__ void mpa_bwd_finalize_kernel(const float* __restrict__ part, long long nparts, int c, int K, const float* __restrict__ ctr,
-                                        float* __restrict__ d_ctr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c * K) return;
-  const int k = i % K;
+// d_ctr[ch][k] = sum over every (image, chunk) partial, in index order, minus ctr * sum of the 2 dl_k column.
+// blockDim = (32 outputs, kFinRows): row r adds the partials p = r, r + kFinRows, ... (double), then the rows are added
+// in order - deterministic, and 16 x more loads in flight than one thread per output.
+constexpr int kFinRows = 16;
+__global__ void __launch_bounds__(32 * kFinRows)
+mpa_bwd_finalize_kernel(const float* __restrict__ part, long long nparts, int c, int K, const float* __restrict__ ctr,
+                        float* __restrict__ d_ctr) {
+  __shared__ double ss[kFinRows][32], sd[kFinRows][32];
+  const int i = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y;
+  const bool live = i < c * K;
+  const int k = live ? i % K : 0;
   double s = 0.0, d = 0.0;
-  for (long long p = 0; p < nparts; ++p) {
-    const float* row = part + p * (c + 1) * K;
-    s += static_cast<double>(row[i]);
-    d += static_cast<double>(row[c * K + k]);
+  if (live) {
+#pragma unroll 4
+    for (long long p = r; p < nparts; p += kFinRows) {
+      const float* row = part + p * (c + 1) * K;
+      s += static_cast<double>(__ldg(row + i));
+      d += static_cast<double>(__ldg(row + c * K + k));
+    }
   }
-  d_ctr[i] = static_cast<float>(s - static_cast<double>(__ldg(ctr + i)) * d);
+  ss[r][threadIdx.x] = s;
+  sd[r][threadIdx.x] = d;
+  __syncthreads();
+  if (r == 0 && live) {
+    s = 0.0;
+    d = 0.0;
+    for (int j = 0; j < kFinRows; ++j) {
+      s += ss[j][threadIdx.x];
+      d += sd[j][threadIdx.x];
+    }
+    d_ctr[i] = static_cast<float>(s - static_cast<double>(__ldg(ctr + i)) * d);
+  }
 }
 
 struct BwdPlan {
@@ -405,29 +509,31 @@ BwdPlan bwd_plan(int N, int hw) {
   return p;
 }
 size_t cos_smem(int c, int K) {
-  return (static_cast<size_t>(c) * kLd + static_cast<size_t>(c) * K + kBW * (K + 1) * 32 + (K + 1) * 32 + 32 * K + 64 + 32 + 64) * 4;
+  const size_t KP = K, NA = KP + 1;
+  return (static_cast<size_t>(c) * kLd + static_cast<size_t>(c) * KP + kBW * NA * 32 + NA * 32 + 32 * KP + 64 + 32 + 64) * 4;
 }
 size_t mpa_smem(int c, int K) {
-  return (static_cast<size_t>(c) * kLd + 2 * static_cast<size_t>(c) * K + kBW * 2 * K * 32 + 2 * K * 32 + 2 * 32 * K + 2 * K) * 4;
+  const size_t KP = K, NA = 2 * KP;
+  return (static_cast<size_t>(c) * kLd + 2 * static_cast<size_t>(c) * KP + kBW * NA * 32 + NA * 32 + 2 * 32 * KP + 2 * K) * 4;
 }
 
 template <int K>
 int launch_cos_bwd(const float* qry, long long ep, int Q, const float* pn, const float* g_pred, int N, int c, int hw,
-                   const BwdPlan& pl, float scalar, float* dq, float* part, cudaStream_t st) {
+                   const BwdPlan& pl, float scalar, float* dq, long long d_ep, float* part, cudaStream_t st) {
   const size_t smem = cos_smem(c, K);
   cudaError_t e = cudaFuncSetAttribute(cosine_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  cosine_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(qry, ep, Q, pn, g_pred, c, hw, pl.ntiles, scalar, dq, part);
+  cosine_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(qry, ep, Q, pn, g_pred, c, hw, pl.ntiles, scalar, dq, d_ep, part);
   return PEMP_OK;
 }
 template <int K>
 int launch_mpa_bwd(const float* fts, long long ep, int S, const float* ctr, const float* coef, const float* beta, const float* fg,
-                   const float* bg, long long mask_stride, int N, int c, int hw, const BwdPlan& pl, float* dfts, float* part,
-                   cudaStream_t st) {
+                   const float* bg, long long mask_stride, int N, int c, int hw, const BwdPlan& pl, float* dfts, long long d_ep,
+                   float* part, cudaStream_t st) {
   const size_t smem = mpa_smem(c, K);
   cudaError_t e = cudaFuncSetAttribute(mpa_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  mpa_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, c, hw, pl.ntiles, dfts, part);
+  mpa_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, c, hw, pl.ntiles, dfts, d_ep, part);
   return PEMP_OK;
 }
 
@@ -443,7 +549,8 @@ extern "C" size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, in
 
 extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
                                      const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
-                                     float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+                                     long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace,
+                                     size_t workspace_bytes, pemp_stream_t stream) {
   PEMP_REQUIRE(qry && fg_proto && bg_proto && g_pred && d_qry && d_fg && d_bg, PEMP_E_NULL);
   PEMP_REQUIRE(N > 0 && N <= 65535 && Bp > 0 && c > 0 && hw > 0 && N % Bp == 0, PEMP_E_SHAPE);
   PEMP_REQUIRE(P >= 1 && P <= 4 && c <= kMaxCPT * kBT && cos_smem(c, 2 * P) <= 227 * 1024, PEMP_E_SHAPE);
@@ -456,13 +563,14 @@ extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_str
   float* nrm = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(Bp) * c * K * 4, 256));
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(nrm) + align_up(static_cast<size_t>(Bp) * K * 4, 256));
   const long long ep = qry_episode_stride ? qry_episode_stride : static_cast<long long>(Q) * c * hw;
+  const long long d_ep = d_qry_episode_stride ? d_qry_episode_stride : static_cast<long long>(Q) * c * hw;
   proto_norm_kernel<<<Bp, kBT, 0, st>>>(fg_proto, bg_proto, c, P, pn, nrm);
   int rc;
   switch (P) {
-    case 1: rc = launch_cos_bwd<2>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
-    case 2: rc = launch_cos_bwd<4>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
-    case 3: rc = launch_cos_bwd<6>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
-    default: rc = launch_cos_bwd<8>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, part, st); break;
+    case 1: rc = launch_cos_bwd<2>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
+    case 2: rc = launch_cos_bwd<4>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
+    case 3: rc = launch_cos_bwd<6>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
+    default: rc = launch_cos_bwd<8>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
   }
   if (rc != PEMP_OK) return rc;
   cosine_bwd_finalize_kernel<<<Bp, kBT, 0, st>>>(part, pn, nrm, Q, pl.chunks, c, P, d_fg, d_bg);
@@ -479,7 +587,8 @@ extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, 
 extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
                                         const float* bg, long long mask_stride, const float* shot_centre, const float* shot_den,
                                         const float* g_fg, const float* g_bg, int B, int S, int c, int hw, int p, float* d_fts,
-                                        float* d_ctr, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+                                        long long d_fts_episode_stride, float* d_ctr, void* workspace, size_t workspace_bytes,
+                                        pemp_stream_t stream) {
   PEMP_REQUIRE(fts && ctr && fg && bg && shot_centre && shot_den && g_fg && g_bg && d_fts && d_ctr, PEMP_E_NULL);
   PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
   PEMP_REQUIRE(p >= 1 && p <= 4 && c <= kMaxCPT * kBT && mpa_smem(c, 2 * p) <= 227 * 1024, PEMP_E_SHAPE);
@@ -492,15 +601,16 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
   float* beta = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(N) * c * K * 4, 256));
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(beta) + align_up(static_cast<size_t>(N) * 2 * K * 4, 256));
   const long long ep = fts_episode_stride ? fts_episode_stride : static_cast<long long>(S) * c * hw;
+  const long long d_ep = d_fts_episode_stride ? d_fts_episode_stride : static_cast<long long>(S) * c * hw;
   mpa_bwd_prepare_kernel<<<N, kBT, 0, st>>>(g_fg, g_bg, shot_centre, shot_den, ctr, S, c, p, coef, beta);
   int rc;
   switch (p) {
-    case 1: rc = launch_mpa_bwd<2>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
-    case 2: rc = launch_mpa_bwd<4>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
-    case 3: rc = launch_mpa_bwd<6>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
-    default: rc = launch_mpa_bwd<8>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, part, st); break;
+    case 1: rc = launch_mpa_bwd<2>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
+    case 2: rc = launch_mpa_bwd<4>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
+    case 3: rc = launch_mpa_bwd<6>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
+    default: rc = launch_mpa_bwd<8>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
   }
   if (rc != PEMP_OK) return rc;
-  mpa_bwd_finalize_kernel<<<(c * K + 255) / 256, 256, 0, st>>>(part, static_cast<long long>(N) * pl.chunks, c, K, ctr, d_ctr);
+  mpa_bwd_finalize_kernel<<<(c * K + 31) / 32, dim3(32, kFinRows), 0, st>>>(part, static_cast<long long>(N) * pl.chunks, c, K, ctr, d_ctr);
   return launch_status();
 }

@@ -428,8 +428,21 @@ def meta_proto_attn_train(fts, ctr, fg, bg, B, S, eps=1e-6):
     return out_f, out_b, (fts, ep, ctr, keep[0], keep[1] if keep[1] is not None else keep[0], centre, den)
 
 
-def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S):
-    """-> (d_fts [B*S, c, hw], d_ctr [c, 2p]) from the gradients of fg_proto / bg_proto [B, c, p]."""
+def _grad_out(out, B, S, c, hw, device):
+    """Gradient destination: a fresh dense [B*S, c, hw] tensor, or `out` = a [B, S, c, h, w] slice of the gradient of the
+    encoder output (written in place through its episode stride).  -> (tensor, episode_stride)"""
+    if out is None:
+        return torch.empty(B * S, c, hw, dtype=torch.float32, device=device), 0
+    if out.dtype != torch.float32 or not out.is_cuda or out.dim() != 5 or tuple(out.shape[:3]) != (B, S, c) or \
+            out.shape[3] * out.shape[4] != hw:
+        raise ValueError(f"out must be a CUDA float32 [{B}, {S}, {c}, h, w] tensor")
+    if not (out.stride(4) == 1 and out.stride(3) == out.shape[4] and out.stride(2) == hw and (S == 1 or out.stride(1) == c * hw)):
+        raise ValueError("out must be contiguous inside an episode")
+    return out, (out.stride(0) if B > 1 else S * c * hw)
+
+
+def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S, out=None):
+    """-> (d_fts [B*S, c, hw] or `out`, d_ctr [c, 2p]) from the gradients of fg_proto / bg_proto [B, c, p]."""
     fts, ep, ctr, fg, bg, centre, den = saved
     c, p = ctr.shape[0], ctr.shape[1] // 2
     hw = fg.shape[1]
@@ -441,18 +454,18 @@ def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S):
     L = _cabi.lib()
     dev = fts.device
     ws = _ws(L.pemp_meta_proto_attn_bwd_workspace_bytes(B, S, c, hw, p), dev)
-    d_fts = torch.empty(B * S, c, hw, dtype=torch.float32, device=dev)
+    d_fts, d_ep = _grad_out(out, B, S, c, hw, dev)
     d_ctr = torch.empty(c, 2 * p, dtype=torch.float32, device=dev)
     _cabi.check(L.pemp_meta_proto_attn_bwd(fts.data_ptr(), ep, ctr.data_ptr(), fgp, bgp, stride, centre.data_ptr(), den.data_ptr(),
-                                           g_fg.data_ptr(), g_bg.data_ptr(), B, S, c, hw, p, d_fts.data_ptr(), d_ctr.data_ptr(),
+                                           g_fg.data_ptr(), g_bg.data_ptr(), B, S, c, hw, p, d_fts.data_ptr(), d_ep, d_ctr.data_ptr(),
                                            ws.data_ptr(), ws.numel(), _stream()), "pemp_meta_proto_attn_bwd")
     _count(3)
     del keep
     return d_fts, d_ctr
 
 
-def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0):
-    """Backward of `cosine_match(...)["pred"]`: qry as in the forward, g_pred [N, 2, hw] -> (d_qry [N, c, hw],
+def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0, out=None):
+    """Backward of `cosine_match(...)["pred"]`: qry as in the forward, g_pred [N, 2, hw] -> (d_qry [N, c, hw] or `out`,
     d_fg, d_bg shaped like the prototypes)."""
     fg_proto = _need(fg_proto, torch.float32, "fg_proto")
     bg_proto = _need(bg_proto, torch.float32, "bg_proto")
@@ -466,10 +479,31 @@ def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0):
     L = _cabi.lib()
     dev = qry.device
     ws = _ws(L.pemp_cosine_match_bwd_workspace_bytes(n_maps, Bp, c, hw, P), dev)
-    d_qry = torch.empty(n_maps, c, hw, dtype=torch.float32, device=dev)
+    d_qry, d_ep = _grad_out(out, Bp, n_maps // Bp, c, hw, dev)
     d_fg, d_bg = torch.empty_like(fg_proto), torch.empty_like(bg_proto)
     _cabi.check(L.pemp_cosine_match_bwd(qry.data_ptr(), ep, fg_proto.data_ptr(), bg_proto.data_ptr(), g_pred.data_ptr(), n_maps, Bp,
-                                        c, hw, P, float(scalar), d_qry.data_ptr(), d_fg.data_ptr(), d_bg.data_ptr(),
+                                        c, hw, P, float(scalar), d_qry.data_ptr(), d_ep, d_fg.data_ptr(), d_bg.data_ptr(),
                                         ws.data_ptr(), ws.numel(), _stream()), "pemp_cosine_match_bwd")
     _count(3)
     return d_qry, d_fg, d_bg
+
+
+def upsample_ce(pred, target, want_grad=True):
+    """Mean cross entropy (255 ignored) of the bilinear align_corners up-sampling of pred [N,2,h,w] to target [N,H,W]
+    (int64 or uint8) -> (loss [1], d_pred [N,2,h,w] or None)   (entry/pemp_stage1.py:51,57-60)."""
+    pred = _need(pred, torch.float32, "pred")
+    if not isinstance(target, torch.Tensor) or not target.is_cuda or target.dtype not in (torch.int64, torch.uint8):
+        raise ValueError("target must be a CUDA int64 or uint8 tensor")
+    target = target.contiguous()
+    N, two, h, w = pred.shape
+    if two != 2 or target.dim() != 3 or target.shape[0] != N:
+        raise ValueError("pred must be [N,2,h,w] and target [N,H,W]")
+    H, W = target.shape[1:]
+    L = _cabi.lib()
+    ws = _ws(L.pemp_upsample_ce_workspace_bytes(N, h, w, H, W), pred.device)
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    d_pred = torch.empty_like(pred) if want_grad else None
+    _cabi.check(L.pemp_upsample_ce(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.uint8), N, h, w, H, W,
+                                   loss.data_ptr(), _ptr(d_pred), ws.data_ptr(), ws.numel(), _stream()), "pemp_upsample_ce")
+    _count(4 if want_grad else 2)
+    return loss, d_pred

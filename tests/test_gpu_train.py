@@ -160,3 +160,31 @@ def test_training_ops_refuse_cpu_tensors():
         A.meta_proto_attn(feats[:, :1], ctr, fg, bg)
     with pytest.raises(ValueError):
         A.cosine_match(feats[:, 1:], torch.zeros(1, 16, 3), torch.zeros(1, 16, 3))
+
+
+@pytest.mark.parametrize("N,h,w,H,W,dtype", [(3, 51, 51, 401, 401, torch.int64), (2, 13, 17, 57, 83, torch.uint8), (1, 4, 4, 1, 7, torch.int64),
+                                              (4, 51, 51, 333, 500, torch.uint8), (2, 9, 9, 9, 9, torch.int64), (2, 20, 20, 11, 13, torch.int64)])
+def test_upsample_ce_loss_and_gradient(N, h, w, H, W, dtype):
+    """K13 against F.interpolate + cross_entropy(ignore_index=255) and their autograd in float64."""
+    from pemp_b200 import autograd as A
+    g = torch.Generator().manual_seed(N * H + w)
+    pred = torch.randn(N, 2, h, w, generator=g) * 5
+    target = torch.randint(0, 2, (N, H, W), generator=g)
+    target[torch.rand(N, H, W, generator=g) < 0.1] = 255
+    p64 = pred.double().requires_grad_(True)
+    lg = torch.nn.functional.interpolate(p64, size=(H, W), mode="bilinear", align_corners=True)
+    loss64 = torch.nn.functional.cross_entropy(lg, target, ignore_index=255)
+    (loss64 * 3.0).backward()
+    p_cu = pred.cuda().requires_grad_(True)
+    loss = A.upsample_ce(p_cu, target.to(dtype).cuda())
+    (loss * 3.0).backward()
+    assert abs(float(loss.detach()) - float(loss64.detach())) <= 2e-6 * max(1.0, abs(float(loss64.detach())))
+    assert nrel(p_cu.grad.cpu(), p64.grad.float()) < 1e-5
+
+
+def test_upsample_ce_with_nothing_valid_is_nan_like_torch():
+    from pemp_b200 import ops
+    pred = torch.randn(1, 2, 5, 5).cuda()
+    target = torch.full((1, 9, 9), 255, dtype=torch.int64).cuda()
+    loss, _ = ops.upsample_ce(pred, target)
+    assert torch.isnan(loss).all()
