@@ -216,6 +216,11 @@ int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const 
                           long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes,
                           pemp_stream_t stream);
 
+/* backward of pemp_map_pool_lowres (K1; training path of the baseline and PANet heads, entry/panet.py:108-115):
+ * g_fg / g_bg [B, c] -> d_fts, addressed like pemp_meta_proto_attn_bwd's.  bg and g_bg may both be NULL.            */
+int pemp_map_pool_lowres_bwd(const float* fg, const float* bg, long long mask_stride, const float* g_fg, const float* g_bg,
+                             int B, int S, int c, int hw, float eps, float* d_fts, long long d_fts_episode_stride,
+                             pemp_stream_t stream);
 /* K13  loss of the training step and its gradient (entry/pemp_stage1.py:51,57-60): mean cross entropy, 255 ignored, of the
  * bilinear (align_corners) up-sampling of pred [N, 2, h, w] to the target [N, H, W] (int64, or uint8 when target_is_u8).
  * loss [1]; d_pred [N, 2, h, w] = d loss / d pred (nullable: loss only).                                              */

@@ -49,6 +49,32 @@ class _CosineMatch(torch.autograd.Function):
         return d_qry.view(qry.shape), d_fg, d_bg, None
 
 
+class _MapPoolLowres(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sup_fts, fg, bg, eps):
+        B, S, c = sup_fts.shape[:3]
+        fgp, bgp = ops.map_pool_lowres(sup_fts, fg, bg, B, S, eps)
+        ctx.save_for_backward(fg, bg)
+        ctx.shape, ctx.eps = tuple(sup_fts.shape), eps
+        return fgp, bgp
+
+    @staticmethod
+    def backward(ctx, g_fg, g_bg):
+        fg, bg = ctx.saved_tensors
+        B, S, c = ctx.shape[:3]
+        z = lambda g: torch.zeros(B, c, dtype=torch.float32, device=fg.device) if g is None else g.contiguous()
+        d = ops.map_pool_lowres_bwd(fg, bg, z(g_fg), z(g_bg), B, S, c, ctx.eps)
+        return d.view(ctx.shape), None, None, None
+
+
+def map_pool_lowres(sup_fts, sup_fg, sup_bg, eps=1e-5):
+    """Masked average pooling at feature resolution (`pemp_stage1.py:223-227`, the baseline head's prototypes):
+    sup_fts [B, S, c, h, w], masks [B*S, h*w] -> fg_proto, bg_proto [B, c]; differentiable in sup_fts."""
+    if sup_fts.dim() != 5:
+        raise ValueError("sup_fts must be [B, S, c, h, w]")
+    return _MapPoolLowres.apply(sup_fts, sup_fg, sup_bg, eps)
+
+
 class _UpsampleCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):

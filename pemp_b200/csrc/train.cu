@@ -84,6 +84,20 @@ struct Pad {
   static constexpr int H = KP / 2;
 };
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// The tile buffer is single (two CTAs per SM overlap instead), so the next tile's rows are pulled into L2 while this tile
+// is being worked on: phase A then waits for L2, not for HBM (long-scoreboard stalls were the top stall reason).
+#ifndef PEMP_BWD_PREFETCH
+#define PEMP_BWD_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_tile(const float* src, int c, int hw, int x0) {
+  if (!PEMP_BWD_PREFETCH || x0 >= hw) return;
+  const int x1 = min(x0 + 31, hw - 1);
+  for (int ch = threadIdx.x; ch < c; ch += kBT) {
+    const float* row = src + static_cast<long long>(ch) * hw;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + x0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + x1));
+  }
+}
 template <int KP>
 __device__ __forceinline__ void load_row(const float* row, float2 (&r)[KP / 2]) {
 #pragma unroll
@@ -156,6 +170,7 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
       red[(warp * NA + 2 * j + 1) * 32 + lane] = acc[j].y;
     }
     red[(warp * NA + KP) * 32 + lane] = nacc;
+    if (t + 1 < t1) prefetch_tile(src, c, hw, (t + 1) * 32);
     __syncthreads();
     for (int i = tid; i < NA * 32; i += kBT) {
       float s = 0.f;
@@ -372,6 +387,7 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
       red[(warp * NA + KP + 2 * j) * 32 + lane] = accA[j].x;
       red[(warp * NA + KP + 2 * j + 1) * 32 + lane] = accA[j].y;
     }
+    if (t + 1 < t1) prefetch_tile(src, c, hw, (t + 1) * 32);
     __syncthreads();
     for (int i = tid; i < NA * 32; i += kBT) {
       float s = 0.f;
@@ -538,6 +554,74 @@ int launch_mpa_bwd(const float* fts, long long ep, int S, const float* ctr, cons
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------ K1 backward
+// proto_g[b, c] = mean_s sum_x f m_g / (sum_x m_g + eps)  =>  d f[b, s, c, x] = (g_fg[b, c] m_fg[x] / den_fg + g_bg[b, c] m_bg[x]
+// / den_bg) / S: a rank-2 outer product per image - write only, the features are not needed.
+namespace {
+__global__ void __launch_bounds__(256)
+map_pool_bwd_kernel(const float* __restrict__ fg, const float* __restrict__ bg, long long mask_stride, const float* __restrict__ g_fg,
+                    const float* __restrict__ g_bg, int S, int c, int hw, int rows_per_cta, float eps, float* __restrict__ d_fts,
+                    long long d_ep_stride) {
+  extern __shared__ float wm[];      // [2][hw] masks divided by S * den
+  __shared__ float scratch[2][8];
+  const int n = blockIdx.y, b = n / S, si = n - b * S;
+  const float* mf = fg + static_cast<long long>(n) * mask_stride;
+  const float* mb = bg ? bg + static_cast<long long>(n) * mask_stride : nullptr;
+  float sf = 0.f, sb = 0.f;
+  for (int i = threadIdx.x; i < hw; i += 256) {
+    const float a = __ldg(mf + i), q = mb ? __ldg(mb + i) : 0.f;
+    wm[i] = a;
+    wm[hw + i] = q;
+    sf += a;
+    sb += q;
+  }
+  sf = warp_sum(sf);
+  sb = warp_sum(sb);
+  if ((threadIdx.x & 31) == 0) {
+    scratch[0][threadIdx.x >> 5] = sf;
+    scratch[1][threadIdx.x >> 5] = sb;
+  }
+  __syncthreads();
+  sf = sb = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    sf += scratch[0][w];
+    sb += scratch[1][w];
+  }
+  const float kf = 1.0f / (static_cast<float>(S) * (sf + eps)), kb = 1.0f / (static_cast<float>(S) * (sb + eps));
+  const int c0 = blockIdx.x * rows_per_cta, c1 = min(c, c0 + rows_per_cta);
+  float* dst = d_fts + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(si) * c * hw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ch = c0 + warp; ch < c1; ch += 8) {
+    const float gf = __ldg(g_fg + static_cast<long long>(b) * c + ch) * kf;
+    const float gb = g_bg ? __ldg(g_bg + static_cast<long long>(b) * c + ch) * kb : 0.f;
+    float* row = dst + static_cast<long long>(ch) * hw;
+    for (int i = lane; i < hw; i += 32) row[i] = fmaf(gf, wm[i], gb * wm[hw + i]);
+  }
+}
+}  // namespace
+
+extern "C" int pemp_map_pool_lowres_bwd(const float* fg, const float* bg, long long mask_stride, const float* g_fg, const float* g_bg,
+                                        int B, int S, int c, int hw, float eps, float* d_fts, long long d_fts_episode_stride,
+                                        pemp_stream_t stream) {
+  PEMP_REQUIRE(fg && g_fg && d_fts, PEMP_E_NULL);
+  PEMP_REQUIRE((bg == nullptr) == (g_bg == nullptr), PEMP_E_NULL);
+  PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && hw > 0 && static_cast<long long>(B) * S <= 65535, PEMP_E_SHAPE);
+  const size_t smem = static_cast<size_t>(hw) * 2 * sizeof(float);
+  PEMP_REQUIRE(smem <= 200 * 1024, PEMP_E_SHAPE);
+  const int N = B * S;
+  int chunks = (4 * 148 + N - 1) / N;
+  if (chunks > c / 8) chunks = c / 8;
+  if (chunks < 1) chunks = 1;
+  const int rows = (c + chunks - 1) / chunks;
+  chunks = (c + rows - 1) / rows;
+  cudaError_t e = cudaFuncSetAttribute(map_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long d_ep = d_fts_episode_stride ? d_fts_episode_stride : static_cast<long long>(S) * c * hw;
+  map_pool_bwd_kernel<<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(fg, bg, mask_stride, g_fg, g_bg, S, c, hw, rows, eps, d_fts, d_ep);
+  return launch_status();
+}
 
 extern "C" size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P) {
   if (N <= 0 || Bp <= 0 || c <= 0 || hw <= 0 || P < 1 || P > 4) return 0;

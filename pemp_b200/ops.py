@@ -507,3 +507,24 @@ def upsample_ce(pred, target, want_grad=True):
                                    loss.data_ptr(), _ptr(d_pred), ws.data_ptr(), ws.numel(), _stream()), "pemp_upsample_ce")
     _count(4 if want_grad else 2)
     return loss, d_pred
+
+
+def map_pool_lowres_bwd(fg, bg, g_fg, g_bg, B, S, c, eps=1e-5, out=None):
+    """Backward of `map_pool_lowres`: masks [B*S, hw], g_fg / g_bg [B, c] -> d_fts [B*S, c, hw] (or `out`, a
+    [B, S, c, h, w] slice of the gradient of the encoder output)."""
+    n_img = B * S
+    fg = _need_loose(fg, "fg")
+    hw = fg.numel() // n_img
+    fg = fg.reshape(n_img, hw)
+    bg = None if bg is None else _need_loose(bg, "bg").reshape(n_img, hw)
+    g_fg = _need(g_fg, torch.float32, "g_fg")
+    g_bg = None if bg is None else _need(g_bg, torch.float32, "g_bg")
+    if tuple(g_fg.shape) != (B, c):
+        raise ValueError(f"g_fg must be [{B}, {c}]")
+    fgp, bgp, stride, keep = _mask_pair(fg, bg, n_img, hw)
+    d_fts, d_ep = _grad_out(out, B, S, c, hw, fg.device)
+    _cabi.check(_cabi.lib().pemp_map_pool_lowres_bwd(fgp, bgp, stride, g_fg.data_ptr(), _ptr(g_bg), B, S, c, hw, float(eps),
+                                                     d_fts.data_ptr(), d_ep, _stream()), "pemp_map_pool_lowres_bwd")
+    _count(1)
+    del keep
+    return d_fts

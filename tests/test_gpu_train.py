@@ -188,3 +188,22 @@ def test_upsample_ce_with_nothing_valid_is_nan_like_torch():
     target = torch.full((1, 9, 9), 255, dtype=torch.int64).cuda()
     loss, _ = ops.upsample_ce(pred, target)
     assert torch.isnan(loss).all()
+
+
+@pytest.mark.parametrize("B,S,Q,c,h,w", [(2, 2, 1, 64, 9, 11), (1, 5, 1, 512, 51, 51), (3, 1, 2, 32, 7, 5)])
+def test_baseline_head_gradients(B, S, Q, c, h, w):
+    """K1 + K3 with one prototype per class (the baseline / PANet heads in training, entry/panet.py:108-115)."""
+    from pemp_b200 import autograd as A
+    feats, _, fg, bg = _case(B, S, Q, c, h, w, 1, seed=5 + c)
+    g = torch.Generator().manual_seed(9)
+    wgt = torch.randn(B * Q, 2, h, w, generator=g)
+    f64 = feats.double().requires_grad_(True)
+    of, ob = O.map_pool_lowres(f64[:, :S].reshape(B * S, c, h * w), fg.double(), bg.double(), B, S)
+    p64, _ = O.reduce_over_protos(O.cosine_match(f64[:, S:].reshape(B * Q, c, h * w), of, ob, 20.0))
+    (p64 * wgt.double().view(B * Q, 2, h * w)).sum().backward()
+    f_cu = feats.cuda().requires_grad_(True)
+    kf, kb = A.map_pool_lowres(f_cu[:, :S], fg.cuda(), bg.cuda())
+    pred = A.cosine_match(f_cu[:, S:], kf, kb, 20.0)
+    assert nrel(pred.detach().cpu().view(B * Q, 2, h * w), p64.detach().float()) < 1e-5
+    (pred * wgt.cuda()).sum().backward()
+    assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
