@@ -75,6 +75,52 @@ def map_pool_lowres(sup_fts, sup_fg, sup_bg, eps=1e-5):
     return _MapPoolLowres.apply(sup_fts, sup_fg, sup_bg, eps)
 
 
+class _MapPoolFullres(torch.autograd.Function):
+    """K6 forward; backward = the K1 backward kernel on the adjoint weight maps U^T mask (pooling the up-sampled features
+    with the mask equals pooling the features with U^T mask, and sum(U^T mask) = sum(mask))."""
+
+    @staticmethod
+    def forward(ctx, sup_fts, sup_mask, eps):
+        B, S = sup_fts.shape[:2]
+        fgp, bgp = ops.map_pool_fullres(sup_fts, sup_mask, B, S, eps)
+        ctx.save_for_backward(sup_mask)
+        ctx.shape, ctx.eps = tuple(sup_fts.shape), eps
+        return fgp, bgp
+
+    @staticmethod
+    def backward(ctx, g_fg, g_bg):
+        (sup_mask,) = ctx.saved_tensors
+        B, S, c, h, w = ctx.shape
+        wt, _ = ops.bilinear_adjoint(sup_mask, (h, w), want_sum=False)                 # [BS, 2, h, w]
+        wt = wt.view(B * S, 2, h * w)
+        z = lambda g: torch.zeros(B, c, dtype=torch.float32, device=wt.device) if g is None else g.contiguous()
+        d = ops.map_pool_lowres_bwd(wt[:, 0], wt[:, 1], z(g_fg), z(g_bg), B, S, c, ctx.eps)
+        return d.view(ctx.shape), None, None
+
+
+def map_pool_fullres(sup_fts, sup_mask, eps=1e-5):
+    """Masked average pooling at mask resolution (`baseline.py:100-110`, `panet.py:99-109`): sup_fts [B, S, c, h, w],
+    sup_mask [B*S, 2, H, W] -> fg_proto, bg_proto [B, c]; differentiable in sup_fts."""
+    if sup_fts.dim() != 5:
+        raise ValueError("sup_fts must be [B, S, c, h, w]")
+    return _MapPoolFullres.apply(sup_fts, sup_mask, eps)
+
+
+def panet_align_loss(qry_fts, pred, sup_fts, sup_mask_fg, scalar=20.0):
+    """PANet's prototype-alignment loss (`panet.py:158-194`) from the differentiable pieces: query prototypes pooled with
+    the arg-max masks of `pred` (no gradient through the arg-max), every support map matched against them, cross entropy
+    against the support foreground mask.  qry_fts [B, Q, c, h, w], pred [B*Q, 2, h, w], sup_fts [B, S, c, h, w],
+    sup_mask_fg [B*S, H, W] -> 0-dim loss; differentiable in qry_fts and sup_fts."""
+    B, Q = qry_fts.shape[:2]
+    with torch.no_grad():
+        fgm = (pred[:, 1] > pred[:, 0]).float().reshape(B * Q, -1)
+        bgm = 1.0 - fgm
+        target = sup_mask_fg.long()
+    fgp, bgp = map_pool_lowres(qry_fts, fgm, bgm, 1e-5)
+    rev = cosine_match(sup_fts, fgp, bgp, scalar)
+    return upsample_ce(rev, target)
+
+
 class _UpsampleCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):

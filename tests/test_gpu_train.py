@@ -207,3 +207,49 @@ def test_baseline_head_gradients(B, S, Q, c, h, w):
     assert nrel(pred.detach().cpu().view(B * Q, 2, h * w), p64.detach().float()) < 1e-5
     (pred * wgt.cuda()).sum().backward()
     assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
+
+
+def _panet_reference_losses(f64, sup_mask, target, B, S, Q, scalar=20.0):
+    """The oracle's `baseline_head` + `panet_align_loss` with the (NumPy, not differentiable) up-sampler of the oracle
+    replaced by `F.interpolate(align_corners=True)` - the op the reference itself calls (baseline.py:100, panet.py:190)."""
+    up = lambda t, size: torch.nn.functional.interpolate(t, size=size, mode="bilinear", align_corners=True)
+    _, _, c, h, w = f64.shape
+    H, W = sup_mask.shape[-2:]
+    sup = f64[:, :S].reshape(B * S, c, h, w)
+    qry = f64[:, S:].reshape(B * Q, c, h, w)
+    big = up(sup, (H, W))
+    fgm, bgm = sup_mask[:, 0:1], sup_mask[:, 1:2]
+    fgp = ((big * fgm).sum(dim=(2, 3)) / (fgm.sum(dim=(2, 3)) + 1e-5)).view(B, S, c).mean(dim=1)
+    bgp = ((big * bgm).sum(dim=(2, 3)) / (bgm.sum(dim=(2, 3)) + 1e-5)).view(B, S, c).mean(dim=1)
+    pred = O.cosine_match(qry.reshape(B * Q, c, h * w), fgp, bgp, scalar)[:, :, 0].reshape(B * Q, 2, h, w)
+    ce = torch.nn.functional.cross_entropy(up(pred, tuple(target.shape[-2:])), target, ignore_index=255)
+    winner = O.argmax2(pred.detach()).view(B * Q, h * w)
+    q = qry.reshape(B * Q, c, h * w)
+    qf = O.masked_average(q, (winner == 1).double(), 1e-5).view(B, Q, c).mean(dim=1)
+    qb = O.masked_average(q, (winner == 0).double(), 1e-5).view(B, Q, c).mean(dim=1)
+    rev = O.cosine_match(sup.reshape(B * S, c, h * w), qf, qb, scalar)[:, :, 0].reshape(B * S, 2, h, w)
+    al = torch.nn.functional.cross_entropy(up(rev, (H, W)), sup_mask[:, 0].long())
+    return ce, al
+
+
+@pytest.mark.parametrize("B,S,Q,c,h,w,H,W", [(2, 2, 1, 32, 9, 9, 33, 33), (1, 3, 2, 64, 13, 11, 50, 41)])
+def test_panet_training_step_gradients(B, S, Q, c, h, w, H, W):
+    """`entry/panet.py:108-115`: loss = CE(query) + alignLoss, with the prototypes pooled at mask resolution (K6)."""
+    from pemp_b200 import autograd as A
+    g = torch.Generator().manual_seed(21 + c)
+    feats = torch.randn(B, S + Q, c, h, w, generator=g)
+    fgm = (torch.rand(B * S, 1, H, W, generator=g) > 0.6).float()
+    sup_mask = torch.cat((fgm, 1.0 - fgm), dim=1)
+    target = torch.randint(0, 2, (B * Q, H, W), generator=g)
+    target[:, :2] = 255
+    f64 = feats.double().requires_grad_(True)
+    ce64, al64 = _panet_reference_losses(f64, sup_mask.double(), target, B, S, Q)
+    (ce64 + al64).backward()
+    f_cu = feats.cuda().requires_grad_(True)
+    fgp, bgp = A.map_pool_fullres(f_cu[:, :S], sup_mask.cuda())
+    pred = A.cosine_match(f_cu[:, S:], fgp, bgp)
+    ce = A.upsample_ce(pred, target.cuda())
+    al = A.panet_align_loss(f_cu[:, S:], pred.detach(), f_cu[:, :S], sup_mask[:, 0].cuda())
+    (ce + al).backward()
+    assert abs(float(ce.detach()) - float(ce64.detach())) < 1e-5 and abs(float(al.detach()) - float(al64.detach())) < 1e-5
+    assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
