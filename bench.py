@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_JSON_OUT = sys.stdout
+
 WORKLOADS = {
     "stage2_5shot": dict(shot=5, stages=2, desc="PEMP Stage-2 ResNet-50 5-shot prototype head (stage-1 head -> prior -> stage-2 head -> IoU)"),
     "stage1_1shot": dict(shot=1, stages=1, desc="PEMP Stage-1 ResNet-50 1-shot prototype head"),
@@ -191,7 +193,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "episodes/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Python reference cannot travel to the GPU box: this is oracle/restate.py (bit-exact CPU restatement of the "
-                "reference head, pinned by tests/test_oracle_pinned.py) on torch CPU with all host threads"}))
+                "reference head, pinned by tests/test_oracle_pinned.py) on torch CPU with all host threads"}),
+          file=_JSON_OUT, flush=True)
 
 
 def run_ours(args):
@@ -369,17 +372,20 @@ def run_ours(args):
         er = out["episode_roofline"]
         er["episodes_per_s_at_hbm_peak"] = peaks["hbm_gbs"] * 1e3 / er["algorithmic_MB_per_episode"]
         er["frac"] = (value / world) / er["episodes_per_s_at_hbm_peak"]
-        print(json.dumps(out))
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
 def main():
     args = parse()
-    # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, the image default)
-    # goes to stdout too, so keep NCCL at WARN unless the caller asked for more
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line.  Native libraries write there too (NCCL prints its "NCCL version ..." banner on
+    # stdout at every debug level the image or the caller may set), so file descriptor 1 is pointed at stderr for the whole
+    # run and the JSON line goes out through a private copy of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

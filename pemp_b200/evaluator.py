@@ -57,7 +57,7 @@ class GraphedStep:
         cur.wait_stream(side)
         n0 = ops.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may touch CUDA
             self.prior, self.mask = pipe.step(*args)
         self.launches = ops.launch_count() - n0      # kernels recorded in the graph (capturing does not run them)
         ops._count(-self.launches)
