@@ -223,10 +223,18 @@ int pemp_map_pool_lowres_bwd(const float* fg, const float* bg, long long mask_st
                              pemp_stream_t stream);
 /* K13  loss of the training step and its gradient (entry/pemp_stage1.py:51,57-60): mean cross entropy, 255 ignored, of the
  * bilinear (align_corners) up-sampling of pred [N, 2, h, w] to the target [N, H, W] (int64, or uint8 when target_is_u8).
- * loss [1]; d_pred [N, 2, h, w] = d loss / d pred (nullable: loss only).                                              */
+ * loss [1]; d_pred [N, 2, h, w] = d loss / d pred (nullable: loss only); weight [N, H, W] nullable (see K14).          */
 size_t pemp_upsample_ce_workspace_bytes(int N, int h, int w, int H, int W);
-int pemp_upsample_ce(const float* pred, const void* target, int target_is_u8, int N, int h, int w, int H, int W,
-                     float* loss, float* d_pred, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+int pemp_upsample_ce(const float* pred, const void* target, int target_is_u8, const float* weight, int N, int h, int w,
+                     int H, int W, float* loss, float* d_pred, void* workspace, size_t workspace_bytes,
+                     pemp_stream_t stream);
+/* K14  CELossDT (core/losses.py:17-43): weight [N, H, W] = exp(-d / sigma^2) + 1, d = exact Euclidean
+ * distance to the nearest boundary pixel of (target == 1) - the reference computes it with scipy on the host every step.
+ * Passing the result as `weight` to pemp_upsample_ce gives CELossDT's loss: sum(w * ce) / sum(w) (weight == NULL: plain
+ * mean over the valid pixels).                                                                                          */
+size_t pemp_boundary_weight_workspace_bytes(int N, int H, int W);
+int pemp_boundary_weight(const void* target, int target_is_u8, int N, int H, int W, float sigma, float* weight,
+                         void* workspace, size_t workspace_bytes, pemp_stream_t stream);
 
 #ifdef __cplusplus
 }

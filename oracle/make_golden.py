@@ -212,6 +212,24 @@ def comm_cases():
               feat=_np(feat), pooled=_np(pooled))
 
 
+def cedt_cases():
+    """`CELossDT` (core/losses.py:17-43), SURVEY 8f row 4: the reference's own class on CPU tensors."""
+    g = torch.Generator().manual_seed(99)
+    for name, (N, H, W, sigma) in (("cedt_a", (3, 41, 57, 5.0)), ("cedt_b", (2, 64, 64, 2.0))):
+        target = torch.zeros(N, H, W, dtype=torch.int64)
+        for n in range(N):
+            for _ in range(2):
+                y0, x0 = int(torch.randint(0, H - 8, (1,), generator=g)), int(torch.randint(0, W - 8, (1,), generator=g))
+                hh, ww = int(torch.randint(3, H // 2, (1,), generator=g)), int(torch.randint(3, W // 2, (1,), generator=g))
+                target[n, y0:y0 + hh, x0:x0 + ww] = 1
+        target[0, :, :3][target[0, :, :3] == 0] = 255                 # an ignore band
+        target[N - 1] = 0                                             # a plane without any foreground (no boundary)
+        target[N - 1, :2] = 255
+        inputs = torch.randn(N, 2, H, W, generator=g) * 3
+        loss, weight = R.ce_loss_dt(inputs, target, sigma)
+        _save(name, inputs=_np(inputs), target=_np(target), sigma=sigma, loss=_np(loss), weight=_np(weight))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -221,6 +239,7 @@ def main():
     pfenet_cases()
     metric_cases()
     comm_cases()
+    cedt_cases()
 
 
 if __name__ == "__main__":

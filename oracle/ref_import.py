@@ -140,3 +140,33 @@ def comm(variant, x, mask, weight, bias, spq, stride):
         if bias is not None:
             linear.bias.copy_(bias)
         return cls.comm(types.SimpleNamespace(spq=spq), x, mask, linear, stride=stride)
+
+
+def ce_loss_dt(inputs, target, sigma):
+    """Run the reference's own `CELossDT.__call__` / `boundary2weight` (core/losses.py:17-43) on CPU tensors.
+    Two things of the reference do not run in this image and are shimmed without touching its code: `__init__` puts the
+    3x3 kernel on a GPU (`.cuda()`), so the instance is built without `__init__` and given the same attributes on the CPU;
+    `boundary2weight` uses `np.bool`, removed in NumPy 1.24+, which is aliased to `bool` for the duration of the call.
+    Returns (loss, weight [bs, H, W])."""
+    import numpy as np
+    losses = module("core.losses")
+    obj = object.__new__(losses.CELossDT)
+    obj.sigma = sigma
+    obj.loss_obj = nn.CrossEntropyLoss(ignore_index=255, reduction='none')
+    obj.kernel = torch.ones(1, 1, 3, 3, dtype=torch.float)
+    had = hasattr(np, "bool")
+    if not had:
+        np.bool = bool
+    try:
+        seen = {}
+        orig = obj.boundary2weight
+
+        def spy(boundary):
+            seen["weight"] = orig(boundary)
+            return seen["weight"]
+        obj.boundary2weight = spy
+        loss = obj(inputs, target)
+    finally:
+        if not had:
+            del np.bool
+    return loss, seen["weight"]

@@ -31,7 +31,9 @@ SIGNATURES = {
     "pemp_cosine_match_bwd": (I, [P, LL, P, P, P, I, I, I, I, I, F, P, LL, P, P, P, SZ, P]),
     "pemp_map_pool_lowres_bwd": (I, [P, P, LL, P, P, I, I, I, I, F, P, LL, P]),
     "pemp_upsample_ce_workspace_bytes": (SZ, [I, I, I, I, I]),
-    "pemp_upsample_ce": (I, [P, P, I, I, I, I, I, I, P, P, P, SZ, P]),
+    "pemp_upsample_ce": (I, [P, P, I, P, I, I, I, I, I, P, P, P, SZ, P]),
+    "pemp_boundary_weight_workspace_bytes": (SZ, [I, I, I]),
+    "pemp_boundary_weight": (I, [P, I, I, I, I, F, P, P, SZ, P]),
     "pemp_comm_workspace_bytes": (SZ, [I, I, I, I]),
     "pemp_comm_module": (I, [P, P, I, I, I, I, I, I, I, I, P, P, I, P, P, P, SZ, P]),
     "pemp_debug_mpa_path": (I, [I]),

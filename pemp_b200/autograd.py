@@ -123,15 +123,15 @@ def panet_align_loss(qry_fts, pred, sup_fts, sup_mask_fg, scalar=20.0):
 
 class _UpsampleCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, target):
-        loss, d_pred = ops.upsample_ce(pred, target, want_grad=True)
+    def forward(ctx, pred, target, weight):
+        loss, d_pred = ops.upsample_ce(pred, target, want_grad=True, weight=weight)
         ctx.save_for_backward(d_pred)
         return loss.view(())
 
     @staticmethod
     def backward(ctx, g):
         (d_pred,) = ctx.saved_tensors
-        return d_pred * g, None
+        return d_pred * g, None, None
 
 
 class _PempHead(torch.autograd.Function):
@@ -170,10 +170,16 @@ def pemp_head(features, sup_mask_low, ctr, B, S, Q, scalar=20.0, eps=1e-6):
     return _PempHead.apply(f5, ctr, sup_mask_low[:, 0], sup_mask_low[:, 1], S, scalar, eps).view(B * Q, 2, h, w)
 
 
-def upsample_ce(pred, target):
+def upsample_ce(pred, target, weight=None):
     """loss = CrossEntropyLoss(ignore_index=255)(F.interpolate(pred, target.shape[-2:], bilinear, align_corners=True),
-    target) in one pass, gradient included (K13)."""
-    return _UpsampleCE.apply(pred, target)
+    target) in one pass, gradient included (K13).  With `weight` [N, H, W]: sum(w * ce) / sum(w)."""
+    return _UpsampleCE.apply(pred, target, weight)
+
+
+def ce_loss_dt(pred, target, sigma=5.0):
+    """`CELossDT(sigma)` (core/losses.py:17-43, `loss=cedt`) on the up-sampled prediction: the boundary distance-transform
+    weights are computed on the device (K14; the reference goes through scipy on the host every step)."""
+    return upsample_ce(pred, target, ops.boundary_weight(target, sigma))
 
 
 def meta_proto_attn(sup_fts, ctr, sup_fg, sup_bg, eps=1e-6):

@@ -19,8 +19,9 @@ constexpr int kLossThreads = 256, kLossBand = 16;
 
 template <typename LabelT>
 __global__ void __launch_bounds__(kLossThreads)
-upsample_ce_grad_kernel(const float* __restrict__ pred, const LabelT* __restrict__ target, int h, int w, int H, int W, float sy,
-                        float sx, int bands, float* __restrict__ e, float* __restrict__ part_loss, float* __restrict__ part_cnt) {
+upsample_ce_grad_kernel(const float* __restrict__ pred, const LabelT* __restrict__ target, const float* __restrict__ weight, int h,
+                        int w, int H, int W, float sy, float sx, int bands, float* __restrict__ e, float* __restrict__ part_loss,
+                        float* __restrict__ part_cnt) {
   extern __shared__ float hrow[];                    // [nsrc][2][W]
   const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
   const int Y0 = band * kLossBand, Y1 = min(H, Y0 + kLossBand);
@@ -51,11 +52,18 @@ upsample_ce_grad_kernel(const float* __restrict__ pred, const LabelT* __restrict
       const float d = v1 - v0, t = expf(-fabsf(d));
       const float lse = fmaxf(v0, v1) + log1pf(t);
       const float p1 = d >= 0.f ? 1.0f / (1.0f + t) : t / (1.0f + t);          // sigmoid(v1 - v0)
-      if (valid) {
-        acc += lse - (lb == 1 ? v1 : v0);
-        cnt += 1.0f;
+      if (weight) {          // CELossDT: weighted sum over the sum of ALL weights, ignored pixels included (losses.py:42-43)
+        const float wv = __ldg(weight + base + X);
+        if (valid) acc = fmaf(wv, lse - (lb == 1 ? v1 : v0), acc);
+        cnt += wv;
+        e[base + X] = valid ? wv * (p1 - (lb == 1 ? 1.0f : 0.0f)) : 0.0f;
+      } else {
+        if (valid) {
+          acc += lse - (lb == 1 ? v1 : v0);
+          cnt += 1.0f;
+        }
+        e[base + X] = valid ? p1 - (lb == 1 ? 1.0f : 0.0f) : 0.0f;
       }
-      e[base + X] = valid ? p1 - (lb == 1 ? 1.0f : 0.0f) : 0.0f;
     }
   }
   __shared__ float pa[kLossThreads / 32], pc[kLossThreads / 32];
@@ -73,7 +81,7 @@ upsample_ce_grad_kernel(const float* __restrict__ pred, const LabelT* __restrict
       c2 += pc[i];
     }
     part_loss[blockIdx.x] = a;
-    part_cnt[blockIdx.x] = c2;       // <= 16 * W: exact in fp32
+    part_cnt[blockIdx.x] = c2;       // unweighted: <= 16 * W, exact in fp32
   }
 }
 
@@ -138,8 +146,9 @@ extern "C" size_t pemp_upsample_ce_workspace_bytes(int N, int h, int w, int H, i
   return loss_plan(N, h, w, H, W).total;
 }
 
-extern "C" int pemp_upsample_ce(const float* pred, const void* target, int target_is_u8, int N, int h, int w, int H, int W,
-                                float* loss, float* d_pred, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+extern "C" int pemp_upsample_ce(const float* pred, const void* target, int target_is_u8, const float* weight, int N, int h, int w,
+                                int H, int W, float* loss, float* d_pred, void* workspace, size_t workspace_bytes,
+                                pemp_stream_t stream) {
   PEMP_REQUIRE(pred && target && loss, PEMP_E_NULL);
   PEMP_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0, PEMP_E_SHAPE);
   const LossPlan pl = loss_plan(N, h, w, H, W);
@@ -156,12 +165,12 @@ extern "C" int pemp_upsample_ce(const float* pred, const void* target, int targe
   if (target_is_u8) {
     err = cudaFuncSetAttribute(upsample_ce_grad_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (err != cudaSuccess) return static_cast<int>(err);
-    upsample_ce_grad_kernel<uint8_t><<<pl.nparts, kLossThreads, pl.smem, st>>>(pred, static_cast<const uint8_t*>(target), h, w, H, W, sy, sx,
+    upsample_ce_grad_kernel<uint8_t><<<pl.nparts, kLossThreads, pl.smem, st>>>(pred, static_cast<const uint8_t*>(target), weight, h, w, H, W, sy, sx,
                                                                                 pl.bands, e, part_loss, part_cnt);
   } else {
     err = cudaFuncSetAttribute(upsample_ce_grad_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (err != cudaSuccess) return static_cast<int>(err);
-    upsample_ce_grad_kernel<int64_t><<<pl.nparts, kLossThreads, pl.smem, st>>>(pred, static_cast<const int64_t*>(target), h, w, H, W, sy, sx,
+    upsample_ce_grad_kernel<int64_t><<<pl.nparts, kLossThreads, pl.smem, st>>>(pred, static_cast<const int64_t*>(target), weight, h, w, H, W, sy, sx,
                                                                                 pl.bands, e, part_loss, part_cnt);
   }
   if (d_pred) {
@@ -171,5 +180,124 @@ extern "C" int pemp_upsample_ce(const float* pred, const void* target, int targe
   const long long tot = static_cast<long long>(N) * h * w;
   const int blocks = d_pred ? static_cast<int>(llmin((tot + 255) / 256, 148LL * 4)) : 1;
   ce_grad_finalize_kernel<<<blocks, 256, 0, st>>>(part_loss, part_cnt, pl.nparts, wt, N, h * w, loss, d_pred);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K14
+// CELossDT.boundary2weight on the device (core/losses.py:23-40).  The reference copies the boundary map to
+// the host, runs scipy's exact Euclidean distance transform per image and copies the weights back - a CPU round trip in
+// every training step.  Here: (1) 3x3 boundary map; (2) per column, the vertical distance to the nearest boundary pixel
+// (two scans); (3) per row, D^2(x) = min over x' of (x - x')^2 + g(x')^2 in integers - exact, so sqrt in double equals
+// scipy's value - and weight = exp(-D / sigma^2) + 1 in double, stored as float.  A plane without boundary pixels gets
+// scipy's distances to its virtual zero at (row -1, column 0).
+namespace {
+
+constexpr int kInfDist = 1 << 20;
+
+template <typename LabelT>
+__global__ void boundary_kernel(const LabelT* __restrict__ target, int N, int H, int W, uint8_t* __restrict__ bnd, int* __restrict__ any) {
+  const long long total = static_cast<long long>(N) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const long long t = i / W;
+    const int y = static_cast<int>(t % H);
+    const long long n = t / H;
+    const LabelT* p = target + n * H * W;
+    int s = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) s += static_cast<long long>(p[static_cast<long long>(yy) * W + xx]) == 1;
+      }
+    const bool m = static_cast<long long>(p[static_cast<long long>(y) * W + x]) == 1;
+    const bool b = m ? s < 9 : s > 0;
+    bnd[i] = b;
+    if (b) any[n] = 1;           // benign race: every writer stores 1
+  }
+}
+
+// one thread per column: g[y][x] = distance to the nearest boundary pixel of column x (kInfDist if none)
+__global__ void edt_columns_kernel(const uint8_t* __restrict__ bnd, int H, int W, int* __restrict__ g) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (x >= W) return;
+  const uint8_t* b = bnd + static_cast<long long>(n) * H * W + x;
+  int* out = g + static_cast<long long>(n) * H * W + x;
+  int d = kInfDist;
+  for (int y = 0; y < H; ++y) {
+    d = b[static_cast<long long>(y) * W] ? 0 : (d < kInfDist ? d + 1 : kInfDist);
+    out[static_cast<long long>(y) * W] = d;
+  }
+  d = kInfDist;
+  for (int y = H - 1; y >= 0; --y) {
+    d = b[static_cast<long long>(y) * W] ? 0 : (d < kInfDist ? d + 1 : kInfDist);
+    const int cur = out[static_cast<long long>(y) * W];
+    if (d < cur) out[static_cast<long long>(y) * W] = d;
+  }
+}
+
+// one CTA per (row, image): exact squared distance by the lower envelope search over the row, then the weight
+__global__ void __launch_bounds__(256)
+edt_rows_weight_kernel(const int* __restrict__ g, const int* __restrict__ any, int H, int W, double inv_sigma2,
+                       float* __restrict__ weight) {
+  extern __shared__ long long g2[];      // [W] squared column distances
+  const int y = blockIdx.x, n = blockIdx.y;
+  const int* row = g + (static_cast<long long>(n) * H + y) * W;
+  const bool has = any[n] != 0;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const long long v = row[x];
+    g2[x] = v >= kInfDist ? (1LL << 60) : v * v;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    long long best;
+    if (!has) {
+      best = static_cast<long long>(y + 1) * (y + 1) + static_cast<long long>(x) * x;
+    } else {
+      best = g2[x];
+      // walk outwards; a candidate at horizontal distance d cannot win once d^2 >= best
+      for (int d = 1; d < W; ++d) {
+        const long long dd = static_cast<long long>(d) * d;
+        if (dd >= best) break;
+        if (x - d >= 0) best = min(best, dd + g2[x - d]);
+        if (x + d < W) best = min(best, dd + g2[x + d]);
+      }
+    }
+    const double dist = sqrt(static_cast<double>(best));
+    weight[(static_cast<long long>(n) * H + y) * W + x] = static_cast<float>(exp(-dist * inv_sigma2) + 1.0);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t pemp_boundary_weight_workspace_bytes(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  const size_t px = static_cast<size_t>(N) * H * W;
+  return align_up(px, 256) + align_up(px * sizeof(int), 256) + align_up(static_cast<size_t>(N) * sizeof(int), 256);
+}
+
+extern "C" int pemp_boundary_weight(const void* target, int target_is_u8, int N, int H, int W, float sigma, float* weight,
+                                    void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(target && weight, PEMP_E_NULL);
+  PEMP_REQUIRE(N > 0 && N <= 65535 && H > 0 && H <= 65535 && W > 0 && W <= 16384 && sigma > 0.f, PEMP_E_SHAPE);
+  PEMP_REQUIRE(workspace && workspace_bytes >= pemp_boundary_weight_workspace_bytes(N, H, W), PEMP_E_WORKSPACE);
+  cudaStream_t st = as_stream(stream);
+  const size_t px = static_cast<size_t>(N) * H * W;
+  char* ws = static_cast<char*>(workspace);
+  uint8_t* bnd = reinterpret_cast<uint8_t*>(ws);
+  int* g = reinterpret_cast<int*>(ws + align_up(px, 256));
+  int* any = reinterpret_cast<int*>(ws + align_up(px, 256) + align_up(px * sizeof(int), 256));
+  cudaError_t e = cudaMemsetAsync(any, 0, static_cast<size_t>(N) * sizeof(int), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const unsigned blocks = static_cast<unsigned>(llmin((static_cast<long long>(px) + 255) / 256, 148LL * 16));
+  if (target_is_u8)
+    boundary_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(target), N, H, W, bnd, any);
+  else
+    boundary_kernel<int64_t><<<blocks, 256, 0, st>>>(static_cast<const int64_t*>(target), N, H, W, bnd, any);
+  edt_columns_kernel<<<dim3((W + 127) / 128, N), 128, 0, st>>>(bnd, H, W, g);
+  const double s2 = static_cast<double>(sigma) * static_cast<double>(sigma);
+  edt_rows_weight_kernel<<<dim3(H, N), 256, static_cast<size_t>(W) * sizeof(long long), st>>>(g, any, H, W, 1.0 / s2, weight);
   return launch_status();
 }

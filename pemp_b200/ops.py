@@ -488,22 +488,46 @@ def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0, out=None):
     return d_qry, d_fg, d_bg
 
 
-def upsample_ce(pred, target, want_grad=True):
-    """Mean cross entropy (255 ignored) of the bilinear align_corners up-sampling of pred [N,2,h,w] to target [N,H,W]
-    (int64 or uint8) -> (loss [1], d_pred [N,2,h,w] or None)   (entry/pemp_stage1.py:51,57-60)."""
-    pred = _need(pred, torch.float32, "pred")
+def _labels(target):
     if not isinstance(target, torch.Tensor) or not target.is_cuda or target.dtype not in (torch.int64, torch.uint8):
         raise ValueError("target must be a CUDA int64 or uint8 tensor")
-    target = target.contiguous()
+    if target.dim() != 3:
+        raise ValueError("target must be [N, H, W]")
+    return target.contiguous()
+
+
+def boundary_weight(target, sigma):
+    """`CELossDT.boundary2weight` on the device (core/losses.py:23-40): target [N,H,W] -> weight [N,H,W] float32."""
+    target = _labels(target)
+    N, H, W = target.shape
+    L = _cabi.lib()
+    ws = _ws(L.pemp_boundary_weight_workspace_bytes(N, H, W), target.device)
+    weight = torch.empty(N, H, W, dtype=torch.float32, device=target.device)
+    _cabi.check(L.pemp_boundary_weight(target.data_ptr(), int(target.dtype == torch.uint8), N, H, W, float(sigma),
+                                       weight.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "pemp_boundary_weight")
+    _count(3)
+    return weight
+
+
+def upsample_ce(pred, target, want_grad=True, weight=None):
+    """Cross entropy (255 ignored) of the bilinear align_corners up-sampling of pred [N,2,h,w] to target [N,H,W]
+    (int64 or uint8) -> (loss [1], d_pred [N,2,h,w] or None).  weight None: mean over the valid pixels
+    (entry/pemp_stage1.py:51,57-60); weight [N,H,W]: sum(w * ce) / sum(w), CELossDT (core/losses.py:33-43)."""
+    pred = _need(pred, torch.float32, "pred")
+    target = _labels(target)
     N, two, h, w = pred.shape
     if two != 2 or target.dim() != 3 or target.shape[0] != N:
         raise ValueError("pred must be [N,2,h,w] and target [N,H,W]")
     H, W = target.shape[1:]
+    if weight is not None:
+        weight = _need(weight, torch.float32, "weight")
+        if tuple(weight.shape) != (N, H, W):
+            raise ValueError("weight must have the shape of target")
     L = _cabi.lib()
     ws = _ws(L.pemp_upsample_ce_workspace_bytes(N, h, w, H, W), pred.device)
     loss = torch.empty(1, dtype=torch.float32, device=pred.device)
     d_pred = torch.empty_like(pred) if want_grad else None
-    _cabi.check(L.pemp_upsample_ce(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.uint8), N, h, w, H, W,
+    _cabi.check(L.pemp_upsample_ce(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.uint8), _ptr(weight), N, h, w, H, W,
                                    loss.data_ptr(), _ptr(d_pred), ws.data_ptr(), ws.numel(), _stream()), "pemp_upsample_ce")
     _count(4 if want_grad else 2)
     return loss, d_pred

@@ -253,3 +253,68 @@ def test_panet_training_step_gradients(B, S, Q, c, h, w, H, W):
     (ce + al).backward()
     assert abs(float(ce.detach()) - float(ce64.detach())) < 1e-5 and abs(float(al.detach()) - float(al64.detach())) < 1e-5
     assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
+
+
+# ------------------------------------------------------------------------------------------------ K14 (CELossDT)
+@pytest.mark.parametrize("name", ["cedt_a", "cedt_b"])
+def test_boundary_weight_and_cedt_loss_against_reference_fixtures(name):
+    """Fixtures produced by the reference's own `CELossDT` (core/losses.py:17-43, scipy EDT on the host).  The weights come
+    from exact integer squared distances, so they must match to the last bit of the float64 -> float32 rounding (at most one
+    ulp apart where CUDA's and NumPy's double `exp` differ in their last bit)."""
+    from conftest import golden
+    from pemp_b200 import autograd as A, ops
+    g = golden(name)
+    target = torch.from_numpy(g["target"]).cuda()
+    sigma = float(g["sigma"])
+    for t in (target, target.to(torch.uint8)):
+        wgt = ops.boundary_weight(t, sigma).cpu().numpy()
+        assert np.abs(wgt - g["weight"]).max() <= 2.4e-7
+        assert (wgt != g["weight"]).mean() < 1e-3
+    inputs = torch.from_numpy(g["inputs"])
+    # the reference feeds logits at the target size: identity "up-sampling" (h, w) == (H, W)
+    p_cu = inputs.cuda().requires_grad_(True)
+    loss = A.ce_loss_dt(p_cu, target, sigma)
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    p64 = inputs.double().requires_grad_(True)
+    w64 = torch.from_numpy(g["weight"]).double()
+    ce = torch.nn.functional.cross_entropy(p64, torch.from_numpy(g["target"]), ignore_index=255, reduction="none")
+    ((ce * w64).sum() / w64.sum()).backward()
+    loss.backward()
+    assert nrel(p_cu.grad.cpu(), p64.grad.float()) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,W,sigma", [(2, 401, 401, 5.0), (3, 97, 130, 3.0), (1, 5, 7, 1.0)])
+def test_boundary_weight_random_shapes_against_the_oracle(N, H, W, sigma):
+    from pemp_b200 import ops
+    g = torch.Generator().manual_seed(N * H)
+    target = torch.zeros(N, H, W, dtype=torch.int64)
+    blobs = torch.rand(N, H // 4 + 1, W // 4 + 1, generator=g) > 0.7
+    target[:] = torch.nn.functional.interpolate(blobs[:, None].float(), size=(H, W), mode="nearest")[:, 0].long()
+    target[torch.rand(N, H, W, generator=g) < 0.02] = 255
+    if N > 1:
+        target[1] = 0                                     # no foreground, no boundary
+    want = O.boundary_weight(target, sigma).numpy()
+    got = ops.boundary_weight(target.cuda(), sigma).cpu().numpy()
+    assert np.abs(got - want).max() <= 2.4e-7
+    assert (got != want).mean() < 1e-3
+
+
+def test_cedt_training_step_on_upsampled_prediction():
+    """`loss=cedt` on the PEMP head: pred [N,2,h,w] up-sampled to the target inside the op."""
+    from pemp_b200 import autograd as A
+    N, h, w, H, W, sigma = 2, 13, 13, 97, 97, 5.0
+    g = torch.Generator().manual_seed(4)
+    pred = torch.randn(N, 2, h, w, generator=g) * 4
+    target = torch.zeros(N, H, W, dtype=torch.int64)
+    target[0, 20:60, 30:80] = 1
+    target[1, 5:30, 5:50] = 1
+    target[:, :3] = 255
+    p64 = pred.double().requires_grad_(True)
+    lg = torch.nn.functional.interpolate(p64, size=(H, W), mode="bilinear", align_corners=True)
+    want, _ = O.ce_loss_dt(lg, target, sigma)
+    want.backward()
+    p_cu = pred.cuda().requires_grad_(True)
+    loss = A.ce_loss_dt(p_cu, target.cuda(), sigma)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(want.detach())) <= 2e-6 * abs(float(want.detach()))
+    assert nrel(p_cu.grad.cpu(), p64.grad.float()) < 1e-5

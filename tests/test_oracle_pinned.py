@@ -119,6 +119,17 @@ def test_comm_module_bit_exact(name):
     assert np.array_equal(feat.numpy(), g["feat"])
 
 
+@pytest.mark.parametrize("name", ["cedt_a", "cedt_b"])
+def test_ce_loss_dt_bit_exact(name):
+    """`CELossDT` (core/losses.py:17-43): boundary map, exact distance transform, weights and the weighted loss."""
+    g = golden(name)
+    loss, weight = O.ce_loss_dt(torch.from_numpy(g["inputs"]), torch.from_numpy(g["target"]), float(g["sigma"]))
+    assert np.array_equal(weight.numpy(), g["weight"])
+    assert float(loss) == float(g["loss"])
+    # the plane without foreground gets scipy's distances to its virtual zero at (-1, 0): pixel (0, 0) is at distance 1
+    assert float(weight[-1, 0, 0]) == float(np.float32(np.exp(-1.0 / float(g["sigma"]) ** 2) + 1.0))
+
+
 def test_metric_known_answers():
     """The two episodes the reference ships (`http/static/.../{000_01,001_03}`): expected rows are the
     numbers in SURVEY 4 / BASELINE.md, and the Dice must round to `data.json:"acc"`."""
