@@ -236,6 +236,12 @@ size_t pemp_boundary_weight_workspace_bytes(int N, int H, int W);
 int pemp_boundary_weight(const void* target, int target_is_u8, int N, int H, int W, float sigma, float* weight,
                          void* workspace, size_t workspace_bytes, pemp_stream_t stream);
 
+/* K15  CaNet dense-comparison input (networks/canet.py:172-180): out [N, 2c, hw] = the query maps
+ * (read in place through qry_episode_stride, as in pemp_cosine_match) concatenated with z [Bp, c] tiled over hw.  z is
+ * pemp_map_pool_lowres with the nearest-resized foreground mask (bg = NULL), eps 1e-5.                               */
+int pemp_canet_concat(const float* qry, long long qry_episode_stride, const float* z, int N, int Bp, int c, int hw,
+                      float* out, pemp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -230,6 +230,18 @@ def cedt_cases():
         _save(name, inputs=_np(inputs), target=_np(target), sigma=sigma, loss=_np(loss), weight=_np(weight))
 
 
+def canet_cases():
+    """CaNet's masked average pooling + tiling + concatenation (networks/canet.py:172-180), SURVEY 8f row 4."""
+    g = torch.Generator().manual_seed(123)
+    for name, (B, S, Q, c, h, H) in (("canet_b2s2", (2, 2, 1, 24, 13, 97)), ("canet_b1s1q2", (1, 1, 2, 16, 9, 40))):
+        feats = torch.randn(B, S + Q, c, h, h, generator=g)
+        fg = (torch.rand(B, S, 1, H, H, generator=g) > 0.6).float()
+        fg[0, 0] = 0                                                  # a shot without foreground
+        sup_mask = torch.cat((fg, 1 - fg), dim=2)
+        out = R.canet_map_tile(feats, sup_mask, B, S, Q)
+        _save(name, features=_np(feats), sup_mask=_np(sup_mask), S=S, Q=Q, out=_np(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -240,6 +252,7 @@ def main():
     metric_cases()
     comm_cases()
     cedt_cases()
+    canet_cases()
 
 
 if __name__ == "__main__":

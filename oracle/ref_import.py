@@ -170,3 +170,20 @@ def ce_loss_dt(inputs, target, sigma):
         if not had:
             del np.bool
     return loss, seen["weight"]
+
+
+def canet_map_tile(features, sup_mask, B, S, Q):
+    """Run `networks/canet.py` lines "sup_fts = features[:, :S]..." .. "out = torch.cat((qry_fts, z), dim=1)" (172-180 in
+    the surveyed revision: masked average pooling at feature resolution, mean over shots, tiling, concatenation) verbatim
+    on our tensors.  features [B, S+Q, c, h, w]; sup_mask [B, S, 2, H, W] -> out [BQ, 2c, h, w]."""
+    cn = module("networks.canet")
+    src = inspect.getsource(cn.CaNet.relation).splitlines()
+    start = next(i for i, l in enumerate(src) if l.strip().startswith("sup_fts = features[:, :S]"))
+    stop = next(i for i, l in enumerate(src) if l.strip().startswith("out = torch.cat((qry_fts, z), dim=1)")) + 1
+    block = textwrap.dedent("\n".join(src[start:stop]))
+    _, _, c, h, w = features.shape
+    H, W = sup_mask.shape[-2:]
+    ns = {"torch": torch, "F": torch.nn.functional, "features": features, "sup_mask": sup_mask,
+          "B": B, "S": S, "Q": Q, "c": c, "h": h, "w": w, "H": H, "W": W}
+    exec(compile(block, "<canet.py:map-tile-block>", "exec"), ns)
+    return ns["out"]

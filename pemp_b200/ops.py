@@ -552,3 +552,22 @@ def map_pool_lowres_bwd(fg, bg, g_fg, g_bg, B, S, c, eps=1e-5, out=None):
     _count(1)
     del keep
     return d_fts
+
+
+# ------------------------------------------------------------------------------------------------ K15 (CaNet)
+def canet_map_tile(features, sup_mask, B, S, Q):
+    """CaNet's dense-comparison input (networks/canet.py:172-180): features [B*(S+Q), c, h, w] (encoder output, read in
+    place), sup_mask [B, S, 2, H, W] -> out [B*Q, 2c, h, w] = cat(query features, foreground prototype tiled)."""
+    features = _need(features, torch.float32, "features")
+    sup_mask = _need(sup_mask, torch.float32, "sup_mask")
+    _, c, h, w = features.shape
+    f5 = features.view(B, S + Q, c, h, w)
+    H, W = sup_mask.shape[-2:]
+    low = mask_nearest(sup_mask.view(B * S, 2, H, W), h, w).view(B * S, 2, h * w)
+    z, _ = map_pool_lowres(f5[:, :S], low[:, 0], None, B, S, eps=1e-5)
+    qry, ep, _, hw = _episodes(f5[:, S:], B, Q, "qry")
+    out = torch.empty(B * Q, 2 * c, h, w, dtype=torch.float32, device=features.device)
+    _cabi.check(_cabi.lib().pemp_canet_concat(qry.data_ptr(), ep, z.data_ptr(), B * Q, B, c, hw, out.data_ptr(), _stream()),
+                "pemp_canet_concat")
+    _count(1)
+    return out

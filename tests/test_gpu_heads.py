@@ -274,3 +274,32 @@ def test_graphed_step_replays_the_eager_step(B, c):
         assert torch.equal(prior, e_prior) and torch.equal(mask, e_mask)
         assert torch.equal(g_stat, e_stat)
     assert int(g_stat.sum()) > 7
+
+
+@pytest.mark.parametrize("name", ["canet_b2s2", "canet_b1s1q2"])
+def test_canet_map_tile_against_reference_fixtures(name):
+    """fixtures produced by the reference's own lines networks/canet.py:172-180.  The query half is a copy
+    (bit exact); the tiled prototype is K1 (fp32 sums: 1e-5 norm-wise)."""
+    from conftest import golden
+    from pemp_b200 import ops
+    g = golden(name)
+    f = torch.from_numpy(g["features"])
+    B, SQ, c, h, w = f.shape
+    S, Q = int(g["S"]), int(g["Q"])
+    out = ops.canet_map_tile(f.cuda().view(B * SQ, c, h, w), torch.from_numpy(g["sup_mask"]).cuda(), B, S, Q).cpu()
+    want = torch.from_numpy(g["out"])
+    assert torch.equal(out[:, :c], want[:, :c])
+    assert nrel(out[:, c:], want[:, c:]) < 1e-5
+    assert torch.equal(out[:, c:], out[:, c:, :1, :1].expand(-1, -1, h, w))          # constant over h x w
+
+
+def test_canet_map_tile_bench_shape_against_oracle():
+    from pemp_b200 import ops
+    B, S, Q, c, h, H = 4, 5, 1, 256, 41, 321
+    g = torch.Generator().manual_seed(8)
+    f = torch.randn(B, S + Q, c, h, h, generator=g)
+    fg = (torch.rand(B, S, 1, H, H, generator=g) > 0.5).float()
+    sup_mask = torch.cat((fg, 1 - fg), dim=2)
+    want = O.canet_map_tile(f, sup_mask, B, S, Q)
+    out = ops.canet_map_tile(f.cuda().view(B * (S + Q), c, h, h), sup_mask.cuda(), B, S, Q).cpu()
+    assert torch.equal(out[:, :c], want[:, :c]) and nrel(out[:, c:], want[:, c:]) < 1e-5

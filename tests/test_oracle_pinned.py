@@ -170,3 +170,12 @@ def test_nearest_and_bilinear_match_aten():
         assert torch.equal(O.bilinear_upsample(y, H, W), F.interpolate(y, (H, W), mode="bilinear", align_corners=True))
     q, p = torch.randn(4, 64, 100), torch.randn(4, 64)
     assert torch.equal(O.cosine_to(q, p), F.cosine_similarity(q, p[:, :, None], dim=1))
+
+
+@pytest.mark.parametrize("name", ["canet_b2s2", "canet_b1s1q2"])
+def test_canet_map_tile_bit_exact(name):
+    """networks/canet.py:172-180 through the restatement."""
+    g = golden(name)
+    f = torch.from_numpy(g["features"])
+    out = O.canet_map_tile(f, torch.from_numpy(g["sup_mask"]), f.shape[0], int(g["S"]), int(g["Q"]))
+    assert np.array_equal(out.numpy(), g["out"])

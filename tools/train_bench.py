@@ -71,6 +71,20 @@ def main():
     target = torch.randint(0, 2, (B * Q, 401, 401), device=dev, generator=g)
     low = torch.stack((fg, bg), 1)
 
+    # CELossDT weights (K14) on object-like masks, against the reference's host path (boundary -> host, scipy EDT, back)
+    blob = torch.zeros(B * Q, 401, 401, dtype=torch.int64, device=dev)
+    for n in range(B * Q):
+        blob[n, 40 + n % 50: 250 + n % 90, 60 + n % 70: 300 + n % 40] = 1
+    ms = timeit(lambda: ops.boundary_weight(blob, 5.0))
+    import time
+    from oracle import restate as O     # the CPU restatement of the reference's host path: baseline only
+    host = blob[:8].cpu()
+    t0 = time.perf_counter()
+    O.boundary_weight(host, 5.0)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 * (B * Q) / 8
+    print(json.dumps({"kernel": "K14 boundary_weight (CELossDT)", "ms": round(ms, 4), "images": B * Q, "HxW": "401x401",
+                      "host_scipy_ms_same_batch": round(cpu_ms, 1), "note": "host time excludes the two PCIe copies of the reference"}))
+
     def ours():
         f = feats.view(B * (S + Q), c, h, h).detach().requires_grad_(True)
         cc = ctr.detach().requires_grad_(True)
