@@ -38,7 +38,7 @@ namespace {
 constexpr int kBT = PEMP_BWD_THREADS;   // threads per CTA
 constexpr int kBW = kBT / 32;           // warps
 constexpr int kLd = 33;                 // padded tile row
-constexpr int kMaxCPT = 1024 / kBT;     // channels per thread in phase B2  =>  c <= 1024
+constexpr int kMaxCPT = (1024 + kBT - 1) / kBT;   // channels per thread in phase B2  =>  c <= 1024
 constexpr int kUn = PEMP_BWD_UNROLL;    // feature loads in flight per lane in phase A
 constexpr float kCosEps = 1e-8f;   // F.cosine_similarity's eps
 
@@ -514,14 +514,33 @@ mpa_bwd_finalize_kernel(const float* __restrict__ part, long long nparts, int c,
   }
 }
 
+size_t cos_smem(int c, int K);
+size_t mpa_smem(int c, int K);
 struct BwdPlan {
   int chunks, ntiles;
 };
-BwdPlan bwd_plan(int N, int hw) {
+// How many CTAs share one image.  The grid is N * chunks CTAs of ceil(ntiles / chunks) tiles each on `slots` resident CTAs
+// (two per SM at the PEMP size): pick the split with the smallest  waves * (tiles per CTA + prologue)  - e.g. 80 images of
+// 82 tiles: 8 chunks = 2.16 waves of 11 tiles (a third, nearly empty wave), 11 chunks = 2.97 waves of 8.
+BwdPlan bwd_plan(int N, int hw, size_t smem) {
   BwdPlan p;
   p.ntiles = (hw + 31) / 32;
-  int want = (4 * 148 + N - 1) / N;          // ~2 waves of 2 CTAs per SM
-  p.chunks = want < 1 ? 1 : (want > p.ntiles ? p.ntiles : want);
+  long long per_sm = static_cast<long long>(227 * 1024) / static_cast<long long>(smem + 1024);
+  const long long by_regs = 65536 / (128LL * kBT);
+  if (per_sm > by_regs) per_sm = by_regs;
+  if (per_sm < 1) per_sm = 1;
+  const long long slots = 148 * per_sm;
+  double best = 1e30;
+  p.chunks = 1;
+  const int cmax = p.ntiles < 64 ? p.ntiles : 64;
+  for (int ch = 1; ch <= cmax; ++ch) {
+    const long long waves = (static_cast<long long>(N) * ch + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * ((p.ntiles + ch - 1) / ch + 0.75);
+    if (cost < best - 1e-9) {
+      best = cost;
+      p.chunks = ch;
+    }
+  }
   return p;
 }
 size_t cos_smem(int c, int K) {
@@ -625,7 +644,7 @@ extern "C" int pemp_map_pool_lowres_bwd(const float* fg, const float* bg, long l
 
 extern "C" size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P) {
   if (N <= 0 || Bp <= 0 || c <= 0 || hw <= 0 || P < 1 || P > 4) return 0;
-  const BwdPlan pl = bwd_plan(N, hw);
+  const BwdPlan pl = bwd_plan(N, hw, cos_smem(c, 2 * P));
   const size_t K = 2 * P;
   return align_up(static_cast<size_t>(Bp) * c * K * 4, 256) + align_up(static_cast<size_t>(Bp) * K * 4, 256) +
          align_up(static_cast<size_t>(N) * pl.chunks * c * K * 4, 256);
@@ -640,7 +659,7 @@ extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_str
   PEMP_REQUIRE(P >= 1 && P <= 4 && c <= kMaxCPT * kBT && cos_smem(c, 2 * P) <= 227 * 1024, PEMP_E_SHAPE);
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_cosine_match_bwd_workspace_bytes(N, Bp, c, hw, P), PEMP_E_WORKSPACE);
   cudaStream_t st = as_stream(stream);
-  const BwdPlan pl = bwd_plan(N, hw);
+  const BwdPlan pl = bwd_plan(N, hw, cos_smem(c, 2 * P));
   const int K = 2 * P, Q = N / Bp;
   char* ws = static_cast<char*>(workspace);
   float* pn = reinterpret_cast<float*>(ws);
@@ -664,7 +683,7 @@ extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_str
 extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p) {
   if (B <= 0 || S <= 0 || c <= 0 || hw <= 0 || p < 1 || p > 4) return 0;
   const size_t N = static_cast<size_t>(B) * S, K = 2 * p;
-  const BwdPlan pl = bwd_plan(static_cast<int>(N), hw);
+  const BwdPlan pl = bwd_plan(static_cast<int>(N), hw, mpa_smem(c, 2 * p));
   return align_up(N * c * K * 4, 256) + align_up(N * 2 * K * 4, 256) + align_up(N * pl.chunks * (c + 1) * K * 4, 256);
 }
 
@@ -679,7 +698,7 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_meta_proto_attn_bwd_workspace_bytes(B, S, c, hw, p), PEMP_E_WORKSPACE);
   cudaStream_t st = as_stream(stream);
   const int N = B * S, K = 2 * p;
-  const BwdPlan pl = bwd_plan(N, hw);
+  const BwdPlan pl = bwd_plan(N, hw, mpa_smem(c, 2 * p));
   char* ws = static_cast<char*>(workspace);
   float* coef = reinterpret_cast<float*>(ws);
   float* beta = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(N) * c * K * 4, 256));
