@@ -479,21 +479,26 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
     }
     if (t + 1 < t1) prefetch_tile(src, c, hw, (t + 1) * 32);
     __syncthreads();
-    for (int i = tid; i < NA * 32; i += kBT) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < kBW; ++w) s += red[w * NA * 32 + i];
-      sum[i] = s;
-    }
-    __syncthreads();
-    if (tid < 32) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
+    if (tid < 64) {   // pixel step: warp g handles group g; every thread adds the eight warps' partials it needs itself
+      {
+        const int g = warp;
         const float m = inb ? __ldg((g == 0 ? fg : bg) + static_cast<long long>(n) * mask_stride + x) : 0.f;
+        float sc[P], sa[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          float u = 0.f, v = 0.f;
+#pragma unroll
+          for (int w = 0; w < kBW; ++w) {      // fixed order
+            u += red[(w * NA + g * P + k) * 32 + lane];
+            v += red[(w * NA + KP + g * P + k) * 32 + lane];
+          }
+          sc[k] = u;
+          sa[k] = v;
+        }
         float l[P], mx = -CUDART_INF_F;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-          l[k] = fmaf(2.0f, sum[(g * P + k) * 32 + lane], -konst[g * P + k]);
+          l[k] = fmaf(2.0f, sc[k], -konst[g * P + k]);
           mx = fmaxf(mx, l[k]);
         }
         float z = 0.f;
@@ -507,7 +512,7 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           l[k] *= iz;                                                                // sigma_k
-          ds[k] = m * (sum[(KP + g * P + k) * 32 + lane] + konst[K + g * P + k]);    // d sigma_k
+          ds[k] = m * (sa[k] + konst[K + g * P + k]);                                // d sigma_k
           dot = fmaf(l[k], ds[k], dot);
         }
 #pragma unroll
