@@ -22,7 +22,7 @@ def main(path, bench=None):
         a[0] += 1
         a[1] += float(r[iv].replace(",", ""))
     tot = sum(a[1] for a in agg.values())
-    print("ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline")
+    print("ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph")
     print("(5 steps of 64 five-shot episodes; per-launch times are cold-cache and serialised - compare SHARES; full list: "
           "r01_launches_bench_steps2.csv)")
     print("kernel, launches, total_us, share of our kernels")
