@@ -50,6 +50,35 @@ def test_no_cpu_fallback():
             FewShotMetric(20)
 
 
+def test_training_path_has_no_cpu_fallback_and_plans_on_the_host():
+    """K12-K15 host logic: CPU tensors are refused before the library is touched; the workspace planners are pure host code
+    (the backward planner picks the image split from the wave count - more CTAs per image when there are few images)."""
+    from pemp_b200 import autograd as A, ops
+    f = torch.zeros(1, 2, 16, 4, 4)
+    with pytest.raises(ValueError, match="CUDA"):
+        A.meta_proto_attn(f[:, :1], torch.zeros(16, 6), torch.zeros(1, 16), torch.zeros(1, 16))
+    with pytest.raises(ValueError, match="CUDA"):
+        A.cosine_match(f[:, 1:], torch.zeros(1, 16, 3), torch.zeros(1, 16, 3))
+    with pytest.raises(ValueError, match="CUDA"):
+        A.upsample_ce(torch.zeros(1, 2, 4, 4), torch.zeros(1, 9, 9, dtype=torch.int64))
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.boundary_weight(torch.zeros(1, 9, 9, dtype=torch.int64), 5.0)
+    with pytest.raises(ValueError):
+        A.pemp_head_loss(torch.zeros(2, 16, 4, 4), torch.zeros(1, 2, 16), torch.zeros(16, 6), 1, 1, 1,
+                         torch.zeros(1, 9, 9, dtype=torch.int64), out_shape=(5, 5))
+    lib = _cabi.lib()
+    few = lib.pemp_meta_proto_attn_bwd_workspace_bytes(1, 1, 512, 2601, 3)
+    many = lib.pemp_meta_proto_attn_bwd_workspace_bytes(64, 5, 512, 2601, 3)
+    assert few > 0 and many > few
+    per_image_few = few - 512 * 6 * 4            # minus the coefficient table: partials of one image
+    assert per_image_few > (many / 320) * 2      # one image alone is split over more CTAs than each of 320 images
+    assert lib.pemp_meta_proto_attn_bwd_workspace_bytes(1, 1, 512, 2601, 5) == 0
+    assert lib.pemp_cosine_match_bwd_workspace_bytes(64, 64, 512, 2601, 3) > 0
+    assert lib.pemp_upsample_ce_workspace_bytes(64, 51, 51, 401, 401) >= 64 * 401 * 401 * 4
+    assert lib.pemp_boundary_weight_workspace_bytes(64, 401, 401) >= 64 * 401 * 401 * 5
+    assert lib.pemp_boundary_weight_workspace_bytes(0, 401, 401) == 0
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "pemp_b200")):
         for f in files:
