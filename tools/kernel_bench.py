@@ -60,6 +60,7 @@ def main():
     ref = (torch.rand(B, H, H, device=dev) > 0.5).to(torch.uint8)
     cls = torch.randint(1, 6, (B,), device=dev)
     stat = torch.zeros(21, 3, dtype=torch.int64, device=dev)
+    feats_all = torch.cat((sup.view(B, S, c, h, h), qry.view(B, 1, c, h, h)), dim=1).view(B * (S + 1), c, h, h).contiguous()
     rows = [
         ("K0 mask_nearest", lambda: ops.mask_nearest(sup_mask, h, h), B * S * 2 * hw * 4 * 2),
         ("K2 meta_proto_attn", lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S),
@@ -78,6 +79,10 @@ def main():
          B * ((1 + S) * c * hw * 4 + 2 * hw * 4 + S * H * H * 4)),
         ("K8 weighted_gap", lambda: ops.weighted_gap(sup.view(B * S, c, h, h), low[:, 0].reshape(B * S, 1, h, h)),
          B * S * (c * hw + hw) * 4),
+        # CaNet dense-comparison input (canet.py:172-180): K0 + K1 (fg only) over the supports, then one read of the query maps
+        # and one write of the 2c-channel tensor
+        ("K15 canet_map_tile", lambda: ops.canet_map_tile(feats_all, sup_mask.view(B, S, 2, H, H), B, S, 1),
+         B * (S * (c * hw + hw) * 4 + S * 2 * hw * 8 + c * hw * 4 + 2 * c * hw * 4)),   # K0 samples hw of the H*W mask pixels
     ]
     if not a.only or "K11" in a.only:
         # ResNetCM.comm call site 2 (backbones.py:235): x2 [B*6, 256, 101, 101], stride 1
