@@ -219,23 +219,37 @@ __global__ void boundary_kernel(const LabelT* __restrict__ target, int N, int H,
   }
 }
 
-// one thread per column: g[y][x] = distance to the nearest boundary pixel of column x (kInfDist if none)
-__global__ void edt_columns_kernel(const uint8_t* __restrict__ bnd, int H, int W, int* __restrict__ g) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
-  if (x >= W) return;
-  const uint8_t* b = bnd + static_cast<long long>(n) * H * W + x;
-  int* out = g + static_cast<long long>(n) * H * W + x;
-  int d = kInfDist;
-  for (int y = 0; y < H; ++y) {
-    d = b[static_cast<long long>(y) * W] ? 0 : (d < kInfDist ? d + 1 : kInfDist);
-    out[static_cast<long long>(y) * W] = d;
+// g[y][x] = distance to the nearest boundary pixel of column x (kInfDist if none).  A CTA stages 32 columns of the plane in
+// shared memory with coalesced loads, 32 threads scan their column down and up there (a scan through global memory pays the
+// load latency 2 H times in a row), and all threads write the result back coalesced.
+constexpr int kColTile = 32;
+__global__ void __launch_bounds__(256)
+edt_columns_kernel(const uint8_t* __restrict__ bnd, int H, int W, int* __restrict__ g) {
+  extern __shared__ int col[];             // [H][kColTile + 1]
+  const int x0 = blockIdx.x * kColTile, n = blockIdx.y;
+  const uint8_t* b = bnd + static_cast<long long>(n) * H * W;
+  int* out = g + static_cast<long long>(n) * H * W;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int y = ty; y < H; y += 8)
+    col[y * (kColTile + 1) + tx] = (x0 + tx < W) ? b[static_cast<long long>(y) * W + x0 + tx] : 0;
+  __syncthreads();
+  if (threadIdx.x < kColTile) {
+    int* cp = col + threadIdx.x;
+    int d = kInfDist;
+    for (int y = 0; y < H; ++y) {
+      d = cp[y * (kColTile + 1)] ? 0 : (d < kInfDist ? d + 1 : kInfDist);
+      cp[y * (kColTile + 1)] = d;
+    }
+    d = kInfDist;
+    for (int y = H - 1; y >= 0; --y) {
+      const int cur = cp[y * (kColTile + 1)];
+      d = cur == 0 ? 0 : (d < kInfDist ? d + 1 : kInfDist);
+      if (d < cur) cp[y * (kColTile + 1)] = d;
+    }
   }
-  d = kInfDist;
-  for (int y = H - 1; y >= 0; --y) {
-    d = b[static_cast<long long>(y) * W] ? 0 : (d < kInfDist ? d + 1 : kInfDist);
-    const int cur = out[static_cast<long long>(y) * W];
-    if (d < cur) out[static_cast<long long>(y) * W] = d;
-  }
+  __syncthreads();
+  for (int y = ty; y < H; y += 8)
+    if (x0 + tx < W) out[static_cast<long long>(y) * W + x0 + tx] = col[y * (kColTile + 1) + tx];
 }
 
 // one CTA per (row, image): exact squared distance by the lower envelope search over the row, then the weight
@@ -296,7 +310,11 @@ extern "C" int pemp_boundary_weight(const void* target, int target_is_u8, int N,
     boundary_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(target), N, H, W, bnd, any);
   else
     boundary_kernel<int64_t><<<blocks, 256, 0, st>>>(static_cast<const int64_t*>(target), N, H, W, bnd, any);
-  edt_columns_kernel<<<dim3((W + 127) / 128, N), 128, 0, st>>>(bnd, H, W, g);
+  const size_t col_smem = static_cast<size_t>(H) * (kColTile + 1) * sizeof(int);
+  PEMP_REQUIRE(col_smem <= 200 * 1024, PEMP_E_SHAPE);
+  cudaError_t ec = cudaFuncSetAttribute(edt_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(col_smem));
+  if (ec != cudaSuccess) return static_cast<int>(ec);
+  edt_columns_kernel<<<dim3((W + kColTile - 1) / kColTile, N), 256, col_smem, st>>>(bnd, H, W, g);
   const double s2 = static_cast<double>(sigma) * static_cast<double>(sigma);
   edt_rows_weight_kernel<<<dim3(H, N), 256, static_cast<size_t>(W) * sizeof(long long), st>>>(g, any, H, W, 1.0 / s2, weight);
   return launch_status();
