@@ -17,6 +17,19 @@ DIST_SCALAR = 20      # `net.dist_scalar`, pemp_stage1.py:23 / baseline.py:22 / 
 # ------------------------------------------------------------------------------------------------------
 # PEMP stage 1 / stage 2
 # ------------------------------------------------------------------------------------------------------
+def _wants_grad(*tensors):
+    """True inside a training step: the reference calls the same methods under autograd (entry/pemp_stage1.py:57-65,
+    entry/panet.py:108-115), so the drop-ins then take the differentiable path (`pemp_b200.autograd`: the same forward
+    kernels plus hand-written backward kernels) instead of the forward-only one."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _upsample(pred, out_shape, differentiable):
+    if differentiable:      # stock differentiable op, as in the reference; `autograd.upsample_ce` fuses it with the loss
+        return torch.nn.functional.interpolate(pred, size=tuple(out_shape), mode="bilinear", align_corners=True)
+    return ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
+
+
 def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=DIST_SCALAR):
     """`compute_similarity` of all four reference models (pemp_stage1.py:233-261, pemp_stage2.py:205-233,
     baseline.py:121-149, panet.py:122-156).
@@ -25,6 +38,10 @@ def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=DIST_SCALA
     fg_proto / bg_proto [B, c, p] with qry_fts [N, c, 1, h, w] -> [N, 2, p, h, w]
     Channel 0 is background, 1 foreground.  N may be a multiple of B (prototypes are expanded b-major,
     panet.py:145-149)."""
+    if _wants_grad(fg_proto, bg_proto, qry_fts):
+        raise NotImplementedError("compute_similarity is forward-only (the per-prototype maps have no backward kernel); "
+                                  "training goes through mpm / pemp_b200.autograd.cosine_match, which fuse the max over "
+                                  "prototypes as the reference's mpm does right after this call")
     if qry_fts.dim() == 5:                      # PEMP passes [N, c, 1, h, w] (pemp_stage1.py:196)
         N, c, _, h, w = qry_fts.shape
     else:
@@ -49,9 +66,24 @@ def mpm(self, sup_fts, qry_fts, sup_fg, sup_bg, ret_ind, protos=None):
     fg, bg = sup_fg.reshape(B * S, hw), sup_bg.reshape(B * S, hw)
     scalar = getattr(self, "dist_scalar", DIST_SCALAR)
     ctr = getattr(self, "ctr", None)
+    if ctr is not None and protos is not None and protos * 2 != ctr.shape[1]:
+        raise ValueError(f"protos={protos} does not match ctr of shape {tuple(ctr.shape)}")
+    if _wants_grad(sup_fts, qry_fts, ctr):
+        from . import autograd as A
+        if ctr is not None:
+            fg_proto, bg_proto = A.meta_proto_attn(sup, ctr, fg, bg, eps=1e-6)
+            if getattr(self, "_pemp_keep_adaptive", False):
+                p = ctr.shape[1] // 2
+                self.adaptive_p = torch.cat((fg_proto, bg_proto), dim=2).detach().view(B, c, 2 * p)
+        else:
+            fg_proto, bg_proto = A.map_pool_lowres(sup, fg, bg, eps=1e-5)
+        pred = A.cosine_match(qry, fg_proto, bg_proto, scalar)
+        if ret_ind and ctr is not None:
+            with torch.no_grad():
+                resp = ops.cosine_match(qry, fg_proto.detach(), bg_proto.detach(), scalar, want_pred=False, want_response=True)
+            return pred, resp["response"].view(B * Q, h, w)
+        return pred
     if ctr is not None:
-        if protos is not None and protos * 2 != ctr.shape[1]:
-            raise ValueError(f"protos={protos} does not match ctr of shape {tuple(ctr.shape)}")
         fg_proto, bg_proto, adaptive = ops.meta_proto_attn(sup, ctr.detach(), fg, bg, B, S, eps=1e-6)
         if getattr(self, "_pemp_keep_adaptive", False):
             self.adaptive_p = adaptive
@@ -77,9 +109,8 @@ def pemp_head(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False):
         out_shape = (H, W)
     if ret_ind and isinstance(pred, tuple):
         pred, response = pred
-        output = ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
-        return output, ops.nearest_resize_labels(response, out_shape)
-    return ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
+        return _upsample(pred, out_shape, pred.requires_grad), ops.nearest_resize_labels(response, out_shape)
+    return _upsample(pred, out_shape, pred.requires_grad)
 
 
 def pemp_stage1_forward(self, sup_img, sup_mask, qry_img, out_shape=None, ret_ind=False):
@@ -116,12 +147,17 @@ def baseline_head(self, features, sup_mask, B, S, Q, out_shape=None, with_align=
     feats = features.view(B, S + Q, c, h, w)
     sup_fts, qry_fts = feats[:, :S], feats[:, S:]   # episode views, read in place
     mask = sup_mask.reshape(B * S, 2, H, W)
-    fg_proto, bg_proto = ops.map_pool_fullres(sup_fts, mask, B, S, eps=1e-5)
     scalar = getattr(self, "dist_scalar", DIST_SCALAR)
-    pred = ops.cosine_match(qry_fts, fg_proto, bg_proto, scalar)["pred"].view(B * Q, 2, h, w)
+    if _wants_grad(features):
+        from . import autograd as A
+        fg_proto, bg_proto = A.map_pool_fullres(sup_fts, mask, eps=1e-5)
+        pred = A.cosine_match(qry_fts, fg_proto, bg_proto, scalar)
+    else:
+        fg_proto, bg_proto = ops.map_pool_fullres(sup_fts, mask, B, S, eps=1e-5)
+        pred = ops.cosine_match(qry_fts, fg_proto, bg_proto, scalar)["pred"].view(B * Q, 2, h, w)
     if out_shape is None:
         out_shape = (H, W)
-    output = ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
+    output = _upsample(pred, out_shape, pred.requires_grad)
     if with_align:
         return output, alignLoss(self, qry_fts, pred, sup_fts, mask[:, 0:1], Q)
     return output
@@ -144,7 +180,15 @@ def panet_forward(self, sup_img, sup_mask, qry_img, out_shape=None):
 def alignLoss(self, qry_fts, pred, sup_fts, sup_mask_fg, Q):
     """`PANet.alignLoss` (panet.py:158-194) -> 0-dim tensor.  Unlike the reference (whose `.view` on an
     expanded tensor raises for B > 1 with S > 1) any B, S, Q combination works."""
-    return ops.panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, getattr(self, "dist_scalar", DIST_SCALAR))
+    scalar = getattr(self, "dist_scalar", DIST_SCALAR)
+    if _wants_grad(qry_fts, sup_fts):
+        from . import autograd as A
+        B = qry_fts.shape[0] if qry_fts.dim() == 5 else qry_fts.shape[0] // Q
+        q5 = qry_fts if qry_fts.dim() == 5 else qry_fts.view(B, Q, *qry_fts.shape[1:])
+        s5 = sup_fts if sup_fts.dim() == 5 else sup_fts.view(B, -1, *sup_fts.shape[1:])
+        H, W = sup_mask_fg.shape[-2:]
+        return A.panet_align_loss(q5, pred.detach(), s5, sup_mask_fg.reshape(-1, H, W), scalar)
+    return ops.panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar)
 
 
 # ------------------------------------------------------------------------------------------------------

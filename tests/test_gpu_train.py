@@ -318,3 +318,48 @@ def test_cedt_training_step_on_upsampled_prediction():
     loss.backward()
     assert abs(float(loss.detach()) - float(want.detach())) <= 2e-6 * abs(float(want.detach()))
     assert nrel(p_cu.grad.cpu(), p64.grad.float()) < 1e-5
+
+
+def test_dropin_heads_take_the_differentiable_path_under_autograd():
+    """The reference trains through the same methods the drop-ins replace: with autograd on, `PEMPHead` / `BaselineHead`
+    (and the patched reference classes, which share these functions) produce gradients equal to float64 autograd over the
+    oracle; under `torch.no_grad()` (core/base_trainer.py:69) they stay on the forward-only kernels."""
+    from pemp_b200 import heads
+    B, S, Q, c, h, w, H, W, P = 2, 2, 1, 64, 9, 9, 33, 33, 3
+    feats, ctr, _, _ = _case(B, S, Q, c, h, w, P, seed=77)
+    g = torch.Generator().manual_seed(5)
+    fgm = (torch.rand(B, S, 1, H, W, generator=g) > 0.6).float()
+    sup_mask = torch.cat((fgm, 1.0 - fgm), dim=2)
+    target = torch.randint(0, 2, (B * Q, H, W), generator=g)
+    target[:, :2] = 255
+    # --- PEMP head
+    head = heads.PEMPHead(out_channels=c, protos=P).cuda()
+    with torch.no_grad():
+        head.ctr.copy_(ctr.cuda())
+    f_cu = feats.cuda().view(B * (S + Q), c, h, w).requires_grad_(True)
+    out = head(f_cu, sup_mask.cuda(), B, S, Q)
+    assert out.requires_grad and tuple(out.shape) == (B * Q, 2, H, W)
+    torch.nn.functional.cross_entropy(out, target.cuda(), ignore_index=255).backward()
+    f64 = feats.double().requires_grad_(True)
+    c64 = ctr.double().requires_grad_(True)
+    low = O.mask_nearest(sup_mask.view(B * S, 2, H, W), h, w).view(B * S, 2, h * w).double()
+    of, ob, _ = O.meta_proto_attention(f64[:, :S].reshape(B * S, c, h * w), low[:, 0], low[:, 1], c64, B, S, P)
+    p64, _ = O.reduce_over_protos(O.cosine_match(f64[:, S:].reshape(B * Q, c, h * w), of, ob, 20.0))
+    lg = torch.nn.functional.interpolate(p64.view(B * Q, 2, h, w), size=(H, W), mode="bilinear", align_corners=True)
+    torch.nn.functional.cross_entropy(lg, target, ignore_index=255).backward()
+    assert nrel(f_cu.grad.cpu().view(B, S + Q, c, h, w), f64.grad.float()) < GTOL
+    assert nrel(head.ctr.grad.cpu(), c64.grad.float()) < GTOL
+    with torch.no_grad():
+        assert not head(f_cu, sup_mask.cuda(), B, S, Q).requires_grad
+    with pytest.raises(NotImplementedError):
+        head.compute_similarity(torch.zeros(B, c, P).cuda(), torch.zeros(B, c, P).cuda(), f_cu[:B].view(B, c, 1, h, w))
+    # --- PANet head (prototypes pooled at mask resolution + alignment loss)
+    pa = heads.BaselineHead(align=True).cuda()
+    f_cu2 = feats.cuda().view(B * (S + Q), c, h, w).requires_grad_(True)
+    out2, align = pa(f_cu2, sup_mask.cuda(), B, S, Q)
+    (torch.nn.functional.cross_entropy(out2, target.cuda(), ignore_index=255) + align).backward()
+    f64b = feats.double().requires_grad_(True)
+    ce64, al64 = _panet_reference_losses(f64b, sup_mask.view(B * S, 2, H, W).double(), target, B, S, Q)
+    (ce64 + al64).backward()
+    assert abs(float(align.detach()) - float(al64.detach())) < 1e-5
+    assert nrel(f_cu2.grad.cpu().view(B, S + Q, c, h, w), f64b.grad.float()) < GTOL
