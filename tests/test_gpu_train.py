@@ -363,3 +363,53 @@ def test_dropin_heads_take_the_differentiable_path_under_autograd():
     (ce64 + al64).backward()
     assert abs(float(align.detach()) - float(al64.detach())) < 1e-5
     assert nrel(f_cu2.grad.cpu().view(B, S + Q, c, h, w), f64b.grad.float()) < GTOL
+
+
+def test_bench_size_properties_of_the_training_step():
+    """BASELINE size (c = 512, 51 x 51 features, 401 x 401 targets, 5-shot; 16 episodes) through properties that need no
+    oracle: (1) the batch holds every episode twice (b and b + 8): the two copies get bit-identical feature gradients
+    (same per-image arithmetic, different CTAs), and a run over one half alone gives the same loss, twice the per-episode
+    feature gradient (half as many valid pixels in the mean) and the same centre gradient; (2) the backward is linear in
+    the upstream gradient; (3) gradients are finite, and a support image whose masks are all zero gets no gradient."""
+    from pemp_b200 import autograd as A, ops
+    B, S, Q, c, h, w, H, W, P = 16, 5, 1, 512, 51, 51, 401, 401, 3
+    g = torch.Generator(device="cuda").manual_seed(3)
+    half = torch.randn(B // 2, S + Q, c, h, w, device="cuda", generator=g)
+    feats = torch.cat((half, half), dim=0).contiguous()
+    ctr = torch.rand(c, 2 * P, device="cuda", generator=g)
+    fg_h = (torch.rand(B // 2 * S, h * w, device="cuda", generator=g) > 0.6).float()
+    fg = torch.cat((fg_h, fg_h), dim=0)
+    low = torch.stack((fg, 1.0 - fg), dim=1).contiguous()
+    tgt_h = torch.randint(0, 2, (B // 2 * Q, H, W), device="cuda", generator=g)
+    tgt_h[:, :3] = 255
+    target = torch.cat((tgt_h, tgt_h), dim=0)
+
+    def run(scale):
+        f = feats.view(B * (S + Q), c, h, w).detach().clone().requires_grad_(True)
+        cc = ctr.detach().clone().requires_grad_(True)
+        loss, _ = A.pemp_head_loss(f, low, cc, B, S, Q, target)
+        (loss * scale).backward()
+        return float(loss.detach()), f.grad.view(B, S + Q, c, h, w), cc.grad
+
+    loss1, gf1, gc1 = run(1.0)
+    assert torch.isfinite(gf1).all() and torch.isfinite(gc1).all() and float(gf1.abs().max()) > 0
+    assert torch.equal(gf1[: B // 2], gf1[B // 2:])                                  # (1) duplicate episodes
+    loss3, gf3, gc3 = run(3.0)                                                       # (2) linearity
+    assert loss1 == loss3
+    assert nrel(gf3.cpu(), (3.0 * gf1).cpu()) < 1e-6 and nrel(gc3.cpu(), (3.0 * gc1).cpu()) < 1e-6
+    # half batch: same per-episode arithmetic, the mean over valid pixels has the same value, gradients per episode are 2 x
+    fh = half.view(B // 2 * (S + Q), c, h, w).detach().clone().requires_grad_(True)
+    ch = ctr.detach().clone().requires_grad_(True)
+    lh, _ = A.pemp_head_loss(fh, low[: B // 2 * S].contiguous(), ch, B // 2, S, Q, tgt_h)
+    lh.backward()
+    assert abs(float(lh.detach()) - loss1) < 1e-6 * max(1.0, abs(loss1))
+    assert nrel((2.0 * gf1[: B // 2]).cpu(), fh.grad.view(B // 2, S + Q, c, h, w).cpu()) < 1e-6
+    assert nrel(gc1.cpu(), ch.grad.cpu()) < 1e-5
+    # (3) a support image whose masks are all zero contributes no gradient to its features
+    low0 = low.clone()
+    low0[0] = 0.0
+    f = feats.view(B * (S + Q), c, h, w).detach().clone().requires_grad_(True)
+    cc = ctr.detach().clone().requires_grad_(True)
+    loss, _ = A.pemp_head_loss(f, low0, cc, B, S, Q, target)
+    loss.backward()
+    assert float(f.grad.view(B, S + Q, c, h, w)[0, 0].abs().max()) == 0.0
