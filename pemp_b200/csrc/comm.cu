@@ -166,7 +166,8 @@ extern "C" int pemp_comm_module(const float* x, const float* mask_in, int N, int
   int chunks = (PEMP_COMM_CTAS_PER_SM * 148 + N - 1) / N;
   if (chunks > c / 8) chunks = c / 8;
   if (chunks < 1) chunks = 1;
-  const int rows = (c + chunks - 1) / chunks;
+  int rows = (c + chunks - 1) / chunks;
+  rows = (rows + 7) / 8 * 8;             // a whole number of rows per warp: 20 rows on 8 warps leaves half of them idle a third of the time
   chunks = (c + rows - 1) / rows;
   const size_t smem = static_cast<size_t>(hw) * sizeof(float);
   if (smem <= 96 * 1024) {
