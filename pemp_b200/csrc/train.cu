@@ -718,7 +718,8 @@ extern "C" int pemp_map_pool_lowres_bwd(const float* fg, const float* bg, long l
   int chunks = (4 * 148 + N - 1) / N;
   if (chunks > c / 8) chunks = c / 8;
   if (chunks < 1) chunks = 1;
-  const int rows = (c + chunks - 1) / chunks;
+  int rows = (c + chunks - 1) / chunks;
+  rows = (rows + 7) / 8 * 8;             // a whole number of rows for each of the 8 warps
   chunks = (c + rows - 1) / rows;
   cudaError_t e = cudaFuncSetAttribute(map_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
