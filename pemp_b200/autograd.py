@@ -30,7 +30,6 @@ class _MetaProtoAttn(torch.autograd.Function):
         p = ctx.saved[2].shape[1] // 2
         like = (B, ctx.shape[2], p)
         d_fts, d_ctr = ops.meta_proto_attn_bwd(ctx.saved, zero(g_fg, like), zero(g_bg, like), B, S)
-        ctx.saved = None
         return d_fts.view(ctx.shape), d_ctr, None, None, None
 
 
@@ -157,7 +156,6 @@ class _PempHead(torch.autograd.Function):
         fgp, bgp = ctx.protos
         _, d_fg, d_bg = ops.cosine_match_bwd(f5[:, S:], fgp, bgp, g_pred.contiguous(), ctx.scalar, out=d_f5[:, S:])
         _, d_ctr = ops.meta_proto_attn_bwd(ctx.saved, d_fg, d_bg, B, S, out=d_f5[:, :S])
-        ctx.saved = ctx.protos = ctx.f5 = None
         return d_f5, d_ctr, None, None, None, None, None
 
 

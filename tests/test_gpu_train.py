@@ -413,3 +413,17 @@ def test_bench_size_properties_of_the_training_step():
     loss, _ = A.pemp_head_loss(f, low0, cc, B, S, Q, target)
     loss.backward()
     assert float(f.grad.view(B, S + Q, c, h, w)[0, 0].abs().max()) == 0.0
+
+
+def test_backward_twice_with_retain_graph():
+    from pemp_b200 import autograd as A
+    B, S, Q, c, h, w, P = 1, 2, 1, 64, 7, 7, 3
+    feats, ctr, fg, bg = _case(B, S, Q, c, h, w, P, seed=6)
+    f_cu = feats.cuda().view(B * (S + Q), c, h, w).requires_grad_(True)
+    c_cu = ctr.cuda().requires_grad_(True)
+    pred = A.pemp_head(f_cu, torch.stack((fg, bg), 1).cuda(), c_cu, B, S, Q)
+    loss = pred.square().mean()
+    loss.backward(retain_graph=True)
+    g1 = f_cu.grad.clone()
+    loss.backward()
+    assert torch.equal(f_cu.grad, 2 * g1)
