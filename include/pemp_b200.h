@@ -53,6 +53,10 @@ int pemp_check_device(void);
  *                                                                networks/pemp_stage2.py:145-147
  * in  [planes, H, W]  ->  out [planes, h, w];  src index = min(floor(dst * (float)in/out), in-1).     */
 int pemp_mask_nearest(const float* in, int planes, int H, int W, int h, int w, float* out, pemp_stream_t stream);
+/* Same down-sampling fed by the label map the data set stores (uint8: 1 = object, 0 = background, 255 = boundary) instead of
+ * the two float planes the loader expands it to:  sup_mask = stack((label == 1), (label == 0))   data_kits/pascal_voc.py:209-210
+ * labels [planes, H, W] uint8  ->  out [planes, 2, h, w] float (fg, bg); bit-identical to pemp_mask_nearest on the expansion. */
+int pemp_mask_nearest_labels(const uint8_t* labels, int planes, int H, int W, int h, int w, float* out, pemp_stream_t stream);
 
 /* ---- K1  low-resolution masked average pooling (+ K8 Weighted_GAP) ----------------------------------
  * replaces  sum(f*m,-1)/(m.sum(-1)+1e-5); view(B,S,c).mean(1)    networks/pemp_stage1.py:223-227,

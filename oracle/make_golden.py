@@ -40,11 +40,22 @@ def _save(name, **arrays):
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
 
 
-def _pemp_case(name, spec, B, ctr_stage, store_inputs, ret_ind=True, out_shape=None, first=0):
-    batch = E.make_batch(spec, range(first, first + B))
+def _pemp_case(name, spec, B, ctr_stage, store_inputs, ret_ind=True, out_shape=None, first=0, screened=False):
+    indices = list(range(first, first + B))
+    if screened:
+        # margin screen (SURVEY 7 hard part 2): the first B episodes >= first whose smallest |fg - bg| logit gap through the
+        # reference head is >= 1e-5, so that masks and counts of the fixture can be compared bit for bit
+        from oracle import screen
+        indices, i = [], first
+        while len(indices) < B:
+            if screen.episode_margin("pemp_stage2", spec, i)[0] >= screen.THRESHOLD:
+                indices.append(i)
+            i += 1
+    batch = E.make_batch(spec, indices)
     S, Q = spec.shot, spec.query
     si, qi = R.dummy_images(B, S, Q, spec.H, spec.W)
-    arrays = {"B": B, "first": first, "spec": json.dumps(spec.__dict__)}
+    arrays = {"B": B, "first": first, "indices": np.array(indices), "spec": json.dumps(spec.__dict__)}
+    margins = []
     for stage, model in ((1, "pemp_stage1"), (2, "pemp_stage2")):
         feats = batch[f"feats{stage}"]
         ctr = E.make_ctr(spec, stage) if ctr_stage else None
@@ -56,6 +67,7 @@ def _pemp_case(name, spec, B, ctr_stage, store_inputs, ret_ind=True, out_shape=N
                 prior = torch.zeros(B * Q, 1, spec.H, spec.W, dtype=torch.int64)    # encoder is stubbed
                 res = net(si, batch["sup_mask"], qi, prior, out_shape, ret_ind and ctr is not None)
         logits, response = res if isinstance(res, tuple) else (res, None)
+        margins.append(float((logits[:, 1] - logits[:, 0]).abs().min()))
         # low-res prediction and prototypes through the reference's own `mpm`
         c, h, w = spec.channels, spec.h, spec.w
         f5 = feats.view(B, S + Q, c, h, w)
@@ -74,6 +86,7 @@ def _pemp_case(name, spec, B, ctr_stage, store_inputs, ret_ind=True, out_shape=N
             arrays[f"s{stage}_response"] = _np(response).astype(np.uint8)
         if stage == 2 and ctr is not None:
             arrays["s2_adaptive_p"] = _np(net.adaptive_p)
+    arrays["min_margin"] = min(margins)          # of the reference's own logits (both stages)
     if store_inputs:
         arrays["sup_fg"] = np.packbits(_np(batch["sup_mask"][:, :, 0]).astype(np.uint8))
         arrays["sup_bg"] = np.packbits(_np(batch["sup_mask"][:, :, 1]).astype(np.uint8))
@@ -92,9 +105,9 @@ def pemp_cases():
     five = E.EpisodeSpec(shot=5, query=1, channels=40, h=11, w=15, H=81, W=113, out_h=81, out_w=113)
     _pemp_case("pemp_small_5shot", five, B=1, ctr_stage=True, store_inputs=True)
     full = E.EpisodeSpec(shot=5)
-    _pemp_case("pemp_full_5shot", full, B=1, ctr_stage=True, store_inputs=False, ret_ind=False)
+    _pemp_case("pemp_full_5shot", full, B=1, ctr_stage=True, store_inputs=False, ret_ind=False, screened=True)
     full1 = E.EpisodeSpec(shot=1)
-    _pemp_case("pemp_full_1shot", full1, B=2, ctr_stage=True, store_inputs=False, ret_ind=False, first=7)
+    _pemp_case("pemp_full_1shot", full1, B=2, ctr_stage=True, store_inputs=False, ret_ind=False, first=7, screened=True)
 
 
 def pemp_masks_noncomplementary():

@@ -29,8 +29,41 @@ import textwrap
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("PEMP_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+# Where the reference lives: the build container has it under /root/reference.  The GPU box does not; there the files that
+# `stage_reference()` (called by `__graft_entry__.build()`) copied UNMODIFIED into the git-ignored `oracle/_ref/reference/`
+# travel with the snapshot exactly as the built `.so` does, so the reference's own code is the CPU arm of `bench.py` and the
+# unpatched side of the drop-in tests on the B200 as well.
+STAGED_ROOT = os.path.join(_HERE, "_ref", "reference")
+_STAGED_FILES = ("networks/pemp_stage1.py", "networks/pemp_stage2.py", "networks/baseline.py", "networks/panet.py",
+                 "networks/pfenet.py", "networks/pfe_resent.py", "networks/backbones.py", "networks/canet.py",
+                 "core/metrics.py", "core/losses.py")
+
+
+def _pick_root():
+    env = os.environ.get("PEMP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/networks/pemp_stage1.py"):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REF_ROOT = _pick_root()
+
+
+def stage_reference(src_root="/root/reference"):
+    """Copy the handful of reference files the hot path lives in, byte for byte, into `oracle/_ref/reference/` (git-ignored:
+    reference sources never enter the history).  No-op where the reference is absent (the GPU box uses the staged copy)."""
+    import shutil
+    if not os.path.isfile(os.path.join(src_root, "networks", "pemp_stage1.py")):
+        return False
+    for rel in _STAGED_FILES:
+        dst = os.path.join(STAGED_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src_root, rel), dst)
+    return True
 
 
 def available():
@@ -187,3 +220,23 @@ def canet_map_tile(features, sup_mask, B, S, Q):
           "B": B, "S": S, "Q": Q, "c": c, "h": h, "w": w, "H": H, "W": W}
     exec(compile(block, "<canet.py:map-tile-block>", "exec"), ns)
     return ns["out"]
+
+
+class _QuietLogger:
+    def info(self, *_a, **_k):
+        pass
+
+
+def pfenet_model(shot, seed=0):
+    """The reference's whole `PFENet(shot, logger)` (networks/pfenet.py:54-155) with seeded random weights: its constructor
+    reads `data/resnet50_v2.pth` through `torch.load` with `strict=False` (pfe_resent.py:203-204), which is stubbed to an empty
+    state dict for the duration of the call - the reference's code is untouched."""
+    pf = module("networks.pfenet")
+    torch.manual_seed(seed)
+    orig = torch.load
+    torch.load = lambda *a, **k: {}
+    try:
+        net = pf.PFENet(shot, _QuietLogger())
+    finally:
+        torch.load = orig
+    return net.eval()

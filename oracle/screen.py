@@ -1,0 +1,96 @@
+"""Decision-margin screen of the synthetic episodes — TEST INFRASTRUCTURE ONLY (hard part 2, tiers T2 / T3).
+
+The argmax mask is bit-exact only when no output pixel is decided by less than the fp32 summation-order noise of the
+low-res logits (~2e-6 absolute at |logit| <= 20).  The reference's own evaluation (restated bit for bit in
+`oracle/restate.py`) tells which episodes contain such a pixel: an episode is *rejected* when the smallest
+|logit_fg - logit_bg| over every up-sampled output pixel of any head of the workload is below `THRESHOLD`.
+
+    python -m oracle.screen [--candidates N]
+
+writes `pemp_b200/episode_screen.json`: per workload signature the number of candidates examined and the rejected
+indices.  `pemp_b200.episodes.screened_indices` reads that table (the product never imports this module); the tests
+re-derive a sample of it from the oracle (`tests/test_oracle_pinned.py::test_episode_screen_table_matches_the_oracle`).
+"""
+import argparse
+import json
+import os
+
+import torch
+
+from oracle import restate as O
+from pemp_b200 import episodes as E
+
+THRESHOLD = 1e-5          # ~5 ulp of a logit of magnitude 20 (hard part 2)
+TABLE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pemp_b200", "episode_screen.json")
+
+
+def min_margin(logits):
+    """Smallest |fg - bg| over the pixels of logits [N, 2, H, W]."""
+    return float((logits[:, 1] - logits[:, 0]).abs().min())
+
+
+def episode_margin(workload, spec, index, outputs=None):
+    """Run the oracle on episode `index` of `workload`; -> (min margin over all heads, oracle outputs)."""
+    b = E.make_batch(spec, [index])
+    S, Q = spec.shot, spec.query
+    with torch.no_grad():
+        if workload == "pemp_stage2":
+            out = O.stage2_episode_batch(b["feats1"], b["feats2"], b["sup_mask"], E.make_ctr(spec, 1), E.make_ctr(spec, 2), 1, S, Q,
+                                         b["qry_msk"].numpy(), b["cls"].numpy(), spec.classes)
+            m = min(min_margin(out["stage1"]["logits"]), min_margin(out["stage2"]["logits"]))
+        elif workload == "pemp_stage1":
+            s1 = O.pemp_head(b["feats1"], b["sup_mask"], E.make_ctr(spec, 1), 1, S, Q, out_shape=(spec.out_h, spec.out_w))
+            mask = O.argmax2(s1["logits"])
+            out = {"mask": mask, "stage1": s1,
+                   "stat": O.few_shot_stat(mask.numpy(), b["qry_msk"].numpy(), b["cls"].numpy(), spec.classes)}
+            m = min_margin(s1["logits"])
+        elif workload in ("baseline", "panet"):
+            head = O.panet_head if workload == "panet" else O.baseline_head
+            r = head(b["feats1"], b["sup_mask"], 1, S, Q, out_shape=(spec.out_h, spec.out_w))
+            mask = O.argmax2(r["logits"])
+            out = dict(r, mask=mask, stat=O.few_shot_stat(mask.numpy(), b["qry_msk"].numpy(), b["cls"].numpy(), spec.classes))
+            # alignLoss thresholds the LOW-RES prediction (panet.py:164): its margin counts as well
+            m = min(min_margin(r["logits"]), min_margin(r["pred_lowres"])) if workload == "panet" else min_margin(r["logits"])
+        else:
+            raise ValueError(workload)
+    return m, out
+
+
+def screen(workload, spec, candidates, threshold=THRESHOLD, verbose=False):
+    rejected, margins = [], []
+    for i in range(candidates):
+        m, _ = episode_margin(workload, spec, i)
+        margins.append(m)
+        if m < threshold:
+            rejected.append(i)
+        if verbose and (i + 1) % 32 == 0:
+            print(f"  {workload}: {i + 1} candidates, {len(rejected)} rejected", flush=True)
+    return rejected, margins
+
+
+# the workloads bench.py and the parity tests draw screened episodes from
+WORKLOADS = {
+    "pemp_stage2": (E.EpisodeSpec(shot=5, stages=2), 1000),
+    "pemp_stage1": (E.EpisodeSpec(shot=1, stages=1), 256),
+    "baseline": (E.EpisodeSpec(shot=1, stages=1), 24),
+    "panet": (E.EpisodeSpec(shot=5, stages=1, classes=80, cls_lo=1, cls_hi=80), 16),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    table = json.load(open(TABLE)) if os.path.exists(TABLE) else {}
+    for name, (spec, n) in WORKLOADS.items():
+        if args.only and name != args.only:
+            continue
+        rejected, margins = screen(name, spec, n, verbose=True)
+        table[E.screen_key(name, spec)] = {"threshold": THRESHOLD, "candidates": n, "rejected": rejected,
+                                           "rejection_rate": len(rejected) / n, "median_min_margin": sorted(margins)[n // 2]}
+        print(name, "rejected", len(rejected), "of", n)
+    json.dump(table, open(TABLE, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

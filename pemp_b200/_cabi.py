@@ -19,6 +19,7 @@ SIGNATURES = {
     "pemp_strerror": (c_char_p, [I]),
     "pemp_check_device": (I, []),
     "pemp_mask_nearest": (I, [P, I, I, I, I, I, P, P]),
+    "pemp_mask_nearest_labels": (I, [P, I, I, I, I, I, P, P]),
     "pemp_map_pool_workspace_bytes": (SZ, [I, I, I, I]),
     "pemp_map_pool_lowres": (I, [P, LL, P, P, LL, I, I, I, I, F, P, P, P, SZ, P]),
     "pemp_weighted_gap": (I, [P, P, I, I, I, P, P, SZ, P]),

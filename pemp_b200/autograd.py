@@ -19,17 +19,20 @@ class _MetaProtoAttn(torch.autograd.Function):
     def forward(ctx, sup_fts, ctr, fg, bg, eps):
         B, S = sup_fts.shape[:2]
         fgp, bgp, saved = ops.meta_proto_attn_train(sup_fts, ctr, fg, bg, B, S, eps)
-        ctx.saved = saved
+        fts, ep, ctr_c, fg_c, bg_c, centre, den = saved
+        ctx.save_for_backward(fts, ctr_c, fg_c, bg_c, centre, den)     # version-checked, released after backward
+        ctx.ep = ep
         ctx.shape = tuple(sup_fts.shape)
         return fgp, bgp
 
     @staticmethod
     def backward(ctx, g_fg, g_bg):
         B, S = ctx.shape[:2]
-        zero = lambda g, like: torch.zeros(like, dtype=torch.float32, device=ctx.saved[0].device) if g is None else g.contiguous()
-        p = ctx.saved[2].shape[1] // 2
+        fts, ctr, fg, bg, centre, den = ctx.saved_tensors
+        zero = lambda g, like: torch.zeros(like, dtype=torch.float32, device=fts.device) if g is None else g.contiguous()
+        p = ctr.shape[1] // 2
         like = (B, ctx.shape[2], p)
-        d_fts, d_ctr = ops.meta_proto_attn_bwd(ctx.saved, zero(g_fg, like), zero(g_bg, like), B, S)
+        d_fts, d_ctr = ops.meta_proto_attn_bwd((fts, ctx.ep, ctr, fg, bg, centre, den), zero(g_fg, like), zero(g_bg, like), B, S)
         return d_fts.view(ctx.shape), d_ctr, None, None, None
 
 
@@ -64,6 +67,30 @@ class _MapPoolLowres(torch.autograd.Function):
         z = lambda g: torch.zeros(B, c, dtype=torch.float32, device=fg.device) if g is None else g.contiguous()
         d = ops.map_pool_lowres_bwd(fg, bg, z(g_fg), z(g_bg), B, S, c, ctx.eps)
         return d.view(ctx.shape), None, None, None
+
+
+class _WeightedGAP(torch.autograd.Function):
+    """PFENet's `Weighted_GAP` (pfenet.py:15-20) for the training path: forward K8, backward = the K1 backward kernel with
+    one mask per image (d f = g (x) m / (sum m + 5e-4)); the mask is a label and gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, supp_feat, mask):
+        out = ops.weighted_gap(supp_feat, mask)
+        ctx.save_for_backward(mask)
+        ctx.shape = tuple(supp_feat.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        B, c, h, w = ctx.shape
+        d = ops.map_pool_lowres_bwd(mask.reshape(B, h * w), None, g.reshape(B, c).contiguous(), None, B, 1, c, 5e-4)
+        return d.view(ctx.shape), None
+
+
+def weighted_gap(supp_feat, mask):
+    """`Weighted_GAP(supp_feat [B,c,h,w], mask [B,1,h,w]) -> [B,c,1,1]`, differentiable in supp_feat."""
+    return _WeightedGAP.apply(supp_feat, mask)
 
 
 def map_pool_lowres(sup_fts, sup_fg, sup_bg, eps=1e-5):
@@ -144,18 +171,21 @@ class _PempHead(torch.autograd.Function):
         sup, qry = f5[:, :S], f5[:, S:]
         fgp, bgp, saved = ops.meta_proto_attn_train(sup, ctr, fg, bg, B, S, eps)
         pred = ops.cosine_match(qry, fgp, bgp, scalar)["pred"]
-        ctx.saved, ctx.protos, ctx.f5 = saved, (fgp, bgp), f5
-        ctx.S, ctx.scalar = S, scalar
+        fts, ep, ctr_c, fg_c, bg_c, centre, den = saved
+        # `fts` is f5[:, :S] itself (read in place) or a dense copy of it; everything goes through save_for_backward so that
+        # an in-place write to the encoder output or to ctr between forward and backward raises instead of corrupting grads
+        ctx.save_for_backward(f5, fts, ctr_c, fg_c, bg_c, centre, den, fgp, bgp)
+        ctx.ep, ctx.S, ctx.scalar = ep, S, scalar
         return pred
 
     @staticmethod
     def backward(ctx, g_pred):
-        f5, S = ctx.f5, ctx.S
+        f5, fts, ctr, fg, bg, centre, den, fgp, bgp = ctx.saved_tensors
+        S = ctx.S
         B = f5.shape[0]
         d_f5 = torch.empty(f5.shape, dtype=torch.float32, device=f5.device)
-        fgp, bgp = ctx.protos
         _, d_fg, d_bg = ops.cosine_match_bwd(f5[:, S:], fgp, bgp, g_pred.contiguous(), ctx.scalar, out=d_f5[:, S:])
-        _, d_ctr = ops.meta_proto_attn_bwd(ctx.saved, d_fg, d_bg, B, S, out=d_f5[:, :S])
+        _, d_ctr = ops.meta_proto_attn_bwd((fts, ctx.ep, ctr, fg, bg, centre, den), d_fg, d_bg, B, S, out=d_f5[:, :S])
         return d_f5, d_ctr, None, None, None, None, None
 
 

@@ -30,6 +30,7 @@ constexpr int kTile = 128;       // pixels per CTA
 constexpr int kWarps = PEMP_COS_WARPS;        // channel-splitting warps per CTA
 constexpr int kPix = kTile / 32; // pixels per lane
 constexpr int kMaxK = 8;         // prototype vectors per image (2P), padded row of the smem table
+static_assert(kWarps >= kMaxK, "one warp per prototype column computes inv_norm: a build with fewer warps leaves it uninitialised");
 constexpr float kCosEps = 1e-8f; // F.cosine_similarity eps
 
 template <int K>

@@ -6,15 +6,15 @@
 //
 // Work: 2*C*HWs*HWq FLOP per shot (53.1 GFLOP at C=2048, 60x60) - the only tensor-core-bound op of the head.
 // Paths (argument `precision`):
-//   1  fp32 CUDA-core tiled GEMM (this file): reference-grade numerics, used as the on-device parity anchor;
-//   0  bf16 tcgen05 GEMM, TMA-fed, TMEM accumulators (prior_tc.cu);
-//   2  3-term bf16 split on tcgen05 (prior_tc.cu), fp32-grade.
-// All paths share the pre-pass (mask multiply + column norms) and the tail (min-max + shot mean) below.
+//   2  3-term bf16 split on tcgen05 (prior_tc.cu), fp32-grade: THE PRODUCT PATH (default of the drop-in);
+//   0  single bf16 product on tcgen05 (prior_tc.cu): 3x faster, cosines to 3e-3 (stated tolerance);
+//   1  fp32 CUDA-core tiled GEMM (this file): a slow, independent implementation kept ONLY as the on-device anchor the
+//      tests compare the tensor-core paths with (12 ms per 5-shot episode; nothing in the product selects it).
 #include "common.cuh"
 
 int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, float* nq, float* ns, int B,
-                         int S, int C, int hw_s, int hw_q, int precision, float* rowmax, char* ws, size_t ws_bytes,
-                         cudaStream_t st);
+                         int S, int C, int hw_s, int hw_q, int precision, float* rowmax, float* prior, char* ws,
+                         size_t ws_bytes, cudaStream_t st);
 size_t pemp_prior_tc_workspace_bytes(int B, int S, int C, int hw_s, int hw_q, int precision);
 
 namespace {
@@ -215,11 +215,10 @@ extern "C" int pemp_prior_mask(const float* q4, const float* s4, const float* sm
     col_norm_kernel<<<dim3((hw_s + 31) / 32, S * B), dim3(32, 8), 0, st>>>(s4, smask, C, hw_s, ns);
     prior_fp32_kernel<<<dim3((hw_q + BM - 1) / BM, S * B), kGemmThreads, 0, st>>>(q4, s4, smask, nq, ns, B, C, hw_s, hw_q,
                                                                                 rowmax);
-  } else {
-    int rc = pemp_prior_tc_launch(q4, s4, smask, nq, ns, B, S, C, hw_s, hw_q, precision, rowmax, ws + pl.off_tc,
-                                  workspace_bytes - pl.off_tc, st);
-    if (rc != PEMP_OK) return rc;
+    prior_tail_kernel<<<B, 1024, 0, st>>>(rowmax, B, S, hw_q, prior);
+    return launch_status();
   }
-  prior_tail_kernel<<<B, 1024, 0, st>>>(rowmax, B, S, hw_q, prior);
-  return launch_status();
+  // tensor-core paths: memset nodes + pre-pass + tcgen05 GEMM (with the min / max of the row maxima) + parallel tail
+  return pemp_prior_tc_launch(q4, s4, smask, nq, ns, B, S, C, hw_s, hw_q, precision, rowmax, prior, ws + pl.off_tc,
+                              workspace_bytes - pl.off_tc, st);
 }

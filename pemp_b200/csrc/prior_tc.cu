@@ -4,13 +4,17 @@
 // replaces the per-shot `torch.bmm(tmp_supp, tmp_query) / (bmm(norms) + eps)` + `.max(1)` of
 // networks/pfenet.py:213-222 (cuBLAS SGEMM + a [B, HWs, HWq] matrix of 52 MB written and re-read per shot).
 //
-// Formulation.  A pre-pass turns the channel-major fp32 maps into K-major bf16 operands that are already
-// divided by their column norms (support also multiplied by its mask):
-//     A[i, :] = q[:, i] / |q[:, i]|          [HWq, C]   (M operand, one row per query pixel)
-//     B[j, :] = m_j s[:, j] / |m_j s[:, j]|   [HWs, C]   (N operand, one row per support pixel; 0 if masked out)
-// so the accumulator D = A B^T holds cosines and the epilogue is a running max over support pixels, one
-// TMEM lane (= query pixel) per thread.  The reference's `+ 1e-7` in the denominator is re-applied exactly
-// (factor 1 / (1 + eps / (|q_i| |s_j|))) on the rare inputs where it is not below fp32 resolution.
+// Formulation.  ONE pass over the channel-major fp32 maps writes them as K-major bf16 operands (a transpose + convert, the
+// values themselves are untouched) and their column norms:
+//     A[i, :] = q[:, i]   [HWq, C]   (M operand, one row per query pixel),    1/|q_i|
+//     B[j, :] = s[:, j]   [HWs, C]   (N operand, one row per support pixel),  w_j = [m_j > 0] / |s_j|
+// The accumulator D = A B^T holds raw dot products; the epilogue (one TMEM lane = query pixel per thread) multiplies each
+// column by w_j while taking the running max over support pixels and scales the row by 1/|q_i| at the end - the mask and
+// both norms of `m_j s_j . q_i / (|m_j s_j| |q_i| + eps)` (pfenet.py:206-221) without a normalised copy of the operands.
+// The reference's `+ 1e-7` in the denominator is re-applied exactly (factor 1 / (1 + eps / (|q_i| |m_j s_j|))) on the rare
+// inputs where it is not below fp32 resolution (the pre-pass keeps the smallest norms with integer atomics for that test).
+// Each CTA also folds the min / max of its 128 row maxima into a per-(shot, image) pair with integer atomics on order-
+// preserving encodings, so the min-max normalisation + shot mean (pfenet.py:223-229) is one fully parallel kernel.
 // precision 0: single bf16 product.  precision 2: three products A_hi B_hi + A_hi B_lo + A_lo B_hi
 // (x = hi + lo, both bf16) accumulated into the same TMEM tile - fp32-grade results at 1/3 of the rate.
 //
@@ -122,11 +126,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ---------------------------------------------------------------------------------------- pre-pass
-// One block per (plane, strip of 32 pixels).  Pass 1: column norms sqrt(sum_c (x*m)^2) (also written to `norm`
-// for the epilogue / the eps test).  Pass 2: the same 32 x C strip (256 KB, still in L2) is transposed through
-// shared memory into K-major bf16 rows scaled by mask / norm (0 where the norm is 0):
-//   x [planes][C][hw] fp32 -> out [planes][nsel][hw][C] bf16;  nsel = 2 also emits lo = bf16(x*scale - hi).
-// Reads and writes are coalesced in both passes.
+// One block per (plane, strip of 32 pixels), ONE pass: 128 channels per step (16 independent 128-byte row loads per thread
+// in flight) go through shared memory and leave as packed bf16x2 stores (a warp writes 128 contiguous bytes of a K-major
+// row) while the squared column norms accumulate in registers:
+//   x [planes][C][hw] fp32 -> out [planes][nsel][hw][C] bf16 (nsel = 2 also emits lo = bf16(x - hi)),
+//   norm[pl][i] = m_i |x_i|  (the norm the reference divides by),  w[pl][i] = [m_i > 0 and |x_i| > 0] / |x_i|,
+//   minw[op] = min over all positive norm[.] (uint-ordered float bits, atomicMin; preset to 0x7f7f7f7f by a memset node).
 // Both operands go through ONE launch (the query planes alone are 113 CTAs at 60 x 60 - less than one per SM):
 // blockIdx.y < planes_q selects the query operand, the rest the support operand.
 struct PrepOperand {
@@ -134,19 +139,18 @@ struct PrepOperand {
   const float* mask;   // nullable
   int hw;
   float* norm;
+  float* w;
   __nv_bfloat16* out;
 };
 __global__ void __launch_bounds__(256)
-prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel) {
+prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel, unsigned* __restrict__ minw) {
   __shared__ float tile[128][33];
   __shared__ float part[8][32];
-  __shared__ float scale_s[32];
   const bool is_q = static_cast<int>(blockIdx.y) < planes_q;
   const PrepOperand& op = is_q ? oq : os;
   const float* __restrict__ x = op.x;
   const float* __restrict__ mask = op.mask;
   const int hw = op.hw;
-  float* __restrict__ norm = op.norm;
   __nv_bfloat16* __restrict__ out = op.out;
   const int pl = is_q ? blockIdx.y : blockIdx.y - planes_q, i0 = blockIdx.x * 32;
   if (i0 >= hw) return;
@@ -154,28 +158,8 @@ prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel
   const float* xp = x + static_cast<long long>(pl) * C * hw;
   const int i = i0 + tx;
   const bool ok = i < hw;
-  const float m = (ok && mask) ? __ldg(mask + static_cast<long long>(pl) * hw + i) : 1.f;
-  // ---- pass 1: norms
-  float acc = 0.f;
   const float* col = xp + (ok ? i : 0);
-#pragma unroll 8
-  for (int c = ty; c < C; c += 8) {
-    float v = ok ? __ldg(col + static_cast<long long>(c) * hw) * m : 0.f;
-    acc = fmaf(v, v, acc);
-  }
-  part[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) s += part[r][tx];
-    const float n = sqrtf(s);
-    if (ok) norm[static_cast<long long>(pl) * hw + i] = n;
-    scale_s[tx] = n > 0.f ? m / n : 0.f;
-  }
-  __syncthreads();
-  // ---- pass 2: transpose + scale + convert, 128 channels per step: 16 independent loads per thread, then each
-  // thread packs two channels of one pixel into a 4-byte store (a warp writes 128 contiguous bytes of a K-major row)
+  float acc = 0.f;
   for (int c0 = 0; c0 < C; c0 += 128) {
     float v[16];
 #pragma unroll
@@ -184,7 +168,10 @@ prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel
       v[r] = (c < C && ok) ? __ldg(col + static_cast<long long>(c) * hw) : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < 16; ++r) tile[ty + 8 * r][tx] = v[r];
+    for (int r = 0; r < 16; ++r) {
+      tile[ty + 8 * r][tx] = v[r];
+      acc = fmaf(v[r], v[r], acc);
+    }
     __syncthreads();
     // thread (tx, ty) -> channel pair c0 + 2*(tx + 32*q), pixel ty + 8*p
 #pragma unroll
@@ -194,8 +181,7 @@ prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel
       for (int pz = 0; pz < 4; ++pz) {
         const int il = ty + 8 * pz, ii = i0 + il;
         if (ii < hw && c < C) {                                     // C % 8 == 0: a pair never straddles the end
-          const float sc = scale_s[il];
-          const float a0 = tile[cl][il] * sc, a1 = tile[cl + 1][il] * sc;
+          const float a0 = tile[cl][il], a1 = tile[cl + 1][il];
           const __nv_bfloat162 hi = __floats2bfloat162_rn(a0, a1);
           const long long o = ((static_cast<long long>(pl) * nsel) * hw + ii) * C + c;
           *reinterpret_cast<__nv_bfloat162*>(out + o) = hi;
@@ -207,35 +193,60 @@ prep_kmajor_kernel(PrepOperand oq, PrepOperand os, int planes_q, int C, int nsel
     }
     __syncthreads();
   }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    float sq = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sq += part[r][tx];
+    const float n = sqrtf(sq);
+    const float m = (ok && mask) ? __ldg(mask + static_cast<long long>(pl) * hw + i) : 1.f;
+    const float nm = n * fabsf(m);                                  // |m x|
+    if (ok) {
+      op.norm[static_cast<long long>(pl) * hw + i] = nm;
+      op.w[static_cast<long long>(pl) * hw + i] = nm > 0.f ? copysignf(1.f / n, m) : 0.f;
+    }
+    unsigned bits = (ok && nm > 0.f) ? __float_as_uint(nm) : 0x7f7f7f7fu;   // positive floats order like their bit patterns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bits = min(bits, __shfl_xor_sync(kFull, bits, o));
+    if (tx == 0) atomicMin(minw + (is_q ? 0 : 1), bits);
+  }
 }
 
-// flag[0] = 1 if the reference's `+ eps` is visible in fp32 for some (i, j): eps / (min|q| * min|s|) > 2^-25
-__global__ void eps_flag_kernel(const float* __restrict__ nq, long long n_q, const float* __restrict__ ns, long long n_s,
-                                float* __restrict__ flag) {
-  __shared__ float red[2][32];
-  float mq = INFINITY, ms = INFINITY;
-  for (long long i = threadIdx.x; i < n_q; i += blockDim.x) { float v = nq[i]; if (v > 0.f) mq = fminf(mq, v); }
-  for (long long i = threadIdx.x; i < n_s; i += blockDim.x) { float v = ns[i]; if (v > 0.f) ms = fminf(ms, v); }
-  for (int o = 16; o > 0; o >>= 1) {
-    mq = fminf(mq, __shfl_xor_sync(kFull, mq, o));
-    ms = fminf(ms, __shfl_xor_sync(kFull, ms, o));
+// order-preserving float <-> unsigned encoding for atomicMin on signed values
+__device__ __forceinline__ unsigned enc_ordered(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+// ---- tail: min-max normalise each shot over the query pixels, then mean over shots (pfenet.py:223-229) ----------------
+// lohi[sb] = {enc(min_i rowmax), enc(-max_i rowmax)} from the GEMM epilogue; one thread per (image, query pixel).
+__global__ void __launch_bounds__(256)
+prior_tail_parallel_kernel(const float* __restrict__ rowmax, const unsigned* __restrict__ lohi, int B, int S, int hw_q,
+                           float* __restrict__ prior) {
+  const long long idx = blockIdx.x * 256LL + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * hw_q) return;
+  const int b = static_cast<int>(idx / hw_q);
+  const int i = static_cast<int>(idx - static_cast<long long>(b) * hw_q);
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const int sb = s * B + b;
+    const float lo = dec_ordered(lohi[2 * sb]), hi = -dec_ordered(lohi[2 * sb + 1]);
+    const float v = (rowmax[static_cast<long long>(sb) * hw_q + i] - lo) / (hi - lo + kEps);
+    acc = s == 0 ? v : acc + v;
   }
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mq; red[1][threadIdx.x >> 5] = ms; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) { mq = fminf(mq, red[0][w]); ms = fminf(ms, red[1][w]); }
-    mq = fminf(red[0][0], mq);
-    ms = fminf(red[1][0], ms);
-    bool visible = isfinite(mq) && isfinite(ms) && (kEps / (mq * ms) > 2.98e-8f);
-    flag[0] = visible ? 1.f : 0.f;
-  }
+  prior[idx] = acc / static_cast<float>(S);
 }
 
 // ------------------------------------------------------------------------------------------- GEMM
 struct __align__(1024) TcSmem {
   uint8_t a[kStages][kBytesA];
   uint8_t b[kStages][kBytesB];
-  float sn[2][BN];                 // 1 / |s_j| of the current N tile (eps-visible path only), double buffered
+  float sn[2][BN];                 // w_j = [m_j > 0] / |s_j| of the current N tile, double buffered
+  float se[2][BN];                 // 1 / |m_j s_j| (eps-visible path only)
   uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
@@ -243,7 +254,8 @@ struct __align__(1024) TcSmem {
 // nsel = 1: one product per k-block.  nsel = 2: rows [0, hw) hold hi, [hw, 2hw) hold lo; three products.
 __global__ void __launch_bounds__(kThreadsTc, 1)
 prior_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const float* __restrict__ nq, const float* __restrict__ ns, const float* __restrict__ eps_flag, int B,
+                const float* __restrict__ nq, const float* __restrict__ ns, const float* __restrict__ wq,
+                const float* __restrict__ wsup, const unsigned* __restrict__ minw, unsigned* __restrict__ lohi, int B,
                 int C, int hw_s, int hw_q, int nsel, float* __restrict__ rowmax) {
   extern __shared__ uint8_t raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -316,22 +328,29 @@ prior_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue: running max over support pixels =====================
+    // ===================== epilogue: column scale + running max over support pixels =====================
     const int q = warp & 3;                                               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                                        // query pixel within the M tile
     const int i = m0 + row;
-    const bool eps_visible = __ldg(eps_flag) != 0.f;
+    // the reference's `+ eps` is visible in fp32 for some (i, j) iff eps / (min|q| * min|m s|) > 2^-25
+    const float mq = __uint_as_float(__ldg(minw)), msup = __uint_as_float(__ldg(minw + 1));
+    const bool eps_visible = kEps / (mq * msup) > 2.98e-8f;
     const float a_i = (eps_visible && i < hw_q) ? kEps / fmaxf(__ldg(nq + static_cast<long long>(b) * hw_q + i), 1e-30f) : 0.f;
     float best = -INFINITY;
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       const uint32_t acc_ph = (t >> 1) & 1;
       const int n0 = t * BN;
-      if (eps_visible) {   // stage 1/|s_j| of this tile for the epilogue warps (named barrier over the 128 epilogue threads)
+      {   // stage w_j (and 1 / |m_j s_j| on the eps path) of this tile; named barrier over the 128 epilogue threads.  Buffer
+          // `acc` was last read for tile t - 2, which every warp finished before arriving at the barrier of tile t - 1.
         const int e = threadIdx.x - 64;
         for (int j = e; j < BN; j += 128) {
-          float v = n0 + j < hw_s ? __ldg(ns + static_cast<long long>(sb) * hw_s + n0 + j) : 0.f;
-          sm.sn[acc][j] = v > 0.f ? 1.f / v : 0.f;
+          const bool in = n0 + j < hw_s;
+          sm.sn[acc][j] = in ? __ldg(wsup + static_cast<long long>(sb) * hw_s + n0 + j) : 0.f;
+          if (eps_visible) {
+            const float v = in ? __ldg(ns + static_cast<long long>(sb) * hw_s + n0 + j) : 0.f;
+            sm.se[acc][j] = v > 0.f ? 1.f / v : 0.f;
+          }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -344,18 +363,33 @@ prior_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint32_t r[32];
         tmem_ld32(taddr + cb * 32, r);
         tmem_ld_wait();
+        const bool full = n0 + cb * 32 + 32 <= hw_s;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]);
-          if (eps_visible) v = v / (1.f + a_i * sm.sn[acc][cb * 32 + j]);
-          if (n0 + cb * 32 + j < hw_s) best = fmaxf(best, v);
+          float v = __uint_as_float(r[j]) * sm.sn[acc][cb * 32 + j];
+          if (eps_visible) v = v / (1.f + a_i * sm.se[acc][cb * 32 + j]);
+          if (full || n0 + cb * 32 + j < hw_s) best = fmaxf(best, v);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.acc_empty[acc]);                     // 4 epilogue warps -> count 4
     }
-    if (i < hw_q) rowmax[static_cast<long long>(sb) * hw_q + i] = best;
+    const bool valid = i < hw_q;
+    if (valid) {
+      best *= __ldg(wq + static_cast<long long>(b) * hw_q + i);           // 1 / |q_i| > 0 commutes with the max (0: zero row)
+      rowmax[static_cast<long long>(sb) * hw_q + i] = best;
+    }
+    unsigned lo = valid ? enc_ordered(best) : 0xffffffffu, hi = valid ? enc_ordered(-best) : 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(kFull, lo, o));
+      hi = min(hi, __shfl_xor_sync(kFull, hi, o));
+    }
+    if (lane == 0) {
+      atomicMin(lohi + 2 * sb, lo);
+      atomicMin(lohi + 2 * sb + 1, hi);
+    }
   }
 
   tc_fence_before();
@@ -398,15 +432,18 @@ int make_map(CUtensorMap* map, const void* base, long long rows, int C, int box_
 
 struct Plan {
   int nsel;
-  size_t off_a, off_b, off_flag, total;
+  size_t off_a, off_b, off_wq, off_ws, off_atom, atom_bytes, total;
 };
 Plan make_plan(int B, int S, int C, int hw_s, int hw_q, int precision) {
   Plan p;
   p.nsel = precision == 2 ? 2 : 1;
   p.off_a = 0;
   p.off_b = align_up(static_cast<size_t>(B) * p.nsel * hw_q * C * 2, 1024);
-  p.off_flag = p.off_b + align_up(static_cast<size_t>(S) * B * p.nsel * hw_s * C * 2, 1024);
-  p.total = p.off_flag + 256;
+  p.off_wq = p.off_b + align_up(static_cast<size_t>(S) * B * p.nsel * hw_s * C * 2, 1024);
+  p.off_ws = p.off_wq + align_up(static_cast<size_t>(B) * hw_q * 4, 256);
+  p.off_atom = p.off_ws + align_up(static_cast<size_t>(S) * B * hw_s * 4, 256);
+  p.atom_bytes = (2 + 2 * static_cast<size_t>(S) * B) * 4;              // minw[2] then lohi[S*B][2]
+  p.total = p.off_atom + align_up(p.atom_bytes, 256);
   return p;
 }
 
@@ -417,21 +454,31 @@ size_t pemp_prior_tc_workspace_bytes(int B, int S, int C, int hw_s, int hw_q, in
 }
 
 int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, float* nq, float* ns, int B,
-                         int S, int C, int hw_s, int hw_q, int precision, float* rowmax, char* ws, size_t ws_bytes,
-                         cudaStream_t st) {
+                         int S, int C, int hw_s, int hw_q, int precision, float* rowmax, float* prior, char* ws,
+                         size_t ws_bytes, cudaStream_t st) {
   PEMP_REQUIRE(C % 8 == 0, PEMP_E_SHAPE);                       // 16-byte row pitch of the bf16 operands (TMA)
   Plan pl = make_plan(B, S, C, hw_s, hw_q, precision);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
   PEMP_REQUIRE(base + pl.total <= ws + ws_bytes, PEMP_E_WORKSPACE);
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(base + pl.off_a);
   __nv_bfloat16* bmat = reinterpret_cast<__nv_bfloat16*>(base + pl.off_b);
-  float* flag = reinterpret_cast<float*>(base + pl.off_flag);
+  float* wq = reinterpret_cast<float*>(base + pl.off_wq);
+  float* wsup = reinterpret_cast<float*>(base + pl.off_ws);
+  unsigned* minw = reinterpret_cast<unsigned*>(base + pl.off_atom);
+  unsigned* lohi = minw + 2;
+
+  // minw presets to 0x7f7f7f7f (3.4e38, "no positive norm seen"), lohi to 0xffffffff (identity of atomicMin): two tiny
+  // memset nodes (graph-capturable, no host sync) instead of the single-CTA flag kernel of round 1
+  cudaError_t e = cudaMemsetAsync(minw, 0x7f, 8, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemsetAsync(lohi, 0xff, 2 * static_cast<size_t>(S) * B * 4, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
 
   dim3 tb(32, 8);   // norms + K-major bf16 operands in one pass per tensor
   const int hw_max = hw_q > hw_s ? hw_q : hw_s;
-  prep_kmajor_kernel<<<dim3((hw_max + 31) / 32, B + S * B), tb, 0, st>>>(PrepOperand{q4, nullptr, hw_q, nq, a},
-                                                                        PrepOperand{s4, smask, hw_s, ns, bmat}, B, C, pl.nsel);
-  eps_flag_kernel<<<1, 1024, 0, st>>>(nq, static_cast<long long>(B) * hw_q, ns, static_cast<long long>(S) * B * hw_s, flag);
+  prep_kmajor_kernel<<<dim3((hw_max + 31) / 32, B + S * B), tb, 0, st>>>(PrepOperand{q4, nullptr, hw_q, nq, wq, a},
+                                                                        PrepOperand{s4, smask, hw_s, ns, wsup, bmat}, B, C, pl.nsel,
+                                                                        minw);
 
   CUtensorMap map_a, map_b;
   int rc = make_map(&map_a, a, static_cast<long long>(B) * pl.nsel * hw_q, C, BM);
@@ -440,9 +487,11 @@ int pemp_prior_tc_launch(const float* q4, const float* s4, const float* smask, f
   if (rc != PEMP_OK) return rc;
 
   const size_t smem = sizeof(TcSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  e = cudaFuncSetAttribute(prior_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid((hw_q + BM - 1) / BM, S * B);
-  prior_tc_kernel<<<grid, kThreadsTc, smem, st>>>(map_a, map_b, nq, ns, flag, B, C, hw_s, hw_q, pl.nsel, rowmax);
+  prior_tc_kernel<<<grid, kThreadsTc, smem, st>>>(map_a, map_b, nq, ns, wq, wsup, minw, lohi, B, C, hw_s, hw_q, pl.nsel, rowmax);
+  const long long n_out = static_cast<long long>(B) * hw_q;
+  prior_tail_parallel_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, st>>>(rowmax, lohi, B, S, hw_q, prior);
   return launch_status();
 }

@@ -33,6 +33,37 @@ extern "C" int pemp_mask_nearest(const float* in, int planes, int H, int W, int 
   return launch_status();
 }
 
+// K0 on the label map the data set stores (one uint8 plane, 1 = object, 0 = background, 255 = boundary / ignore) instead of
+// the two float planes `stack(fg, bg)` the loader expands it to (data_kits/pascal_voc.py:209-210, 226-231): identical low-res
+// masks, 1 byte per pixel on the host link instead of 8.  labels [planes, H, W] -> out [planes, 2, h, w] (fg, bg).
+__global__ void mask_nearest_labels_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int planes, int H, int W,
+                                           int h, int w, float sy, float sx) {
+  long long total = static_cast<long long>(planes) * h * w;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int x = static_cast<int>(i % w);
+    long long t = i / w;
+    int y = static_cast<int>(t % h);
+    long long pl = t / h;
+    const uint8_t v = __ldg(in + (pl * H + nearest_src(y, sy, H)) * W + nearest_src(x, sx, W));
+    float* o = out + (pl * 2 * h + y) * w + x;
+    o[0] = v == 1 ? 1.f : 0.f;
+    o[static_cast<long long>(h) * w] = v == 0 ? 1.f : 0.f;
+  }
+}
+
+extern "C" int pemp_mask_nearest_labels(const uint8_t* labels, int planes, int H, int W, int h, int w, float* out,
+                                        pemp_stream_t stream) {
+  PEMP_REQUIRE(labels && out, PEMP_E_NULL);
+  PEMP_REQUIRE(planes > 0 && H > 0 && W > 0 && h > 0 && w > 0, PEMP_E_SHAPE);
+  long long total = static_cast<long long>(planes) * h * w;
+  int block = 256;
+  int grid = static_cast<int>(llmin((total + block - 1) / block, 148LL * 16));
+  float sy = static_cast<float>(H) / static_cast<float>(h), sx = static_cast<float>(W) / static_cast<float>(w);
+  mask_nearest_labels_kernel<<<grid, block, 0, as_stream(stream)>>>(labels, out, planes, H, W, h, w, sy, sx);
+  return launch_status();
+}
+
 // ------------------------------------------------------------------------------------------------ K5
 __global__ void nearest_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int planes, int h, int w,
                                    int H, int W, float sy, float sx) {

@@ -15,6 +15,8 @@ around the object (exercises `core/metrics.py:16-18`).
 Episode `i` depends only on `(base_seed, i)` - never on the batch or rank it lands in - so a sharded
 run over R ranks sees exactly the episode set of a single-rank run.
 """
+import json
+import os
 from dataclasses import dataclass
 
 import torch
@@ -117,6 +119,52 @@ def make_batch(spec: EpisodeSpec, indices, base_seed: int = REFERENCE_SEED):
         k = f"feats{stage + 1}"
         batch[k] = torch.cat([e[k] for e in eps], dim=0)
     return batch
+
+
+# ------------------------------------------------------------------------------------------------ margin screen
+_SCREEN_TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "episode_screen.json")
+_screen_cache = None
+
+
+def screen_key(workload: str, spec: EpisodeSpec, base_seed: int = REFERENCE_SEED):
+    """Identity of an episode stream: everything `make_episode` (and the head that decides the masks) depends on."""
+    d = spec.__dict__
+    return f"{workload}|seed={base_seed}|" + ",".join(f"{k}={d[k]}" for k in sorted(d))
+
+
+def screen_table():
+    global _screen_cache
+    if _screen_cache is None:
+        _screen_cache = json.load(open(_SCREEN_TABLE)) if os.path.exists(_SCREEN_TABLE) else {}
+    return _screen_cache
+
+
+def screened_indices(workload: str, spec: EpisodeSpec, n: int = None, start: int = 0, step: int = 1):
+    """The benchmark / parity episode set (hard part 2, tier T2): episode indices whose smallest decision margin
+    |logit_fg - logit_bg| through the reference's own head is >= the table's threshold (1e-5, about 5 ulp of a logit), so
+    that the arg-max masks and IoU counts of ANY implementation within fp32 summation-order noise of the reference are
+    bit-identical to the reference's.  The table (`episode_screen.json`) is produced offline by the margin-screen tool of the
+    test infrastructure from the reference's own evaluation; this module only reads it.  Returns the `start`-th, `start+step`-th, ... accepted indices
+    (`step` = world size shards the accepted stream over ranks), `n` of them.  Raises if the table does not cover the
+    request - episodes are never silently unscreened."""
+    entry = screen_table().get(screen_key(workload, spec))
+    if entry is None:
+        raise KeyError(f"no margin-screen table for {screen_key(workload, spec)}; generate it with the margin-screen tool (DESIGN.md 2)")
+    rejected = set(entry["rejected"])
+    accepted = [i for i in range(entry["candidates"]) if i not in rejected]
+    if n is None:
+        return accepted[start::step]
+    picked = accepted[start::step][:n]
+    if len(picked) < n:
+        raise ValueError(f"margin-screen table has {len(accepted)} accepted episodes of {entry['candidates']} candidates; "
+                         f"{n} from position {start} with stride {step} were requested")
+    return picked
+
+
+def screen_stats(workload: str, spec: EpisodeSpec):
+    e = screen_table()[screen_key(workload, spec)]
+    return {"threshold": e["threshold"], "candidates": e["candidates"], "rejected": len(e["rejected"]),
+            "rejection_rate": len(e["rejected"]) / e["candidates"]}
 
 
 def make_ctr(spec: EpisodeSpec, stage: int = 1, base_seed: int = REFERENCE_SEED):

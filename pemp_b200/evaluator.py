@@ -97,13 +97,17 @@ class PEMPStage2Pipeline:
 
     def step(self, sup_feats1, qry_feats1, sup_feats2, qry_feats2, sup_mask, qry_msk, cls, stat, timer=None):
         """One batch of episodes with support and query features stored separately:
-        sup_feats* [B, S, c, h, w], qry_feats* [B, Q, c, h, w], sup_mask [B, S, 2, H, W],
-        qry_msk [B, Q, H', W'] uint8, cls [B] int64; `stat` [(C+1), 3] int64 is accumulated.
+        sup_feats* [B, S, c, h, w], qry_feats* [B, Q, c, h, w], sup_mask [B, S, 2, H, W] float32 as the loader emits it -
+        or the uint8 label map [B, S, H, W] (1 object / 0 background / 255 boundary) it was expanded from, an eighth of the
+        bytes -, qry_msk [B, Q, H', W'] uint8, cls [B] int64; `stat` [(C+1), 3] int64 is accumulated.
         Returns (prior [BQ,H,W] uint8, mask [BQ,H',W'] uint8)."""
         B, S, c, h, w = sup_feats1.shape
         Q = qry_feats1.shape[1]
         H, W = sup_mask.shape[-2:]
-        low = ops.mask_nearest(sup_mask.view(B * S, 2, H, W), h, w).view(B * S, 2, h * w)
+        if sup_mask.dtype == torch.uint8:
+            low = ops.mask_nearest_labels(sup_mask.view(B * S, H, W), h, w).view(B * S, 2, h * w)
+        else:
+            low = ops.mask_nearest(sup_mask.view(B * S, 2, H, W), h, w).view(B * S, 2, h * w)
         out = []
         for sup, qry, ctr, shape in ((sup_feats1, qry_feats1, self.ctr1, (H, W)),
                                      (sup_feats2, qry_feats2, self.ctr2, tuple(qry_msk.shape[-2:]))):

@@ -24,13 +24,22 @@ def _wants_grad(*tensors):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
+def _scalar(self, dist_scalar):
+    """`dist_scalar` precedence: explicit argument (that is where Sacred's `net_ingredient.capture` injects `net.dist_scalar`
+    once `dropin.patch()` has wrapped these functions with it), then a `dist_scalar` attribute of the module, then the
+    reference's default of 20."""
+    if dist_scalar is not None:
+        return dist_scalar
+    return getattr(self, "dist_scalar", DIST_SCALAR) if self is not None else DIST_SCALAR
+
+
 def _upsample(pred, out_shape, differentiable):
     if differentiable:      # stock differentiable op, as in the reference; `autograd.upsample_ce` fuses it with the loss
         return torch.nn.functional.interpolate(pred, size=tuple(out_shape), mode="bilinear", align_corners=True)
     return ops.upsample_argmax(pred, out_shape, want_logits=True, want_mask8=False)["logits"]
 
 
-def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=DIST_SCALAR):
+def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=None):
     """`compute_similarity` of all four reference models (pemp_stage1.py:233-261, pemp_stage2.py:205-233,
     baseline.py:121-149, panet.py:122-156).
 
@@ -46,14 +55,15 @@ def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=DIST_SCALA
         N, c, _, h, w = qry_fts.shape
     else:
         N, c, h, w = qry_fts.shape
-    out = ops.cosine_match(qry_fts.reshape(N, c, h * w), fg_proto, bg_proto, dist_scalar, want_sim=True, want_pred=False)
+    out = ops.cosine_match(qry_fts.reshape(N, c, h * w), fg_proto, bg_proto, _scalar(self, dist_scalar), want_sim=True,
+                           want_pred=False)
     sim = out["sim"]                                              # [N, 2, P, hw]
     if fg_proto.dim() == 2:
         return sim.view(N, 2, h, w)
     return sim.view(N, 2, fg_proto.shape[2], h, w)
 
 
-def mpm(self, sup_fts, qry_fts, sup_fg, sup_bg, ret_ind, protos=None):
+def mpm(self, sup_fts, qry_fts, sup_fg, sup_bg, ret_ind, protos=None, dist_scalar=None):
     """`PEMPStage1.mpm` / `PEMPStage2.mpm` (pemp_stage1.py:166-230, pemp_stage2.py:165-202).
 
     sup_fts [B, S, c, h, w]; qry_fts [B, Q, c, h, w]; sup_fg / sup_bg [BS, h, w]
@@ -64,7 +74,7 @@ def mpm(self, sup_fts, qry_fts, sup_fg, sup_bg, ret_ind, protos=None):
     hw = h * w
     sup, qry = sup_fts, qry_fts                     # 5-D episode views are read in place (episode stride)
     fg, bg = sup_fg.reshape(B * S, hw), sup_bg.reshape(B * S, hw)
-    scalar = getattr(self, "dist_scalar", DIST_SCALAR)
+    scalar = _scalar(self, dist_scalar)
     ctr = getattr(self, "ctr", None)
     if ctr is not None and protos is not None and protos * 2 != ctr.shape[1]:
         raise ValueError(f"protos={protos} does not match ctr of shape {tuple(ctr.shape)}")
@@ -96,7 +106,7 @@ def mpm(self, sup_fts, qry_fts, sup_fg, sup_bg, ret_ind, protos=None):
     return ops.cosine_match(qry, fg_proto, bg_proto, scalar)["pred"].view(B * Q, 2, h, w)
 
 
-def pemp_head(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False):
+def pemp_head(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False, dist_scalar=None):
     """Everything `PEMPStage1.forward` / `PEMPStage2.forward` do after the encoder call
     (pemp_stage1.py:141-163, pemp_stage2.py:140-162): split, nearest mask down-sampling, `mpm`, bilinear
     up-sampling.  features [B(S+Q), c, h, w]; sup_mask [B, S, 2, H, W]."""
@@ -104,7 +114,7 @@ def pemp_head(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False):
     H, W = sup_mask.shape[-2:]
     feats = features.view(B, S + Q, c, h, w)
     low = ops.mask_nearest(sup_mask.reshape(B * S, 2, H, W), h, w)            # [BS, 2, h, w]
-    pred = mpm(self, feats[:, :S], feats[:, S:], low[:, 0], low[:, 1], ret_ind)
+    pred = mpm(self, feats[:, :S], feats[:, S:], low[:, 0], low[:, 1], ret_ind, dist_scalar=dist_scalar)
     if out_shape is None:
         out_shape = (H, W)
     if ret_ind and isinstance(pred, tuple):
@@ -113,16 +123,16 @@ def pemp_head(self, features, sup_mask, B, S, Q, out_shape=None, ret_ind=False):
     return _upsample(pred, out_shape, pred.requires_grad)
 
 
-def pemp_stage1_forward(self, sup_img, sup_mask, qry_img, out_shape=None, ret_ind=False):
+def pemp_stage1_forward(self, sup_img, sup_mask, qry_img, out_shape=None, ret_ind=False, dist_scalar=None):
     """Drop-in `PEMPStage1.forward` (pemp_stage1.py:112-163): stock encoder, B200 head."""
     B, S, channel, H, W = sup_img.size()
     Q = qry_img.size(1)
     img_cat = torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), channel, H, W)
     features = self.encoder(img_cat)
-    return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind)
+    return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind, dist_scalar)
 
 
-def pemp_stage2_forward(self, sup_img, sup_mask, qry_img, qry_prior, out_shape=None, ret_ind=False):
+def pemp_stage2_forward(self, sup_img, sup_mask, qry_img, qry_prior, out_shape=None, ret_ind=False, dist_scalar=None):
     """Drop-in `PEMPStage2.forward` (pemp_stage2.py:104-162): 4-channel input assembly and the ResNetCM
     encoder stay on PyTorch, the head runs on the B200 kernels."""
     B, S, channel, H, W = sup_img.size()
@@ -134,20 +144,20 @@ def pemp_stage2_forward(self, sup_img, sup_mask, qry_img, qry_prior, out_shape=N
     inputs = torch.cat((img_cat, prior_cat), dim=1)
     features = self.encoder((inputs, prior_cat))
     self._pemp_keep_adaptive = True
-    return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind)
+    return pemp_head(self, features, sup_mask, B, S, Q, out_shape, ret_ind, dist_scalar)
 
 
 # ------------------------------------------------------------------------------------------------------
 # Baseline / PANet
 # ------------------------------------------------------------------------------------------------------
-def baseline_head(self, features, sup_mask, B, S, Q, out_shape=None, with_align=False):
+def baseline_head(self, features, sup_mask, B, S, Q, out_shape=None, with_align=False, dist_scalar=None):
     """`Baseline.forward` / `PANet.forward` after the encoder (baseline.py:97-118, panet.py:96-119)."""
     _, c, h, w = features.shape
     H, W = sup_mask.shape[-2:]
     feats = features.view(B, S + Q, c, h, w)
     sup_fts, qry_fts = feats[:, :S], feats[:, S:]   # episode views, read in place
     mask = sup_mask.reshape(B * S, 2, H, W)
-    scalar = getattr(self, "dist_scalar", DIST_SCALAR)
+    scalar = _scalar(self, dist_scalar)
     if _wants_grad(features):
         from . import autograd as A
         fg_proto, bg_proto = A.map_pool_fullres(sup_fts, mask, eps=1e-5)
@@ -159,28 +169,28 @@ def baseline_head(self, features, sup_mask, B, S, Q, out_shape=None, with_align=
         out_shape = (H, W)
     output = _upsample(pred, out_shape, pred.requires_grad)
     if with_align:
-        return output, alignLoss(self, qry_fts, pred, sup_fts, mask[:, 0:1], Q)
+        return output, alignLoss(self, qry_fts, pred, sup_fts, mask[:, 0:1], Q, scalar)
     return output
 
 
-def baseline_forward(self, sup_img, sup_mask, qry_img, out_shape=None):
+def baseline_forward(self, sup_img, sup_mask, qry_img, out_shape=None, dist_scalar=None):
     B, S, C, H, W = sup_img.size()
     Q = qry_img.size(1)
     features = self.encoder(torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), C, H, W))
-    return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=False)
+    return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=False, dist_scalar=dist_scalar)
 
 
-def panet_forward(self, sup_img, sup_mask, qry_img, out_shape=None):
+def panet_forward(self, sup_img, sup_mask, qry_img, out_shape=None, dist_scalar=None):
     B, S, C, H, W = sup_img.size()
     Q = qry_img.size(1)
     features = self.encoder(torch.cat((sup_img, qry_img), dim=1).view(B * (S + Q), C, H, W))
-    return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=True)
+    return baseline_head(self, features, sup_mask, B, S, Q, out_shape, with_align=True, dist_scalar=dist_scalar)
 
 
-def alignLoss(self, qry_fts, pred, sup_fts, sup_mask_fg, Q):
+def alignLoss(self, qry_fts, pred, sup_fts, sup_mask_fg, Q, dist_scalar=None):
     """`PANet.alignLoss` (panet.py:158-194) -> 0-dim tensor.  Unlike the reference (whose `.view` on an
     expanded tensor raises for B > 1 with S > 1) any B, S, Q combination works."""
-    scalar = getattr(self, "dist_scalar", DIST_SCALAR)
+    scalar = _scalar(self, dist_scalar)
     if _wants_grad(qry_fts, sup_fts):
         from . import autograd as A
         B = qry_fts.shape[0] if qry_fts.dim() == 5 else qry_fts.shape[0] // Q
@@ -195,22 +205,40 @@ def alignLoss(self, qry_fts, pred, sup_fts, sup_mask_fg, Q):
 # PFENet
 # ------------------------------------------------------------------------------------------------------
 def Weighted_GAP(supp_feat, mask):
-    """`networks.pfenet.Weighted_GAP` (pfenet.py:15-20): [B,c,h,w], [B,1,h,w] -> [B,c,1,1]."""
+    """`networks.pfenet.Weighted_GAP` (pfenet.py:15-20): [B,c,h,w], [B,1,h,w] -> [B,c,1,1].
+    The reference trains through it (`down_supp` feeds it, pfenet.py:197-198): under autograd the differentiable K8
+    (`autograd.weighted_gap`: K1's backward kernel) runs; a mask that itself requires grad - never the case in the
+    reference, masks are labels - takes the stock expression so that no gradient is ever silently dropped."""
+    if _wants_grad(supp_feat, mask):
+        if mask.requires_grad:
+            area = mask.sum(dim=(2, 3), keepdim=True) + 0.0005
+            return (supp_feat * mask).sum(dim=(2, 3), keepdim=True) / area
+        from . import autograd as A
+        return A.weighted_gap(supp_feat, mask)
     return ops.weighted_gap(supp_feat, mask)
 
 
-def prior_mask(query_feat_4, final_supp_list, mask_list, precision=ops.PRIOR_FP32):
+def prior_mask(query_feat_4, final_supp_list, mask_list, precision=None, out_hw=None):
     """The prior block of `PFENet.forward` (pfenet.py:201-231) as one call.
 
     query_feat_4 [B, C, sp, sp]; final_supp_list: S tensors [B, C, sp, sp]; mask_list: S binary masks
-    [B, 1, H, W] -> corr_query_mask [B, 1, sp, sp].  (The reference's two trailing `F.interpolate` calls
-    are identities because feat-3, feat-4 and `query_feat` share one spatial size)"""
+    [B, 1, H, W] -> corr_query_mask [B, 1, sp, sp] (bilinearly resized to `out_hw`, the feat-3 size of pfenet.py:224-225,
+    when that differs - it does not for the reference's dilated ResNet).
+    precision: `ops.PRIOR_BF16X3` (default; tcgen05 tensor cores, three bf16 products of a hi/lo split = fp32-grade cosines),
+    `ops.PRIOR_BF16` (single product, 3x faster, cosines to 3e-3) or `ops.PRIOR_FP32` (CUDA-core anchor used by the tests).
+    The block runs under `torch.no_grad()` in the reference (its operands come out of the frozen backbone), so it is
+    forward-only here as well."""
+    if precision is None:
+        precision = ops.PRIOR_DEFAULT
     sp_h, sp_w = query_feat_4.shape[-2:]
-    s4 = torch.stack(list(final_supp_list), dim=0)
-    masks = torch.stack(list(mask_list), dim=0)                                # [S, B, 1, H, W]
-    small = ops.bilinear_resize(masks, s4.shape[-2:])[:, :, 0]                 # [S, B, sp, sp]
-    prior = ops.prior_mask(query_feat_4, s4, small, precision)
-    return prior.view(query_feat_4.shape[0], 1, sp_h, sp_w)
+    with torch.no_grad():
+        s4 = torch.stack(list(final_supp_list), dim=0)
+        masks = torch.stack(list(mask_list), dim=0)                                # [S, B, 1, H, W]
+        small = ops.bilinear_resize(masks, s4.shape[-2:])[:, :, 0]                 # [S, B, sp, sp]
+        prior = ops.prior_mask(query_feat_4, s4, small, precision).view(query_feat_4.shape[0], 1, sp_h, sp_w)
+        if out_hw is not None and tuple(out_hw) != (sp_h, sp_w):
+            prior = ops.bilinear_resize(prior, out_hw)
+    return prior
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -252,5 +280,16 @@ class BaselineHead(nn.Module):
 
 def comm(self, x, mask, linear, stride=2):
     """Drop-in for `ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479): same arguments (`linear` is the
-    nn.Linear the backbone passes), same returns `(feat [N, n, h, w], pooled mask [N, 1, h, w])`."""
+    nn.Linear the backbone passes), same returns `(feat [N, n, h, w], pooled mask [N, 1, h, w])`.
+    Stage-2 training back-propagates through `comm` into `x` and the linear layer: K11 is forward-only, so under autograd
+    the same quantities are formed with stock differentiable ops (no gradient is silently dropped); evaluation
+    (`torch.no_grad()`, core/base_trainer.py:69) runs the fused kernel."""
+    if _wants_grad(x, mask, linear.weight, linear.bias):
+        pooled = torch.nn.functional.max_pool2d(mask, 3, stride, 1)
+        N, c, h, w = x.shape
+        spq = self.spq
+        masked = (x * pooled).flatten(2)
+        stats = torch.cat((masked.mean(dim=2), masked.max(dim=2)[0]), dim=1).view(N // spq, spq, 2 * c).mean(dim=1)
+        feat = linear(stats)
+        return feat[:, None, :, None, None].expand(-1, spq, -1, h, w).reshape(N, -1, h, w), pooled
     return ops.comm_module(x, mask, linear.weight, linear.bias, self.spq, stride)

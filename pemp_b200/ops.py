@@ -4,6 +4,8 @@ Each function takes CUDA tensors, passes raw device pointers + the current strea
 `libpemp_b200.so`, and returns freshly allocated CUDA tensors.  Nothing here computes on the host and
 nothing falls back to PyTorch ops.
 """
+import functools
+
 import torch
 
 from . import _cabi
@@ -22,6 +24,35 @@ def _count(n):
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _tensors(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, (tuple, list)):
+            yield from _tensors(a)
+
+
+def _on_device(fn):
+    """Every operand of a call must live on ONE CUDA device, and the call runs with that device current: raw pointers of
+    one GPU are never launched on another GPU's stream (e.g. `FewShotMetric(device='cuda:1')` while cuda:0 is current).
+    `_stream()` inside the call is then the caller's current stream of that device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for t in _tensors(args + tuple(kwargs.values())):
+            if not t.is_cuda:
+                continue                      # reported by the per-argument checks with the argument's name
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise ValueError(f"{fn.__name__}: operands live on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _need(t, dtype, name):
@@ -81,6 +112,7 @@ def _mask_pair(fg, bg, n_img, hw):
 
 
 # ------------------------------------------------------------------------------------------------ K0
+@_on_device
 def mask_nearest(mask, h, w):
     """[..., H, W] float32 -> [..., h, w] (`F.interpolate(mode='nearest')`, pemp_stage1.py:147)."""
     mask = _need(mask, torch.float32, "mask")
@@ -93,7 +125,22 @@ def mask_nearest(mask, h, w):
     return out
 
 
+@_on_device
+def mask_nearest_labels(labels, h, w):
+    """labels [..., H, W] uint8 (1 = object, 0 = background, 255 = boundary; the map `pascal_voc.py:209-210` expands into the
+    float `sup_mask`) -> [..., 2, h, w] float32 (fg, bg): the same low-res masks as `mask_nearest` on the expansion."""
+    labels = _need(labels, torch.uint8, "labels")
+    H, W = labels.shape[-2:]
+    planes = labels.numel() // (H * W)
+    out = torch.empty(*labels.shape[:-2], 2, h, w, dtype=torch.float32, device=labels.device)
+    _cabi.check(_cabi.lib().pemp_mask_nearest_labels(labels.data_ptr(), planes, H, W, h, w, out.data_ptr(), _stream()),
+                "pemp_mask_nearest_labels")
+    _count(1)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ K1 / K8
+@_on_device
 def map_pool_lowres(fts, fg, bg, B, S, eps=1e-5):
     """fts [B*S, c, hw]; fg, bg [B*S, hw] -> (fg_proto [B, c], bg_proto [B, c])  (pemp_stage1.py:223-227)."""
     fts, ep, c, hw = _episodes(fts, B, S, "fts")
@@ -122,6 +169,7 @@ def _need_loose(t, name):
     return t
 
 
+@_on_device
 def weighted_gap(supp_feat, mask):
     """PFENet `Weighted_GAP(supp_feat [B,c,h,w], mask [B,1,h,w]) -> [B,c,1,1]` (pfenet.py:15-20)."""
     supp_feat = _need(supp_feat, torch.float32, "supp_feat")
@@ -139,6 +187,7 @@ def weighted_gap(supp_feat, mask):
 
 
 # ------------------------------------------------------------------------------------------------ K11
+@_on_device
 def comm_module(x, mask, weight, bias, spq, stride=2):
     """`ResNetCM.comm` / `VGG16CM.comm` (backbones.py:208-222, 469-479): x [N,c,h,w], mask [N,1,Hm,Wm], nn.Linear
     weight [n,2c] / bias [n] -> (feat broadcast [N,n,h,w], pooled mask [N,1,h,w])."""
@@ -167,6 +216,7 @@ def comm_module(x, mask, weight, bias, spq, stride=2):
 
 
 # ------------------------------------------------------------------------------------------------ K2
+@_on_device
 def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
     """fts [B*S, c, hw]; ctr [c, 2p]; fg, bg [B*S, hw] -> fg_proto [B,c,p], bg_proto [B,c,p], adaptive_p [B,c,2p]
     (pemp_stage1.py:202-213, pemp_stage2.py:174-186)."""
@@ -196,6 +246,7 @@ def meta_proto_attn(fts, ctr, fg, bg, B, S, eps=1e-6, want_adaptive=True):
 
 
 # ------------------------------------------------------------------------------------------------ K3
+@_on_device
 def cosine_match(qry, fg_proto, bg_proto, scalar=20.0, want_sim=False, want_pred=True, want_response=False):
     """qry [N, c, hw] / [N, c, h, w] or the episode view [Bp, Q, c, h, w]; protos [Bp, c] or [Bp, c, P]
     -> dict(sim [N,2,P,hw], pred [N,2,hw], response [N,hw] int64)
@@ -225,6 +276,7 @@ def cosine_match(qry, fg_proto, bg_proto, scalar=20.0, want_sim=False, want_pred
 
 
 # ------------------------------------------------------------------------------------------------ K4 / K5
+@_on_device
 def upsample_argmax(pred, out_hw, want_logits=False, want_mask8=True, want_mask64=False):
     """pred [N, 2, h, w] -> dict(logits [N,2,H,W], mask8 [N,H,W] uint8, mask64 [N,H,W] int64)
     (F.interpolate bilinear align_corners + argmax, pemp_stage1.py:157-162, entry/pemp_stage1.py:52)."""
@@ -243,6 +295,7 @@ def upsample_argmax(pred, out_hw, want_logits=False, want_mask8=True, want_mask6
     return {"logits": logits, "mask8": m8, "mask64": m64}
 
 
+@_on_device
 def bilinear_resize(x, out_hw):
     """[..., h, w] float32 -> [..., H, W], bilinear align_corners=True (pfenet.py:191,205)."""
     x = _need(x, torch.float32, "x")
@@ -255,6 +308,7 @@ def bilinear_resize(x, out_hw):
     return out
 
 
+@_on_device
 def nearest_resize_labels(lab, out_hw):
     """[..., h, w] int64 -> [..., H, W] nearest (response map, pemp_stage1.py:158-159)."""
     lab = _need(lab, torch.int64, "labels")
@@ -268,6 +322,7 @@ def nearest_resize_labels(lab, out_hw):
 
 
 # ------------------------------------------------------------------------------------------------ K6
+@_on_device
 def map_pool_fullres(fts, sup_mask, B, S, eps=1e-5):
     """fts [B*S, c, h, w]; sup_mask [B*S, 2, H, W] -> (fg_proto [B,c], bg_proto [B,c])  (baseline.py:100-110)."""
     if fts.dim() not in (4, 5):
@@ -290,6 +345,7 @@ def map_pool_fullres(fts, sup_mask, B, S, eps=1e-5):
     return out_f, out_b
 
 
+@_on_device
 def bilinear_adjoint(mask, out_hw, want_sum=True):
     """mask [..., H, W] -> (U^T mask [..., h, w], plane sums [...])."""
     mask = _need(mask, torch.float32, "mask")
@@ -305,6 +361,7 @@ def bilinear_adjoint(mask, out_hw, want_sum=True):
 
 
 # ------------------------------------------------------------------------------------------------ K7
+@_on_device
 def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
     """`PANet.alignLoss(qry_fts [BQ,c,h,w], pred [BQ,2,h,w], sup_fts [BS,c,h,w], sup_mask_fg [BS,1,H,W], Q)`
     -> 0-dim loss tensor (panet.py:158-194)."""
@@ -338,9 +395,11 @@ def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
 
 # ------------------------------------------------------------------------------------------------ K9
 PRIOR_BF16, PRIOR_FP32, PRIOR_BF16X3 = 0, 1, 2
+PRIOR_DEFAULT = PRIOR_BF16X3      # tensor-core path with fp32-grade cosines (three bf16 products of a hi/lo split)
 
 
-def prior_mask(q4, s4, smask, precision=PRIOR_FP32, want_rowmax=False):
+@_on_device
+def prior_mask(q4, s4, smask, precision=PRIOR_DEFAULT, want_rowmax=False):
     """q4 [B, C, hq, wq]; s4 [S, B, C, hs, ws]; smask [S, B, hs, ws] (support mask at feature size)
     -> prior [B, 1, hq, wq] (and rowmax [S, B, hq*wq])  (pfenet.py:201-231)."""
     q4 = _need(q4, torch.float32, "q4")
@@ -363,6 +422,7 @@ def prior_mask(q4, s4, smask, precision=PRIOR_FP32, want_rowmax=False):
 
 
 # ------------------------------------------------------------------------------------------------ K10
+@_on_device
 def upsample_argmax_hist(pred, out_hw, ref, cls, stat):
     """K4 + K10 in one launch: pred [N,2,h,w] -> uint8 argmax mask [N,H,W] at `out_hw`, and the FewShotMetric counts of
     (mask, ref [N,H,W] uint8, cls [N]) added to stat [(C+1),3] (entry/pemp_stage2.py:63-65, core/metrics.py:9-23)."""
@@ -383,6 +443,7 @@ def upsample_argmax_hist(pred, out_hw, ref, cls, stat):
     return m8
 
 
+@_on_device
 def iou_hist(pred, ref, cls, stat):
     """Accumulate `FewShotMetric.update` counts on the device.  pred, ref [N, ...] uint8 (same shape);
     cls [N] int64; stat [(C+1), 3] int64 is updated in place (core/metrics.py:9-23)."""
@@ -402,6 +463,7 @@ def iou_hist(pred, ref, cls, stat):
 
 
 # ------------------------------------------------------------------------------------------------ K12 (training path)
+@_on_device
 def meta_proto_attn_train(fts, ctr, fg, bg, B, S, eps=1e-6):
     """K2 forward for training: -> (fg_proto [B,c,p], bg_proto [B,c,p], saved) where `saved` is what
     `meta_proto_attn_bwd` needs (per-shot centres [BS,c,2p] and denominators [BS,2p])."""
@@ -441,6 +503,7 @@ def _grad_out(out, B, S, c, hw, device):
     return out, (out.stride(0) if B > 1 else S * c * hw)
 
 
+@_on_device
 def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S, out=None):
     """-> (d_fts [B*S, c, hw] or `out`, d_ctr [c, 2p]) from the gradients of fg_proto / bg_proto [B, c, p]."""
     fts, ep, ctr, fg, bg, centre, den = saved
@@ -464,6 +527,7 @@ def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S, out=None):
     return d_fts, d_ctr
 
 
+@_on_device
 def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0, out=None):
     """Backward of `cosine_match(...)["pred"]`: qry as in the forward, g_pred [N, 2, hw] -> (d_qry [N, c, hw] or `out`,
     d_fg, d_bg shaped like the prototypes)."""
@@ -496,6 +560,7 @@ def _labels(target):
     return target.contiguous()
 
 
+@_on_device
 def boundary_weight(target, sigma):
     """`CELossDT.boundary2weight` on the device (core/losses.py:23-40): target [N,H,W] -> weight [N,H,W] float32."""
     target = _labels(target)
@@ -509,6 +574,7 @@ def boundary_weight(target, sigma):
     return weight
 
 
+@_on_device
 def upsample_ce(pred, target, want_grad=True, weight=None):
     """Cross entropy (255 ignored) of the bilinear align_corners up-sampling of pred [N,2,h,w] to target [N,H,W]
     (int64 or uint8) -> (loss [1], d_pred [N,2,h,w] or None).  weight None: mean over the valid pixels
@@ -533,6 +599,7 @@ def upsample_ce(pred, target, want_grad=True, weight=None):
     return loss, d_pred
 
 
+@_on_device
 def map_pool_lowres_bwd(fg, bg, g_fg, g_bg, B, S, c, eps=1e-5, out=None):
     """Backward of `map_pool_lowres`: masks [B*S, hw], g_fg / g_bg [B, c] -> d_fts [B*S, c, hw] (or `out`, a
     [B, S, c, h, w] slice of the gradient of the encoder output)."""
@@ -555,6 +622,7 @@ def map_pool_lowres_bwd(fg, bg, g_fg, g_bg, B, S, c, eps=1e-5, out=None):
 
 
 # ------------------------------------------------------------------------------------------------ K15 (CaNet)
+@_on_device
 def canet_map_tile(features, sup_mask, B, S, Q):
     """CaNet's dense-comparison input (networks/canet.py:172-180): features [B*(S+Q), c, h, w] (encoder output, read in
     place), sup_mask [B, S, 2, H, W] -> out [B*Q, 2c, h, w] = cat(query features, foreground prototype tiled)."""

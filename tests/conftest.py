@@ -47,3 +47,25 @@ def nrel(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def screened_episodes(workload, spec, B, start=0):
+    """The first B episode indices >= start whose smallest decision margin |fg - bg| through the reference restatement is
+    >= 1e-5 (SURVEY 7 hard part 2, tier T2), their stacked batch, and how many candidates were rejected on the way.  For the
+    bench-size streams the committed table (`pemp_b200/episode_screen.json`) answers; other specs are screened here."""
+    from oracle import screen
+    from pemp_b200 import episodes as E
+    key = E.screen_key(workload, spec)
+    if key in E.screen_table():
+        acc = [i for i in E.screened_indices(workload, spec) if i >= start][:B]
+        assert len(acc) == B
+        return E.make_batch(spec, acc), acc, None
+    acc, rejected, i = [], 0, start
+    while len(acc) < B:
+        m, _ = screen.episode_margin(workload, spec, i)
+        if m >= screen.THRESHOLD:
+            acc.append(i)
+        else:
+            rejected += 1
+        i += 1
+    return E.make_batch(spec, acc), acc, rejected

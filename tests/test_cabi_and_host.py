@@ -116,8 +116,16 @@ def test_miou_matches_reference_formula():
     assert np.array_equal(O.miou(g["stat"], g["labels"])[0], mi)
 
 
+def _unwrapped(fn):
+    while hasattr(fn, "__wrapped__"):
+        fn = fn.__wrapped__
+    return fn
+
+
 def test_dropin_binds_reference_classes():
-    """Where the reference tree is present, patch() must rebind its methods to ours and unpatch() restore them."""
+    """Where the reference tree is present (the build container, or the staged copy on the GPU box), patch() must rebind its
+    methods to ours - wrapped in the reference module's own Sacred `capture`, so injected config reaches them - and unpatch()
+    restore them."""
     from oracle import ref_import as R
     if not R.available():
         pytest.skip("reference tree not present on this machine")
@@ -126,20 +134,86 @@ def test_dropin_binds_reference_classes():
     pa = R.module("networks.panet").PANet
     pf = R.module("networks.pfenet")
     cm = R.module("core.metrics")
-    before = (s1.mpm, s1.forward, pa.alignLoss, pf.Weighted_GAP, cm.FewShotMetric)
+    before = (s1.mpm, s1.forward, pa.alignLoss, pf.Weighted_GAP, cm.FewShotMetric, pf.PFENet.forward)
     dropin.patch()
     try:
-        assert s1.mpm is heads.mpm and s1.forward is heads.pemp_stage1_forward
-        assert pa.alignLoss is heads.alignLoss and pf.Weighted_GAP is heads.Weighted_GAP
+        assert _unwrapped(s1.mpm) is heads.mpm and _unwrapped(s1.forward) is heads.pemp_stage1_forward
+        assert _unwrapped(pa.alignLoss) is heads.alignLoss and pf.Weighted_GAP is heads.Weighted_GAP
         assert pf.prior_mask is heads.prior_mask
         assert cm.FewShotMetric.__module__ == "pemp_b200.metrics"
         net = R.head_only("pemp_stage1", torch.zeros(2, 8, 4, 4), torch.rand(8, 6))
         with pytest.raises(ValueError, match="CUDA"):         # our code ran; CPU tensors are refused
             net(torch.zeros(1, 1, 1, 9, 9), torch.zeros(1, 1, 2, 9, 9), torch.zeros(1, 1, 1, 9, 9))
+        # PFENet.forward is now the reference's own source with its inline prior block replaced by one call
+        fwd = pf.PFENet.forward
+        assert "pemp_b200 splice" in fwd.__code__.co_filename
+        assert "_pemp_prior_mask" in fwd.__code__.co_names and "bmm" not in fwd.__code__.co_names
+        assert {"layer4", "down_query", "init_merge", "res2", "cls"} <= set(fwd.__code__.co_names)      # the rest is untouched
     finally:
         dropin.unpatch()
-    assert (s1.mpm, s1.forward, pa.alignLoss, pf.Weighted_GAP, cm.FewShotMetric) == before
+    assert (s1.mpm, s1.forward, pa.alignLoss, pf.Weighted_GAP, cm.FewShotMetric, pf.PFENet.forward) == before
     assert not hasattr(pf, "prior_mask")
+    assert "bmm" in pf.PFENet.forward.__code__.co_names
+
+
+def test_dropin_receives_the_sacred_config():
+    """`net.dist_scalar` is injected by Sacred's `capture` by parameter name (pemp_stage1.py:232-234): a patched model must
+    evaluate with the configured value, not a hard-coded 20."""
+    from oracle import ref_import as R
+    if not R.available():
+        pytest.skip("reference tree not present on this machine")
+    from pemp_b200 import dropin, heads, ops
+    mod = R.module("networks.pemp_stage1")
+    seen = {}
+    real = ops.cosine_match
+
+    def spy(qry, fg, bg, scalar=20.0, **kw):
+        seen["scalar"] = scalar
+        raise RuntimeError("stop here")
+    old_cfg = mod.net_ingredient.cfg.get("dist_scalar")
+    dropin.patch()
+    ops.cosine_match = spy
+    try:
+        mod.net_ingredient.cfg["dist_scalar"] = 7
+        with pytest.raises(RuntimeError, match="stop here"):
+            mod.PEMPStage1.compute_similarity(None, torch.zeros(1, 4), torch.zeros(1, 4), torch.zeros(1, 4, 2, 2))
+        assert seen["scalar"] == 7
+        assert heads._scalar(None, None) == 20 and heads._scalar(None, 3) == 3
+    finally:
+        ops.cosine_match = real
+        mod.net_ingredient.cfg["dist_scalar"] = old_cfg
+        dropin.unpatch()
+
+
+def test_episode_screen_table_is_used_and_never_silently_bypassed():
+    spec = E.EpisodeSpec(shot=5, stages=2)
+    acc = E.screened_indices("pemp_stage2", spec)
+    st = E.screen_stats("pemp_stage2", spec)
+    assert st["threshold"] == 1e-5 and st["candidates"] >= 512 and len(acc) == st["candidates"] - st["rejected"]
+    assert len(acc) >= 512                                   # 8 ranks x 64 disjoint screened episodes
+    shards = [E.screened_indices("pemp_stage2", spec, 64, start=r, step=8) for r in range(8)]
+    flat = [i for sh in shards for i in sh]
+    assert len(set(flat)) == 512 and set(flat) <= set(acc)
+    with pytest.raises(KeyError):
+        E.screened_indices("pemp_stage2", E.EpisodeSpec(shot=4, stages=2), 8)      # no table for this stream: loud
+    with pytest.raises(ValueError):
+        E.screened_indices("pemp_stage2", spec, 10 ** 6)
+
+
+def test_bench_reference_arm_runs_the_reference_code(tmp_path):
+    """`bench.py --impl reference` prints one JSON line produced by the reference's own classes (kind "reference") where its
+    files are present, on the named workload."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "stage1_1shot",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    from oracle import ref_import as R
+    assert out["impl"] == "reference" and out["unit"] == "episodes/s" and out["value"] > 0
+    assert out["cpu_baseline"]["kind"] == ("reference" if R.available() else "port")
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and "stage1_1shot" in out["config"]["workload"]
 
 
 _GLOO_WORKER = r"""

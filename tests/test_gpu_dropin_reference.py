@@ -1,0 +1,151 @@
+"""`dropin.patch()` on the REAL reference classes, on the GPU.
+
+The reference's own files travel to the GPU box in the git-ignored `oracle/_ref/reference/` (staged, unmodified, by
+`__graft_entry__.build()`).  Each test runs the reference class twice on CUDA tensors - as it is (stock PyTorch CUDA ops, TF32
+off: SURVEY 8c's primary oracle) and after `dropin.patch()` rebound its methods to the B200 kernels - and compares.
+Bars: logits 1e-5 norm-wise; arg-max masks identical on every pixel the reference decides by >= 1e-5 (the margin screen of
+SURVEY 7, hard part 2; the number of flips below that margin is printed, not hidden); counts identical."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import nrel
+from oracle import ref_import as R
+from pemp_b200 import episodes as E
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="reference files not staged (run __graft_entry__.build() "
+                                                                            "where /root/reference exists)")]
+MARGIN = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    from pemp_b200 import dropin
+    dropin.unpatch()
+
+
+def _masks_agree(got_logits, ref_logits, tag):
+    ref_mask = ref_logits.argmax(1)
+    got_mask = got_logits.argmax(1)
+    margin = (ref_logits[:, 1] - ref_logits[:, 0]).abs()
+    flips = got_mask != ref_mask
+    print(json.dumps({"case": tag, "pixels": int(flips.numel()), "flips_unscreened": int(flips.sum()),
+                      "pixels_below_margin": int((margin < MARGIN).sum())}))
+    assert not bool((flips & (margin >= MARGIN)).any())
+    return got_mask, ref_mask
+
+
+@pytest.mark.parametrize("model,S,B,Q", [("pemp_stage1", 1, 2, 1), ("pemp_stage1", 5, 1, 1), ("pemp_stage2", 5, 2, 1),
+                                         ("baseline", 1, 2, 1), ("panet", 5, 1, 1)])
+def test_patched_reference_model_equals_unpatched(model, S, B, Q):
+    from pemp_b200 import dropin
+    spec = E.EpisodeSpec(shot=S, query=Q, stages=1, out_h=333, out_w=500)     # BASELINE feature shape, non-square output
+    batch = E.make_batch(spec, range(40, 40 + B))
+    feats = batch["feats1"].cuda()
+    ctr = E.make_ctr(spec, 1).cuda() if model.startswith("pemp") else None
+    net = R.head_only(model, feats, None if ctr is None else ctr.cpu()).cuda()
+    sup_img = torch.zeros(B, S, 1, spec.H, spec.W, device="cuda")
+    qry_img = torch.zeros(B, Q, 1, spec.H, spec.W, device="cuda")
+    sup_mask = batch["sup_mask"].cuda()
+    out_shape = (spec.out_h, spec.out_w)
+
+    def run():
+        with torch.no_grad():
+            if model == "pemp_stage2":
+                prior = torch.zeros(B * Q, 1, spec.H, spec.W, dtype=torch.int64, device="cuda")
+                return net(sup_img, sup_mask, qry_img, prior, out_shape, True)
+            if model == "pemp_stage1":
+                return net(sup_img, sup_mask, qry_img, out_shape, True)
+            return net(sup_img, sup_mask, qry_img, out_shape)
+
+    want = run()
+    dropin.patch()
+    mod = R.module(f"networks.{model}")
+    assert "pemp_b200" in mod.ModelClass.forward.__module__            # the class now runs our forward
+    got = run()
+    dropin.unpatch()
+    if model == "panet":
+        (want, want_loss), (got, got_loss) = want, got
+        assert abs(float(got_loss) - float(want_loss)) < 1e-5 * max(1.0, abs(float(want_loss)))
+    response = None
+    if isinstance(want, tuple):
+        (want, want_resp), (got, response) = want, got
+    assert got.shape == want.shape and nrel(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+    got_mask, ref_mask = _masks_agree(got, want, f"{model} S={S} B={B}")
+    if response is not None:
+        assert response.dtype == torch.int64 and response.shape == want_resp.shape
+        same = (response == want_resp)
+        assert float(same.float().mean()) > 0.995
+    # FewShotMetric: the reference's NumPy class on the reference mask vs the patched class on ours
+    ref_metric = R.few_shot_metric(spec.classes)
+    ref_metric.update(ref_mask.cpu().numpy(), batch["qry_msk"].numpy(), batch["cls"])
+    dropin.patch()
+    cm = R.module("core.metrics")
+    ours = cm.FewShotMetric(spec.classes)
+    assert type(ours).__module__ == "pemp_b200.metrics"
+    ours.update(ref_mask, batch["qry_msk"].cuda(), batch["cls"].cuda())
+    dropin.unpatch()
+    assert np.array_equal(ours.stat, ref_metric.stat)
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(ours.mIoU(list(range(1, 6)))[0], ref_metric.mIoU(list(range(1, 6)))[0])
+        np.testing.assert_array_equal(ours.mIoU(None, binary=True)[0], ref_metric.mIoU(None, binary=True)[0])
+
+
+def test_patched_stage2_keeps_adaptive_p_side_effect():
+    from pemp_b200 import dropin
+    spec = E.EpisodeSpec(shot=2, stages=1)
+    B, S, Q = 2, 2, 1
+    batch = E.make_batch(spec, range(3, 3 + B))
+    net = R.head_only("pemp_stage2", batch["feats1"].cuda(), E.make_ctr(spec, 2)).cuda()
+    args = (torch.zeros(B, S, 1, spec.H, spec.W, device="cuda"), batch["sup_mask"].cuda(), torch.zeros(B, Q, 1, spec.H, spec.W, device="cuda"),
+            torch.zeros(B * Q, 1, spec.H, spec.W, dtype=torch.int64, device="cuda"))
+    with torch.no_grad():
+        net(*args)
+        want = net.adaptive_p.clone()
+        dropin.patch()
+        net(*args)
+        got = net.adaptive_p
+    dropin.unpatch()
+    assert got.shape == want.shape and nrel(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("shot,size", [(1, 201), (5, 473)])
+def test_patched_pfenet_forward_reaches_the_tensor_core_prior(shot, size):
+    """The whole reference `PFENet.forward` (ResNet-50 with seeded random weights, eval mode) before / after `patch()`: the patched
+    class runs a forward re-compiled from the reference's own source whose inline prior block (pfenet.py:201-229) is one call of
+    `heads.prior_mask` -> `pemp_prior_mask` on tcgen05 (default precision bf16x3) and whose `Weighted_GAP` is K8."""
+    from pemp_b200 import dropin, ops
+    net = R.pfenet_model(shot, seed=3).cuda()
+    g = torch.Generator().manual_seed(shot * 1000 + size)
+    B = 1
+    sup_img = torch.randn(B, shot, 3, size, size, generator=g).cuda()
+    qry_img = torch.randn(B, 1, 3, size, size, generator=g).cuda()
+    fg = torch.zeros(B, shot, size, size)
+    for s in range(shot):
+        y0, y1, x0, x1 = E._rect(g, size, size)
+        fg[:, s, y0:y1, x0:x1] = 1.0
+    sup_mask = torch.stack((fg, 1 - fg), dim=2).cuda()
+    qry_mask = torch.zeros(B, 1, size, size, dtype=torch.int64).cuda()
+    with torch.no_grad():
+        want = net(sup_img, sup_mask, qry_img, qry_mask)
+    n0 = ops.launch_count()
+    dropin.patch()
+    pf = R.module("networks.pfenet")
+    assert "pemp_b200 splice" in pf.PFENet.forward.__code__.co_filename
+    with torch.no_grad():
+        got = net(sup_img, sup_mask, qry_img, qry_mask)
+    dropin.unpatch()
+    assert ops.launch_count() - n0 >= 2 * shot + 3          # S weighted-GAP calls + mask resize + the prior op ran on our kernels
+    assert got.shape == want.shape == (B, 2, size, size)
+    # the prior map enters the pyramid as one of 513 input channels of `init_merge`; its own tolerance (normalised map: the
+    # reference's fp32 result is itself ~1e-5 from fp64, SURVEY 7 hard part 5) is checked in test_gpu_kernels; here the output
+    err = nrel(got.cpu().numpy(), want.cpu().numpy())
+    print(json.dumps({"case": f"pfenet shot={shot} size={size}", "out_nrel": err}))
+    assert err < 1e-4

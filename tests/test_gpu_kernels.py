@@ -346,6 +346,34 @@ def test_iou_hist_random_with_ignore(ops, N, H, W):
     assert np.array_equal(stat.cpu().numpy(), 2 * expect)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_iou_counts_coco_shaped_80_classes(ops, fused):
+    """COCO-20i shape (BASELINE config 4): C = 80, `cls` in 1..80 (`data_kits/coco.py:444`, `core/metrics.py:7`): the 81-row
+    count table of K10 and of the fused K4 + K10 kernel against the NumPy restatement, every class present at least once."""
+    g = torch.Generator().manual_seed(80)
+    N, h, w, H, W = 96, 51, 51, 401, 401
+    cls = torch.cat((torch.arange(1, 81), torch.randint(1, 81, (N - 80,), generator=g)))[torch.randperm(N, generator=g)]
+    ref = (torch.rand(N, H, W, generator=g) > 0.6).to(torch.uint8)
+    ref[:, ::37] = 255
+    pred = torch.randn(N, 2, h, w, generator=g)
+    stat = torch.zeros(81, 3, dtype=torch.int64, device="cuda")
+    if fused:
+        mask = ops.upsample_argmax_hist(cu(pred), (H, W), cu(ref), cu(cls), stat)
+        assert torch.equal(mask, ops.upsample_argmax(cu(pred), (H, W), want_mask8=True)["mask8"])
+    else:
+        mask = ops.upsample_argmax(cu(pred), (H, W), want_mask8=True)["mask8"]
+        ops.iou_hist(mask, cu(ref), cu(cls), stat)
+    want = O.few_shot_stat(mask.cpu().numpy(), ref.numpy(), cls.numpy(), 80)
+    assert want.shape == (81, 3) and (want[1:].sum(axis=1) > 0).all()
+    assert np.array_equal(stat.cpu().numpy(), want)
+    # same masks through the drop-in FewShotMetric(80) and the reference's mIoU over a COCO split's 20 labels
+    from pemp_b200.metrics import FewShotMetric
+    fm = FewShotMetric(80)
+    fm.update(mask, cu(ref), cu(cls))
+    assert np.array_equal(fm.stat, want.astype(np.float64))
+    assert fm.mIoU(list(range(21, 41)))[1] == O.miou(want, list(range(21, 41)))[1]
+
+
 def test_iou_hist_golden_random(ops):
     g = golden("metric_random")
     stat = torch.zeros(21, 3, dtype=torch.int64, device="cuda")
@@ -410,6 +438,26 @@ def test_baseline_panet_golden(ops, name):
     if "align_loss" in g:
         loss = ops.panet_align(qry.view(B * Q, c, h, w), pred, sup, cu(sup_mask.view(B * S, 2, H, W)[:, 0:1]), Q)
         assert abs(float(loss) - float(g["align_loss"])) < 1e-5 * max(1.0, abs(float(g["align_loss"])))
+
+
+def test_panet_align_at_the_baseline_shape(ops):
+    """K7 at BASELINE config 4's size: 5 shots, c = 512, 51 x 51 features, 401 x 401 masks (`panet.py:158-194`) against the
+    oracle; the low-res prediction that alignLoss thresholds comes from the oracle so both sides see identical masks."""
+    spec = E.EpisodeSpec(shot=5, stages=1, classes=80, cls_hi=80)
+    B, S, Q, c, h, w = 1, 5, 1, spec.channels, spec.h, spec.w
+    batch = E.make_batch(spec, [2])
+    want = O.panet_head(batch["feats1"], batch["sup_mask"], B, S, Q)
+    f5 = cu(batch["feats1"]).view(B, S + Q, c, h, w)
+    mask = cu(batch["sup_mask"]).view(B * S, 2, spec.H, spec.W)
+    loss = ops.panet_align(f5[:, S:], cu(want["pred_lowres"]), f5[:, :S], mask[:, 0:1], Q)
+    assert abs(float(loss) - float(want["align_loss"])) < 1e-5 * max(1.0, abs(float(want["align_loss"])))
+    # the whole PANet head on our kernels: prototypes (K6), logits (K3 + K4), loss (K7)
+    fgp, bgp = ops.map_pool_fullres(f5[:, :S], mask, B, S)
+    assert nrel(fgp.cpu(), want["fg_proto"]) < TOL and nrel(bgp.cpu(), want["bg_proto"]) < TOL
+    pred = ops.cosine_match(f5[:, S:], fgp, bgp, 20.0)["pred"].view(B * Q, 2, h, w)
+    assert nrel(pred.cpu(), want["pred_lowres"]) < TOL
+    loss2 = ops.panet_align(f5[:, S:], pred, f5[:, :S], mask[:, 0:1], Q)
+    assert abs(float(loss2) - float(want["align_loss"])) < 2e-5 * max(1.0, abs(float(want["align_loss"])))
 
 
 @pytest.mark.parametrize("B,S,c,h,w,H,W", [(2, 2, 24, 13, 13, 97, 97), (1, 3, 16, 9, 12, 50, 77), (1, 1, 8, 20, 20, 11, 15),
@@ -481,6 +529,28 @@ def test_prior_tensor_core_paths(ops, precision, tol, B, S, C, sp):
     assert float((prior - p32).abs().max()) < 2 * tol * max(1.0, amp)
 
 
+@pytest.mark.parametrize("precision,tol", [(0, 3e-3), (2, 1e-5)])
+def test_prior_tensor_core_paths_at_the_baseline_shape(ops, precision, tol):
+    """BASELINE config 5 (PFENet 5-shot, 473 x 473): B = 1, S = 5, C = 2048, 60 x 60 -> a 3600 x 3600 x 2048 contraction per
+    shot, both tensor-core precisions against the oracle's fp32 `bmm` restatement and against float64.
+    Bars on the PRE-normalisation cosine maxima (SURVEY 7 hard part 5): bf16 x 3 (the drop-in default) 1e-5 = north_star's
+    fp32 tolerance; single bf16 product 3e-3 (stated tolerance of the bf16 path).  The final map's error is the same
+    error times 1 / (max - min) of the row maxima (the min-max normalisation); that factor is measured and applied."""
+    import json
+    q4, s4, small, ref = _prior_case(1, 5, 2048, 60, seed=77)
+    prior, rowmax = ops.prior_mask(cu(q4), cu(s4), cu(small), precision=precision, want_rowmax=True)
+    ref64 = torch.stack([O.pfenet_rowmax(q4.double(), s4[s].double(), small[s][:, None].double()) for s in range(5)])
+    e_ref, e_64, ref_64 = nrel(rowmax.cpu(), ref), nrel(rowmax.cpu(), ref64), nrel(ref, ref64)
+    want = O.pfenet_prior(q4, list(s4), [m[:, None] for m in small])              # masks already at feature size
+    amp = float(1.0 / (ref.max(dim=2).values - ref.min(dim=2).values).min())
+    e_map = float((prior.cpu() - want).abs().max())
+    print(json.dumps({"case": f"K9 3600x3600x2048 S=5 precision={precision}", "rowmax_vs_ref_fp32": e_ref, "rowmax_vs_fp64": e_64,
+                      "ref_fp32_vs_fp64": ref_64, "minmax_amplification": amp, "prior_map_max_abs_err": e_map}))
+    assert e_ref < tol and e_64 < tol
+    assert e_map < 2 * tol * max(1.0, amp)
+    assert tuple(prior.shape) == (1, 1, 60, 60)
+
+
 def test_prior_tensor_core_eps_visible(ops):
     """Tiny feature norms make the reference's `+ 1e-7` visible; the epilogue re-applies it exactly."""
     q4, s4, small, ref = _prior_case(1, 2, 64, 13, seed=5, scale=1e-4)
@@ -524,33 +594,33 @@ def test_pemp_head_golden_small(ops, name, out_shape):
         assert nrel(up["logits"].cpu().numpy(), g[f"s{stage}_logits"]) < TOL
         want = unpack_bits(g[f"s{stage}_mask"], g[f"s{stage}_mask_shape"])
         margin = np.abs(g[f"s{stage}_logits"][:, 1] - g[f"s{stage}_logits"][:, 0])
-        flips = up["mask64"].cpu().numpy() != want
-        assert not flips[margin > 2e-4].any()          # only pixels the reference itself decides by < 2e-4 may differ
-        assert flips.sum() <= 2, flips.sum()
+        assert margin.min() >= 1e-5                     # the fixture episodes pass the margin screen (SURVEY 7 hard part 2)
+        assert int((up["mask64"].cpu().numpy() != want).sum()) == 0
     if adaptive is not None and "s2_adaptive_p" in g:
         assert nrel(adaptive.cpu().numpy(), g["s2_adaptive_p"]) < TOL
 
 
 @pytest.mark.parametrize("name", ["pemp_full_5shot", "pemp_full_1shot"])
 def test_pemp_head_golden_full_size(ops, name):
-    """BASELINE shape: c=512, 51x51 features, 401x401 masks; inputs regenerated from the seed."""
+    """BASELINE shape: c=512, 51x51 features, 401x401 masks; inputs regenerated from the seed.  The fixture episodes were chosen
+    by the margin screen when the unmodified reference produced the fixture (`indices`, `min_margin` in the file), so masks
+    and the count table are compared bit for bit, unconditionally."""
     g = golden(name)
     spec = E.EpisodeSpec(**json.loads(str(g["spec"])))
-    B, first = int(g["B"]), int(g["first"])
-    batch = E.make_batch(spec, range(first, first + B))
+    B = int(g["B"])
+    assert float(g["min_margin"]) >= 1e-5
+    batch = E.make_batch(spec, [int(i) for i in g["indices"]])
     for stage in (1, 2):
         m, up, adaptive = _run_head(ops, batch[f"feats{stage}"], batch["sup_mask"], E.make_ctr(spec, stage), B, spec.shot,
                                     spec.query, (spec.H, spec.W))
         want_low = g[f"s{stage}_pred_lowres"]
         assert nrel(m["pred"].cpu().numpy().reshape(want_low.shape), want_low) < TOL
         want = unpack_bits(g[f"s{stage}_mask"], g[f"s{stage}_mask_shape"])
-        flips = int((up["mask64"].cpu().numpy() != want).sum())
-        assert flips <= 2, flips                        # near-tie pixels only (SURVEY 7, hard part 2)
+        assert int((up["mask64"].cpu().numpy() != want).sum()) == 0
     assert nrel(adaptive.cpu().numpy(), g["s2_adaptive_p"]) < TOL
     stat = torch.zeros(spec.classes + 1, 3, dtype=torch.int64, device="cuda")
     ops.iou_hist(up["mask64"].to(torch.uint8), cu(batch["qry_msk"]), cu(batch["cls"]), stat)
-    if flips == 0:
-        assert np.array_equal(stat.cpu().numpy(), g["stat"])
+    assert np.array_equal(stat.cpu().numpy(), g["stat"])
 
 
 # ------------------------------------------------------------------------------------------------ errors

@@ -29,7 +29,7 @@ def test_pemp_head_small_bit_exact(name, out_shape):
     spec, B = _spec(g), int(g["B"])
     sup_mask = _sup_mask(g, spec, B)
     # the generator must reproduce the stored inputs (fixtures with seeds-only rely on it)
-    batch = E.make_batch(spec, range(int(g["first"]), int(g["first"]) + B))
+    batch = E.make_batch(spec, [int(i) for i in g["indices"]])
     assert torch.equal(batch["sup_mask"], sup_mask)
     for stage in (1, 2):
         feats = torch.from_numpy(g[f"s{stage}_feats"])
@@ -54,16 +54,18 @@ def test_pemp_head_full_size(name):
     """BASELINE shape (c=512, 51x51 -> 401x401); inputs come from the seeded generator."""
     g = golden(name)
     spec, B = _spec(g), int(g["B"])
-    first = int(g["first"])
-    batch = E.make_batch(spec, range(first, first + B))
+    batch = E.make_batch(spec, [int(i) for i in g["indices"]])       # margin-screened when the reference produced the fixture
+    margins = []
     for stage in (1, 2):
         out = O.pemp_head(batch[f"feats{stage}"], batch["sup_mask"], E.make_ctr(spec, stage), B, spec.shot, spec.query)
+        margins.append(float((out["logits"][:, 1] - out["logits"][:, 0]).abs().min()))
         assert np.array_equal(out["pred_lowres"].numpy(), g[f"s{stage}_pred_lowres"])
         mask = unpack_bits(g[f"s{stage}_mask"], g[f"s{stage}_mask_shape"])
         assert np.array_equal(O.argmax2(out["logits"]).numpy(), mask)
     assert np.array_equal(out["adaptive_p"].numpy(), g["s2_adaptive_p"])
     stat = O.few_shot_stat(O.argmax2(out["logits"]).numpy(), batch["qry_msk"].numpy(), batch["cls"].numpy(), spec.classes)
     assert np.array_equal(stat, g["stat"])
+    assert min(margins) == float(g["min_margin"]) >= 1e-5         # the screen the reference run applied holds for the restatement
 
 
 def test_pemp_general_masks():
@@ -179,3 +181,38 @@ def test_canet_map_tile_bit_exact(name):
     f = torch.from_numpy(g["features"])
     out = O.canet_map_tile(f, torch.from_numpy(g["sup_mask"]), f.shape[0], int(g["S"]), int(g["Q"]))
     assert np.array_equal(out.numpy(), g["out"])
+
+
+def test_episode_screen_table_matches_the_oracle():
+    """`pemp_b200/episode_screen.json` (read by the product's episode generator) is what `oracle/screen.py` derives from the
+    reference restatement: re-derive a sample of accepted and rejected indices of the headline workload."""
+    from oracle import screen
+    from pemp_b200 import episodes as E
+    spec = E.EpisodeSpec(shot=5, stages=2)
+    entry = E.screen_table()[E.screen_key("pemp_stage2", spec)]
+    rejected = set(entry["rejected"])
+    sample = sorted(rejected)[:3] + [i for i in range(entry["candidates"]) if i not in rejected][:3]
+    for i in sample:
+        m, _ = screen.episode_margin("pemp_stage2", spec, i)
+        assert (m < screen.THRESHOLD) == (i in rejected), (i, m)
+
+
+def test_reference_runner_equals_the_port():
+    """`oracle/ref_run.py` drives the reference's own classes the way its evaluator does; masks, counts and margins equal the
+    restatement's bit for bit (so parity blocks mean the same whichever of the two is available)."""
+    from oracle import ref_import as R, ref_run
+    from pemp_b200 import episodes as E
+    if not R.available():
+        pytest.skip("reference tree not present on this machine")
+    small = dict(channels=64, h=13, w=13, H=97, W=97, out_h=90, out_w=75)
+    for wl, spec in (("pemp_stage2", E.EpisodeSpec(shot=2, **small)), ("pemp_stage1", E.EpisodeSpec(shot=1, stages=1, **small)),
+                     ("baseline", E.EpisodeSpec(shot=1, stages=1, **small)),
+                     ("panet", E.EpisodeSpec(shot=3, stages=1, classes=80, cls_hi=80, **small))):
+        b = E.make_batch(spec, [5])
+        r = ref_run.runner(wl, spec)
+        assert r.kind == "reference"
+        a = r.episode(b)
+        r.kind = "port"
+        p = r.episode(b)
+        assert torch.equal(a["mask"], p["mask"]) and np.array_equal(a["stat"], p["stat"]) and a["margin"] == p["margin"]
+        assert a.get("align_loss") == p.get("align_loss")
