@@ -173,8 +173,8 @@ class PempWorkload:
             low = ops.mask_nearest_labels(masks.view(n * S, H, W), h, wd).view(n * S, 2, h * wd)
         else:
             low = ops.mask_nearest(masks.view(n * S, 2, H, W), h, wd).view(n * S, 2, h * wd)
-        return None, self.pipe.stage2_mask(b["feats1"], low, n, S, Q, tuple(b["qry_msk"].shape[-2:]), timer,
-                                           hist=(b["qry_msk"], b["cls"], st))
+        return None, self.pipe._head(b["feats1"], low, self.ctr1, n, S, Q, tuple(b["qry_msk"].shape[-2:]), timer,
+                                     hist=(b["qry_msk"], b["cls"], st))      # the stage-1 model: its own `ctr`
 
     def step(self, st, timer=None):
         return self._run(self.batch, st, timer, self.B)

@@ -119,6 +119,58 @@ upsample_ce_band_kernel(const float* __restrict__ rev, const float* __restrict__
   }
 }
 
+// Round-2 version of the banded kernel.  With two classes the loss of a pixel depends on the logits only through their
+// difference d = v1 - v0:  lse(v0, v1) - v_label = softplus(-d) for label 1 and softplus(d) for label 0, and bilinear
+// up-sampling is linear, so ONE plane (rev1 - rev0, formed while the horizontal pass reads the low-res rows) is up-sampled
+// instead of two: half the shared-memory rows, loads and lerps per pixel.  softplus(t) = max(t, 0) + log(1 + exp(-|t|)) with
+// ex2 / lg2 approximations (|error| < 3e-7 per pixel, the loss is a mean over S*H*W pixels compared at 1e-5).  A thread keeps
+// its columns and walks the rows of the band with the label loads of four rows in flight.
+#ifndef PEMP_CE_BAND
+#define PEMP_CE_BAND 32
+#endif
+constexpr int kCeBand2 = PEMP_CE_BAND;
+__global__ void __launch_bounds__(kCeThreads)
+upsample_ce_band2_kernel(const float* __restrict__ rev, const float* __restrict__ label, long long label_stride, int h, int w,
+                         int H, int W, float sy, float sx, int bands, float* __restrict__ partial) {
+  extern __shared__ float hrow[];                    // [nsrc][W]  horizontal pass of (rev1 - rev0)
+  const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
+  const int Y0 = band * kCeBand2, Y1 = min(H, Y0 + kCeBand2);
+  const int src0 = lerp_coeff(Y0, sy, h).i0, nsrc = lerp_coeff(Y1 - 1, sy, h).i1 - src0 + 1;
+  const int hw = h * w;
+  const float* p0 = rev + static_cast<long long>(n) * 2 * hw + src0 * w;
+  for (int X = threadIdx.x; X < W; X += kCeThreads) {
+    const Lerp lx = lerp_coeff(X, sx, w);
+    for (int r = 0; r < nsrc; ++r) {
+      const float* row = p0 + r * w;
+      const float a = __ldg(row + hw + lx.i0) - __ldg(row + lx.i0), b = __ldg(row + hw + lx.i1) - __ldg(row + lx.i1);
+      hrow[r * W + X] = lerp2(lx.l0, a, lx.l1, b);
+    }
+  }
+  __syncthreads();
+  const float* lab = label + n * label_stride;
+  float acc = 0.f;
+  for (int X = threadIdx.x; X < W; X += kCeThreads) {
+    const float* lcol = lab + static_cast<long long>(Y0) * W + X;
+#pragma unroll 4
+    for (int Y = Y0; Y < Y1; ++Y) {
+      const Lerp ly = lerp_coeff(Y, sy, h);
+      const float d = lerp2(ly.l0, hrow[(ly.i0 - src0) * W + X], ly.l1, hrow[(ly.i1 - src0) * W + X]);
+      const int lb = static_cast<int>(__ldg(lcol + static_cast<long long>(Y - Y0) * W));      // .long() truncation
+      const float t = lb == 1 ? -d : d;
+      acc += fmaxf(t, 0.f) + __logf(1.0f + __expf(-fabsf(t)));
+    }
+  }
+  __shared__ float part[kCeThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s2 = threadIdx.x < kCeThreads / 32 ? part[threadIdx.x] : 0.f;
+    s2 = warp_sum(s2);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s2;
+  }
+}
+
 // single CTA: add the block partials in index order in double, divide by the element count
 __global__ void ce_finalize_kernel(const float* __restrict__ partial, int n, double count, float* __restrict__ loss) {
   __shared__ double part[32];
@@ -143,7 +195,7 @@ Plan make_plan(int B, int S, int Q, int c, int h, int w, int H, int W) {
   const size_t hw = static_cast<size_t>(h) * w;
   long long total = static_cast<long long>(B) * S * H * W;
   p.ce_blocks = static_cast<int>(llmin((total + kCeThreads - 1) / kCeThreads, 148LL * 16));
-  const long long band_blocks = static_cast<long long>(B) * S * ((H + kCeBand - 1) / kCeBand);
+  const long long band_blocks = static_cast<long long>(B) * S * ((H + (kCeBand < kCeBand2 ? kCeBand : kCeBand2) - 1) / (kCeBand < kCeBand2 ? kCeBand : kCeBand2));
   if (band_blocks > p.ce_blocks) p.ce_blocks = static_cast<int>(band_blocks);   // the banded kernel writes one partial per band
   p.off_qmask = 0;
   p.off_proto = align_up(static_cast<size_t>(B) * Q * 2 * hw * sizeof(float), 256);
@@ -189,9 +241,20 @@ extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stri
   if (rc != PEMP_OK) return rc;
   long long total = static_cast<long long>(B) * S * H * W;
   const float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
+  int nparts;
+#ifndef PEMP_CE_V1
+  const int nsrc2 = static_cast<int>((kCeBand2 - 1) * sy) + 3;
+  const size_t smem2 = static_cast<size_t>(nsrc2 < h ? nsrc2 : h) * W * sizeof(float);
+  if (smem2 <= 48 * 1024) {
+    const int bands = (H + kCeBand2 - 1) / kCeBand2;
+    nparts = B * S * bands;
+    upsample_ce_band2_kernel<<<nparts, kCeThreads, smem2, st>>>(rev, sup_mask_fg, mask_stride, h, w, H, W, sy, sx, bands, partial);
+    ce_finalize_kernel<<<1, 256, 0, st>>>(partial, nparts, static_cast<double>(total), loss);
+    return launch_status();
+  }
+#endif
   const int nsrc_max = static_cast<int>((kCeBand - 1) * sy) + 3;
   const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
-  int nparts;
   if (nsrc_max <= kCeMaxSrc && smem <= 48 * 1024) {
     const int bands = (H + kCeBand - 1) / kCeBand;
     nparts = B * S * bands;

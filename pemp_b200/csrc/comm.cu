@@ -46,12 +46,13 @@ __global__ void comm_maxpool_kernel(const float* __restrict__ in, float* __restr
 
 constexpr int kCommThreads = 256;
 #ifndef PEMP_COMM_U
-#define PEMP_COMM_U 16
+#define PEMP_COMM_U 32
 #endif
 #ifndef PEMP_COMM_CTAS_PER_SM
 #define PEMP_COMM_CTAS_PER_SM 8
 #endif
-constexpr int kCU = PEMP_COMM_U;   // independent loads per lane
+constexpr int kCU = PEMP_COMM_U;   // independent loads per lane (ncu: the kernel waits for loads, long_scoreboard 24 warps per issue)
+constexpr int kCA = 4;             // accumulator chains per lane (the batch's values fold into them round robin)
 
 // stats[n][0][ch] = sum_x x*m / hw,  stats[n][1][ch] = max_x x*m.   kSmemMask: the image's mask is staged in smem.
 template <bool kSmemMask>
@@ -70,32 +71,40 @@ comm_pool_kernel(const float* __restrict__ x, const float* __restrict__ mask, in
   const float inv_hw = 1.0f / static_cast<float>(hw);
   for (int ch = c0 + warp; ch < c1; ch += kCommThreads / 32) {
     const float* row = x + (static_cast<long long>(n) * c + ch) * hw;
-    float s[kCU], mx[kCU];
+    float s[kCA], mx[kCA];
 #pragma unroll
-    for (int u = 0; u < kCU; ++u) {
+    for (int u = 0; u < kCA; ++u) {
       s[u] = 0.f;
       mx[u] = -CUDART_INF_F;
     }
     int i = lane;
-    for (; i + (kCU - 1) * 32 < hw; i += kCU * 32) {
+    for (; i + (kCU - 1) * 32 < hw; i += kCU * 32) {      // full batches: kCU unpredicated loads per lane in flight
       float v[kCU];
 #pragma unroll
       for (int u = 0; u < kCU; ++u) v[u] = __ldg(row + i + 32 * u);
 #pragma unroll
       for (int u = 0; u < kCU; ++u) {
         const float p = v[u] * (kSmemMask ? mp[i + 32 * u] : __ldg(mp + i + 32 * u));
-        s[u] += p;
-        mx[u] = fmaxf(mx[u], p);
+        s[u % kCA] += p;
+        mx[u % kCA] = fmaxf(mx[u % kCA], p);
       }
     }
-    for (; i < hw; i += 32) {
-      const float p = __ldg(row + i) * (kSmemMask ? mp[i] : __ldg(mp + i));
-      s[0] += p;
-      mx[0] = fmaxf(mx[0], p);
+    if (i < hw) {     // the last, partial batch of the row, issued the same way (hw = 10201: 31 of 32 loads)
+      float v[kCU];
+#pragma unroll
+      for (int u = 0; u < kCU; ++u) v[u] = (i + 32 * u < hw) ? __ldg(row + i + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < kCU; ++u) {
+        if (i + 32 * u < hw) {
+          const float p = v[u] * (kSmemMask ? mp[i + 32 * u] : __ldg(mp + i + 32 * u));
+          s[u % kCA] += p;
+          mx[u % kCA] = fmaxf(mx[u % kCA], p);
+        }
+      }
     }
     float st = 0.f, mt = -CUDART_INF_F;
 #pragma unroll
-    for (int u = 0; u < kCU; ++u) {      // fixed order
+    for (int u = 0; u < kCA; ++u) {      // fixed order
       st += s[u];
       mt = fmaxf(mt, mx[u]);
     }

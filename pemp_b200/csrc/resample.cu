@@ -507,18 +507,213 @@ __global__ void adjoint_combine_kernel(const float* __restrict__ ab, const float
   }
 }
 
+// ---- K6 adjoint, table-driven version (round 2) ---------------------------------------------------------------
+// adjoint_rows_kernel above spends most of a CTA's life before its first mask load: thread 0 walks lerp_coeff to find the row
+// range, a barrier, the row weights, a barrier, 401 lerp_coeff evaluations for the column coefficients.  All of that depends
+// only on (H, W, h, w): `adjoint_tables_kernel` (one CTA, once per call) writes
+//   rowinfo[y] = {first mask row with i0 == y, number of such rows},  wab[y][r] = {weight into row y, weight into row y + 1},
+//   xlo[x], xn[x], xw[x][t]: the contiguous run of mask columns that feed low-res column x and their weights,
+// and `adjoint_rows2_kernel` starts with its loads: CTA (y, image) reads the mask rows of NP planes (fg and bg of one support
+// image: 2 x 2 columns x ~8 rows = 32 independent loads per thread), one barrier, the column pass as a dot product with the
+// tap table (no compares), and the row sums.  Same a / b / rsum outputs as before, same combine kernel.
+constexpr int kAdjMaxTaps = 64;
+struct AdjTables {
+  int2* rowinfo;      // [h]
+  float2* wab;        // [h][kAdjMaxRows]
+  int2* xinfo;        // [w]  {xlo, xn}
+  float* xw;          // [kAdjMaxTaps][w]  (tap-major: the lanes of a warp own consecutive x and read consecutive floats)
+};
+__global__ void adjoint_tables_kernel(AdjTables t, int H, int W, int h, int w, float sy, float sx) {
+  for (int y = threadIdx.x; y < h; y += blockDim.x) {
+    int Ylo = 0, Yhi = H - 1;
+    if (sy > 0.f) {
+      Ylo = max(0, static_cast<int>(floorf(y / sy)) - 1);
+      Yhi = min(H - 1, static_cast<int>(ceilf((y + 1) / sy)) + 1);
+    }
+    while (Ylo <= Yhi && lerp_coeff(Ylo, sy, h).i0 != y) ++Ylo;
+    while (Yhi >= Ylo && lerp_coeff(Yhi, sy, h).i0 != y) --Yhi;
+    const int nr = max(0, Yhi - Ylo + 1);
+    t.rowinfo[y] = make_int2(Ylo, nr);
+    for (int r = 0; r < nr && r < kAdjMaxRows; ++r) {
+      const Lerp l = lerp_coeff(Ylo + r, sy, h);
+      t.wab[y * kAdjMaxRows + r] = make_float2(l.l0 + (l.i1 == y ? l.l1 : 0.f), l.i1 == y ? 0.f : l.l1);
+    }
+  }
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    int Xlo = 0, Xhi = W - 1;
+    if (sx > 0.f) {
+      Xlo = max(0, static_cast<int>(floorf((x - 1) / sx)) - 1);
+      Xhi = min(W - 1, static_cast<int>(ceilf((x + 1) / sx)) + 1);
+    }
+    int first = -1, n = 0;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      const Lerp lx = lerp_coeff(X, sx, w);
+      const float wgt = lx.i0 == x ? lx.l0 : ((lx.i0 + 1 == x && lx.i1 != lx.i0) ? lx.l1 : 0.f);
+      const bool feeds = lx.i0 == x || (lx.i0 + 1 == x && lx.i1 != lx.i0);
+      if (feeds) {
+        if (first < 0) first = X;
+        if (X - first < kAdjMaxTaps) t.xw[(X - first) * w + x] = wgt;
+        n = X - first + 1;
+      }
+    }
+    t.xinfo[x] = make_int2(first < 0 ? 0 : first, n);
+  }
+}
+
+// shared-memory index of column X: one pad float per 32 columns.  The column pass reads column xlo(x) + k with lane <-> x, i.e.
+// at a lane stride of ~W/w (8) floats - an 8-way bank conflict in a plain row (ncu: 10.1 M of 14.6 M wavefronts); with the pad
+// lanes 4m + j land on banks m + 8j: conflict-free, and the row pass (lane <-> consecutive X of one 32-aligned group) stays so.
+__device__ __forceinline__ int adj_pad(int X) { return X + (X >> 5); }
+__host__ __device__ constexpr int adj_row_floats(int W) { return W + (W >> 5) + 1; }
+
+#ifndef PEMP_ADJ_THREADS
+#define PEMP_ADJ_THREADS 128
+#endif
+#ifndef PEMP_ADJ_MINB
+#define PEMP_ADJ_MINB 8
+#endif
+constexpr int kAdjT = PEMP_ADJ_THREADS;
+constexpr int kAdjUnroll = 9;      // mask rows per low-res row at the usual 8x geometry: 8, 9 at some rows
+// KW > 0: the row pitch is a compile-time constant, so the (row, plane) offsets of a thread's loads are instruction immediates
+// (KW = 0 takes W from the argument; ncu of that version: 51 % of all instructions were 64-bit address arithmetic).
+template <int NP, int KW>
+__global__ void __launch_bounds__(kAdjT, PEMP_ADJ_MINB)
+adjoint_rows2_kernel(const float* __restrict__ mask, AdjTables t, float* __restrict__ ab, float* __restrict__ rsum, int H,
+                     int W_arg, int h, int w) {
+  const int W = KW > 0 ? KW : W_arg;
+  extern __shared__ float sh[];      // [NP][2][Wp]: A (-> row y) and B (-> row y + 1) of every plane, padded rows
+  __shared__ float red[NP][kAdjT / 32];
+  const int Wp = adj_row_floats(W);
+  const int y = blockIdx.x, img = blockIdx.y;
+  const int2 ri = t.rowinfo[y];
+  const int Ylo = ri.x, nr = ri.y;
+  const float2* __restrict__ wab = t.wab + y * kAdjMaxRows;
+  // 32-bit offsets from one CTA-uniform base: the first version spent 51 % of its instructions (ncu: IMAD / LEA / IADD3, 6.6 per
+  // load) on 64-bit address arithmetic of the form ((p * H + r) * W + X)
+  const float* m = mask + (static_cast<long long>(img) * NP * H + Ylo) * W;
+  const int PS = H * W;
+  float s[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) s[p] = 0.f;
+  for (int X = threadIdx.x; X < W; X += kAdjT) {
+    float a[NP], b[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) a[p] = b[p] = 0.f;
+    const float* q = m + X;
+    if (KW > 0 && nr <= kAdjUnroll) {
+      const float* qp[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) qp[p] = q + p * PS;
+#pragma unroll
+      for (int r = 0; r < kAdjUnroll; ++r) {
+        if (r < nr) {
+          const float2 wr = __ldg(wab + r);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const float v = __ldg(qp[p] + r * KW);
+            s[p] += v;
+            a[p] = fmaf(wr.x, v, a[p]);
+            b[p] = fmaf(wr.y, v, b[p]);
+          }
+        }
+      }
+    } else {
+      int off = 0;
+#pragma unroll 8
+      for (int r = 0; r < nr; ++r, off += W) {
+        const float2 wr = __ldg(wab + r);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const float v = __ldg(q + (off + p * PS));
+          s[p] += v;
+          a[p] = fmaf(wr.x, v, a[p]);
+          b[p] = fmaf(wr.y, v, b[p]);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      sh[(p * 2 + 0) * Wp + adj_pad(X)] = a[p];
+      sh[(p * 2 + 1) * Wp + adj_pad(X)] = b[p];
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    s[p] = warp_sum(s[p]);
+    if ((threadIdx.x & 31) == 0) red[p][threadIdx.x >> 5] = s[p];
+  }
+  __syncthreads();
+  if (threadIdx.x < NP) {
+    float tsum = 0.f;
+    for (int i = 0; i < kAdjT / 32; ++i) tsum += red[threadIdx.x][i];
+    rsum[(img * NP + threadIdx.x) * h + y] = tsum;
+  }
+  // column pass: output (plane p, which in {a, b}, x) = sum_t xw[x][t] * row[xlo[x] + t]
+  for (int i = threadIdx.x; i < NP * 2 * w; i += kAdjT) {
+    const int pw = i / w, x = i - pw * w;             // pw = p * 2 + which
+    const int2 xi = __ldg(t.xinfo + x);
+    const float* r = sh + pw * Wp;
+    const float* wx = t.xw + x;
+    float acc = 0.f;
+    int X = xi.x;
+    for (int k = 0; k < xi.y; ++k, ++X, wx += w) acc = fmaf(__ldg(wx), r[X + (X >> 5)], acc);
+    const int p = pw >> 1, which = pw & 1;
+    ab[((static_cast<long long>(img * NP + p) * h + y) * 2 + which) * w + x] = acc;
+  }
+}
+
+// instantiations for the mask widths of the reference's data sets (401 PASCAL, 417 COCO / PANet, 473 PFENet, 321); others: KW = 0
+template <int NP>
+static void adjoint_rows2_launch(dim3 grid, size_t smem, cudaStream_t st, const float* mask, AdjTables t, float* ab, float* rsum,
+                                 int H, int W, int h, int w) {
+  switch (W) {
+    case 401: adjoint_rows2_kernel<NP, 401><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 417: adjoint_rows2_kernel<NP, 417><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 473: adjoint_rows2_kernel<NP, 473><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 321: adjoint_rows2_kernel<NP, 321><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    default: adjoint_rows2_kernel<NP, 0><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+  }
+}
+
+static size_t adj_tables_bytes(int h, int w) {
+  return align_up(static_cast<size_t>(h) * sizeof(int2), 256) + align_up(static_cast<size_t>(h) * kAdjMaxRows * sizeof(float2), 256) +
+         align_up(static_cast<size_t>(w) * sizeof(int2), 256) + align_up(static_cast<size_t>(w) * kAdjMaxTaps * sizeof(float), 256);
+}
 size_t pemp_adjoint_scratch_bytes(int planes, int h, int w) {
-  return align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256) + align_up(static_cast<size_t>(planes) * h * sizeof(float), 256);
+  return align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256) + align_up(static_cast<size_t>(planes) * h * sizeof(float), 256) +
+         adj_tables_bytes(h, w);
 }
 int pemp_adjoint_launch(const float* mask, int planes, int H, int W, int h, int w, float* wt, float* msum, char* scratch,
                         cudaStream_t st) {
-  // the fast kernel keeps five rows of W floats in shared memory and at most kAdjMaxRows mask rows per low-res row
-  if (5 * W * sizeof(float) > 48 * 1024 || (H > h && (H + h - 1) / h + 2 > kAdjMaxRows))
+  // the fast kernels keep a few rows of W floats in shared memory and bound the rows / columns one low-res row / column owns
+  if (5 * W * sizeof(float) > 48 * 1024 || (H > h && (H + h - 1) / h + 2 > kAdjMaxRows) || (W > w && 2 * ((W + w - 1) / w) + 3 > kAdjMaxTaps))
     return pemp_bilinear_adjoint(mask, planes, H, W, h, w, wt, msum, reinterpret_cast<pemp_stream_t>(st));
   float* ab = reinterpret_cast<float*>(scratch);
-  float* rsum = reinterpret_cast<float*>(scratch + align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256));
-  adjoint_rows_kernel<<<dim3(h, planes), 256, 5 * W * sizeof(float), st>>>(mask, ab, rsum, H, W, h, w, lerp_scale(h, H),
-                                                                          lerp_scale(w, W));
+  char* p = scratch + align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256);
+  float* rsum = reinterpret_cast<float*>(p);
+  p += align_up(static_cast<size_t>(planes) * h * sizeof(float), 256);
+  AdjTables t;
+  t.rowinfo = reinterpret_cast<int2*>(p);
+  p += align_up(static_cast<size_t>(h) * sizeof(int2), 256);
+  t.wab = reinterpret_cast<float2*>(p);
+  p += align_up(static_cast<size_t>(h) * kAdjMaxRows * sizeof(float2), 256);
+  t.xinfo = reinterpret_cast<int2*>(p);
+  p += align_up(static_cast<size_t>(w) * sizeof(int2), 256);
+  t.xw = reinterpret_cast<float*>(p);
+  const float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
+#ifdef PEMP_ADJ_V1
+  adjoint_rows_kernel<<<dim3(h, planes), 256, 5 * W * sizeof(float), st>>>(mask, ab, rsum, H, W, h, w, sy, sx);
+#else
+  adjoint_tables_kernel<<<1, 256, 0, st>>>(t, H, W, h, w, sy, sx);
+#ifdef PEMP_ADJ_NP1
+  if (false)
+#else
+  if (planes % 2 == 0)
+#endif
+    adjoint_rows2_launch<2>(dim3(h, planes / 2), 4 * adj_row_floats(W) * sizeof(float), st, mask, t, ab, rsum, H, W, h, w);
+  else
+    adjoint_rows2_launch<1>(dim3(h, planes), 2 * adj_row_floats(W) * sizeof(float), st, mask, t, ab, rsum, H, W, h, w);
+#endif
   adjoint_combine_kernel<<<planes, 256, 0, st>>>(ab, rsum, wt, msum, h, w);
   return launch_status();
 }
