@@ -52,7 +52,7 @@ WORKLOADS = {
     "pfenet_5shot": dict(kind="pfenet", shot=5, batch=8, config=5, C=2048, sp=60, image=473, c_mid=256,
                          desc="PFENet ResNet-50 5-shot prior-mask stress test (3600 x 3600 x 2048 contraction per shot) + Weighted_GAP"),
 }
-MARGIN = 1e-5
+MARGIN = 2e-5
 
 
 def parse():
@@ -438,7 +438,7 @@ def config_of(args, wl, w, world):
         cfg.update({"query": s.query, "channels": s.channels, "feature_hw": [s.h, s.w], "image_hw": [s.H, s.W], "protos": s.protos,
                     "classes": s.classes})
         from pemp_b200 import episodes as E
-        cfg["episodes"] = dict(E.screen_stats(w["screen"], s), note="margin-screened synthetic episodes (min reference |fg-bg| >= 1e-5)",
+        cfg["episodes"] = dict(E.screen_stats(w["screen"], s), note="margin-screened synthetic episodes (min reference |fg-bg| >= the threshold)",
                                repeated_to_fill_batch=wl.repeated)
     else:
         cfg.update({"channels": w["C"], "feature_hw": [w["sp"], w["sp"]], "image_hw": [w["image"], w["image"]],
@@ -521,16 +521,28 @@ def run_ours(args):
     B = wl.B
     peaks, how = measured_peaks()
 
+    ar_events = []
+
     def loop(n, st, timer=None):
         for _ in range(n):
             wl.step(st, timer)
-        if st is not None:
-            pdist.all_reduce_stat(st)          # once per evaluation round, inside the timed region
+        if st is not None:                     # once per evaluation round, inside the timed region
+            if world > 1:
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                pdist.all_reduce_stat(st)
+                a1.record()
+                ar_events.append((a0, a1))
+            else:
+                pdist.all_reduce_stat(st)
 
     # ---------------- value: device-resident inputs ------------------------------------------------------
+    import gc
     scratch = wl.new_result()
-    loop(max(args.warmup, 3), scratch)
+    loop(max(args.warmup, 3), scratch, KernelTimer())       # warm-up through the same code path (event pool, allocator, NCCL)
     torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()                                              # no collector pause inside a 17 ms timed region
     pdist.barrier()
     timer = KernelTimer()
     stat = wl.new_result()
@@ -544,8 +556,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall1 = time.time()
     launches = ops.launch_count() - launches0
+    gc.enable()
     pdist.barrier()
     ms_total = pdist.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    ms_mine = ev0.elapsed_time(ev1)
+    allreduce_ms = ar_events[-1][0].elapsed_time(ar_events[-1][1]) if ar_events else None     # includes waiting for the slowest rank
     ms_per_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total / 1e3)
 
@@ -715,7 +730,10 @@ def run_ours(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32" if w["kind"] != "pfenet" else f"f32 in / {args.prior_precision} tensor-core products, f32 accumulate",
                "data": "synthetic", "config": config_of(args, wl, w, world), "clocks": clocks, "e2e": e2e, "sustained": sustained,
-               "graphed": graphed, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+               "graphed": graphed, "gpu_launches": launches, "allreduce": None if allreduce_ms is None else {
+                   "ms_on_rank0": allreduce_ms, "rank0_timed_region_ms": ms_mine, "max_over_ranks_ms": ms_total,
+                   "note": "one all-reduce of the count table per evaluation round, issued after the K steps; its time on a rank "
+                           "includes waiting for the slowest rank"}, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                "episode_roofline": {"algorithmic_MB_per_episode": wl.alg_bytes_per_episode / 1e6, "episodes_per_s_at_hbm_peak": hbm_eps,
                                     "frac": (value / world) / hbm_eps, "note": "whole step against the HBM roofline of its algorithmic bytes"},
                "roofline_extra": extra}

@@ -203,7 +203,10 @@ int pemp_comm_module(const float* x, const float* mask_in, int N, int c, int h, 
  *   d_fts + b * d_fts_episode_stride + s * c * hw; stride 0 = dense [B*S, c, hw] - a non-zero stride writes straight into
  *   the support half of the gradient of the encoder output [B, S+Q, c, hw]), d_ctr [c, 2p].  Masks get no gradient.
  * pemp_cosine_match_bwd: g_pred [N, 2, hw] = gradient of pred (after the max over prototypes; the arg-max is recomputed,
- *   first maximum wins)  ->  d_qry (same addressing with d_qry_episode_stride), d_fg / d_bg [Bp, c, P].  c <= 1024.   */
+ *   first maximum wins)  ->  d_qry (same addressing with d_qry_episode_stride), d_fg / d_bg [Bp, c, P].  c <= 1024.
+ * pemp_cosine_sim_bwd: the same for the per-prototype maps of `compute_similarity` used on their own under autograd
+ *   (networks/pemp_stage1.py:233-261, baseline.py:121-149, panet.py:122-156): g_sim [N, 2, P, hw] = gradient of
+ *   `sim` of pemp_cosine_match (channel 0 background), no arg-max.  Workspace: pemp_cosine_match_bwd_workspace_bytes. */
 int pemp_meta_proto_attn_train(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
                                const float* bg, long long mask_stride, int B, int S, int c, int hw, int p, float eps,
                                float* fg_proto, float* bg_proto, float* shot_centre, float* shot_den, void* workspace,
@@ -219,6 +222,10 @@ int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const 
                           const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
                           long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes,
                           pemp_stream_t stream);
+int pemp_cosine_sim_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
+                        const float* g_sim, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
+                        long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes,
+                        pemp_stream_t stream);
 
 /* backward of pemp_map_pool_lowres (K1; training path of the baseline and PANet heads, entry/panet.py:108-115):
  * g_fg / g_bg [B, c] -> d_fts, addressed like pemp_meta_proto_attn_bwd's.  bg and g_bg may both be NULL.            */

@@ -44,7 +44,7 @@ def _pemp_case(name, spec, B, ctr_stage, store_inputs, ret_ind=True, out_shape=N
     indices = list(range(first, first + B))
     if screened:
         # margin screen (SURVEY 7 hard part 2): the first B episodes >= first whose smallest |fg - bg| logit gap through the
-        # reference head is >= 1e-5, so that masks and counts of the fixture can be compared bit for bit
+        # reference head is >= screen.THRESHOLD, so that masks and counts of the fixture can be compared bit for bit
         from oracle import screen
         indices, i = [], first
         while len(indices) < B:

@@ -20,7 +20,12 @@ import torch
 from oracle import restate as O
 from pemp_b200 import episodes as E
 
-THRESHOLD = 1e-5          # ~5 ulp of a logit of magnitude 20 (hard part 2)
+# SURVEY 7 (hard part 2) proposed 1e-5 (~5 ulp of a logit of magnitude 20).  Measured on the B200 (tools/probes/margin_probe.py,
+# profiles/r02_margin_probe.txt): over 384 heads x 160 801 pixels of raw episodes the kernels' decision variable differs from
+# the reference's by up to 8.7e-5 at isolated pixels (median of the per-head maximum 1.1e-5 - both evaluations carry ~5e-6
+# norm-wise fp32 rounding of |logit| <= 20), and the 8 pixels that flipped had reference margins of 7e-7 .. 1.01e-5.  The screen
+# therefore rejects below 2e-5: twice the largest margin at which a flip was ever observed.
+THRESHOLD = 2e-5
 TABLE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pemp_b200", "episode_screen.json")
 
 
@@ -70,9 +75,9 @@ def screen(workload, spec, candidates, threshold=THRESHOLD, verbose=False):
 
 # the workloads bench.py and the parity tests draw screened episodes from
 WORKLOADS = {
-    "pemp_stage2": (E.EpisodeSpec(shot=5, stages=2), 1000),
-    "pemp_stage1": (E.EpisodeSpec(shot=1, stages=1), 256),
-    "baseline": (E.EpisodeSpec(shot=1, stages=1), 24),
+    "pemp_stage2": (E.EpisodeSpec(shot=5, stages=2), 1900),
+    "pemp_stage1": (E.EpisodeSpec(shot=1, stages=1), 400),
+    "baseline": (E.EpisodeSpec(shot=1, stages=1), 32),
     "panet": (E.EpisodeSpec(shot=5, stages=1, classes=80, cls_lo=1, cls_hi=80), 16),
 }
 
@@ -87,7 +92,8 @@ def main():
             continue
         rejected, margins = screen(name, spec, n, verbose=True)
         table[E.screen_key(name, spec)] = {"threshold": THRESHOLD, "candidates": n, "rejected": rejected,
-                                           "rejection_rate": len(rejected) / n, "median_min_margin": sorted(margins)[n // 2]}
+                                           "rejection_rate": len(rejected) / n, "median_min_margin": sorted(margins)[n // 2],
+                                           "min_margins": [float(f"{m:.3e}") for m in margins]}
         print(name, "rejected", len(rejected), "of", n)
     json.dump(table, open(TABLE, "w"), indent=1, sort_keys=True)
 

@@ -30,6 +30,7 @@ SIGNATURES = {
     "pemp_meta_proto_attn_bwd": (I, [P, LL, P, P, P, LL, P, P, P, P, I, I, I, I, I, P, LL, P, P, SZ, P]),
     "pemp_cosine_match_bwd_workspace_bytes": (SZ, [I, I, I, I, I]),
     "pemp_cosine_match_bwd": (I, [P, LL, P, P, P, I, I, I, I, I, F, P, LL, P, P, P, SZ, P]),
+    "pemp_cosine_sim_bwd": (I, [P, LL, P, P, P, I, I, I, I, I, F, P, LL, P, P, P, SZ, P]),
     "pemp_map_pool_lowres_bwd": (I, [P, P, LL, P, P, I, I, I, I, F, P, LL, P]),
     "pemp_canet_concat": (I, [P, LL, P, I, I, I, I, P, P]),
     "pemp_upsample_ce_workspace_bytes": (SZ, [I, I, I, I, I]),

@@ -51,6 +51,30 @@ class _CosineMatch(torch.autograd.Function):
         return d_qry.view(qry.shape), d_fg, d_bg, None
 
 
+class _CosineSim(torch.autograd.Function):
+    """The per-prototype similarity maps of `compute_similarity` (pemp_stage1.py:233-261) with their backward kernel
+    (`pemp_cosine_sim_bwd`: the gradient tile is a rank-2P combination of the normalised prototypes)."""
+
+    @staticmethod
+    def forward(ctx, qry_fts, fg_proto, bg_proto, scalar):
+        out = ops.cosine_match(qry_fts, fg_proto, bg_proto, scalar, want_sim=True, want_pred=False)["sim"]
+        ctx.save_for_backward(qry_fts, fg_proto, bg_proto)
+        ctx.scalar = scalar
+        return out
+
+    @staticmethod
+    def backward(ctx, g_sim):
+        qry, fgp, bgp = ctx.saved_tensors
+        d_qry, d_fg, d_bg = ops.cosine_match_bwd(qry, fgp, bgp, g_sim.contiguous(), ctx.scalar, dense=True)
+        return d_qry.view(qry.shape), d_fg, d_bg, None
+
+
+def cosine_sim(qry_fts, fg_proto, bg_proto, scalar=20.0):
+    """qry_fts [N, c, hw]; prototypes [Bp, c] or [Bp, c, P] -> sim [N, 2, P, hw] (channel 0 background), differentiable in
+    all three."""
+    return _CosineSim.apply(qry_fts, fg_proto, bg_proto, scalar)
+
+
 class _MapPoolLowres(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sup_fts, fg, bg, eps):

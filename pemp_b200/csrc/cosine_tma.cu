@@ -52,9 +52,12 @@ constexpr int kPLd = 29;                         // pixel pitch of a value row i
 constexpr int kMaxGrid = 148;
 constexpr float kCosEps = 1e-8f;
 
+#ifndef PEMP_COS_DUP
+#define PEMP_COS_DUP 0      // 1: table rows as {p0,p0,p1,p1,...} (FFMA2 operands as loaded, 3 LDS.128 per row at K = 6); 0: {p0,p1,...}
+#endif                      // (LDS.128 + LDS.64 and one register copy per value: fewer shared-memory wavefronts - ncu: the pipe is the limit)
 template <int K>
 struct CosSmem {
-  static constexpr int TL = (2 * K + 3) / 4 * 4;  // floats per table row: {p0,p0,p1,p1,...}
+  static constexpr int TL = PEMP_COS_DUP ? (2 * K + 3) / 4 * 4 : (K + 1) / 2 * 2;  // floats per table row
   alignas(1024) float ring[kNB][kBoxFloats];
   alignas(16) float table[kC * TL];
   alignas(16) float part[kPB][kCons][(1 + K) * kPLd]; // [buffer][warp][value][pixel], odd pitch: see finalize
@@ -223,8 +226,12 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
 #pragma unroll
         for (int w2 = 0; w2 < kCons; ++w2) ss += sm.red[w2][kk];
         const float v = raw[kk] * (1.0f / fmaxf(sqrtf(ss), kCosEps));
-        sm.table[R * TL + 2 * kk] = v;
-        sm.table[R * TL + 2 * kk + 1] = v;
+        if (PEMP_COS_DUP) {
+          sm.table[R * TL + 2 * kk] = v;
+          sm.table[R * TL + 2 * kk + 1] = v;
+        } else {
+          sm.table[R * TL + kk] = v;
+        }
       }
       named_bar(1, kCons * 32);
     }
@@ -247,8 +254,14 @@ cosine_tma_kernel(const __grid_constant__ CUtensorMap map, int Qper, int hw, int
       acc[1][0] = ffma2(f23, f23, acc[1][0]);
 #pragma unroll
       for (int kk = 0; kk < K; kk += 2) {
-        const float4 t4 = *reinterpret_cast<const float4*>(trow + 2 * kk);
-        const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
+        float2 ta, tb;
+        if (PEMP_COS_DUP) {
+          const float4 t4 = *reinterpret_cast<const float4*>(trow + 2 * kk);
+          ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
+        } else {
+          const float2 t2 = *reinterpret_cast<const float2*>(trow + kk);
+          ta = make_float2(t2.x, t2.x), tb = make_float2(t2.y, t2.y);
+        }
         acc[0][1 + kk] = ffma2(f01, ta, acc[0][1 + kk]);
         acc[1][1 + kk] = ffma2(f23, ta, acc[1][1 + kk]);
         acc[0][2 + kk] = ffma2(f01, tb, acc[0][2 + kk]);

@@ -59,7 +59,10 @@ constexpr int kBoxRows = kC / 4;                 // 128 channel groups
 constexpr int kBoxFloats = kBoxRows * kTW;       // 4096
 constexpr uint32_t kBoxBytes = kBoxFloats * 4;   // 16 KB
 #ifndef PEMP_MPA_TMA_DUP
-#define PEMP_MPA_TMA_DUP 1                       // table rows as {t0,t0,t1,t1,t2,t2,t3,t3}: no MOVs to form FFMA2 operands
+#define PEMP_MPA_TMA_DUP 0                       // 1: table rows as {t0,t0,t1,t1,t2,t2,t3,t3} (FFMA2 operands as loaded, two LDS.128 per row);
+                                                 // 0: {t0,t1,t2,t3}, one LDS.128 + four register copies.  Round 1 measured 1 as +6 %; with
+                                                 // the softmax warps and the 12-slot ring the shared-memory pipe became the limit
+                                                 // (ncu: 76 % busy, table loads 2/3 of phase A's wavefronts) and 0 is +3.5 % (r02)
 #endif
 #ifndef PEMP_MPA_TMA_SLOTS
 #define PEMP_MPA_TMA_SLOTS 12                     // 3 tiles: two held by the consumers, one in flight (11 slots: -10 %)
@@ -125,36 +128,9 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   const int G = gridDim.x, cta = blockIdx.x;
   const long long t0 = T * cta / G, t1 = T * (cta + 1) / G;
 
-  for (int i = tid; i < kC * 4; i += kThreadsT) {
-    const int R = i >> 2, d = i & 3;
-    const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
-    const int g = d >> 1, j = (d & 1) + 1;
-    // exact difference, then one rounding of the product with 2 log2(e): the dots come out in log2 units
-    const float v = static_cast<float>(2.8853900817779268 *
-                                       (static_cast<double>(__ldg(ctr + ch * kK + g * kP + j)) - __ldg(ctr + ch * kK + g * kP)));
-    if (kTD == 8) {
-      sm.table[R * 8 + 2 * d] = v;
-      sm.table[R * 8 + 2 * d + 1] = v;
-    } else {
-      sm.table[R * 4 + d] = v;
-    }
-  }
-  if (warp < 4) {
-    const int g = warp >> 1, j = (warp & 1) + 1;
-    double s = 0.0;
-    for (int ch = lane; ch < kC; ch += 32) {
-      const double a = __ldg(ctr + ch * kK + g * kP + j), b = __ldg(ctr + ch * kK + g * kP);
-      s += (a - b) * (a + b);
-    }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-    if (lane == 0) sm.konst[warp] = static_cast<float>(-s * 1.4426950408889634);
-  }
-  // partials an image ends up with = CTAs its tile range touches (64-bit divisions: once per image, for the finalize)
-  for (int i = cta * kThreadsT + tid; i < imgs; i += G * kThreadsT) {
-    const long long first = static_cast<long long>(i) * nt_img;
-    nparts[i] = owner_of(first + nt_img - 1, T, G) - owner_of(first, T, G) + 1;
-  }
-  for (int i = tid; i < 2 * 2 * 2 * kWPairs * 8; i += kThreadsT) (&sm.wpx[0][0][0][0])[i] = 0.f;   // padding stays 0
+  // The mbarriers come first so that the producer can start filling the ring while the other 19 warps build the table:
+  // the first boxes are on their way during the ~3 us of prologue (matters for short launches: 64 one-shot images give
+  // every CTA only 40 tiles).
   if (tid == 0) {
     for (int s = 0; s < kNB; ++s) {
       mbar_init(&sm.full[s], 1);
@@ -168,10 +144,51 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  // register re-allocation first (whole warpgroups), so that the producer can leave at once
+  if (warp >= kCons) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCons));
+  }
+  constexpr int kBuild = kCons * 32;                            // the 16 consumer warps build the table
+  constexpr int kAfterBuild = kBuild + 64;                      // ... and the two softmax warps wait for it with them
+  if (warp < kCons) {
+    const int tix = tid;
+    for (int i = tix; i < kC * 4; i += kBuild) {
+      const int R = i >> 2, d = i & 3;
+      const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
+      const int g = d >> 1, j = (d & 1) + 1;
+      // exact difference, then one rounding of the product with 2 log2(e): the dots come out in log2 units
+      const float v = static_cast<float>(2.8853900817779268 *
+                                         (static_cast<double>(__ldg(ctr + ch * kK + g * kP + j)) - __ldg(ctr + ch * kK + g * kP)));
+      if (kTD == 8) {
+        sm.table[R * 8 + 2 * d] = v;
+        sm.table[R * 8 + 2 * d + 1] = v;
+      } else {
+        sm.table[R * 4 + d] = v;
+      }
+    }
+    if (warp < 4) {
+      const int g = warp >> 1, j = (warp & 1) + 1;
+      double s = 0.0;
+      for (int ch = lane; ch < kC; ch += 32) {
+        const double a = __ldg(ctr + ch * kK + g * kP + j), b = __ldg(ctr + ch * kK + g * kP);
+        s += (a - b) * (a + b);
+      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+      if (lane == 0) sm.konst[warp] = static_cast<float>(-s * 1.4426950408889634);
+    }
+    // partials an image ends up with = CTAs its tile range touches (64-bit divisions: once per image, for the finalize)
+    for (int i = cta * kBuild + tix; i < imgs; i += G * kBuild) {
+      const long long first = static_cast<long long>(i) * nt_img;
+      nparts[i] = owner_of(first + nt_img - 1, T, G) - owner_of(first, T, G) + 1;
+    }
+    for (int i = tix; i < 2 * 2 * 2 * kWPairs * 8; i += kBuild) (&sm.wpx[0][0][0][0])[i] = 0.f;   // padding stays 0
+    named_bar(1, kAfterBuild);                                // table / constants / zero padding visible to consumers + softmax warps
+  }
 
   if (warp >= kCons) {
     // ============================ producer: one lane feeds the ring ============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProd));
     if (warp == kCons && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
       int slot = 0;
@@ -205,6 +222,7 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
       // turns them into the 3 weights of its group (x mask) and publishes them in both pair alignments, together with
       // the live-pixel bit mask; it also owns the denominators of its group.  The consumers never compute a weight.
       const int g = warp - kCons - 1;
+      named_bar(1, kAfterBuild);                              // konst / zeroed weight padding written by the consumer warps
       const float k0 = sm.konst[g * 2], k1 = sm.konst[g * 2 + 1];
       const float* mrow = g ? bg : fg;
       const int pl = lane < kStep ? lane : kStep - 1;             // clamped pixel for addressing
@@ -266,7 +284,6 @@ mpa_tma_kernel(const __grid_constant__ CUtensorMap map, int S, int hw, int nt_im
   }
 
   // ============================ consumers ============================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCons));
   // a scheduler (warp & 3) hosts one channel class with all four column groups: with e = warp >> 2 it hosted one
   // column group of all classes, and the group whose last columns are outside the tile had less to do (+1.3 %)
   const int e = warp & 3, cp = warp >> 2;

@@ -159,7 +159,11 @@ __device__ __forceinline__ void cos_bwd_phase_b1(float* __restrict__ dst, int c,
   }
 }
 
-template <int K>
+// DENSE = false: g_pred [N][2][hw], gradient of pred = max over the prototypes of a class (first maximum wins, recomputed here).
+// DENSE = true : g_pred is g_sim [N][K][hw], the gradient of every per-prototype map of `compute_similarity`
+//                (pemp_stage1.py:233-261; k < P background, k >= P foreground = its channel order): no arg-max, the gradient
+//                tile is a rank-K combination of the table rows.
+template <int K, bool DENSE>
 __global__ void __launch_bounds__(kBT, 2)
 cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, const float* __restrict__ pn,
                   const float* __restrict__ g_pred, int c, int hw, int ntiles, float scalar, float* __restrict__ dq,
@@ -221,8 +225,16 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
       const float nq = sqrtf(sum[KP * 32 + lane]);
       const float invq = 1.0f / fmaxf(nq, kCosEps);
       float tsum = 0.f;
+      if (DENSE) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+        for (int k = 0; k < K; ++k) {
+          const float gk = inb ? __ldg(g_pred + (static_cast<long long>(n) * K + k) * hw + x) * scalar : 0.f;
+          wts[lane * KP + k] = gk * invq;
+          tsum = fmaf(gk, sum[k * 32 + lane], tsum);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 2 && !DENSE; ++g) {
         int best = 0;
         float bv = sum[(g * P) * 32 + lane];
 #pragma unroll
@@ -244,7 +256,26 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
       tq[lane] = (nq < kCosEps) ? 0.f : tsum * invq * invq * invq;
     }
     __syncthreads();
-    {   // B1: dq tile
+    if (DENSE) {   // B1: dq tile = sum_k a_k pn_k - t q
+      float a[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[k] = wts[lane * KP + k];
+      const float tv = -tq[lane];
+      float* dst = dq + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(qi) * c * hw + x +
+                   static_cast<long long>(warp) * hw;
+      const float* tp = tile + warp * kLd + lane;
+      const float* rp = tab + warp * K;
+      const long long gstep = static_cast<long long>(kBW) * hw;
+      for (int ch = warp; ch < c; ch += kBW) {
+        float val = tv * *tp;
+#pragma unroll
+        for (int k = 0; k < K; ++k) val = fmaf(a[k], rp[k], val);
+        if (inb) *dst = val;
+        dst += gstep;
+        tp += kBW * kLd;
+        rp += kBW * K;
+      }
+    } else {   // B1: dq tile
       const float c0 = cg[lane], c1 = cg[32 + lane], tv = -tq[lane];
       const int s0 = sel[lane], s1 = sel[32 + lane];
       float* dst = dq + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(qi) * c * hw + x;
@@ -637,13 +668,13 @@ size_t mpa_smem(int c, int K) {
   return (static_cast<size_t>(c) * kLd + 2 * static_cast<size_t>(c) * KP + kBW * NA * 32 + NA * 32 + 2 * 32 * KP + 2 * K) * 4;
 }
 
-template <int K>
+template <int K, bool DENSE>
 int launch_cos_bwd(const float* qry, long long ep, int Q, const float* pn, const float* g_pred, int N, int c, int hw,
                    const BwdPlan& pl, float scalar, float* dq, long long d_ep, float* part, cudaStream_t st) {
   const size_t smem = cos_smem(c, K);
-  cudaError_t e = cudaFuncSetAttribute(cosine_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(cosine_bwd_kernel<K, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  cosine_bwd_kernel<K><<<dim3(pl.chunks, N), kBT, smem, st>>>(qry, ep, Q, pn, g_pred, c, hw, pl.ntiles, scalar, dq, d_ep, part);
+  cosine_bwd_kernel<K, DENSE><<<dim3(pl.chunks, N), kBT, smem, st>>>(qry, ep, Q, pn, g_pred, c, hw, pl.ntiles, scalar, dq, d_ep, part);
   return PEMP_OK;
 }
 template <int K>
@@ -736,11 +767,11 @@ extern "C" size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, in
          align_up(static_cast<size_t>(N) * pl.chunks * c * K * 4, 256);
 }
 
-extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
-                                     const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
-                                     long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace,
-                                     size_t workspace_bytes, pemp_stream_t stream) {
-  PEMP_REQUIRE(qry && fg_proto && bg_proto && g_pred && d_qry && d_fg && d_bg, PEMP_E_NULL);
+namespace {
+int cosine_bwd_common(bool dense, const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
+                      const float* g, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry, long long d_qry_episode_stride,
+                      float* d_fg, float* d_bg, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(qry && fg_proto && bg_proto && g && d_qry && d_fg && d_bg, PEMP_E_NULL);
   PEMP_REQUIRE(N > 0 && N <= 65535 && Bp > 0 && c > 0 && hw > 0 && N % Bp == 0, PEMP_E_SHAPE);
   PEMP_REQUIRE(P >= 1 && P <= 4 && c <= kMaxCPT * kBT && cos_smem(c, 2 * P) <= 227 * 1024, PEMP_E_SHAPE);
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_cosine_match_bwd_workspace_bytes(N, Bp, c, hw, P), PEMP_E_WORKSPACE);
@@ -755,15 +786,36 @@ extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_str
   const long long d_ep = d_qry_episode_stride ? d_qry_episode_stride : static_cast<long long>(Q) * c * hw;
   proto_norm_kernel<<<Bp, kBT, 0, st>>>(fg_proto, bg_proto, c, P, pn, nrm);
   int rc;
+#define PEMP_COS_BWD(KK)                                                                                                        \
+  rc = dense ? launch_cos_bwd<KK, true>(qry, ep, Q, pn, g, N, c, hw, pl, scalar, d_qry, d_ep, part, st)                        \
+             : launch_cos_bwd<KK, false>(qry, ep, Q, pn, g, N, c, hw, pl, scalar, d_qry, d_ep, part, st)
   switch (P) {
-    case 1: rc = launch_cos_bwd<2>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
-    case 2: rc = launch_cos_bwd<4>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
-    case 3: rc = launch_cos_bwd<6>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
-    default: rc = launch_cos_bwd<8>(qry, ep, Q, pn, g_pred, N, c, hw, pl, scalar, d_qry, d_ep, part, st); break;
+    case 1: PEMP_COS_BWD(2); break;
+    case 2: PEMP_COS_BWD(4); break;
+    case 3: PEMP_COS_BWD(6); break;
+    default: PEMP_COS_BWD(8); break;
   }
+#undef PEMP_COS_BWD
   if (rc != PEMP_OK) return rc;
   cosine_bwd_finalize_kernel<<<Bp, kBT, 0, st>>>(part, pn, nrm, Q, pl.chunks, c, P, d_fg, d_bg);
   return launch_status();
+}
+}  // namespace
+
+extern "C" int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
+                                     const float* g_pred, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
+                                     long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace,
+                                     size_t workspace_bytes, pemp_stream_t stream) {
+  return cosine_bwd_common(false, qry, qry_episode_stride, fg_proto, bg_proto, g_pred, N, Bp, c, hw, P, scalar, d_qry,
+                           d_qry_episode_stride, d_fg, d_bg, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pemp_cosine_sim_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
+                                   const float* g_sim, int N, int Bp, int c, int hw, int P, float scalar, float* d_qry,
+                                   long long d_qry_episode_stride, float* d_fg, float* d_bg, void* workspace,
+                                   size_t workspace_bytes, pemp_stream_t stream) {
+  return cosine_bwd_common(true, qry, qry_episode_stride, fg_proto, bg_proto, g_sim, N, Bp, c, hw, P, scalar, d_qry,
+                           d_qry_episode_stride, d_fg, d_bg, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p) {

@@ -3,8 +3,10 @@
 Function names, argument order and return shapes follow the reference methods they replace, so they can be
 bound onto the reference classes unchanged (`pemp_b200.dropin.patch`) or used through the small stand-alone
 classes at the bottom.  Sacred-injected config values (`dist_scalar=20`, `protos=3`; `pemp_stage1.py:21-29`)
-are ordinary keyword defaults here.  Everything is forward-only (the reference evaluates under
-`torch.no_grad()`, `core/base_trainer.py:69`) and runs on CUDA tensors only.
+are keyword arguments here (injected by the reference's own Sacred ingredient once `dropin.patch()` re-applies its `capture`).
+Under `torch.no_grad()` (`core/base_trainer.py:69`) the forward-only kernels run; when autograd is recording and an input
+requires grad every function takes a differentiable path (`pemp_b200.autograd`), so a patched model trains correctly.
+CUDA tensors only.
 """
 import torch
 import torch.nn as nn
@@ -47,17 +49,16 @@ def compute_similarity(self, fg_proto, bg_proto, qry_fts, dist_scalar=None):
     fg_proto / bg_proto [B, c, p] with qry_fts [N, c, 1, h, w] -> [N, 2, p, h, w]
     Channel 0 is background, 1 foreground.  N may be a multiple of B (prototypes are expanded b-major,
     panet.py:145-149)."""
-    if _wants_grad(fg_proto, bg_proto, qry_fts):
-        raise NotImplementedError("compute_similarity is forward-only (the per-prototype maps have no backward kernel); "
-                                  "training goes through mpm / pemp_b200.autograd.cosine_match, which fuse the max over "
-                                  "prototypes as the reference's mpm does right after this call")
     if qry_fts.dim() == 5:                      # PEMP passes [N, c, 1, h, w] (pemp_stage1.py:196)
         N, c, _, h, w = qry_fts.shape
     else:
         N, c, h, w = qry_fts.shape
-    out = ops.cosine_match(qry_fts.reshape(N, c, h * w), fg_proto, bg_proto, _scalar(self, dist_scalar), want_sim=True,
-                           want_pred=False)
-    sim = out["sim"]                                              # [N, 2, P, hw]
+    if _wants_grad(fg_proto, bg_proto, qry_fts):        # training: same forward kernel + pemp_cosine_sim_bwd
+        from . import autograd as A
+        sim = A.cosine_sim(qry_fts.reshape(N, c, h * w), fg_proto, bg_proto, _scalar(self, dist_scalar))
+    else:
+        sim = ops.cosine_match(qry_fts.reshape(N, c, h * w), fg_proto, bg_proto, _scalar(self, dist_scalar), want_sim=True,
+                               want_pred=False)["sim"]
     if fg_proto.dim() == 2:
         return sim.view(N, 2, h, w)
     return sim.view(N, 2, fg_proto.shape[2], h, w)

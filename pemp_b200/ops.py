@@ -528,9 +528,10 @@ def meta_proto_attn_bwd(saved, g_fg, g_bg, B, S, out=None):
 
 
 @_on_device
-def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0, out=None):
+def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0, out=None, dense=False):
     """Backward of `cosine_match(...)["pred"]`: qry as in the forward, g_pred [N, 2, hw] -> (d_qry [N, c, hw] or `out`,
-    d_fg, d_bg shaped like the prototypes)."""
+    d_fg, d_bg shaped like the prototypes).  dense=True: g_pred is the gradient [N, 2, P, hw] of `["sim"]`, the per-prototype
+    maps `compute_similarity` returns (no arg-max)."""
     fg_proto = _need(fg_proto, torch.float32, "fg_proto")
     bg_proto = _need(bg_proto, torch.float32, "bg_proto")
     g_pred = _need(g_pred, torch.float32, "g_pred")
@@ -538,16 +539,18 @@ def cosine_match_bwd(qry, fg_proto, bg_proto, g_pred, scalar=20.0, out=None):
     P = 1 if fg_proto.dim() == 2 else fg_proto.shape[2]
     n_maps = qry.shape[0] * qry.shape[1] if qry.dim() == 5 else qry.shape[0]
     qry, ep, c, hw = _episodes(qry, Bp, n_maps // Bp, "qry")
-    if tuple(g_pred.shape) != (n_maps, 2, hw):
-        raise ValueError(f"g_pred must be [{n_maps}, 2, {hw}], got {tuple(g_pred.shape)}")
+    want = (n_maps, 2, P, hw) if dense else (n_maps, 2, hw)
+    if tuple(g_pred.shape) != want:
+        raise ValueError(f"g_pred must be {list(want)}, got {tuple(g_pred.shape)}")
     L = _cabi.lib()
     dev = qry.device
     ws = _ws(L.pemp_cosine_match_bwd_workspace_bytes(n_maps, Bp, c, hw, P), dev)
     d_qry, d_ep = _grad_out(out, Bp, n_maps // Bp, c, hw, dev)
     d_fg, d_bg = torch.empty_like(fg_proto), torch.empty_like(bg_proto)
-    _cabi.check(L.pemp_cosine_match_bwd(qry.data_ptr(), ep, fg_proto.data_ptr(), bg_proto.data_ptr(), g_pred.data_ptr(), n_maps, Bp,
-                                        c, hw, P, float(scalar), d_qry.data_ptr(), d_ep, d_fg.data_ptr(), d_bg.data_ptr(),
-                                        ws.data_ptr(), ws.numel(), _stream()), "pemp_cosine_match_bwd")
+    fn = L.pemp_cosine_sim_bwd if dense else L.pemp_cosine_match_bwd
+    _cabi.check(fn(qry.data_ptr(), ep, fg_proto.data_ptr(), bg_proto.data_ptr(), g_pred.data_ptr(), n_maps, Bp,
+                   c, hw, P, float(scalar), d_qry.data_ptr(), d_ep, d_fg.data_ptr(), d_bg.data_ptr(),
+                   ws.data_ptr(), ws.numel(), _stream()), "pemp_cosine_sim_bwd" if dense else "pemp_cosine_match_bwd")
     _count(3)
     return d_qry, d_fg, d_bg
 

@@ -189,7 +189,7 @@ def test_episode_screen_table_is_used_and_never_silently_bypassed():
     spec = E.EpisodeSpec(shot=5, stages=2)
     acc = E.screened_indices("pemp_stage2", spec)
     st = E.screen_stats("pemp_stage2", spec)
-    assert st["threshold"] == 1e-5 and st["candidates"] >= 512 and len(acc) == st["candidates"] - st["rejected"]
+    assert st["threshold"] == 2e-5 and st["candidates"] >= 512 and len(acc) == st["candidates"] - st["rejected"]
     assert len(acc) >= 512                                   # 8 ranks x 64 disjoint screened episodes
     shards = [E.screened_indices("pemp_stage2", spec, 64, start=r, step=8) for r in range(8)]
     flat = [i for sh in shards for i in sh]

@@ -3,7 +3,7 @@
 The reference's own files travel to the GPU box in the git-ignored `oracle/_ref/reference/` (staged, unmodified, by
 `__graft_entry__.build()`).  Each test runs the reference class twice on CUDA tensors - as it is (stock PyTorch CUDA ops, TF32
 off: SURVEY 8c's primary oracle) and after `dropin.patch()` rebound its methods to the B200 kernels - and compares.
-Bars: logits 1e-5 norm-wise; arg-max masks identical on every pixel the reference decides by >= 1e-5 (the margin screen of
+Bars: logits 1e-5 norm-wise; arg-max masks identical on every pixel the reference decides by >= 2e-5 (the margin screen of
 SURVEY 7, hard part 2; the number of flips below that margin is printed, not hidden); counts identical."""
 import json
 
@@ -17,7 +17,7 @@ from pemp_b200 import episodes as E
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="reference files not staged (run __graft_entry__.build() "
                                                                             "where /root/reference exists)")]
-MARGIN = 1e-5
+MARGIN = 2e-5
 
 
 @pytest.fixture(autouse=True)

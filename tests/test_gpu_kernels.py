@@ -594,7 +594,7 @@ def test_pemp_head_golden_small(ops, name, out_shape):
         assert nrel(up["logits"].cpu().numpy(), g[f"s{stage}_logits"]) < TOL
         want = unpack_bits(g[f"s{stage}_mask"], g[f"s{stage}_mask_shape"])
         margin = np.abs(g[f"s{stage}_logits"][:, 1] - g[f"s{stage}_logits"][:, 0])
-        assert margin.min() >= 1e-5                     # the fixture episodes pass the margin screen (SURVEY 7 hard part 2)
+        assert margin.min() >= 2e-5                     # the fixture episodes pass the margin screen (SURVEY 7 hard part 2)
         assert int((up["mask64"].cpu().numpy() != want).sum()) == 0
     if adaptive is not None and "s2_adaptive_p" in g:
         assert nrel(adaptive.cpu().numpy(), g["s2_adaptive_p"]) < TOL
@@ -608,7 +608,7 @@ def test_pemp_head_golden_full_size(ops, name):
     g = golden(name)
     spec = E.EpisodeSpec(**json.loads(str(g["spec"])))
     B = int(g["B"])
-    assert float(g["min_margin"]) >= 1e-5
+    assert float(g["min_margin"]) >= 2e-5
     batch = E.make_batch(spec, [int(i) for i in g["indices"]])
     for stage in (1, 2):
         m, up, adaptive = _run_head(ops, batch[f"feats{stage}"], batch["sup_mask"], E.make_ctr(spec, stage), B, spec.shot,

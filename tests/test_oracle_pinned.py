@@ -65,7 +65,7 @@ def test_pemp_head_full_size(name):
     assert np.array_equal(out["adaptive_p"].numpy(), g["s2_adaptive_p"])
     stat = O.few_shot_stat(O.argmax2(out["logits"]).numpy(), batch["qry_msk"].numpy(), batch["cls"].numpy(), spec.classes)
     assert np.array_equal(stat, g["stat"])
-    assert min(margins) == float(g["min_margin"]) >= 1e-5         # the screen the reference run applied holds for the restatement
+    assert min(margins) == float(g["min_margin"]) >= 2e-5         # the screen the reference run applied holds for the restatement
 
 
 def test_pemp_general_masks():
