@@ -379,16 +379,29 @@ mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__
 // Phase A / B1 of mpa_bwd_kernel.  FAST: the tile lies inside the row (no per-element bounds predicate) and c is a multiple of
 // the per-iteration channel count (no channel predicate) - the common case runs without the branch / predicate scaffolding,
 // which was ~40 % of the instructions of the first version.  Pointers advance by constants instead of being recomputed.
+// One table row per channel: { ctr[ch][0..K), coef[ch][0..K) } = 2K floats = K/2 LDS.128 (the first version kept two tables and
+// read a row as 2 x K/2 LDS.64: the table loads were a third of the instructions of phase A and B1).
+template <int K>
+__device__ __forceinline__ void load_row2(const float* row, float2 (&rc)[K / 2], float2 (&ra)[K / 2]) {
+  float4 q[K / 2];
+#pragma unroll
+  for (int j = 0; j < K / 2; ++j) q[j] = reinterpret_cast<const float4*>(row)[j];
+#pragma unroll
+  for (int j = 0; j < K / 2; ++j) {
+    const float4 lo = q[j / 2], hi = q[(K / 2 + j) / 2];
+    rc[j] = (j & 1) ? make_float2(lo.z, lo.w) : make_float2(lo.x, lo.y);
+    ra[j] = ((K / 2 + j) & 1) ? make_float2(hi.z, hi.w) : make_float2(hi.x, hi.y);
+  }
+}
+
 template <int K, bool FAST>
 __device__ __forceinline__ void mpa_bwd_phase_a(const float* __restrict__ src, int c, int hw, int x, bool inb, int warp, int lane,
-                                                float* tile, const float* ctab, const float* atab, float2 (&accC)[K / 2],
-                                                float2 (&accA)[K / 2]) {
+                                                float* tile, const float* tab, float2 (&accC)[K / 2], float2 (&accA)[K / 2]) {
   constexpr int H = K / 2;
   const float* gp = src + static_cast<long long>(warp) * hw + x;
   const long long gstep = static_cast<long long>(kBW) * hw;
   float* tp = tile + warp * kLd + lane;
-  const float* cp = ctab + warp * K;
-  const float* ap = atab + warp * K;
+  const float* rp = tab + warp * 2 * K;
   for (int ch0 = warp; ch0 < c; ch0 += kBW * kUn) {
     float vv[kUn];
 #pragma unroll
@@ -405,8 +418,7 @@ __device__ __forceinline__ void mpa_bwd_phase_a(const float* __restrict__ src, i
         const float v = vv[u];
         tp[u * kBW * kLd] = v;
         float2 rc[H], ra[H];
-        load_row<K>(cp + u * kBW * K, rc);
-        load_row<K>(ap + u * kBW * K, ra);
+        load_row2<K>(rp + u * kBW * 2 * K, rc, ra);
         const float2 v2 = make_float2(v, v);
 #pragma unroll
         for (int j = 0; j < H; ++j) {
@@ -417,35 +429,31 @@ __device__ __forceinline__ void mpa_bwd_phase_a(const float* __restrict__ src, i
     }
     gp += kUn * gstep;
     tp += kUn * kBW * kLd;
-    cp += kUn * kBW * K;
-    ap += kUn * kBW * K;
+    rp += kUn * kBW * 2 * K;
   }
 }
 
 template <int K, bool FAST>
-__device__ __forceinline__ void mpa_bwd_phase_b1(float* __restrict__ dst, int c, int hw, bool inb, int warp, const float* ctab,
-                                                 const float* atab, const float2 (&a)[K / 2], const float2 (&d)[K / 2]) {
+__device__ __forceinline__ void mpa_bwd_phase_b1(float* __restrict__ dst, int c, int hw, bool inb, int warp, const float* tab,
+                                                 const float2 (&a)[K / 2], const float2 (&d)[K / 2]) {
   constexpr int H = K / 2;
   const long long gstep = static_cast<long long>(kBW) * hw;
   dst += static_cast<long long>(warp) * hw;
-  const float* cp = ctab + warp * K;
-  const float* ap = atab + warp * K;
+  const float* rp = tab + warp * 2 * K;
 #pragma unroll 4
   for (int ch = warp; ch < c; ch += kBW) {
     float2 rc[H], ra[H];
-    load_row<K>(cp, rc);
-    load_row<K>(ap, ra);
-    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+    load_row2<K>(rp, rc, ra);
+    float2 v = make_float2(0.f, 0.f);                 // one accumulator pair: a single horizontal add per element
 #pragma unroll
     for (int j = 0; j < H; ++j) {
-      v0 = ffma2(a[j], ra[j], v0);
-      v1 = ffma2(d[j], rc[j], v1);
+      v = ffma2(a[j], ra[j], v);
+      v = ffma2(d[j], rc[j], v);
     }
-    const float val = (v0.x + v0.y) + (v1.x + v1.y);
+    const float val = v.x + v.y;
     if (FAST || inb) *dst = val;
     dst += gstep;
-    cp += kBW * K;
-    ap += kBW * K;
+    rp += kBW * 2 * K;
   }
 }
 
@@ -457,9 +465,8 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
                long long d_ep_stride, float* __restrict__ part) {
   constexpr int P = K / 2, KP = Pad<K>::KP, H = Pad<K>::H, NA = 2 * KP;
   extern __shared__ __align__(16) float sm[];
-  float* ctab = sm;                        // [c][KP]  centres
-  float* atab = ctab + c * KP;             // [c][KP]  gradient coefficients of this image
-  float* av = atab + c * KP;               // [32][KP] a_k
+  float* tab = sm;                         // [c][2 KP]  { centres | gradient coefficients of this image }
+  float* av = tab + 2 * c * KP;            // [32][KP] a_k
   float* dv = av + 32 * KP;                // [32][KP] 2 dl_k
   float* tile = dv + 32 * KP;              // [c][33]
   float* red = tile + c * kLd;             // [kBW][NA][32]
@@ -470,8 +477,8 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
   const float* src = fts + static_cast<long long>(b) * ep_stride + static_cast<long long>(si) * c * hw;
   for (int i = tid; i < c * KP; i += kBT) {
     const int ch = i / KP, k = i - ch * KP;
-    ctab[i] = k < K ? __ldg(ctr + ch * K + k) : 0.f;
-    atab[i] = k < K ? __ldg(coef + (static_cast<long long>(n) * c + ch) * K + k) : 0.f;
+    tab[ch * 2 * KP + k] = k < K ? __ldg(ctr + ch * K + k) : 0.f;
+    tab[ch * 2 * KP + KP + k] = k < K ? __ldg(coef + (static_cast<long long>(n) * c + ch) * K + k) : 0.f;
   }
   for (int i = tid; i < 32 * KP; i += kBT) {
     av[i] = 0.f;
@@ -498,9 +505,9 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
     for (int j = 0; j < H; ++j) accC[j] = accA[j] = make_float2(0.f, 0.f);
     const bool fast = (t * 32 + 32 <= hw) && (c % (kBW * kUn) == 0);
     if (fast)
-      mpa_bwd_phase_a<K, true>(src, c, hw, x, inb, warp, lane, tile, ctab, atab, accC, accA);
+      mpa_bwd_phase_a<K, true>(src, c, hw, x, inb, warp, lane, tile, tab, accC, accA);
     else
-      mpa_bwd_phase_a<K, false>(src, c, hw, x, inb, warp, lane, tile, ctab, atab, accC, accA);
+      mpa_bwd_phase_a<K, false>(src, c, hw, x, inb, warp, lane, tile, tab, accC, accA);
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       red[(warp * NA + 2 * j) * 32 + lane] = accC[j].x;
@@ -560,22 +567,24 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
       load_row<KP>(dv + lane * KP, d);
       float* dst = dfts + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(si) * c * hw + x;
       if (fast)
-        mpa_bwd_phase_b1<K, true>(dst, c, hw, inb, warp, ctab, atab, a, d);
+        mpa_bwd_phase_b1<K, true>(dst, c, hw, inb, warp, tab, a, d);
       else
-        mpa_bwd_phase_b1<K, false>(dst, c, hw, inb, warp, ctab, atab, a, d);
+        mpa_bwd_phase_b1<K, false>(dst, c, hw, inb, warp, tab, a, d);
     }
-#pragma unroll
-    for (int i = 0; i < kMaxCPT; ++i) {   // B2: sum_x 2 dl_k f
-      const int ch = tid + i * kBT;
-      if (ch < c) {
+    {   // B2: sum_x 2 dl_k f - the weight row of a pixel is loaded once for all channels of the thread
 #pragma unroll 4
-        for (int xx = 0; xx < 32; ++xx) {
-          const float v = tile[ch * kLd + xx];
-          float2 r[H];
-          load_row<KP>(dv + xx * KP, r);
-          const float2 v2 = make_float2(v, v);
+      for (int xx = 0; xx < 32; ++xx) {
+        float2 r[H];
+        load_row<KP>(dv + xx * KP, r);
 #pragma unroll
-          for (int k = 0; k < H; ++k) accB[i][k] = ffma2(r[k], v2, accB[i][k]);
+        for (int i = 0; i < kMaxCPT; ++i) {
+          const int ch = tid + i * kBT;
+          if (ch < c) {
+            const float v = tile[ch * kLd + xx];
+            const float2 v2 = make_float2(v, v);
+#pragma unroll
+            for (int k = 0; k < H; ++k) accB[i][k] = ffma2(r[k], v2, accB[i][k]);
+          }
         }
       }
     }
