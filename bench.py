@@ -577,7 +577,7 @@ def run_ours(args):
         allreduce_ok = bool(torch.equal(summed, torch.stack(gathered).sum(dim=0))) and bool(torch.equal(summed * args.steps, stat))
 
     # ---------------- sustained: the same step >= 200 times back to back ---------------------------------
-    sus_n = max(args.sustained_steps, args.steps)
+    sus_n = max(args.sustained_steps, args.steps, int(400.0 / ms_per_step))      # >= 0.4 s: several clock samples under load
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     pdist.barrier()

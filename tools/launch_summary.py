@@ -22,9 +22,10 @@ def main(path, bench=None):
         a[0] += 1
         a[1] += float(r[iv].replace(",", ""))
     tot = sum(a[1] for a in agg.values())
-    print("ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph")
-    print("(5 steps of 64 five-shot episodes; per-launch times are cold-cache and serialised - compare SHARES; full list: "
-          "r01_launches_bench_steps2.csv)")
+    print("ncu --metrics gpu__time_duration.sum --clock-control none -c 400 : python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline "
+          "--no-graph --no-extra")
+    print("(first 400 launches of the command: warm-up, timed and sustained steps of 64 five-shot episodes; per-launch times are "
+          "cold-cache and serialised - compare SHARES; full list beside this file)")
     print("kernel, launches, total_us, share of our kernels")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:45s} {a[0]:4d} {a[1] / 1e3:9.1f} {100 * a[1] / tot:5.1f}%")
