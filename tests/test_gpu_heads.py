@@ -225,6 +225,27 @@ def test_stage2_bench_batch_of_64_episodes_equals_the_oracle():
     assert np.array_equal(stat, w_stat)
 
 
+def test_pipeline_step_takes_label_maps_or_float_masks():
+    """`PEMPStage2Pipeline.step` fed with the uint8 label maps (what a host-side caller ships: an eighth of the bytes) equals the
+    step fed with the loader's float `sup_mask`, bit for bit - including shots with a 255 boundary band."""
+    from pemp_b200.evaluator import PEMPStage2Pipeline
+    spec = E.EpisodeSpec(shot=3, channels=64, h=13, w=13, H=97, W=97, out_h=90, out_w=75)
+    B, S, Q, c, h, w = 2, spec.shot, spec.query, spec.channels, spec.h, spec.w
+    batch = {k: v.cuda() for k, v in E.make_batch(spec, range(B)).items()}
+    labels = (batch["sup_mask"][:, :, 0] > 0.5).to(torch.uint8)
+    labels[:, 0, 40:44] = 255                                         # a boundary band: neither foreground nor background
+    sup_mask = torch.stack(((labels == 1).float(), (labels == 0).float()), dim=2)
+    pipe = PEMPStage2Pipeline(E.make_ctr(spec, 1).cuda(), E.make_ctr(spec, 2).cuda(), spec.classes)
+    f1 = batch["feats1"].view(B, S + Q, c, h, w)
+    f2 = batch["feats2"].view(B, S + Q, c, h, w)
+    outs = []
+    for masks in (sup_mask, labels):
+        stat = torch.zeros(spec.classes + 1, 3, dtype=torch.int64, device="cuda")
+        prior, mask = pipe.step(f1[:, :S], f1[:, S:], f2[:, :S], f2[:, S:], masks, batch["qry_msk"], batch["cls"], stat)
+        outs.append((prior, mask, stat))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
 def test_episode_view_equals_dense_copy():
     from pemp_b200 import ops
     torch.manual_seed(2)

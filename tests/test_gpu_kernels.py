@@ -34,6 +34,23 @@ def test_mask_nearest_bit_exact(ops, H, W, h, w):
     assert torch.equal(ops.mask_nearest(cu(x), h, w).cpu(), O.mask_nearest(x, h, w))
 
 
+@pytest.mark.parametrize("H,W,h,w", [(401, 401, 51, 51), (333, 500, 42, 63), (97, 97, 13, 13), (9, 7, 9, 7), (5, 3, 11, 8)])
+def test_mask_nearest_labels_equals_the_expanded_float_masks(ops, H, W, h, w):
+    """The uint8 label map the data set stores (1 object / 0 background / 255 boundary) through `pemp_mask_nearest_labels` gives
+    bit for bit the low-res masks of `F.interpolate(nearest)` on the loader's expansion `stack((label == 1), (label == 0))`
+    (data_kits/pascal_voc.py:209-210, 226-231; pemp_stage1.py:147) - including the boundary band, where fg and bg are both 0."""
+    g = torch.Generator().manual_seed(H + w)
+    lab = torch.randint(0, 3, (2, 3, H, W), generator=g).to(torch.uint8)
+    lab[lab == 2] = 255
+    expanded = torch.stack(((lab == 1).float(), (lab == 0).float()), dim=2)             # [B, S, 2, H, W]
+    want = O.mask_nearest(expanded.view(6, 2, H, W), h, w)
+    got = ops.mask_nearest_labels(cu(lab), h, w)
+    assert got.shape == (2, 3, 2, h, w) and torch.equal(got.cpu().view(6, 2, h, w), want)
+    assert torch.equal(ops.mask_nearest(cu(expanded), h, w).cpu().view(6, 2, h, w), want)
+    with pytest.raises(ValueError):
+        ops.mask_nearest_labels(cu(lab).float(), h, w)                                   # labels must be uint8
+
+
 @pytest.mark.parametrize("h,w,H,W", [(51, 51, 401, 401), (51, 51, 333, 500), (13, 13, 97, 97), (7, 9, 50, 41), (5, 5, 5, 5),
                                      (51, 51, 21, 23), (60, 60, 473, 473), (3, 4, 401, 7)])
 def test_upsample_argmax_bit_exact_given_same_input(ops, h, w, H, W):
