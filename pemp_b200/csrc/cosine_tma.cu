@@ -47,7 +47,10 @@ constexpr int kNB = PEMP_COS_NB;                 // ring slots (the consumers ho
 static_assert(kNB % 4 == 0, "ring slots must be a multiple of the 4 boxes of a tile");
 constexpr int kCons = 16;
 constexpr int kThreadsC = (kCons + 3) * 32;      // + producer warp + two finishing warps
-constexpr int kPB = 2;                           // exchange buffers (handed back by the finishing warps: free_bar)
+#ifndef PEMP_COS_PB
+#define PEMP_COS_PB 2
+#endif
+constexpr int kPB = PEMP_COS_PB;                 // exchange buffers (handed back by the finishing warps: free_bar)
 constexpr int kPLd = 29;                         // pixel pitch of a value row in `part`
 constexpr int kMaxGrid = 148;
 constexpr float kCosEps = 1e-8f;
