@@ -18,7 +18,7 @@ dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 B, S, c, h, H = a.B, 5, 512, 51, 401
 hw = h * h
-if a.op in ("K6", "K7", "K2", "K3", "K2s1"):
+if a.op in ("K6", "K7", "K2", "K3", "K2s1", "K4", "K4h"):
     if a.op == "K2s1":
         S = 1
     sup = torch.randn(B * S, c, hw, device=dev, generator=g) * 0.5
@@ -34,7 +34,11 @@ if a.op in ("K6", "K7", "K2", "K3", "K2s1"):
           "K7": lambda: ops.panet_align(qry.view(B, c, h, h), pred, sup.view(B * S, c, h, h), fgfull, 1),
           "K2": lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S),
           "K2s1": lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S),
-          "K3": lambda: ops.cosine_match(qry, fgp, bgp)}[a.op]
+          "K3": lambda: ops.cosine_match(qry, fgp, bgp),
+          "K4": lambda: ops.upsample_argmax(pred, (H, H), want_mask8=True),
+          "K4h": lambda: ops.upsample_argmax_hist(pred, (H, H), (torch.rand(B, H, H, device=dev) > 0.5).to(torch.uint8),
+                                                  torch.ones(B, dtype=torch.int64, device=dev),
+                                                  torch.zeros(21, 3, dtype=torch.int64, device=dev))}[a.op]
 elif a.op == "K11":
     Nc, cc, hc = 16 * 6, 256, 101
     xc = torch.randn(Nc, cc, hc, hc, device=dev, generator=g)
