@@ -372,3 +372,28 @@ def test_canet_map_tile_bench_shape_against_oracle():
     want = O.canet_map_tile(f, sup_mask, B, S, Q)
     out = ops.canet_map_tile(f.cuda().view(B * (S + Q), c, h, h), sup_mask.cuda(), B, S, Q).cpu()
     assert torch.equal(out[:, :c], want[:, :c]) and nrel(out[:, c:], want[:, c:]) < 1e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_follow_the_device_of_their_operands():
+    """raw pointers of one GPU must never be launched on another GPU's stream.  A call whose tensors live on
+    cuda:1 while cuda:0 is current runs under cuda:1 (same result as on cuda:0); operands on two devices are refused."""
+    from pemp_b200 import ops
+    from pemp_b200.metrics import FewShotMetric
+    torch.manual_seed(4)
+    B, S, c, h, w = 2, 2, 64, 9, 9
+    f = torch.randn(B * S, c, h * w)
+    fg = (torch.rand(B * S, h * w) > 0.5).float()
+    ctr = torch.rand(c, 6)
+    assert torch.cuda.current_device() == 0
+    a = ops.meta_proto_attn(f.cuda(0), ctr.cuda(0), fg.cuda(0), (1 - fg).cuda(0), B, S)
+    b = ops.meta_proto_attn(f.cuda(1), ctr.cuda(1), fg.cuda(1), (1 - fg).cuda(1), B, S)
+    assert b[0].device.index == 1 and all(torch.equal(x.cpu(), y.cpu()) for x, y in zip(a, b))
+    assert torch.cuda.current_device() == 0
+    with pytest.raises(ValueError, match="different devices"):
+        ops.meta_proto_attn(f.cuda(0), ctr.cuda(1), fg.cuda(0), (1 - fg).cuda(0), B, S)
+    fm = FewShotMetric(20, device="cuda:1")
+    pred = (torch.rand(3, 33, 33) > 0.5).to(torch.uint8)
+    ref = (torch.rand(3, 33, 33) > 0.5).to(torch.uint8)
+    fm.update(pred.numpy(), ref.numpy(), [1, 2, 3])
+    assert np.array_equal(fm.stat, O.few_shot_stat(pred.numpy(), ref.numpy(), [1, 2, 3], 20).astype(np.float64))
