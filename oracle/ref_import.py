@@ -240,3 +240,20 @@ def pfenet_model(shot, seed=0):
     finally:
         torch.load = orig
     return net.eval()
+
+
+def full_model(name, seed=0, shot=1, query=1):
+    """The reference's WHOLE model (`networks/<name>.py::ModelClass`: real ResNet-50 / VGG encoder + head) with seeded random
+    weights: the checkpoint paths of `pretrained_weights` are set to None so that the constructors skip `torch.load`
+    (backbones.py:103-104, 187-188); everything else - Sacred-injected config included - is the reference's own code."""
+    mod = module(f"networks.{name}")
+    weights = getattr(mod, "pretrained_weights", None)
+    if weights is not None:
+        for k in list(weights):
+            weights[k] = None
+    torch.manual_seed(seed)
+    if name == "pemp_stage2":
+        net = mod.ModelClass(shot, query, _QuietLogger())
+    else:
+        net = mod.ModelClass(_QuietLogger())
+    return net.eval()

@@ -149,3 +149,41 @@ def test_patched_pfenet_forward_reaches_the_tensor_core_prior(shot, size):
     err = nrel(got.cpu().numpy(), want.cpu().numpy())
     print(json.dumps({"case": f"pfenet shot={shot} size={size}", "out_nrel": err}))
     assert err < 1e-4
+
+
+@pytest.mark.parametrize("comm", [False, True])
+def test_two_stage_evaluation_step_with_the_real_encoders(comm):
+    """`Evaluator.test_step` of entry/pemp_stage2.py:58-65 on the reference's WHOLE models - real ResNet-50 encoders (seeded random
+    weights, eval mode), Stage-1 -> arg-max prior -> Stage-2 at the query-mask size - unpatched (stock PyTorch on the B200) against
+    `dropin.patch()`.  The encoders are the same stock code on both sides; with `comm=True` the communication module inside the
+    Stage-2 backbone (backbones.py:208-222) runs on K11 as well, which perturbs the encoder output at the 1e-6 level."""
+    from pemp_b200 import dropin, ops
+    torch.backends.cudnn.deterministic = True
+    S, H = 1, 401
+    s1 = R.full_model("pemp_stage1", seed=1).cuda()
+    s2 = R.full_model("pemp_stage2", seed=2, shot=S, query=1).cuda()
+    g = torch.Generator().manual_seed(11)
+    sup_img = torch.randn(1, S, 3, H, H, generator=g).cuda()
+    qry_img = torch.randn(1, 1, 3, H, H, generator=g).cuda()
+    fg = torch.zeros(1, S, H, H)
+    fg[:, :, 120:300, 90:310] = 1.0
+    sup_mask = torch.stack((fg, 1 - fg), dim=2).cuda()
+    out_shape = (333, 500)
+
+    def step(prior=None):
+        with torch.no_grad():
+            l1 = s1(sup_img, sup_mask, qry_img)                                  # entry/pemp_stage2.py:59
+            p1 = l1.argmax(dim=1, keepdim=True) if prior is None else prior       # :60
+            l2 = s2(sup_img, sup_mask, qry_img, p1, out_shape)                    # :62
+        return l1, p1, l2
+
+    want_l1, want_p1, want_l2 = step()
+    n0 = ops.launch_count()
+    dropin.patch(comm=comm)
+    got_l1, _, got_l2 = step(prior=want_p1)            # same prior on both sides: stage 2 is compared on identical inputs
+    dropin.unpatch()
+    assert ops.launch_count() - n0 >= 8                # both heads ran on the library's kernels
+    e1, e2 = nrel(got_l1.cpu().numpy(), want_l1.cpu().numpy()), nrel(got_l2.cpu().numpy(), want_l2.cpu().numpy())
+    print(json.dumps({"case": f"two-stage step, real encoders, comm={comm}", "stage1_logits_nrel": e1, "stage2_logits_nrel": e2}))
+    assert got_l2.shape == (1, 2, *out_shape)
+    assert e1 < 1e-5 and e2 < (1e-4 if comm else 1e-5)
