@@ -19,7 +19,8 @@
 // Math.  K3: sim_gk = scalar * (q . pn_gk) / max(|q|, eps), pred_g = max_k sim_gk (first maximum wins)
 //   dq  = sum_g gp_g * scalar * (pn_gk* / |q| - (q . pn_gk*) q / |q|^3)          (second term 0 when |q| < eps)
 //   dpn_gk = sum_x [k = k*] gp_g * scalar * q / |q|;   dproto = (dpn - pn (pn . dpn)) / |proto|   (dpn / eps if clamped)
-// K2: l_k = 2 f . ctr_k - |ctr_k|^2 (the |f|^2 term cancels in the softmax), sigma = softmax over the group,
+// K2: l_k = 2 f . ctr_k - |ctr_k|^2 (the |f|^2 term cancels in the softmax; evaluated as differences to the first prototype of the
+//   group, l_k - l_g0 = 2 f . (ctr_k - ctr_g0) - (|ctr_k|^2 - |ctr_g0|^2), which the soft-max cannot tell apart), sigma = softmax over the group,
 //   a_k = m_g sigma_k, centre_k = sum_x f a_k / den_k, den_k = sum_x a_k + eps, with A_k = g_centre_k / den_k:
 //   da_k = f . A_k - A_k . centre_k;  dl_k = sigma_k (m da_k - sum_j sigma_j m da_j)
 //   df = sum_k (a_k A_k + 2 dl_k ctr_k);   dctr_k = sum_x 2 dl_k f - ctr_k sum_x 2 dl_k
@@ -346,8 +347,8 @@ cosine_bwd_finalize_kernel(const float* __restrict__ part, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ K2 backward
-// coef [BS][c][K] = g_centre / (S * den); beta [BS][2K] = { -sum_c coef * centre, |ctr_k|^2 }.   Columns k < P: foreground
-// group.  |ctr_k|^2 is a bias common to every pixel's logit, so it is summed in double (as the forward does).
+// coef [BS][c][K] = g_centre / (S * den); beta [BS][2K] = { -sum_c coef * centre, |ctr_k|^2 - |ctr_g0|^2 }.   Columns k < P:
+// foreground group.  The squared-norm differences are a bias common to every pixel's logit, so they are summed in double.
 __global__ void __launch_bounds__(kBT)
 mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__ g_bg, const float* __restrict__ shot_centre,
                        const float* __restrict__ shot_den, const float* __restrict__ ctr, int S, int c, int P,
@@ -367,10 +368,13 @@ mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__
     if (threadIdx.x == 0) beta[n * 2 * K + k] = -s;
   }
   if (threadIdx.x < K) {
+    // |ctr_k|^2 - |ctr_g0|^2 with g0 the first prototype of k's group: the soft-max of a group only sees differences of logits,
+    // and the backward kernel works with ctr_k - ctr_g0 throughout (see mpa_bwd_kernel), as the forward does
+    const int k0 = (threadIdx.x / P) * P;
     double s2 = 0.0;
     for (int ch = 0; ch < c; ++ch) {
-      const double v = static_cast<double>(__ldg(ctr + ch * K + threadIdx.x));
-      s2 = fma(v, v, s2);
+      const double v = static_cast<double>(__ldg(ctr + ch * K + threadIdx.x)), v0 = static_cast<double>(__ldg(ctr + ch * K + k0));
+      s2 += (v - v0) * (v + v0);
     }
     beta[n * 2 * K + K + threadIdx.x] = static_cast<float>(s2);
   }
@@ -477,7 +481,11 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
   const float* src = fts + static_cast<long long>(b) * ep_stride + static_cast<long long>(si) * c * hw;
   for (int i = tid; i < c * KP; i += kBT) {
     const int ch = i / KP, k = i - ch * KP;
-    tab[ch * 2 * KP + k] = k < K ? __ldg(ctr + ch * K + k) : 0.f;
+    // centre columns as differences to the first prototype of their group (exact in double, one rounding): the logits
+    // l_k - l_g0 = 2 f.(ctr_k - ctr_g0) - (|ctr_k|^2 - |ctr_g0|^2) are O(10) instead of O(|f.ctr|) ~ 300, and since the
+    // soft-max gradient sums to zero over a group, sum_k dl_k ctr_k = sum_k dl_k (ctr_k - ctr_g0): phase B1 needs no more
+    tab[ch * 2 * KP + k] = k < K ? static_cast<float>(static_cast<double>(__ldg(ctr + ch * K + k)) -
+                                                      static_cast<double>(__ldg(ctr + ch * K + (k / P) * P))) : 0.f;
     tab[ch * 2 * KP + KP + k] = k < K ? __ldg(coef + (static_cast<long long>(n) * c + ch) * K + k) : 0.f;
   }
   for (int i = tid; i < 32 * KP; i += kBT) {
