@@ -65,13 +65,14 @@ def splice_pfenet_forward(mod, precision=None):
     new_src = "\n".join(lines[:first[0]] + [call] + lines[last[0] + 1:])
     # drop decorators of the original definition (e.g. @net_ingredient.capture): the caller re-applies capture
     new_src = new_src[new_src.index("def forward"):]
-    scope = dict(vars(mod))
-    if precision is None:
-        scope["_pemp_prior_mask"] = heads.prior_mask
-    else:
-        scope["_pemp_prior_mask"] = lambda q, s, m, out_hw=None: heads.prior_mask(q, s, m, precision=precision, out_hw=out_hw)
-    exec(compile(new_src, f"<pemp_b200 splice of {getattr(mod, '__file__', 'networks/pfenet.py')}>", "exec"), scope)
-    fn = scope["forward"]
+    # compiled against the module's OWN globals (not a copy): `Weighted_GAP`, `F`, `nn`, ... resolve exactly as in the original
+    # forward, including later rebinding; the one new name, `_pemp_prior_mask`, is installed on the module by `patch()`
+    hook = heads.prior_mask if precision is None else (
+        lambda q, s_, m, out_hw=None: heads.prior_mask(q, s_, m, precision=precision, out_hw=out_hw))
+    _set(mod, "_pemp_prior_mask", hook)
+    local = {}
+    exec(compile(new_src, f"<pemp_b200 splice of {getattr(mod, '__file__', 'networks/pfenet.py')}>", "exec"), vars(mod), local)
+    fn = local["forward"]
     fn.__qualname__ = "PFENet.forward"
     return fn
 
