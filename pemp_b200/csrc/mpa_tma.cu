@@ -495,10 +495,12 @@ __global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, cons
                                         float* __restrict__ shot_den) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(B) * kC * kK) return;
+  // thread <-> (b, tile row R, k): consecutive threads read consecutive floats of a partial (the first version walked the
+  // channels in natural order, i.e. 24-byte pieces 3 KB apart); the few output stores are the strided side now
   const int k = static_cast<int>(i % kK);
   const long long t = i / kK;
-  const int ch = static_cast<int>(t % kC), b = static_cast<int>(t / kC);
-  const int R = (ch & 3) * kBoxRows + (ch >> 2);
+  const int R = static_cast<int>(t % kC), b = static_cast<int>(t / kC);
+  const int ch = 4 * (R & (kBoxRows - 1)) + (R >> 7);
   float accum = 0.f;
   for (int s = 0; s < S; ++s) {
     const long long img = static_cast<long long>(b) * S + s;
