@@ -506,9 +506,21 @@ __global__ void mpa_tma_finalize_kernel(const float* __restrict__ part_num, cons
     const long long img = static_cast<long long>(b) * S + s;
     const int n = __ldg(nparts + img);
     float num = 0.f, den = 0.f;
-    for (int sp = 0; sp < n; ++sp) {
-      num += part_num[((img * maxp + sp) * kC + R) * kK + k];
-      den += part_den[(img * maxp + sp) * 8 + k];
+    // four partials per batch with all eight loads in flight (an image has 2-3 partials at the bench shape); the sums still run
+    // in CTA order, and a missing partial adds an exact 0
+    for (int sp0 = 0; sp0 < n; sp0 += 4) {
+      float nv[4], dv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool on = sp0 + j < n;
+        nv[j] = on ? part_num[((img * maxp + sp0 + j) * kC + R) * kK + k] : 0.f;
+        dv[j] = on ? part_den[(img * maxp + sp0 + j) * 8 + k] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        num += nv[j];
+        den += dv[j];
+      }
     }
     accum += num / (den + eps);
     if (shot_centre) {      // training forward (see mpa.cu)
