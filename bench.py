@@ -692,8 +692,10 @@ def run_ours(args):
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": ms_e2e / args.e2e_steps,
                "h2d_GBps_per_gpu": h2d_bytes / (ms_e2e / args.e2e_steps) / 1e6,
                "h2d_GBps_aggregate": h2d_bytes * world / (ms_e2e / args.e2e_steps) / 1e6,
-               "limiter": "host->device link: %.1f MB of fp32 features per episode cross PCIe (device time of the step is %.1f%% of "
-                          "the e2e step)" % (h2d_bytes / B / 1e6, 100 * ms_per_step / (ms_e2e / args.e2e_steps)),
+               "limiter": ("host->device link: %.1f MB of inputs per episode cross PCIe (device time of the step is %.1f%% of the "
+                           "e2e step)" % (h2d_bytes / B / 1e6, 100 * ms_per_step / (ms_e2e / args.e2e_steps))) + (
+                   "" if world == 1 else "; %d ranks share the host side of the box (one NUMA node, shared PCIe uplinks): %.1f GB/s per "
+                   "GPU against ~55 GB/s for one GPU alone" % (world, h2d_bytes / (ms_e2e / args.e2e_steps) / 1e6)),
                "host_binding": binding, "path": wl.e2e_path}
         del chunks, bufs
 
