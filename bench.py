@@ -269,8 +269,14 @@ class BaselineWorkload:
         from pemp_b200 import ops
         S, Q, c, h, wd = self.S, self.Q, self.c, self.h, self.wd
         f5 = b["feats1"].view(n, S + Q, c, h, wd)
-        H, W = b["sup_mask"].shape[-2:]
-        mask = b["sup_mask"].view(n * S, 2, H, W)
+        if "labels" in b:                                     # the uint8 label map a host-side caller ships (e2e)
+            H, W = b["labels"].shape[-2:]
+            mask = b["labels"].view(n * S, H, W)
+            mask_fg = mask
+        else:                                                 # the float masks the loader emits (drop-in tensor contract)
+            H, W = b["sup_mask"].shape[-2:]
+            mask = b["sup_mask"].view(n * S, 2, H, W)
+            mask_fg = mask[:, 0:1]
         k6 = lambda: ops.map_pool_fullres(f5[:, :S], mask, n, S)
         fgp, bgp = timer.bracket(k6) if (timer is not None and not self.align) else k6()
         pred = ops.cosine_match(f5[:, S:], fgp, bgp, 20.0)["pred"].view(n * Q, 2, h, wd)
@@ -278,7 +284,7 @@ class BaselineWorkload:
         m8 = ops.upsample_argmax_hist(pred, out_hw, b["qry_msk"].view(n * Q, *out_hw), b["cls"], st)
         loss = None
         if self.align:
-            k7 = lambda: ops.panet_align(f5[:, S:], pred, f5[:, :S], mask[:, 0:1], Q)
+            k7 = lambda: ops.panet_align(f5[:, S:], pred, f5[:, :S], mask_fg, Q)
             loss = timer.bracket(k7) if timer is not None else k7()
         return loss, m8
 
@@ -286,15 +292,18 @@ class BaselineWorkload:
         return self._run(self.batch, st, timer, self.B)
 
     def host_chunks(self, chunk):
+        h = dict(self.host)
+        h["labels"] = (h.pop("sup_mask")[:, :, 0] > 0.5).to(torch.uint8)          # synthetic masks are binary and complementary
         per = self.S + self.Q
         return [{k: (v[i * per:(i + chunk) * per] if k.startswith("feats") else v[i:i + chunk]).contiguous().pin_memory()
-                 for k, v in self.host.items()} for i in range(0, self.B, chunk)]
+                 for k, v in h.items()} for i in range(0, self.B, chunk)]
 
     def step_chunk(self, b, st, n):
         return self._run(b, st, None, n)
 
     e2e_chunk = 8
-    e2e_path = "pinned host features / float masks as the loader emits them -> double-buffered cudaMemcpyAsync -> head kernels -> count table D2H"
+    e2e_path = ("pinned host features / uint8 label maps (K6 and K7 form the float planes on the fly) -> double-buffered "
+                "cudaMemcpyAsync -> head kernels -> count table D2H")
 
     def cpu_runner(self):
         from oracle import ref_run

@@ -137,6 +137,13 @@ size_t pemp_map_pool_fullres_workspace_bytes(int B, int S, int c, int h, int w);
 int pemp_map_pool_fullres(const float* fts, long long fts_episode_stride, const float* sup_mask, int B, int S, int c, int h, int w, int H, int W,
                           float eps, float* fg_proto, float* bg_proto,
                           void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+/* The same pooling fed by the label map the data set stores (uint8 [B*S, H, W]: 1 object, 0 background, 255 boundary) instead of
+ * its float expansion  sup_mask = stack((label == 1), (label == 0))   data_kits/pascal_voc.py:209-210, 226-231.
+ * Identical prototypes; an eighth of the mask bytes.                                                               */
+size_t pemp_map_pool_fullres_labels_workspace_bytes(int B, int S, int c, int h, int w, int H, int W);
+int pemp_map_pool_fullres_labels(const float* fts, long long fts_episode_stride, const uint8_t* labels, int B, int S, int c,
+                                 int h, int w, int H, int W, float eps, float* fg_proto, float* bg_proto, void* workspace,
+                                 size_t workspace_bytes, pemp_stream_t stream);
 /* the adjoint resampler on its own: mask [planes, H, W] -> wt [planes, h, w], msum [planes] (nullable) =
  * plain sum of the mask plane.                                                                          */
 int pemp_bilinear_adjoint(const float* mask, int planes, int H, int W, int h, int w, float* wt, float* msum,
@@ -153,6 +160,13 @@ int pemp_panet_align(const float* qry_fts, long long qry_episode_stride, const f
                      const float* sup_mask_fg, long long mask_stride,
                      int B, int S, int Q, int c, int h, int w, int H, int W, float scalar,
                      float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
+/* The same loss against the uint8 label map (plane i at labels + i*label_stride, [H, W]; 1 = object, everything else is not
+ * foreground) that `sup_mask_fg = (label == 1)` was expanded from  (data_kits/pascal_voc.py:209-210).                 */
+int pemp_panet_align_labels(const float* qry_fts, long long qry_episode_stride, const float* pred,
+                            const float* sup_fts, long long sup_episode_stride,
+                            const uint8_t* labels, long long label_stride,
+                            int B, int S, int Q, int c, int h, int w, int H, int W, float scalar,
+                            float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream);
 
 /* ---- K9  PFENet prior mask ----------------------------------------------------------------------------
  * replaces  the prior block of PFENet.forward()                  networks/pfenet.py:201-231

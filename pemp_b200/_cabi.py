@@ -49,9 +49,12 @@ SIGNATURES = {
     "pemp_nearest_resize_i64": (I, [P, I, I, I, I, I, P, P]),
     "pemp_map_pool_fullres_workspace_bytes": (SZ, [I, I, I, I, I]),
     "pemp_map_pool_fullres": (I, [P, LL, P, I, I, I, I, I, I, I, F, P, P, P, SZ, P]),
+    "pemp_map_pool_fullres_labels_workspace_bytes": (SZ, [I, I, I, I, I, I, I]),
+    "pemp_map_pool_fullres_labels": (I, [P, LL, P, I, I, I, I, I, I, I, F, P, P, P, SZ, P]),
     "pemp_bilinear_adjoint": (I, [P, I, I, I, I, I, P, P, P]),
     "pemp_panet_align_workspace_bytes": (SZ, [I, I, I, I, I, I, I, I]),
     "pemp_panet_align": (I, [P, LL, P, P, LL, P, LL, I, I, I, I, I, I, I, I, F, P, P, SZ, P]),
+    "pemp_panet_align_labels": (I, [P, LL, P, P, LL, P, LL, I, I, I, I, I, I, I, I, F, P, P, SZ, P]),
     "pemp_prior_mask_workspace_bytes": (SZ, [I, I, I, I, I, I]),
     "pemp_prior_mask": (I, [P, P, P, I, I, I, I, I, I, P, P, P, SZ, P]),
     "pemp_iou_hist": (I, [P, P, P, I, LL, I, P, P]),

@@ -18,6 +18,17 @@ namespace {
 
 constexpr int kCeThreads = 256;
 
+// class of a pixel of the support mask: float plane `sup_mask_fg` (`.long()` truncation, panet.py:190) or the uint8 label map it
+// was expanded from (1 object; 0 background and 255 boundary are not foreground)
+template <typename LT>
+__device__ __forceinline__ int ce_label(const LT* __restrict__ label, long long idx) {
+  if constexpr (sizeof(LT) == 1) {
+    return __ldg(label + idx) == 1 ? 1 : 0;
+  } else {
+    return static_cast<int>(__ldg(label + idx));
+  }
+}
+
 // pred [N, 2, hw] -> mask [N, 2, hw]: plane 0 = (argmax == 1), plane 1 = (argmax == 0)
 __global__ void argmax_masks_kernel(const float* __restrict__ pred, float* __restrict__ mask, long long total, int hw) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -32,8 +43,9 @@ __global__ void argmax_masks_kernel(const float* __restrict__ pred, float* __res
 }
 
 // rev [N, 2, h, w] low-res reverse logits, label planes [N][H*W] floats -> partial[blockIdx] = sum of NLL
+template <typename LT>
 __global__ void __launch_bounds__(kCeThreads)
-upsample_ce_kernel(const float* __restrict__ rev, const float* __restrict__ label, long long label_stride, long long total,
+upsample_ce_kernel(const float* __restrict__ rev, const LT* __restrict__ label, long long label_stride, long long total,
                    int h, int w, int H, int W, float sy, float sx, float* __restrict__ partial) {
   const long long HW = static_cast<long long>(H) * W;
   const int hw = h * w;
@@ -52,7 +64,7 @@ upsample_ce_kernel(const float* __restrict__ rev, const float* __restrict__ labe
       float c = __ldg(p + ly.i1 * w + lx.i0), d = __ldg(p + ly.i1 * w + lx.i1);
       v[ch] = lerp2(ly.l0, lerp2(lx.l0, a, lx.l1, b), ly.l1, lerp2(lx.l0, c, lx.l1, d));
     }
-    const int lab = static_cast<int>(__ldg(label + n * label_stride + r));   // .long() truncation
+    const int lab = ce_label<LT>(label, n * label_stride + r);
     const float m = fmaxf(v[0], v[1]);
     const float lse = m + logf(expf(v[0] - m) + expf(v[1] - m));
     acc += lse - (lab == 1 ? v[1] : v[0]);
@@ -74,8 +86,9 @@ upsample_ce_kernel(const float* __restrict__ rev, const float* __restrict__ labe
 // then needs 4 shared loads, 2 lerps, one exp and one log per pixel:  lse - v_label = max + log(1 + exp(-|v0 - v1|)) -
 // v_label.  The label rows of a band are one contiguous, coalesced range.  partial[image * bands + band].
 constexpr int kCeBand = 16, kCeMaxSrc = 8;
+template <typename LT>
 __global__ void __launch_bounds__(kCeThreads)
-upsample_ce_band_kernel(const float* __restrict__ rev, const float* __restrict__ label, long long label_stride, int h, int w,
+upsample_ce_band_kernel(const float* __restrict__ rev, const LT* __restrict__ label, long long label_stride, int h, int w,
                         int H, int W, float sy, float sx, int bands, float* __restrict__ partial) {
   extern __shared__ float hrow[];                    // [nsrc][2][W]
   const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
@@ -93,17 +106,17 @@ upsample_ce_band_kernel(const float* __restrict__ rev, const float* __restrict__
       }
   }
   __syncthreads();
-  const float* lab = label + n * label_stride;
+  const long long lab0 = n * label_stride;
   float acc = 0.f;
   for (int Y = Y0; Y < Y1; ++Y) {
     const Lerp ly = lerp_coeff(Y, sy, h);
     const float* rt = hrow + (ly.i0 - src0) * 2 * W;
     const float* rb = hrow + (ly.i1 - src0) * 2 * W;
-    const float* lrow = lab + static_cast<long long>(Y) * W;
+    const long long lrow = lab0 + static_cast<long long>(Y) * W;
     for (int X = threadIdx.x; X < W; X += blockDim.x) {
       const float v0 = lerp2(ly.l0, rt[X], ly.l1, rb[X]);
       const float v1 = lerp2(ly.l0, rt[W + X], ly.l1, rb[W + X]);
-      const int lb = static_cast<int>(__ldg(lrow + X));                       // .long() truncation
+      const int lb = ce_label<LT>(label, lrow + X);
       const float m = fmaxf(v0, v1);
       acc += (m + logf(1.0f + expf(-fabsf(v0 - v1)))) - (lb == 1 ? v1 : v0);
     }
@@ -129,8 +142,9 @@ upsample_ce_band_kernel(const float* __restrict__ rev, const float* __restrict__
 #define PEMP_CE_BAND 32
 #endif
 constexpr int kCeBand2 = PEMP_CE_BAND;
+template <typename LT>
 __global__ void __launch_bounds__(kCeThreads)
-upsample_ce_band2_kernel(const float* __restrict__ rev, const float* __restrict__ label, long long label_stride, int h, int w,
+upsample_ce_band2_kernel(const float* __restrict__ rev, const LT* __restrict__ label, long long label_stride, int h, int w,
                          int H, int W, float sy, float sx, int bands, float* __restrict__ partial) {
   extern __shared__ float hrow[];                    // [nsrc][W]  horizontal pass of (rev1 - rev0)
   const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
@@ -147,15 +161,14 @@ upsample_ce_band2_kernel(const float* __restrict__ rev, const float* __restrict_
     }
   }
   __syncthreads();
-  const float* lab = label + n * label_stride;
   float acc = 0.f;
   for (int X = threadIdx.x; X < W; X += kCeThreads) {
-    const float* lcol = lab + static_cast<long long>(Y0) * W + X;
+    const long long lcol = n * label_stride + static_cast<long long>(Y0) * W + X;
 #pragma unroll 4
     for (int Y = Y0; Y < Y1; ++Y) {
       const Lerp ly = lerp_coeff(Y, sy, h);
       const float d = lerp2(ly.l0, hrow[(ly.i0 - src0) * W + X], ly.l1, hrow[(ly.i1 - src0) * W + X]);
-      const int lb = static_cast<int>(__ldg(lcol + static_cast<long long>(Y - Y0) * W));      // .long() truncation
+      const int lb = ce_label<LT>(label, lcol + static_cast<long long>(Y - Y0) * W);
       const float t = lb == 1 ? -d : d;
       acc += fmaxf(t, 0.f) + __logf(1.0f + __expf(-fabsf(t)));
     }
@@ -213,10 +226,12 @@ extern "C" size_t pemp_panet_align_workspace_bytes(int B, int S, int Q, int c, i
   return make_plan(B, S, Q, c, h, w, H, W).total;
 }
 
-extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stride, const float* pred,
-                                const float* sup_fts, long long sup_episode_stride, const float* sup_mask_fg,
-                                long long mask_stride, int B, int S, int Q, int c, int h, int w, int H, int W,
-                                float scalar, float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+namespace {
+template <typename LT>
+int panet_align_impl(const float* qry_fts, long long qry_episode_stride, const float* pred, const float* sup_fts,
+                     long long sup_episode_stride, const LT* sup_mask_fg, long long mask_stride, int B, int S, int Q,
+                     int c, int h, int w, int H, int W, float scalar, float* loss, void* workspace, size_t workspace_bytes,
+                     pemp_stream_t stream) {
   PEMP_REQUIRE(qry_fts && pred && sup_fts && sup_mask_fg && loss, PEMP_E_NULL);
   PEMP_REQUIRE(B > 0 && S > 0 && Q > 0 && c > 0 && h > 0 && w > 0 && H > 0 && W > 0, PEMP_E_SHAPE);
   Plan pl = make_plan(B, S, Q, c, h, w, H, W);
@@ -248,7 +263,7 @@ extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stri
   if (smem2 <= 48 * 1024) {
     const int bands = (H + kCeBand2 - 1) / kCeBand2;
     nparts = B * S * bands;
-    upsample_ce_band2_kernel<<<nparts, kCeThreads, smem2, st>>>(rev, sup_mask_fg, mask_stride, h, w, H, W, sy, sx, bands, partial);
+    upsample_ce_band2_kernel<LT><<<nparts, kCeThreads, smem2, st>>>(rev, sup_mask_fg, mask_stride, h, w, H, W, sy, sx, bands, partial);
     ce_finalize_kernel<<<1, 256, 0, st>>>(partial, nparts, static_cast<double>(total), loss);
     return launch_status();
   }
@@ -258,11 +273,29 @@ extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stri
   if (nsrc_max <= kCeMaxSrc && smem <= 48 * 1024) {
     const int bands = (H + kCeBand - 1) / kCeBand;
     nparts = B * S * bands;
-    upsample_ce_band_kernel<<<nparts, kCeThreads, smem, st>>>(rev, sup_mask_fg, mask_stride, h, w, H, W, sy, sx, bands, partial);
+    upsample_ce_band_kernel<LT><<<nparts, kCeThreads, smem, st>>>(rev, sup_mask_fg, mask_stride, h, w, H, W, sy, sx, bands, partial);
   } else {
     nparts = static_cast<int>(llmin((total + kCeThreads - 1) / kCeThreads, 148LL * 16));
-    upsample_ce_kernel<<<nparts, kCeThreads, 0, st>>>(rev, sup_mask_fg, mask_stride, total, h, w, H, W, sy, sx, partial);
+    upsample_ce_kernel<LT><<<nparts, kCeThreads, 0, st>>>(rev, sup_mask_fg, mask_stride, total, h, w, H, W, sy, sx, partial);
   }
   ce_finalize_kernel<<<1, 256, 0, st>>>(partial, nparts, static_cast<double>(total), loss);
   return launch_status();
+}
+}  // namespace
+
+extern "C" int pemp_panet_align(const float* qry_fts, long long qry_episode_stride, const float* pred,
+                                const float* sup_fts, long long sup_episode_stride, const float* sup_mask_fg,
+                                long long mask_stride, int B, int S, int Q, int c, int h, int w, int H, int W,
+                                float scalar, float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  return panet_align_impl<float>(qry_fts, qry_episode_stride, pred, sup_fts, sup_episode_stride, sup_mask_fg, mask_stride, B, S, Q, c, h, w,
+                          H, W, scalar, loss, workspace, workspace_bytes, stream);
+}
+
+// the same loss against the uint8 label map [B*S, H, W] (1 = object) the float `sup_mask_fg` was expanded from
+extern "C" int pemp_panet_align_labels(const float* qry_fts, long long qry_episode_stride, const float* pred,
+                                       const float* sup_fts, long long sup_episode_stride, const uint8_t* labels,
+                                       long long label_stride, int B, int S, int Q, int c, int h, int w, int H, int W,
+                                       float scalar, float* loss, void* workspace, size_t workspace_bytes, pemp_stream_t stream) {
+  return panet_align_impl<uint8_t>(qry_fts, qry_episode_stride, pred, sup_fts, sup_episode_stride, labels, label_stride, B, S, Q, c, h, w,
+                          H, W, scalar, loss, workspace, workspace_bytes, stream);
 }

@@ -18,6 +18,10 @@ size_t pemp_adjoint_scratch_bytes(int planes, int h, int w);
 int pemp_adjoint_launch(const float* mask, int planes, int H, int W, int h, int w, float* wt, float* msum, char* scratch,
                         cudaStream_t st);
 
+size_t pemp_adjoint_labels_extra_bytes(int images, int H, int W, int h, int w);
+int pemp_adjoint_launch_labels(const uint8_t* labels, int images, int H, int W, int h, int w, float* wt, float* msum, char* scratch,
+                               float* expanded, cudaStream_t st);
+
 namespace {
 struct Plan {
   size_t off_wt, off_sum, off_adj, off_pool, total;
@@ -55,4 +59,31 @@ extern "C" int pemp_map_pool_fullres(const float* fts, long long fts_episode_str
   const int hw = h * w;
   return pemp_pool_launch(fts, fts_episode_stride, wt, wt + hw, 2LL * hw, B, S, c, hw, eps, msum, fg_proto, bg_proto, ws + pl.off_pool,
                           workspace_bytes - pl.off_pool, as_stream(stream));
+}
+
+// ---- the same pooling fed by the label map the data set stores (1 object / 0 background / 255 boundary) ---------------------
+// instead of the two float planes the loader expands it to (data_kits/pascal_voc.py:209-210): identical prototypes (the planes
+// are formed on the fly, fg = (label == 1), bg = (label == 0)), an eighth of the mask bytes from HBM and from the host.
+extern "C" size_t pemp_map_pool_fullres_labels_workspace_bytes(int B, int S, int c, int h, int w, int H, int W) {
+  if (B <= 0 || S <= 0 || c <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
+  return make_plan(B, S, c, h, w).total + pemp_adjoint_labels_extra_bytes(B * S, H, W, h, w);
+}
+
+extern "C" int pemp_map_pool_fullres_labels(const float* fts, long long fts_episode_stride, const uint8_t* labels, int B, int S, int c,
+                                            int h, int w, int H, int W, float eps, float* fg_proto, float* bg_proto, void* workspace,
+                                            size_t workspace_bytes, pemp_stream_t stream) {
+  PEMP_REQUIRE(fts && labels && fg_proto && bg_proto, PEMP_E_NULL);
+  PEMP_REQUIRE(B > 0 && S > 0 && c > 0 && h > 0 && w > 0 && H > 0 && W > 0, PEMP_E_SHAPE);
+  Plan pl = make_plan(B, S, c, h, w);
+  const size_t extra = pemp_adjoint_labels_extra_bytes(B * S, H, W, h, w);
+  PEMP_REQUIRE(workspace && workspace_bytes >= pl.total + extra, PEMP_E_WORKSPACE);
+  char* ws = static_cast<char*>(workspace);
+  float* wt = reinterpret_cast<float*>(ws + pl.off_wt);
+  float* msum = reinterpret_cast<float*>(ws + pl.off_sum);
+  float* expanded = extra ? reinterpret_cast<float*>(ws + pl.total) : nullptr;
+  int rc = pemp_adjoint_launch_labels(labels, B * S, H, W, h, w, wt, msum, ws + pl.off_adj, expanded, as_stream(stream));
+  if (rc != PEMP_OK) return rc;
+  const int hw = h * w;
+  return pemp_pool_launch(fts, fts_episode_stride, wt, wt + hw, 2LL * hw, B, S, c, hw, eps, msum, fg_proto, bg_proto, ws + pl.off_pool,
+                          pl.total - pl.off_pool, as_stream(stream));
 }

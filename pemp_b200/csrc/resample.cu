@@ -564,9 +564,24 @@ constexpr int kAdjT = PEMP_ADJ_THREADS;
 constexpr int kAdjUnroll = 9;      // mask rows per low-res row at the usual 8x geometry: 8, 9 at some rows
 // KW > 0: the row pitch is a compile-time constant, so the (row, plane) offsets of a thread's loads are instruction immediates
 // (KW = 0 takes W from the argument; ncu of that version: 51 % of all instructions were 64-bit address arithmetic).
-template <int NP, int KW>
+// T = float: NP planes of floats per image.  T = uint8_t: ONE label plane per image (1 object / 0 background / 255 boundary, the
+// map data_kits/pascal_voc.py:209-210 expands into the float `sup_mask`); a byte yields both planes, fg = (b == 1), bg = (b == 0):
+// half the loads and an eighth of the mask bytes (`pemp_map_pool_fullres_labels`).
+template <int NP, typename T>
+__device__ __forceinline__ void adj_load(const T* p, int PS, float (&v)[NP]) {
+  if constexpr (sizeof(T) == 1) {
+    static_assert(sizeof(T) != 1 || NP == 2, "a label byte stands for the fg and the bg plane");
+    const unsigned b = __ldg(p);
+    v[0] = b == 1u ? 1.f : 0.f;
+    v[NP - 1] = b == 0u ? 1.f : 0.f;
+  } else {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) v[q] = __ldg(p + q * PS);
+  }
+}
+template <int NP, int KW, typename T>
 __global__ void __launch_bounds__(kAdjT, PEMP_ADJ_MINB)
-adjoint_rows2_kernel(const float* __restrict__ mask, AdjTables t, float* __restrict__ ab, float* __restrict__ rsum, int H,
+adjoint_rows2_kernel(const T* __restrict__ mask, AdjTables t, float* __restrict__ ab, float* __restrict__ rsum, int H,
                      int W_arg, int h, int w) {
   const int W = KW > 0 ? KW : W_arg;
   extern __shared__ float sh[];      // [NP][2][Wp]: A (-> row y) and B (-> row y + 1) of every plane, padded rows
@@ -578,7 +593,8 @@ adjoint_rows2_kernel(const float* __restrict__ mask, AdjTables t, float* __restr
   const float2* __restrict__ wab = t.wab + y * kAdjMaxRows;
   // 32-bit offsets from one CTA-uniform base: the first version spent 51 % of its instructions (ncu: IMAD / LEA / IADD3, 6.6 per
   // load) on 64-bit address arithmetic of the form ((p * H + r) * W + X)
-  const float* m = mask + (static_cast<long long>(img) * NP * H + Ylo) * W;
+  constexpr int kPlanesIn = sizeof(T) == 1 ? 1 : NP;       // stored planes per image
+  const T* m = mask + (static_cast<long long>(img) * kPlanesIn * H + Ylo) * W;
   const int PS = H * W;
   float s[NP];
 #pragma unroll
@@ -587,21 +603,19 @@ adjoint_rows2_kernel(const float* __restrict__ mask, AdjTables t, float* __restr
     float a[NP], b[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) a[p] = b[p] = 0.f;
-    const float* q = m + X;
+    const T* q = m + X;
     if (KW > 0 && nr <= kAdjUnroll) {
-      const float* qp[NP];
-#pragma unroll
-      for (int p = 0; p < NP; ++p) qp[p] = q + p * PS;
 #pragma unroll
       for (int r = 0; r < kAdjUnroll; ++r) {
         if (r < nr) {
           const float2 wr = __ldg(wab + r);
+          float v[NP];
+          adj_load<NP, T>(q + r * KW, PS, v);
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
-            const float v = __ldg(qp[p] + r * KW);
-            s[p] += v;
-            a[p] = fmaf(wr.x, v, a[p]);
-            b[p] = fmaf(wr.y, v, b[p]);
+            s[p] += v[p];
+            a[p] = fmaf(wr.x, v[p], a[p]);
+            b[p] = fmaf(wr.y, v[p], b[p]);
           }
         }
       }
@@ -610,12 +624,13 @@ adjoint_rows2_kernel(const float* __restrict__ mask, AdjTables t, float* __restr
 #pragma unroll 8
       for (int r = 0; r < nr; ++r, off += W) {
         const float2 wr = __ldg(wab + r);
+        float v[NP];
+        adj_load<NP, T>(q + off, PS, v);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const float v = __ldg(q + (off + p * PS));
-          s[p] += v;
-          a[p] = fmaf(wr.x, v, a[p]);
-          b[p] = fmaf(wr.y, v, b[p]);
+          s[p] += v[p];
+          a[p] = fmaf(wr.x, v[p], a[p]);
+          b[p] = fmaf(wr.y, v[p], b[p]);
         }
       }
     }
@@ -651,15 +666,15 @@ adjoint_rows2_kernel(const float* __restrict__ mask, AdjTables t, float* __restr
 }
 
 // instantiations for the mask widths of the reference's data sets (401 PASCAL, 417 COCO / PANet, 473 PFENet, 321); others: KW = 0
-template <int NP>
-static void adjoint_rows2_launch(dim3 grid, size_t smem, cudaStream_t st, const float* mask, AdjTables t, float* ab, float* rsum,
+template <int NP, typename T>
+static void adjoint_rows2_launch(dim3 grid, size_t smem, cudaStream_t st, const T* mask, AdjTables t, float* ab, float* rsum,
                                  int H, int W, int h, int w) {
   switch (W) {
-    case 401: adjoint_rows2_kernel<NP, 401><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
-    case 417: adjoint_rows2_kernel<NP, 417><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
-    case 473: adjoint_rows2_kernel<NP, 473><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
-    case 321: adjoint_rows2_kernel<NP, 321><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
-    default: adjoint_rows2_kernel<NP, 0><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 401: adjoint_rows2_kernel<NP, 401, T><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 417: adjoint_rows2_kernel<NP, 417, T><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 473: adjoint_rows2_kernel<NP, 473, T><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    case 321: adjoint_rows2_kernel<NP, 321, T><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
+    default: adjoint_rows2_kernel<NP, 0, T><<<grid, kAdjT, smem, st>>>(mask, t, ab, rsum, H, W, h, w); break;
   }
 }
 
@@ -671,38 +686,85 @@ size_t pemp_adjoint_scratch_bytes(int planes, int h, int w) {
   return align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256) + align_up(static_cast<size_t>(planes) * h * sizeof(float), 256) +
          adj_tables_bytes(h, w);
 }
+static bool adj_fast_geometry(int H, int W, int h, int w) {
+  // the fast kernels keep a few rows of W floats in shared memory and bound the rows / columns one low-res row / column owns
+  return !(5 * W * sizeof(float) > 48 * 1024 || (H > h && (H + h - 1) / h + 2 > kAdjMaxRows) ||
+           (W > w && 2 * ((W + w - 1) / w) + 3 > kAdjMaxTaps));
+}
+struct AdjScratch {
+  float* ab;
+  float* rsum;
+  AdjTables t;
+};
+static AdjScratch adj_scratch(char* scratch, int planes, int h, int w) {
+  AdjScratch a;
+  a.ab = reinterpret_cast<float*>(scratch);
+  char* p = scratch + align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256);
+  a.rsum = reinterpret_cast<float*>(p);
+  p += align_up(static_cast<size_t>(planes) * h * sizeof(float), 256);
+  a.t.rowinfo = reinterpret_cast<int2*>(p);
+  p += align_up(static_cast<size_t>(h) * sizeof(int2), 256);
+  a.t.wab = reinterpret_cast<float2*>(p);
+  p += align_up(static_cast<size_t>(h) * kAdjMaxRows * sizeof(float2), 256);
+  a.t.xinfo = reinterpret_cast<int2*>(p);
+  p += align_up(static_cast<size_t>(w) * sizeof(int2), 256);
+  a.t.xw = reinterpret_cast<float*>(p);
+  return a;
+}
+
 int pemp_adjoint_launch(const float* mask, int planes, int H, int W, int h, int w, float* wt, float* msum, char* scratch,
                         cudaStream_t st) {
-  // the fast kernels keep a few rows of W floats in shared memory and bound the rows / columns one low-res row / column owns
-  if (5 * W * sizeof(float) > 48 * 1024 || (H > h && (H + h - 1) / h + 2 > kAdjMaxRows) || (W > w && 2 * ((W + w - 1) / w) + 3 > kAdjMaxTaps))
+  if (!adj_fast_geometry(H, W, h, w))
     return pemp_bilinear_adjoint(mask, planes, H, W, h, w, wt, msum, reinterpret_cast<pemp_stream_t>(st));
-  float* ab = reinterpret_cast<float*>(scratch);
-  char* p = scratch + align_up(static_cast<size_t>(planes) * h * 2 * w * sizeof(float), 256);
-  float* rsum = reinterpret_cast<float*>(p);
-  p += align_up(static_cast<size_t>(planes) * h * sizeof(float), 256);
-  AdjTables t;
-  t.rowinfo = reinterpret_cast<int2*>(p);
-  p += align_up(static_cast<size_t>(h) * sizeof(int2), 256);
-  t.wab = reinterpret_cast<float2*>(p);
-  p += align_up(static_cast<size_t>(h) * kAdjMaxRows * sizeof(float2), 256);
-  t.xinfo = reinterpret_cast<int2*>(p);
-  p += align_up(static_cast<size_t>(w) * sizeof(int2), 256);
-  t.xw = reinterpret_cast<float*>(p);
+  const AdjScratch a = adj_scratch(scratch, planes, h, w);
   const float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
 #ifdef PEMP_ADJ_V1
-  adjoint_rows_kernel<<<dim3(h, planes), 256, 5 * W * sizeof(float), st>>>(mask, ab, rsum, H, W, h, w, sy, sx);
+  adjoint_rows_kernel<<<dim3(h, planes), 256, 5 * W * sizeof(float), st>>>(mask, a.ab, a.rsum, H, W, h, w, sy, sx);
 #else
-  adjoint_tables_kernel<<<1, 256, 0, st>>>(t, H, W, h, w, sy, sx);
+  adjoint_tables_kernel<<<1, 256, 0, st>>>(a.t, H, W, h, w, sy, sx);
 #ifdef PEMP_ADJ_NP1
   if (false)
 #else
   if (planes % 2 == 0)
 #endif
-    adjoint_rows2_launch<2>(dim3(h, planes / 2), 4 * adj_row_floats(W) * sizeof(float), st, mask, t, ab, rsum, H, W, h, w);
+    adjoint_rows2_launch<2, float>(dim3(h, planes / 2), 4 * adj_row_floats(W) * sizeof(float), st, mask, a.t, a.ab, a.rsum, H, W, h, w);
   else
-    adjoint_rows2_launch<1>(dim3(h, planes), 2 * adj_row_floats(W) * sizeof(float), st, mask, t, ab, rsum, H, W, h, w);
+    adjoint_rows2_launch<1, float>(dim3(h, planes), 2 * adj_row_floats(W) * sizeof(float), st, mask, a.t, a.ab, a.rsum, H, W, h, w);
 #endif
-  adjoint_combine_kernel<<<planes, 256, 0, st>>>(ab, rsum, wt, msum, h, w);
+  adjoint_combine_kernel<<<planes, 256, 0, st>>>(a.ab, a.rsum, wt, msum, h, w);
+  return launch_status();
+}
+
+// labels [images, H, W] uint8 -> the float planes stack((label == 1), (label == 0)) [images, 2, H, W] (only for geometries
+// the fast adjoint does not cover; `expanded` is workspace)
+__global__ void labels_expand_kernel(const uint8_t* __restrict__ lab, float* __restrict__ out, long long images, long long HW) {
+  const long long total = images * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / HW, r = i - n * HW;
+    const uint8_t v = __ldg(lab + i);
+    out[(n * 2 + 0) * HW + r] = v == 1 ? 1.f : 0.f;
+    out[(n * 2 + 1) * HW + r] = v == 0 ? 1.f : 0.f;
+  }
+}
+size_t pemp_adjoint_labels_extra_bytes(int images, int H, int W, int h, int w) {
+  return adj_fast_geometry(H, W, h, w) ? 0 : align_up(static_cast<size_t>(images) * 2 * H * W * sizeof(float), 256);
+}
+// Same as pemp_adjoint_launch for the label map of `images` support images (2 * images weight planes come out).
+int pemp_adjoint_launch_labels(const uint8_t* labels, int images, int H, int W, int h, int w, float* wt, float* msum, char* scratch,
+                               float* expanded, cudaStream_t st) {
+  const int planes = 2 * images;
+  if (!adj_fast_geometry(H, W, h, w)) {
+    if (!expanded) return PEMP_E_WORKSPACE;
+    const long long total = static_cast<long long>(images) * H * W;
+    labels_expand_kernel<<<static_cast<unsigned>(llmin((total + 255) / 256, 148LL * 16)), 256, 0, st>>>(labels, expanded, images,
+                                                                                                      static_cast<long long>(H) * W);
+    return pemp_bilinear_adjoint(expanded, planes, H, W, h, w, wt, msum, reinterpret_cast<pemp_stream_t>(st));
+  }
+  const AdjScratch a = adj_scratch(scratch, planes, h, w);
+  adjoint_tables_kernel<<<1, 256, 0, st>>>(a.t, H, W, h, w, lerp_scale(h, H), lerp_scale(w, W));
+  adjoint_rows2_launch<2, uint8_t>(dim3(h, images), 4 * adj_row_floats(W) * sizeof(float), st, labels, a.t, a.ab, a.rsum, H, W, h, w);
+  adjoint_combine_kernel<<<planes, 256, 0, st>>>(a.ab, a.rsum, wt, msum, h, w);
   return launch_status();
 }
 

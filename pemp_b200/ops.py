@@ -324,24 +324,37 @@ def nearest_resize_labels(lab, out_hw):
 # ------------------------------------------------------------------------------------------------ K6
 @_on_device
 def map_pool_fullres(fts, sup_mask, B, S, eps=1e-5):
-    """fts [B*S, c, h, w]; sup_mask [B*S, 2, H, W] -> (fg_proto [B,c], bg_proto [B,c])  (baseline.py:100-110)."""
+    """fts [B*S, c, h, w]; sup_mask [B*S, 2, H, W] float32 (fg, bg) - or the uint8 label map [B*S, H, W] (1 object / 0 background /
+    255 boundary) the loader expands it from - -> (fg_proto [B,c], bg_proto [B,c])  (baseline.py:100-110)."""
     if fts.dim() not in (4, 5):
         raise ValueError("fts must be [B*S, c, h, w] or [B, S, c, h, w]")
     h, w = fts.shape[-2:]
     fts, ep, c, _ = _episodes(fts, B, S, "fts")
-    sup_mask = _need(sup_mask, torch.float32, "sup_mask")
     n_img = B * S
-    if sup_mask.shape[:2] != (n_img, 2):
-        raise ValueError(f"expected sup_mask [{B * S},2,H,W], got {tuple(sup_mask.shape)}")
+    labels = isinstance(sup_mask, torch.Tensor) and sup_mask.dtype == torch.uint8
+    if labels:
+        sup_mask = _need(sup_mask, torch.uint8, "sup_mask")
+        if sup_mask.dim() < 3 or sup_mask.numel() // (sup_mask.shape[-2] * sup_mask.shape[-1]) != n_img:
+            raise ValueError(f"expected labels [{n_img},H,W], got {tuple(sup_mask.shape)}")
+    else:
+        sup_mask = _need(sup_mask, torch.float32, "sup_mask")
+        if sup_mask.shape[:2] != (n_img, 2):
+            raise ValueError(f"expected sup_mask [{B * S},2,H,W], got {tuple(sup_mask.shape)}")
     H, W = sup_mask.shape[-2:]
     L = _cabi.lib()
-    ws = _ws(L.pemp_map_pool_fullres_workspace_bytes(B, S, c, h, w), fts.device)
     out_f = torch.empty(B, c, dtype=torch.float32, device=fts.device)
     out_b = torch.empty(B, c, dtype=torch.float32, device=fts.device)
-    _cabi.check(L.pemp_map_pool_fullres(fts.data_ptr(), ep, sup_mask.data_ptr(), B, S, c, h, w, H, W, float(eps),
-                                        out_f.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-                "pemp_map_pool_fullres")
-    _count(4)
+    if labels:
+        ws = _ws(L.pemp_map_pool_fullres_labels_workspace_bytes(B, S, c, h, w, H, W), fts.device)
+        _cabi.check(L.pemp_map_pool_fullres_labels(fts.data_ptr(), ep, sup_mask.data_ptr(), B, S, c, h, w, H, W, float(eps),
+                                                   out_f.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                    "pemp_map_pool_fullres_labels")
+    else:
+        ws = _ws(L.pemp_map_pool_fullres_workspace_bytes(B, S, c, h, w), fts.device)
+        _cabi.check(L.pemp_map_pool_fullres(fts.data_ptr(), ep, sup_mask.data_ptr(), B, S, c, h, w, H, W, float(eps),
+                                            out_f.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                    "pemp_map_pool_fullres")
+    _count(5)
     return out_f, out_b
 
 
@@ -364,9 +377,11 @@ def bilinear_adjoint(mask, out_hw, want_sum=True):
 @_on_device
 def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
     """`PANet.alignLoss(qry_fts [BQ,c,h,w], pred [BQ,2,h,w], sup_fts [BS,c,h,w], sup_mask_fg [BS,1,H,W], Q)`
-    -> 0-dim loss tensor (panet.py:158-194)."""
+    -> 0-dim loss tensor (panet.py:158-194).  `sup_mask_fg` may also be the uint8 label map [BS,H,W] (1 = object) that the float
+    foreground plane was expanded from."""
     pred = _need(pred, torch.float32, "pred")
-    sup_mask_fg = _need_loose(sup_mask_fg, "sup_mask_fg")
+    labels = isinstance(sup_mask_fg, torch.Tensor) and sup_mask_fg.dtype == torch.uint8
+    sup_mask_fg = _need(sup_mask_fg, torch.uint8, "sup_mask_fg") if labels else _need_loose(sup_mask_fg, "sup_mask_fg")
     h, w = qry_fts.shape[-2:]
     BQ = qry_fts.shape[0] * qry_fts.shape[1] if qry_fts.dim() == 5 else qry_fts.shape[0]
     BS = sup_fts.shape[0] * sup_fts.shape[1] if sup_fts.dim() == 5 else sup_fts.shape[0]
@@ -386,9 +401,10 @@ def panet_align(qry_fts, pred, sup_fts, sup_mask_fg, Q, scalar=20.0):
     L = _cabi.lib()
     ws = _ws(L.pemp_panet_align_workspace_bytes(B, S, Q, c, h, w, H, W), qry_fts.device)
     loss = torch.empty((), dtype=torch.float32, device=qry_fts.device)
-    _cabi.check(L.pemp_panet_align(qry_fts.data_ptr(), qep, pred.data_ptr(), sup_fts.data_ptr(), sep, m.data_ptr(), stride, B, S, Q,
-                                   c, h, w, H, W, float(scalar), loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-                "pemp_panet_align")
+    fn = L.pemp_panet_align_labels if labels else L.pemp_panet_align
+    _cabi.check(fn(qry_fts.data_ptr(), qep, pred.data_ptr(), sup_fts.data_ptr(), sep, m.data_ptr(), stride, B, S, Q,
+                   c, h, w, H, W, float(scalar), loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "pemp_panet_align_labels" if labels else "pemp_panet_align")
     _count(6)
     return loss
 

@@ -492,6 +492,33 @@ def test_map_pool_fullres_vs_restatement(ops, B, S, c, h, w, H, W):
     assert nrel(of.cpu(), rf) < TOL and nrel(ob.cpu(), rb) < TOL
 
 
+@pytest.mark.parametrize("B,S,c,h,w,H,W", [(2, 2, 24, 13, 13, 97, 97), (1, 3, 16, 9, 12, 50, 77), (1, 1, 8, 20, 20, 11, 15),
+                                           (2, 5, 512, 51, 51, 401, 401), (1, 2, 64, 53, 53, 417, 417)])
+def test_fullres_pooling_and_align_loss_take_label_maps(ops, B, S, c, h, w, H, W):
+    """K6 / K7 fed by the uint8 label map the data set stores (1 object / 0 background / 255 boundary) give bit for bit what they
+    give on the loader's float expansion `stack((label == 1), (label == 0))` (data_kits/pascal_voc.py:209-210) - the planes are
+    formed on the fly from one byte per pixel (an eighth of the mask bytes); geometries the fast adjoint does not cover go
+    through an on-device expansion."""
+    g = torch.Generator().manual_seed(H + c)
+    lab = torch.randint(0, 3, (B * S, H, W), generator=g).to(torch.uint8)
+    lab[lab == 2] = 255
+    lab[:, H // 4: H // 2, W // 5: W // 2] = 1                                   # a solid object as well
+    planes = torch.stack(((lab == 1).float(), (lab == 0).float()), dim=1)       # [BS, 2, H, W]
+    f = torch.randn(B, S + 1, c, h, w, generator=g)
+    f_cu = cu(f)
+    a = ops.map_pool_fullres(f_cu[:, :S], cu(planes), B, S)
+    b = ops.map_pool_fullres(f_cu[:, :S], cu(lab), B, S)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    rf, rb = O.map_pool_fullres(f[:, :S].reshape(B * S, c, h, w), planes, B, S)
+    assert nrel(b[0].cpu(), rf) < TOL and nrel(b[1].cpu(), rb) < TOL
+    pred = ops.cosine_match(f_cu[:, S:], b[0], b[1], 20.0)["pred"].view(B, 2, h, w)
+    l_float = ops.panet_align(f_cu[:, S:], pred, f_cu[:, :S], cu(planes[:, 0:1]), 1)
+    l_label = ops.panet_align(f_cu[:, S:], pred, f_cu[:, :S], cu(lab), 1)
+    assert torch.equal(l_float, l_label)
+    with pytest.raises(ValueError):
+        ops.map_pool_fullres(f_cu[:, :S], cu(torch.cat((lab, lab[:1]))), B, S)       # one label plane too many
+
+
 def test_bilinear_adjoint_identity(ops):
     """sum_YX m (U f) == sum_yx f (U^T m) and sum(U^T m) == sum(m)."""
     torch.manual_seed(8)

@@ -54,6 +54,7 @@ def run(B=64, S=5, c=512, h=51, H=401, only="", k9_batch=2, emit=None):
     fgfull = torch.zeros(B * S, 1, H, H, device=dev)
     fgfull[:, :, 100:300, 80:330] = 1
     sup_mask = torch.cat((fgfull, 1 - fgfull), 1)
+    lab8 = fgfull[:, 0].to(torch.uint8)
     low = ops.mask_nearest(sup_mask, h, h).view(B * S, 2, hw)
     fgp, bgp, _ = ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S)
     fg1, bg1 = ops.map_pool_lowres(sup, low[:, 0], low[:, 1], B, S)
@@ -78,6 +79,8 @@ def run(B=64, S=5, c=512, h=51, H=401, only="", k9_batch=2, emit=None):
          B * (2 * hw * 4 + 2 * H * H)),
         ("K6 map_pool_fullres", lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
          B * (S * (c * hw * 4 + 2 * H * H * 4) + 2 * c * 4)),
+        ("K6 map_pool_fullres (uint8 label maps)", lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), lab8, B, S),
+         B * (S * (c * hw * 4 + H * H) + 2 * c * 4)),
         # PANet alignLoss (panet.py:158-194): query pooling + S cosine passes over the support maps + fused up-sample / CE
         ("K7 panet_align", lambda: ops.panet_align(qry.view(B, c, h, h), pred, sup.view(B * S, c, h, h), fgfull, 1),
          B * ((1 + S) * c * hw * 4 + 2 * hw * 4 + S * H * H * 4)),
