@@ -42,6 +42,7 @@ SIGNATURES = {
     "pemp_debug_mpa_path": (I, [I]),
     "pemp_debug_cosine_path": (I, [I]),
     "pemp_debug_pool_path": (I, [I]),
+    "pemp_debug_bwd_path": (I, [I]),
     "pemp_meta_proto_attn": (I, [P, LL, P, P, P, LL, I, I, I, I, I, F, P, P, P, P, SZ, P]),
     "pemp_cosine_match": (I, [P, LL, P, P, I, I, I, I, I, F, P, P, P, P]),
     "pemp_upsample_argmax": (I, [P, I, I, I, I, I, P, P, P, P]),

@@ -28,6 +28,14 @@
 
 #include "common.cuh"
 
+// train_mma.cu: K2 backward with the per-tile products on the warp-level tensor path (P = 3, c in {128, 256, 512, 1024})
+size_t pemp_mpa_bwd_mma_smem(int c);
+bool pemp_mpa_bwd_mma_shape(int c, int p);
+int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int S, const float* ctr, const float* coef, const float* beta,
+                            const float* fg, const float* bg, long long mask_stride, int N, int c, int hw, int chunks, int ntiles,
+                            float* dfts, long long d_ep, float* part, cudaStream_t st);
+static int g_bwd_path = 0;   // diagnostic switch, see pemp_debug_bwd_path
+
 namespace {
 
 #ifndef PEMP_BWD_THREADS
@@ -835,11 +843,21 @@ extern "C" int pemp_cosine_sim_bwd(const float* qry, long long qry_episode_strid
                            d_qry_episode_stride, d_fg, d_bg, workspace, workspace_bytes, stream);
 }
 
+extern "C" int pemp_debug_bwd_path(int mode) {
+  const int old = g_bwd_path;
+  if (mode == 0 || mode == 1) g_bwd_path = mode;
+  return old;
+}
+
 extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p) {
   if (B <= 0 || S <= 0 || c <= 0 || hw <= 0 || p < 1 || p > 4) return 0;
   const size_t N = static_cast<size_t>(B) * S, K = 2 * p;
-  const BwdPlan pl = bwd_plan(static_cast<int>(N), hw, mpa_smem(c, 2 * p));
-  return align_up(N * c * K * 4, 256) + align_up(N * 2 * K * 4, 256) + align_up(N * pl.chunks * (c + 1) * K * 4, 256);
+  int chunks = bwd_plan(static_cast<int>(N), hw, mpa_smem(c, 2 * p)).chunks;
+  if (pemp_mpa_bwd_mma_shape(c, p)) {            // room for either kernel's split (the diagnostic switch picks at launch time)
+    const int m = bwd_plan(static_cast<int>(N), hw, pemp_mpa_bwd_mma_smem(c)).chunks;
+    if (m > chunks) chunks = m;
+  }
+  return align_up(N * c * K * 4, 256) + align_up(N * 2 * K * 4, 256) + align_up(N * chunks * (c + 1) * K * 4, 256);
 }
 
 extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
@@ -853,7 +871,8 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_meta_proto_attn_bwd_workspace_bytes(B, S, c, hw, p), PEMP_E_WORKSPACE);
   cudaStream_t st = as_stream(stream);
   const int N = B * S, K = 2 * p;
-  const BwdPlan pl = bwd_plan(N, hw, mpa_smem(c, 2 * p));
+  const bool mma = g_bwd_path == 0 && pemp_mpa_bwd_mma_shape(c, p);
+  const BwdPlan pl = bwd_plan(N, hw, mma ? pemp_mpa_bwd_mma_smem(c) : mpa_smem(c, 2 * p));
   char* ws = static_cast<char*>(workspace);
   float* coef = reinterpret_cast<float*>(ws);
   float* beta = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(N) * c * K * 4, 256));
@@ -862,6 +881,9 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
   const long long d_ep = d_fts_episode_stride ? d_fts_episode_stride : static_cast<long long>(S) * c * hw;
   mpa_bwd_prepare_kernel<<<N, kBT, 0, st>>>(g_fg, g_bg, shot_centre, shot_den, ctr, S, c, p, coef, beta);
   int rc;
+  if (mma) {
+    rc = pemp_mpa_bwd_mma_launch(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl.chunks, pl.ntiles, d_fts, d_ep, part, st);
+  } else
   switch (p) {
     case 1: rc = launch_mpa_bwd<2>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
     case 2: rc = launch_mpa_bwd<4>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;

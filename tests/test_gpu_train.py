@@ -26,7 +26,9 @@ def _case(B, S, Q, c, h, w, P, seed, scale=1.0):
 
 
 @pytest.mark.parametrize("B,S,c,h,w,P", [(2, 2, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (2, 5, 512, 13, 13, 3),
-                                          (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (1, 3, 1024, 6, 7, 2)])
+                                          (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (1, 3, 1024, 6, 7, 2),
+                                          # the tensor-path kernel (P = 3, c in {128, 256, 512, 1024}), ragged last tiles
+                                          (2, 3, 128, 9, 11, 3), (1, 2, 256, 13, 7, 3), (1, 1, 1024, 6, 7, 3), (1, 2, 512, 5, 5, 3)])
 def test_meta_proto_attn_backward_matches_autograd_of_the_oracle(B, S, c, h, w, P):
     from pemp_b200 import autograd as A
     feats, ctr, fg, bg = _case(B, S, 1, c, h, w, P, seed=c + h)
@@ -53,6 +55,29 @@ def test_meta_proto_attn_backward_matches_autograd_of_the_oracle(B, S, c, h, w, 
     assert float(f_cu.grad[:, S:].abs().max()) == 0.0
     assert nrel(d_sup, sup64.grad.float()) <= tol_f
     assert nrel(ctr_cu.grad.cpu(), ctr64.grad.float()) <= tol_c
+
+
+def test_meta_proto_attn_backward_tensor_path_vs_cuda_core_kernel_full_size():
+    """The two implementations of the K2 backward (train_mma.cu: 3 x TF32 on the warp-level tensor path; train.cu: CUDA cores)
+    on the same full-size input through `pemp_debug_bwd_path`: they agree to fp32 summation-order noise."""
+    from pemp_b200 import _cabi, ops
+    B, S, c, h, P = 2, 5, 512, 51, 3
+    feats, ctr, fg, bg = _case(B, S, 1, c, h, h, P, seed=11)
+    g = torch.Generator().manual_seed(3)
+    gf, gb = torch.randn(B, c, P, generator=g).cuda(), torch.randn(B, c, P, generator=g).cuda()
+    f_cu, ctr_cu, fg_cu, bg_cu = feats.cuda(), ctr.cuda(), fg.cuda(), bg.cuda()
+    _, _, saved = ops.meta_proto_attn_train(f_cu[:, :S], ctr_cu, fg_cu, bg_cu, B, S)
+    d1, c1 = ops.meta_proto_attn_bwd(saved, gf, gb, B, S)
+    d1b, c1b = ops.meta_proto_attn_bwd(saved, gf, gb, B, S)
+    assert torch.equal(d1, d1b) and torch.equal(c1, c1b)            # deterministic
+    _cabi.lib().pemp_debug_bwd_path(1)
+    try:
+        d0, c0 = ops.meta_proto_attn_bwd(saved, gf, gb, B, S)
+    finally:
+        _cabi.lib().pemp_debug_bwd_path(0)
+    ef, ec = nrel(d1.cpu(), d0.cpu()), nrel(c1.cpu(), c0.cpu())
+    print({"case": "K2 backward tensor path vs CUDA cores", "d_fts": ef, "d_ctr": ec})
+    assert ef < 1e-5 and ec < 1e-5
 
 
 @pytest.mark.parametrize("B,Q,c,h,w,P", [(2, 1, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (2, 2, 512, 13, 13, 3),

@@ -1,5 +1,5 @@
 """Run ONE op of the library a few times at its BASELINE shape (the short command to put under ncu).
-    python tools/prof_op.py --op K6|K7|K11|K9|K9x3|K2|K3|K2s1 [--iters 3]"""
+    python tools/prof_op.py --op K6|K7|K11|K9|K9x3|K2|K3|K2s1|K2b|K3b [--iters 3]"""
 import argparse
 import os
 import sys
@@ -18,7 +18,7 @@ dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 B, S, c, h, H = a.B, 5, 512, 51, 401
 hw = h * h
-if a.op in ("K6", "K7", "K2", "K3", "K2s1", "K4", "K4h"):
+if a.op in ("K6", "K7", "K2", "K3", "K2s1", "K4", "K4h", "K2b", "K3b"):
     if a.op == "K2s1":
         S = 1
     sup = torch.randn(B * S, c, hw, device=dev, generator=g) * 0.5
@@ -30,7 +30,13 @@ if a.op in ("K6", "K7", "K2", "K3", "K2s1", "K4", "K4h"):
     low = ops.mask_nearest(sup_mask, h, h).view(B * S, 2, hw)
     fgp, bgp, _ = ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S)
     pred = ops.cosine_match(qry, fgp, bgp)["pred"].view(B, 2, h, h)
-    fn = {"K6": lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
+    if a.op in ("K2b", "K3b"):          # backward kernels of the training path (K12)
+        _, _, saved = ops.meta_proto_attn_train(sup, ctr, low[:, 0], low[:, 1], B, S)
+        gfp, gbp = torch.randn(B, c, 3, device=dev, generator=g), torch.randn(B, c, 3, device=dev, generator=g)
+        gpred = torch.randn(B, 2, hw, device=dev, generator=g)
+    fn = {"K2b": lambda: ops.meta_proto_attn_bwd(saved, gfp, gbp, B, S),
+          "K3b": lambda: ops.cosine_match_bwd(qry, fgp, bgp, gpred),
+          "K6": lambda: ops.map_pool_fullres(sup.view(B * S, c, h, h), sup_mask, B, S),
           "K7": lambda: ops.panet_align(qry.view(B, c, h, h), pred, sup.view(B * S, c, h, h), fgfull, 1),
           "K2": lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S),
           "K2s1": lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S),
