@@ -79,17 +79,18 @@ static inline EncodeTiledFn encode_fn() {
 
 // [episodes][images_per_episode * c/4 groups][4*hw floats] over `base` (16-byte aligned), episode stride in floats
 // (a multiple of 4); box = 32 floats x c/4 groups x 1.  false: not encodable (the caller falls back to a generic kernel).
+// box_rows: groups per box (default c/4 = all channels of one class; the backward kernel loads half boxes).
 static inline bool make_rows4_map(CUtensorMap* map, const float* base, int episodes, int images_per_episode, int c, int hw,
-                                  long long episode_stride) {
+                                  long long episode_stride, int box_rows = 0, CUtensorMapL2promotion promo = PEMP_TMA_L2PROMO) {
   EncodeTiledFn fn = encode_fn();
   if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (episode_stride & 3) != 0 || (c & 3) != 0) return false;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(4) * hw, static_cast<cuuint64_t>(images_per_episode) * (c / 4),
                         static_cast<cuuint64_t>(episodes)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(16) * hw, static_cast<cuuint64_t>(episode_stride) * 4};
-  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(c / 4), 1};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows > 0 ? box_rows : c / 4), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, PEMP_TMA_L2PROMO,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

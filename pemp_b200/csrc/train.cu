@@ -30,10 +30,12 @@
 
 // train_mma.cu: K2 backward with the per-tile products on the warp-level tensor path (P = 3, c in {128, 256, 512, 1024})
 size_t pemp_mpa_bwd_mma_smem(int c);
-bool pemp_mpa_bwd_mma_shape(int c, int p);
-int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int S, const float* ctr, const float* coef, const float* beta,
-                            const float* fg, const float* bg, long long mask_stride, int N, int c, int hw, int chunks, int ntiles,
-                            float* dfts, long long d_ep, float* part, cudaStream_t st);
+bool pemp_mpa_bwd_mma_shape(int c, int p, int hw);
+int pemp_mpa_bwd_mma_tiles(int hw);
+size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
+int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
+                            const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
+                            float* dfts, long long d_ep, float* part, float* img_part, int* done, cudaStream_t st);
 static int g_bwd_path = 0;   // diagnostic switch, see pemp_debug_bwd_path
 
 namespace {
@@ -359,32 +361,62 @@ cosine_bwd_finalize_kernel(const float* __restrict__ part, const float* __restri
 // foreground group.  The squared-norm differences are a bias common to every pixel's logit, so they are summed in double.
 __global__ void __launch_bounds__(kBT)
 mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__ g_bg, const float* __restrict__ shot_centre,
-                       const float* __restrict__ shot_den, const float* __restrict__ ctr, int S, int c, int P,
+                       const float* __restrict__ shot_den, const float* __restrict__ ctr, int N, int S, int c, int P,
                        float* __restrict__ coef, float* __restrict__ beta) {
-  __shared__ float scratch[kBW];
-  const int n = blockIdx.x, b = n / S, K = 2 * P;
-  for (int k = 0; k < K; ++k) {
-    const float* g = (k < P ? g_fg : g_bg) + static_cast<long long>(b) * c * P + (k < P ? k : k - P);
-    const float inv = 1.0f / (static_cast<float>(S) * __ldg(shot_den + n * K + k));
-    float s = 0.f;
-    for (int ch = threadIdx.x; ch < c; ch += kBT) {
-      const float a = __ldg(g + static_cast<long long>(ch) * P) * inv;
-      coef[(static_cast<long long>(n) * c + ch) * K + k] = a;
-      s = fmaf(a, __ldg(shot_centre + (static_cast<long long>(n) * c + ch) * K + k), s);
-    }
-    s = block_sum(s, scratch);
-    if (threadIdx.x == 0) beta[n * 2 * K + k] = -s;
-  }
-  if (threadIdx.x < K) {
+  // One pass over the channels with all 2P columns at once and ONE block reduction (the first version ran 2P block sums in a
+  // row and had 2P threads of EVERY CTA add the c squared-norm terms serially in double: 49 us of a 430-us backward at 80
+  // images).  Block N computes the squared-norm differences, which do not depend on the image, once for the launch.
+  __shared__ double dscr[kBW][8];
+  const int n = blockIdx.x, K = 2 * P, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.0;
+  if (n == N) {
     // |ctr_k|^2 - |ctr_g0|^2 with g0 the first prototype of k's group: the soft-max of a group only sees differences of logits,
-    // and the backward kernel works with ctr_k - ctr_g0 throughout (see mpa_bwd_kernel), as the forward does
-    const int k0 = (threadIdx.x / P) * P;
-    double s2 = 0.0;
-    for (int ch = 0; ch < c; ++ch) {
-      const double v = static_cast<double>(__ldg(ctr + ch * K + threadIdx.x)), v0 = static_cast<double>(__ldg(ctr + ch * K + k0));
-      s2 += (v - v0) * (v + v0);
+    // and the backward kernels work with ctr_k - ctr_g0 throughout, as the forward does
+    for (int ch = threadIdx.x; ch < c; ch += kBT) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < K) {
+          const double v = static_cast<double>(__ldg(ctr + ch * K + k)), v0 = static_cast<double>(__ldg(ctr + ch * K + (k / P) * P));
+          s[k] += (v - v0) * (v + v0);
+        }
+      }
     }
-    beta[n * 2 * K + K + threadIdx.x] = static_cast<float>(s2);
+  } else {
+    const int b = n / S;
+    for (int ch = threadIdx.x; ch < c; ch += kBT) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < K) {
+          const float* g = (k < P ? g_fg : g_bg) + static_cast<long long>(b) * c * P + (k < P ? k : k - P);
+          const float inv = 1.0f / (static_cast<float>(S) * __ldg(shot_den + n * K + k));
+          const float a = __ldg(g + static_cast<long long>(ch) * P) * inv;
+          coef[(static_cast<long long>(n) * c + ch) * K + k] = a;
+          s[k] += static_cast<double>(a * __ldg(shot_centre + (static_cast<long long>(n) * c + ch) * K + k));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(kFull, s[k], o);
+    if (lane == 0) dscr[warp][k] = s[k];
+  }
+  __syncthreads();
+  if (n == N) {
+    for (int i = threadIdx.x; i < N * K; i += kBT) {
+      const int k = i % K;
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBW; ++w) t += dscr[w][k];
+      beta[(i / K) * 2 * K + K + k] = static_cast<float>(t);
+    }
+  } else if (threadIdx.x < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBW; ++w) t += dscr[w][threadIdx.x];
+    beta[n * 2 * K + threadIdx.x] = static_cast<float>(-t);
   }
 }
 
@@ -624,7 +656,7 @@ mpa_bwd_kernel(const float* __restrict__ fts, long long ep_stride, int S, const 
 // d_ctr[ch][k] = sum over every (image, chunk) partial, in index order, minus ctr * sum of the 2 dl_k column.
 // blockDim = (32 outputs, kFinRows): row r adds the partials p = r, r + kFinRows, ... (double), then the rows are added
 // in order - deterministic, and 16 x more loads in flight than one thread per output.
-constexpr int kFinRows = 16;
+constexpr int kFinRows = 32;     // (16 rows with 4 loads in flight: 29 us for 880 partials - the loop is a chain of DRAM round trips)
 __global__ void __launch_bounds__(32 * kFinRows)
 mpa_bwd_finalize_kernel(const float* __restrict__ part, long long nparts, int c, int K, const float* __restrict__ ctr,
                         float* __restrict__ d_ctr) {
@@ -634,7 +666,7 @@ mpa_bwd_finalize_kernel(const float* __restrict__ part, long long nparts, int c,
   const int k = live ? i % K : 0;
   double s = 0.0, d = 0.0;
   if (live) {
-#pragma unroll 4
+#pragma unroll 8
     for (long long p = r; p < nparts; p += kFinRows) {
       const float* row = part + p * (c + 1) * K;
       s += static_cast<double>(__ldg(row + i));
@@ -663,9 +695,9 @@ struct BwdPlan {
 // How many CTAs share one image.  The grid is N * chunks CTAs of ceil(ntiles / chunks) tiles each on `slots` resident CTAs
 // (two per SM at the PEMP size): pick the split with the smallest  waves * (tiles per CTA + prologue)  - e.g. 80 images of
 // 82 tiles: 8 chunks = 2.16 waves of 11 tiles (a third, nearly empty wave), 11 chunks = 2.97 waves of 8.
-BwdPlan bwd_plan(int N, int hw, size_t smem) {
+BwdPlan bwd_plan(int N, int hw, size_t smem, int ntiles = 0) {
   BwdPlan p;
-  p.ntiles = (hw + 31) / 32;
+  p.ntiles = ntiles > 0 ? ntiles : (hw + 31) / 32;
   long long per_sm = static_cast<long long>(227 * 1024) / static_cast<long long>(smem + 1024);
   const long long by_regs = 65536 / (128LL * kBT);
   if (per_sm > by_regs) per_sm = by_regs;
@@ -849,15 +881,34 @@ extern "C" int pemp_debug_bwd_path(int mode) {
   return old;
 }
 
-extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p) {
-  if (B <= 0 || S <= 0 || c <= 0 || hw <= 0 || p < 1 || p > 4) return 0;
-  const size_t N = static_cast<size_t>(B) * S, K = 2 * p;
-  int chunks = bwd_plan(static_cast<int>(N), hw, mpa_smem(c, 2 * p)).chunks;
-  if (pemp_mpa_bwd_mma_shape(c, p)) {            // room for either kernel's split (the diagnostic switch picks at launch time)
-    const int m = bwd_plan(static_cast<int>(N), hw, pemp_mpa_bwd_mma_smem(c)).chunks;
+namespace {
+// workspace of the K2 backward: coef [N][c][K] | beta [N][2K] | partials [N][chunks][(c + 1) K] | image tables of the tensor-path
+// kernel.  `chunks` is the larger of the two kernels' splits (the diagnostic switch picks the kernel at launch time).
+struct MpaBwdWs {
+  size_t off_beta, off_part, off_tab, off_img, off_done, total;
+};
+MpaBwdWs mpa_bwd_ws(int N, int c, int hw, int p) {
+  const size_t n = static_cast<size_t>(N), K = 2 * p;
+  const bool mma = pemp_mpa_bwd_mma_shape(c, p, hw);
+  int chunks = bwd_plan(N, hw, mpa_smem(c, 2 * p)).chunks;
+  if (mma) {
+    const int m = bwd_plan(N, hw, pemp_mpa_bwd_mma_smem(c), pemp_mpa_bwd_mma_tiles(hw)).chunks;
     if (m > chunks) chunks = m;
   }
-  return align_up(N * c * K * 4, 256) + align_up(N * 2 * K * 4, 256) + align_up(N * chunks * (c + 1) * K * 4, 256);
+  MpaBwdWs w;
+  w.off_beta = align_up(n * c * K * 4, 256);
+  w.off_part = w.off_beta + align_up(n * 2 * K * 4, 256);
+  w.off_tab = w.off_part + align_up(n * chunks * (c + 1) * K * 4, 256);
+  w.off_img = w.off_tab + (mma ? align_up(pemp_mpa_bwd_mma_table_bytes(N, c), 256) : 0);      // per-image sums of the partials
+  w.off_done = w.off_img + (mma ? align_up(n * (c + 1) * K * 4, 256) : 0);                     // per-image arrival counters
+  w.total = w.off_done + (mma ? align_up(n * sizeof(int), 256) : 0);
+  return w;
+}
+}  // namespace
+
+extern "C" size_t pemp_meta_proto_attn_bwd_workspace_bytes(int B, int S, int c, int hw, int p) {
+  if (B <= 0 || S <= 0 || c <= 0 || hw <= 0 || p < 1 || p > 4) return 0;
+  return mpa_bwd_ws(B * S, c, hw, p).total;
 }
 
 extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, const float* ctr, const float* fg,
@@ -871,19 +922,30 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_meta_proto_attn_bwd_workspace_bytes(B, S, c, hw, p), PEMP_E_WORKSPACE);
   cudaStream_t st = as_stream(stream);
   const int N = B * S, K = 2 * p;
-  const bool mma = g_bwd_path == 0 && pemp_mpa_bwd_mma_shape(c, p);
-  const BwdPlan pl = bwd_plan(N, hw, mma ? pemp_mpa_bwd_mma_smem(c) : mpa_smem(c, 2 * p));
+  const bool mma = g_bwd_path == 0 && pemp_mpa_bwd_mma_shape(c, p, hw);
+  const BwdPlan pl = bwd_plan(N, hw, mpa_smem(c, 2 * p));
   char* ws = static_cast<char*>(workspace);
+  const MpaBwdWs wl = mpa_bwd_ws(N, c, hw, p);
   float* coef = reinterpret_cast<float*>(ws);
-  float* beta = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(N) * c * K * 4, 256));
-  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(beta) + align_up(static_cast<size_t>(N) * 2 * K * 4, 256));
+  float* beta = reinterpret_cast<float*>(ws + wl.off_beta);
+  float* part = reinterpret_cast<float*>(ws + wl.off_part);
   const long long ep = fts_episode_stride ? fts_episode_stride : static_cast<long long>(S) * c * hw;
   const long long d_ep = d_fts_episode_stride ? d_fts_episode_stride : static_cast<long long>(S) * c * hw;
-  mpa_bwd_prepare_kernel<<<N, kBT, 0, st>>>(g_fg, g_bg, shot_centre, shot_den, ctr, S, c, p, coef, beta);
-  int rc;
-  if (mma) {
-    rc = pemp_mpa_bwd_mma_launch(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl.chunks, pl.ntiles, d_fts, d_ep, part, st);
-  } else
+  mpa_bwd_prepare_kernel<<<N + 1, kBT, 0, st>>>(g_fg, g_bg, shot_centre, shot_den, ctr, N, S, c, p, coef, beta);
+  int rc = PEMP_E_ALIGN;
+  long long nparts = static_cast<long long>(N) * pl.chunks;
+  if (mma) {                                     // PEMP_E_ALIGN: the operand has no tensor map - the CUDA-core kernel takes it
+    const BwdPlan pm = bwd_plan(N, hw, pemp_mpa_bwd_mma_smem(c), pemp_mpa_bwd_mma_tiles(hw));
+    float* tabg = reinterpret_cast<float*>(ws + wl.off_tab);
+    float* img_part = reinterpret_cast<float*>(ws + wl.off_img);
+    rc = pemp_mpa_bwd_mma_launch(fts, ep, B, S, ctr, coef, beta, fg, bg, mask_stride, c, hw, pm.chunks, tabg, d_fts, d_ep, part,
+                                 img_part, reinterpret_cast<int*>(ws + wl.off_done), st);
+    if (rc == PEMP_OK) {                         // the main kernel has already added the partials of an image
+      nparts = N;
+      part = img_part;
+    }
+  }
+  if (rc == PEMP_E_ALIGN)
   switch (p) {
     case 1: rc = launch_mpa_bwd<2>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
     case 2: rc = launch_mpa_bwd<4>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
@@ -891,6 +953,6 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
     default: rc = launch_mpa_bwd<8>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, N, c, hw, pl, d_fts, d_ep, part, st); break;
   }
   if (rc != PEMP_OK) return rc;
-  mpa_bwd_finalize_kernel<<<(c * K + 31) / 32, dim3(32, kFinRows), 0, st>>>(part, static_cast<long long>(N) * pl.chunks, c, K, ctr, d_ctr);
+  mpa_bwd_finalize_kernel<<<(c * K + 31) / 32, dim3(32, kFinRows), 0, st>>>(part, nparts, c, K, ctr, d_ctr);
   return launch_status();
 }

@@ -1,49 +1,58 @@
 // K12: backward of meta-prototype attention with the three thin products of a tile on the warp-level tensor
-// path (`mma.sync.m16n8k8` tf32, SASS HMMA.1688), 3 x TF32 split = fp32-grade.  Same math, inputs, outputs and partial layout
-// as `mpa_bwd_kernel` (train.cu; reference: what autograd records for networks/pemp_stage1.py:202-213), P = 3, c % 128 == 0.
+// path (`mma.sync.m16n8k8` tf32, SASS HMMA.1688), 3 x TF32 split = fp32-grade, the tile fed by TMA.  Same math, inputs, outputs
+// and partial layout as `mpa_bwd_kernel` (train.cu; reference: what autograd records for networks/pemp_stage1.py:202-213),
+// P = 3, c in {128, 256, 512, 1024}, hw >= 32, TMA-encodable operand; everything else takes the CUDA-core kernel.
 //
-// Why.  Per 32-pixel tile the backward is three products with a 10-column table  T[ch] = { coef[ch][0..6) | ctr_k - ctr_g0 }:
+// Why.  Per pixel tile the backward is three products with a 10-column table  T[ch] = { coef[ch][0..6) | ctr_k - ctr_g0 }:
 //   phase A   dots[k][x]  = sum_ch T[ch][k] f[ch][x]            (10 x 32, contraction over the c channels)
 //   phase B1  df[x][ch]   = sum_k  W[x][k]  T[ch][k]            (32 x c,  contraction over the 10 columns; W from the pixel step)
-//   phase B2  dctr[ch][k] = sum_x  f[ch][x] dv[x][k]            (c x 6,   contraction over the 32 pixels)
+//   phase B2  dctr[ch][k] = sum_x  f[ch][x] dv[x][k]            (c x 6,   contraction over the pixels)
 // On CUDA cores every FMA of A and B1 needs a table value that is uniform over the warp (lane = pixel), and a broadcast
 // LDS.128 still costs four cycles of the 128 B/clk shared-memory crossbar: 12 cycles per channel and warp in A and again in B1
 // = ~14 800 crossbar cycles per tile against the ~5 300 clocks the tile's 128 KB take at the HBM rate - the round-2 kernel sat
 // at 0.31-0.33 of the HBM peak with the shared pipe 63 % busy.  With register fragments a table / weight value is read once per
-// 8 x 8 block: ~2 400 crossbar cycles and ~1 000 issue slots per warp and tile (2 800 before).  tcgen05 is not an option here:
-// its operands live in shared memory behind descriptors (T as hi + lo K-major panels = 48-64 KB next to the 64-KB tile, twice
-// per SM) and the three products contract over three different axes of the same tile; 240 m16n8k8 per warp and tile keep the
-// legacy pipe (measured 2.0 clk per instruction and SM, tools/probes/mma_sync_probe.cu) ~45 % busy at 0.6 of the HBM peak.
+// 8 x 8 block (~3 000 crossbar cycles per tile).  tcgen05 is not an option here: its operands live in shared memory behind
+// descriptors (T as hi + lo K-major panels = 48-64 KB next to the 64-KB tile, twice per SM) and the three products contract
+// over three different axes of the same tile; 240 m16n8k8 per warp and tile keep the legacy pipe (measured 2.0 clk per
+// instruction and SM, tools/probes/mma_sync_probe.cu) a quarter busy.
 //
 // 3 x TF32: x = hi + lo with hi = x & 0xffffe000 (what the tensor core reads of an fp32 register) and lo = x - hi (exact);
 // a.b ~ lo_a hi_b + hi_a lo_b + hi_a hi_b, small products first (see K9), error ~2^-21 per product.
 //
-// Structure: 256 threads, two CTAs per SM; a CTA owns a run of 32-pixel tiles of one image.  Warp w owns the channels
-// [w c/8, (w+1) c/8) in every phase, so the tile buffer is warp-private: it is filled by 4-byte `cp.async` (rows start at
-// arbitrary 4-byte phases: hw is odd) one phase ahead - the loads of tile t+1 are issued after B2(t), run under B1(t), which
-// needs no features - and only two block barriers per tile remain (dots -> pixel step -> weights).
-//   tile [ch][32] with column x stored at x ^ s(ch), s = (ch & 3) << 3 | ((ch >> 2) & 1) << 2: conflict-free for the
-//   row-contiguous fill, the B fragments of phase A (4 channels x 8 pixels) and the A fragments of B2 (8 channels x 4 pixels).
+// Structure: 256 threads, two CTAs per SM; a CTA owns a run of 28-pixel tiles of one image.  The features come through the
+// "four rows per group" tensor map of the forward kernels (tma_common.cuh): warp w = e + 4 half owns rows [CW half, CW half +
+// CW) of the class-e box of a tile (channels 4 g + e; CW = c/8), i.e. its own 128-byte-swizzled half box with its own mbarrier -
+// the tile buffer is warp-private in every phase, one lane issues ONE bulk-tensor load per warp and tile (the first version
+// filled it with 64 four-byte cp.async per thread: a third of all stall samples sat in that loop, ncu), the load of tile t+1 is
+// issued after B2(t) and runs under B1(t), which needs no features, and only two block barriers per tile remain (dots -> pixel
+// step -> weights).  Box column i of class e is pixel x_nom + i - o_e, o_e = (e hw + x_nom) & 3 (aligned box origins).
 #include <math_constants.h>
 
-#include "common.cuh"
+#include "tma_common.cuh"
 
 size_t pemp_mpa_bwd_mma_smem(int c);
-bool pemp_mpa_bwd_mma_shape(int c, int p);
-int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int S, const float* ctr, const float* coef, const float* beta,
-                            const float* fg, const float* bg, long long mask_stride, int N, int c, int hw, int chunks, int ntiles,
-                            float* dfts, long long d_ep, float* part, cudaStream_t st);
+bool pemp_mpa_bwd_mma_shape(int c, int p, int hw);
+int pemp_mpa_bwd_mma_tiles(int hw);
+size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
+int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
+                            const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
+                            float* dfts, long long d_ep, float* part, float* img_part, int* done, cudaStream_t st);
 
 namespace {
+
+using namespace pemp_tma;
 
 constexpr int kT = 256, kW = 8;                  // threads / warps per CTA
 constexpr int kP = 3, kK = 2 * kP;               // prototypes per group, coefficient columns
 constexpr int kND = 2 * (kP - 1);                // centre-difference columns (the first prototype of a group has none)
 constexpr int kNK = kK + kND;                    // 10 table columns: [0, 6) coef, [6, 8) fg differences, [8, 10) bg differences
-constexpr int kN1 = kNK - 8;                     // columns of the second 8-wide block
-constexpr int kRedLd = 40;                       // pixel pitch of a dot row in `red` (conflict-free 64-bit fragment stores)
+constexpr int kTLd = 12;                         // table row pitch: conflict-free for the fragments of phase A and of B1
+constexpr int kStep = 28;                        // pixels a tile advances (32 box columns cover them for every class)
+constexpr int kRedLd = 40;                       // pixel pitch of a dot row in `red`
 constexpr int kWtLd = 12;                        // W[x][0..10) + two zero columns (conflict-free fragment reads)
-static_assert(kN1 == 2, "the second column block is laid out for two columns");
+constexpr int kStgLd = 36;                       // pixel pitch of a staged gradient row (conflict-free fragment stores)
+constexpr int kDvRows = 32 + 3;                  // dv rows for pixels -3 .. 31 of a tile (rows outside [0, 28) stay zero)
+static_assert(kNK > 8 && kNK <= kTLd, "two 8-wide column blocks, the second one inside the row padding");
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(v) & 0xffffe000u;
@@ -55,7 +64,8 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 // fragments: A 16 x 8 (a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)), B 8 x 8 (b0 (t, g) b1 (t+4, g)),
-// C 16 x 8 (c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)) with g = lane >> 2, t = lane & 3
+// C 16 x 8 (c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)) with g = lane >> 2, t = lane & 3.  The contraction index may
+// be permuted freely as long as both operands agree: phases A and B1 use it that way to stay bank-conflict free.
 struct FragA {
   uint32_t hi[4], lo[4];
 };
@@ -67,128 +77,148 @@ __device__ __forceinline__ void mma3(float (&d)[4], const FragA& a, const FragB&
   mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], b.lo[0], b.lo[1]);
   mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], b.hi[0], b.hi[1]);
 }
+// element (row, col) of a 128-byte-swizzled box whose rows are 32 floats: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+__device__ __forceinline__ int box_at(int row, int col) { return row * 32 + ((((col >> 2) ^ row) & 7) << 2) + (col & 3); }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, uint32_t nbytes) {   // nbytes 0: zero fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-}
+template <int MB>                                // 16-row blocks per warp: c = 128 MB
+struct Smem {
+  static constexpr int c = 128 * MB, CW = 16 * MB;
+  alignas(1024) float tile[kW][CW * 32];         // warp w: rows [CW half, CW half + CW) of the class-e box, e = w & 3, half = w >> 2
+  alignas(16) float tab[c * kTLd];               // row R = w CW + r  <->  channel 4 (CW half + r) + e
+  alignas(16) float red[kW][kNK * kRedLd];       // partial dots of the warps: [k][pixel of the tile]
+  alignas(16) float wt[32 * kWtLd];              // [pixel]{ a_k (6) | 2 dl_k of the non-first prototypes (4) | 0 0 }
+  alignas(16) float dv[kDvRows * 8];             // [pixel + 3]{ 2 dl_k (6) | 0 0 }
+  alignas(16) float stage[kW][8 * kStgLd];       // per warp: one 8-row block of the gradient tile on its way out
+  float konst[2 * kK];                           // |ctr_k|^2 - |ctr_g0|^2, beta
+  int last;                                      // this CTA finished its image last
+  alignas(8) uint64_t full[kW];
+};
 
-template <int MB>                                // 16-channel blocks per warp: c = 128 MB
+template <int MB>
 __global__ void __launch_bounds__(kT, MB <= 4 ? 2 : 1)
-mpa_bwd_mma_kernel(const float* __restrict__ fts, long long ep_stride, int S, const float* __restrict__ ctr,
-                   const float* __restrict__ coef, const float* __restrict__ beta, const float* __restrict__ fg,
-                   const float* __restrict__ bg, long long mask_stride, int hw, int ntiles, float* __restrict__ dfts,
-                   long long d_ep_stride, float* __restrict__ part) {
-  constexpr int c = 128 * MB, CW = 16 * MB;      // channels; channels per warp
-  extern __shared__ __align__(16) float sm[];
-  float* tile = sm;                              // [c][32] swizzled
-  float* t0 = tile + c * 32;                     // [c][8]   table columns 0..7, column k stored at k ^ (((ch >> 2) & 1) << 2)
-  float* t1 = t0 + c * 8;                        // [c][2]   table columns 8, 9
-  float* red = t1 + c * kN1;                     // [kW][kNK][kRedLd] partial dots of the warps
-  float* wt = red + kW * kNK * kRedLd;           // [32][kWtLd] { a_k (6) | 2 dl_k of the non-first prototypes (4) | 0 0 }
-  float* dv = wt + 32 * kWtLd;                   // [32][8]  { 2 dl_k (6) | 0 0 }
-  float* konst = dv + 32 * 8;                    // [kK] |ctr_k|^2 - |ctr_g0|^2, [kK] beta
+mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* __restrict__ tabg,
+                   const float* __restrict__ beta, const float* __restrict__ fg, const float* __restrict__ bg,
+                   long long mask_stride, int hw, int ntiles, float* __restrict__ dfts, long long d_ep_stride,
+                   float* __restrict__ part, float* __restrict__ img_part, int* __restrict__ done) {
+  constexpr int c = 128 * MB, CW = 16 * MB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem<MB>& sm = *reinterpret_cast<Smem<MB>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+  const int e = warp & 3, half = warp >> 2;
   const int n = blockIdx.y, b = n / S, si = n - b * S;
-  const int wch = warp * CW;                     // this warp's channels [wch, wch + CW)
-  const float* src = fts + static_cast<long long>(b) * ep_stride + static_cast<long long>(si) * c * hw;
   float* dst = dfts + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(si) * c * hw;
   const int tb = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
   const int te = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
+  float* box = sm.tile[warp];
+  const float* trow = sm.tab + warp * CW * kTLd;  // this warp's table rows
 
-  // fill of the warp's rows of one tile: lane = pixel, 128 contiguous bytes per row, zero fill past the end of the row
-  const uint32_t tile_s = smem_u32(tile);
-  auto fill = [&](int t) {
-    const int x = t * 32 + lane;
-    const uint32_t nb = x < hw ? 4u : 0u;
-    const float* gp = src + static_cast<long long>(wch) * hw + (x < hw ? x : hw - 1);
-#pragma unroll 8
-    for (int r = 0; r < CW; ++r) {               // CW is a multiple of 16, wch of 16: s(ch) only depends on r & 7
-      const int sw = ((r & 3) << 3) | (((r >> 2) & 1) << 2);
-      cp_async4(tile_s + 4u * static_cast<uint32_t>((wch + r) * 32 + (lane ^ sw)), gp, nb);
-      gp += hw;
+  constexpr int NH = MB >= 2 ? 2 : 1;            // the half box is refilled in NH pieces, each as soon as B2 is done with its rows
+  if (tid == 0) {
+    for (int w = 0; w < kW; ++w) mbar_init(&sm.full[w], NH);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // NH bulk-tensor loads per warp and tile: CW / NH rows x 32 floats of class e each
+  auto fill = [&](int t, int h) {
+    if (lane == 0) {
+      mbar_expect_tx(&sm.full[warp], CW / NH * 32 * 4);
+      tma_load_3d(&map, &sm.full[warp], box + h * (CW / NH) * 32, (e * hw + t * kStep) & ~3,
+                  si * (c / 4) + CW * half + h * (CW / NH), b);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (tb < te) fill(tb);
+  if (tb < te) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) fill(tb, h);
+  }
 
-  // tables of this image (the first tile is on its way meanwhile)
-  for (int i = tid; i < c * kNK; i += kT) {
-    const int ch = i / kNK, k = i - ch * kNK;
-    float v;
-    if (k < kK) {
-      v = __ldg(coef + (static_cast<long long>(n) * c + ch) * kK + k);
-    } else {
-      // centre columns as differences to the first prototype of their group (exact in double, one rounding), see train.cu
-      const int j = k - kK, grp = j / (kP - 1), kk = grp * kP + 1 + (j - grp * (kP - 1));
-      v = static_cast<float>(static_cast<double>(__ldg(ctr + ch * kK + kk)) - static_cast<double>(__ldg(ctr + ch * kK + grp * kP)));
-    }
-    if (k < 8)
-      t0[ch * 8 + (k ^ (((ch >> 2) & 1) << 2))] = v;
-    else
-      t1[ch * kN1 + (k - 8)] = v;
+  // table of this image, laid out by mpa_bwd_mma_table_kernel: a straight 16-byte copy (the first tile is on its way meanwhile;
+  // when every CTA built its table from coef / ctr itself the prologue was 15 % of all stall samples at ~8 tiles per CTA)
+  {
+    const float4* tsrc = reinterpret_cast<const float4*>(tabg + static_cast<long long>(n) * c * kTLd);
+    float4* tdst = reinterpret_cast<float4*>(sm.tab);
+#pragma unroll
+    for (int i = 0; i < (c * kTLd / 4 + kT - 1) / kT; ++i)
+      if (tid + i * kT < c * kTLd / 4) tdst[tid + i * kT] = __ldg(tsrc + tid + i * kT);
   }
-  for (int i = tid; i < 32 * kWtLd; i += kT) wt[i] = 0.f;
-  for (int i = tid; i < 32 * 8; i += kT) dv[i] = 0.f;
+  for (int i = tid; i < 32 * kWtLd; i += kT) sm.wt[i] = 0.f;
+  for (int i = tid; i < kDvRows * 8; i += kT) sm.dv[i] = 0.f;
   if (tid < kK) {
-    konst[tid] = __ldg(beta + n * 2 * kK + kK + tid);
-    konst[kK + tid] = __ldg(beta + n * 2 * kK + tid);
+    sm.konst[tid] = __ldg(beta + n * 2 * kK + kK + tid);
+    sm.konst[kK + tid] = __ldg(beta + n * 2 * kK + tid);
   }
-  float accB[MB][4];                             // dctr partial: (ch = wch + 16 mb + g (+8), k = 2 tg (+1))
+  float accB[MB][4];                             // dctr partial: (row 16 mb + g (+8) of the warp, k = 2 tg (+1))
 #pragma unroll
   for (int i = 0; i < MB; ++i) accB[i][0] = accB[i][1] = accB[i][2] = accB[i][3] = 0.f;
   float dsum[kP] = {0.f, 0.f, 0.f};              // lane 0 of warps 0 / 1: sum_x 2 dl_k of its group
   __syncthreads();
 
   for (int t = tb; t < te; ++t) {
-    const int x0 = t * 32;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    // ---------------- phase A: dots^T [k 16 (10 used)] x [px 8] per pixel block, contraction over the warp's channels
+    const int x0 = t * kStep;
+    const int o = (e * hw + x0) & 3;              // box column i is pixel x0 + i - o
+    // the pixel-step warps fetch their mask value now: its latency used to sit between the two barriers of the tile
+    float m_px = 0.f;
+    if (warp < 2 && lane < kStep && x0 + lane < hw)
+      m_px = __ldg((warp == 0 ? fg : bg) + static_cast<long long>(n) * mask_stride + x0 + lane);
+    mbar_wait(&sm.full[warp], (t - tb) & 1);
+    // ---------------- phase A: dots^T [k 16 (10 used)] x [column 8] per column block, contraction over the warp's rows
+    // (contraction slots tg / tg + 4 of a block are its rows 2 tg / 2 tg + 1: conflict-free against the box swizzle)
     float dacc[4][4];
 #pragma unroll
     for (int pb = 0; pb < 4; ++pb) dacc[pb][0] = dacc[pb][1] = dacc[pb][2] = dacc[pb][3] = 0.f;
 #pragma unroll 2
     for (int cb = 0; cb < CW / 8; ++cb) {
-      const int ch0 = wch + cb * 8 + tg;         // channels of a0 / b0; a2 / b1: + 4 (bit 2 set: swizzles flip)
+      const int r0 = cb * 8 + 2 * tg;
+      const float* ta = trow + r0 * kTLd + g;
       FragA a;
-      split_tf32(t0[ch0 * 8 + g], a.hi[0], a.lo[0]);
-      split_tf32(t0[(ch0 + 4) * 8 + (g ^ 4)], a.hi[2], a.lo[2]);
-      const float u1 = g < kN1 ? t1[ch0 * kN1 + g] : 0.f, u3 = g < kN1 ? t1[(ch0 + 4) * kN1 + g] : 0.f;
-      split_tf32(u1, a.hi[1], a.lo[1]);
-      split_tf32(u3, a.hi[3], a.lo[3]);
-      const float* r0 = tile + ch0 * 32;
-      const float* r1 = tile + (ch0 + 4) * 32;
+      split_tf32(ta[0], a.hi[0], a.lo[0]);
+      split_tf32(g < kNK - 8 ? ta[8] : 0.f, a.hi[1], a.lo[1]);
+      split_tf32(ta[kTLd], a.hi[2], a.lo[2]);
+      split_tf32(g < kNK - 8 ? ta[kTLd + 8] : 0.f, a.hi[3], a.lo[3]);
+      FragB f[4];
 #pragma unroll
       for (int pb = 0; pb < 4; ++pb) {
-        const int px = pb * 8 + g;
-        FragB f;
-        split_tf32(r0[px ^ (tg << 3)], f.hi[0], f.lo[0]);
-        split_tf32(r1[px ^ ((tg << 3) | 4)], f.hi[1], f.lo[1]);
-        mma3(dacc[pb], a, f);
+        split_tf32(box[box_at(r0, pb * 8 + g)], f[pb].hi[0], f[pb].lo[0]);
+        split_tf32(box[box_at(r0 + 1, pb * 8 + g)], f[pb].hi[1], f[pb].lo[1]);
       }
+      // the three products of a block as three rounds over the four independent accumulators (no back-to-back dependence)
+#pragma unroll
+      for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.lo[0], a.lo[1], a.lo[2], a.lo[3], f[pb].hi[0], f[pb].hi[1]);
+#pragma unroll
+      for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.hi[0], a.hi[1], a.hi[2], a.hi[3], f[pb].lo[0], f[pb].lo[1]);
+#pragma unroll
+      for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.hi[0], a.hi[1], a.hi[2], a.hi[3], f[pb].hi[0], f[pb].hi[1]);
     }
     {
-      float* rw = red + warp * (kNK * kRedLd);
+      float* rw = sm.red[warp];
 #pragma unroll
       for (int pb = 0; pb < 4; ++pb) {
-        *reinterpret_cast<float2*>(rw + g * kRedLd + pb * 8 + 2 * tg) = make_float2(dacc[pb][0], dacc[pb][1]);
-        if (g < kN1) *reinterpret_cast<float2*>(rw + (g + 8) * kRedLd + pb * 8 + 2 * tg) = make_float2(dacc[pb][2], dacc[pb][3]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int p = pb * 8 + 2 * tg + j - o;
+          if (p >= 0 && p < kStep) {
+            rw[g * kRedLd + p] = dacc[pb][j];
+            if (g < kNK - 8) rw[(g + 8) * kRedLd + p] = dacc[pb][2 + j];
+          }
+        }
       }
     }
     __syncthreads();
-    // ---------------- pixel step: warp 0 = foreground group, warp 1 = background group, lane = pixel
+    // ---------------- pixel step: warp 0 = foreground group, warp 1 = background group, lane = pixel of the tile
     if (warp < 2) {
       const int grp = warp, x = x0 + lane;
-      const float m = x < hw ? __ldg((grp == 0 ? fg : bg) + static_cast<long long>(n) * mask_stride + x) : 0.f;
+      const bool live = lane < kStep && x < hw;
+      const int pl = lane < kStep ? lane : kStep - 1;
+      const float m = m_px;
       float sa[kP], sc[kP];
 #pragma unroll
       for (int k = 0; k < kP; ++k) {
         float u = 0.f, v = 0.f;
 #pragma unroll
         for (int w = 0; w < kW; ++w) {            // fixed order
-          u += red[(w * kNK + grp * kP + k) * kRedLd + lane];
-          if (k > 0) v += red[(w * kNK + kK + grp * (kP - 1) + k - 1) * kRedLd + lane];
+          u += sm.red[w][(grp * kP + k) * kRedLd + pl];
+          if (k > 0) v += sm.red[w][(kK + grp * (kP - 1) + k - 1) * kRedLd + pl];
         }
         sa[k] = u;
         sc[k] = v;
@@ -196,7 +226,7 @@ mpa_bwd_mma_kernel(const float* __restrict__ fts, long long ep_stride, int S, co
       float l[kP], mx = -CUDART_INF_F;
 #pragma unroll
       for (int k = 0; k < kP; ++k) {
-        l[k] = fmaf(2.0f, sc[k], -konst[grp * kP + k]);
+        l[k] = fmaf(2.0f, sc[k], -sm.konst[grp * kP + k]);
         mx = fmaxf(mx, l[k]);
       }
       float z = 0.f;
@@ -210,53 +240,71 @@ mpa_bwd_mma_kernel(const float* __restrict__ fts, long long ep_stride, int S, co
 #pragma unroll
       for (int k = 0; k < kP; ++k) {
         l[k] *= iz;                                                              // sigma_k
-        ds[k] = m * (sa[k] + konst[kK + grp * kP + k]);                         // d sigma_k
+        ds[k] = m * (sa[k] + sm.konst[kK + grp * kP + k]);                      // d sigma_k
         dot = fmaf(l[k], ds[k], dot);
       }
 #pragma unroll
       for (int k = 0; k < kP; ++k) {
-        const float d2 = 2.0f * l[k] * (ds[k] - dot);
-        wt[lane * kWtLd + grp * kP + k] = m * l[k];
-        dv[lane * 8 + grp * kP + k] = d2;
-        if (k > 0) wt[lane * kWtLd + kK + grp * (kP - 1) + k - 1] = d2;
+        const float d2 = live ? 2.0f * l[k] * (ds[k] - dot) : 0.f;
+        if (lane < kStep) {
+          sm.wt[lane * kWtLd + grp * kP + k] = m * l[k];
+          sm.dv[(lane + 3) * 8 + grp * kP + k] = d2;
+          if (k > 0) sm.wt[lane * kWtLd + kK + grp * (kP - 1) + k - 1] = d2;
+        }
         const float tot = warp_sum(d2);
         if (lane == 0) dsum[k] += tot;
       }
     }
     __syncthreads();
-    // ---------------- phase B2: dctr [ch 16] x [k 8 (6 used)] per channel block, contraction over the 32 pixels
+    // ---------------- phase B2: dctr [row 16] x [k 8 (6 used)] per row block, contraction over the 32 box columns
     {
       FragB d[4];
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        split_tf32(dv[(kb * 8 + tg) * 8 + g], d[kb].hi[0], d[kb].lo[0]);
-        split_tf32(dv[(kb * 8 + tg + 4) * 8 + g], d[kb].hi[1], d[kb].lo[1]);
+        const float* dp = sm.dv + (kb * 8 + tg - o + 3) * 8 + g;
+        split_tf32(dp[0], d[kb].hi[0], d[kb].lo[0]);
+        split_tf32(dp[4 * 8], d[kb].hi[1], d[kb].lo[1]);
       }
-      const int sw = ((g & 3) << 3) | (((g >> 2) & 1) << 2);
+      constexpr int MG = MB / NH < 4 ? MB / NH : 4;   // row blocks in flight: independent accumulators, products in rounds
 #pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
-        const float* r0 = tile + (wch + mb * 16 + g) * 32;
-        const float* r1 = r0 + 8 * 32;
+      for (int m0 = 0; m0 < MB; m0 += MG) {
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           const int px = kb * 8 + tg;
-          FragA a;
-          split_tf32(r0[px ^ sw], a.hi[0], a.lo[0]);
-          split_tf32(r1[px ^ sw], a.hi[1], a.lo[1]);
-          split_tf32(r0[(px + 4) ^ sw], a.hi[2], a.lo[2]);
-          split_tf32(r1[(px + 4) ^ sw], a.hi[3], a.lo[3]);
-          mma3(accB[mb], a, d[kb]);
+          FragA a[MG];
+#pragma unroll
+          for (int j = 0; j < MG; ++j) {
+            const int r0 = (m0 + j) * 16 + g;
+            split_tf32(box[box_at(r0, px)], a[j].hi[0], a[j].lo[0]);
+            split_tf32(box[box_at(r0 + 8, px)], a[j].hi[1], a[j].lo[1]);
+            split_tf32(box[box_at(r0, px + 4)], a[j].hi[2], a[j].lo[2]);
+            split_tf32(box[box_at(r0 + 8, px + 4)], a[j].hi[3], a[j].lo[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < MG; ++j)
+            mma_tf32(accB[m0 + j], a[j].lo[0], a[j].lo[1], a[j].lo[2], a[j].lo[3], d[kb].hi[0], d[kb].hi[1]);
+#pragma unroll
+          for (int j = 0; j < MG; ++j)
+            mma_tf32(accB[m0 + j], a[j].hi[0], a[j].hi[1], a[j].hi[2], a[j].hi[3], d[kb].lo[0], d[kb].lo[1]);
+#pragma unroll
+          for (int j = 0; j < MG; ++j)
+            mma_tf32(accB[m0 + j], a[j].hi[0], a[j].hi[1], a[j].hi[2], a[j].hi[3], d[kb].hi[0], d[kb].hi[1]);
+        }
+        // the warp is done with these rows of its half box: fetch them for the next tile (under the rest of B2 and B1)
+        if (NH > 1 && m0 + MG == MB / NH) {
+          __syncwarp();
+          if (t + 1 < te) fill(t + 1, 0);
         }
       }
     }
-    __syncwarp();                                 // the warp is done with its rows of the tile: fetch the next one under B1
-    if (t + 1 < te) fill(t + 1);
-    // ---------------- phase B1: df^T [px 16] x [ch 8] per block, contraction over the 10 columns (8 + 2)
+    __syncwarp();
+    if (t + 1 < te) fill(t + 1, NH - 1);
+    // ---------------- phase B1: df^T [pixel 16] x [row 8] per block, contraction over the 10 columns (8 + 2)
     {
       FragA w0[2], w1[2];
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb) {
-        const float* p0 = wt + (mb * 16 + g) * kWtLd + tg;
+        const float* p0 = sm.wt + (mb * 16 + g) * kWtLd + tg;
         const float* p1 = p0 + 8 * kWtLd;
         split_tf32(p0[0], w0[mb].hi[0], w0[mb].lo[0]);
         split_tf32(p1[0], w0[mb].hi[1], w0[mb].lo[1]);
@@ -266,33 +314,46 @@ mpa_bwd_mma_kernel(const float* __restrict__ fts, long long ep_stride, int S, co
         split_tf32(p1[8], w1[mb].hi[1], w1[mb].lo[1]);
         w1[mb].hi[2] = w1[mb].hi[3] = w1[mb].lo[2] = w1[mb].lo[3] = 0u;
       }
-      const int rem = hw - x0;                    // valid pixels of this tile (>= 32 except for the last one)
-      const int sw = ((g >> 2) & 1) << 2;
-      float* orow = dst + static_cast<long long>(wch + 2 * tg) * hw + x0 + g;
+      const int rem = min(kStep, hw - x0);        // valid pixels of this tile
+      // C fragment: (pixel 16 mb + g (+8), rows 2 tg / 2 tg + 1 of the block).  Stored straight from the fragments a warp
+      // instruction wrote 4 channel rows x 32 bytes (4-8 L1 requests, and the next block's MMAs waited on the stores' data
+      // registers: 14 % of all stall samples, ncu); the block goes through 1 KB of shared memory instead and leaves as 8 rows
+      // of 112 contiguous bytes.
+      float* stg = sm.stage[warp];
+      float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + x0 + lane;   // row j of a block: + 4 j hw
 #pragma unroll 2
       for (int nb = 0; nb < CW / 8; ++nb) {
-        const int ch = wch + nb * 8 + g;
+        const float* tb0 = trow + (nb * 8 + g) * kTLd + tg;
         FragB b0, b1;
-        split_tf32(t0[ch * 8 + (tg ^ sw)], b0.hi[0], b0.lo[0]);
-        split_tf32(t0[ch * 8 + ((tg + 4) ^ sw)], b0.hi[1], b0.lo[1]);
-        split_tf32(tg < kN1 ? t1[ch * kN1 + tg] : 0.f, b1.hi[0], b1.lo[0]);
+        split_tf32(tb0[0], b0.hi[0], b0.lo[0]);
+        split_tf32(tb0[4], b0.hi[1], b0.lo[1]);
+        split_tf32(tb0[8], b1.hi[0], b1.lo[0]);             // columns 8 + tg: 10, 11 hold zeros
         b1.hi[1] = b1.lo[1] = 0u;
+        float d[2][4];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) d[mb][0] = d[mb][1] = d[mb][2] = d[mb][3] = 0.f;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w1[mb], b1);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w0[mb], b0);
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
-          float d[4] = {0.f, 0.f, 0.f, 0.f};
-          mma3(d, w1[mb], b1);
-          mma3(d, w0[mb], b0);
-          float* o = orow + mb * 16;
-          if (mb * 16 + g < rem) {
-            o[0] = d[0];
-            o[hw] = d[1];
-          }
-          if (mb * 16 + g + 8 < rem) {
-            o[8] = d[2];
-            o[hw + 8] = d[3];
-          }
+          float* sp = stg + 2 * tg * kStgLd + mb * 16 + g;
+          sp[0] = d[mb][0];
+          sp[kStgLd] = d[mb][1];
+          sp[8] = d[mb][2];
+          sp[kStgLd + 8] = d[mb][3];
         }
-        orow += 8LL * hw;
+        __syncwarp();
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = stg[j * kStgLd + lane];
+        __syncwarp();
+        if (lane < rem) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) orow[4LL * j * hw] = v[j];
+        }
+        orow += 32LL * hw;                        // 8 rows of the box = channels 4 apart
       }
     }
   }
@@ -300,44 +361,97 @@ mpa_bwd_mma_kernel(const float* __restrict__ fts, long long ep_stride, int S, co
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
     if (tg < kK / 2) {
-      const int ch = wch + mb * 16 + g;
+      const int ch = 4 * (CW * half + mb * 16 + g) + e;
       *reinterpret_cast<float2*>(dstp + ch * kK + 2 * tg) = make_float2(accB[mb][0], accB[mb][1]);
-      *reinterpret_cast<float2*>(dstp + (ch + 8) * kK + 2 * tg) = make_float2(accB[mb][2], accB[mb][3]);
+      *reinterpret_cast<float2*>(dstp + (ch + 32) * kK + 2 * tg) = make_float2(accB[mb][2], accB[mb][3]);
     }
   }
   if (warp < 2 && lane == 0) {
 #pragma unroll
     for (int k = 0; k < kP; ++k) dstp[c * kK + warp * kP + k] = dsum[k];
   }
+  // The CTA that finishes an image last adds the image's partials in chunk order (the order is fixed, whoever does it): the
+  // finalize kernel then reads one partial per image instead of one per CTA (880 x 12 KB = 22 us at 80 images before).
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sm.last = atomicAdd(done + n, 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (sm.last) {
+    __threadfence();
+    const float* pp = part + static_cast<long long>(n) * gridDim.x * (c + 1) * kK;
+    float* ip = img_part + static_cast<long long>(n) * (c + 1) * kK;
+    for (int i = tid; i < (c + 1) * kK; i += kT) {
+      double sum = 0.0;
+      for (unsigned ch = 0; ch < gridDim.x; ++ch) sum += static_cast<double>(__ldcg(pp + static_cast<long long>(ch) * (c + 1) * kK + i));
+      ip[i] = static_cast<float>(sum);
+    }
+  }
+}
+
+// tabg [N][c][kTLd] in the row order of the main kernel (row R = w CW + r <-> channel 4 (CW (w >> 2) + r) + (w & 3)):
+// { coef[ch][0..6) | ctr_k - ctr_g0 of the non-first prototypes (exact in double, one rounding; see train.cu) | 0 0 }
+__global__ void __launch_bounds__(256)
+mpa_bwd_mma_table_kernel(const float* __restrict__ coef, const float* __restrict__ ctr, int c, float* __restrict__ tabg) {
+  const int n = blockIdx.y, CW = c / kW;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= c * kTLd) return;
+  const int R = i / kTLd, k = i - R * kTLd;
+  const int w = R / CW, r = R - w * CW, ch = 4 * (CW * (w >> 2) + r) + (w & 3);
+  float v = 0.f;
+  if (k < kK) {
+    v = __ldg(coef + (static_cast<long long>(n) * c + ch) * kK + k);
+  } else if (k < kNK) {
+    const int j = k - kK, grp = j / (kP - 1), kk = grp * kP + 1 + (j - grp * (kP - 1));
+    v = static_cast<float>(static_cast<double>(__ldg(ctr + ch * kK + kk)) - static_cast<double>(__ldg(ctr + ch * kK + grp * kP)));
+  }
+  tabg[static_cast<long long>(n) * c * kTLd + i] = v;
+}
+
+template <int MB>
+int launch(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
+           long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part, int* done,
+           cudaStream_t st) {
+  const size_t smem = sizeof(Smem<MB>);
+  cudaError_t err = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return static_cast<int>(err);
+  mpa_bwd_mma_kernel<MB><<<dim3(chunks, N), kT, smem, st>>>(map, S, tabg, beta, fg, bg, mask_stride, hw,
+                                                           pemp_mpa_bwd_mma_tiles(hw), dfts, d_ep, part, img_part, done);
+  return PEMP_OK;
 }
 
 }  // namespace
 
-bool pemp_mpa_bwd_mma_shape(int c, int p) { return p == kP && (c == 128 || c == 256 || c == 512 || c == 1024); }
+bool pemp_mpa_bwd_mma_shape(int c, int p, int hw) { return p == kP && (c == 128 || c == 256 || c == 512 || c == 1024) && hw >= 32; }
+int pemp_mpa_bwd_mma_tiles(int hw) { return (hw + kStep - 1) / kStep; }
 
 size_t pemp_mpa_bwd_mma_smem(int c) {
-  return (static_cast<size_t>(c) * (32 + 8 + kN1) + kW * kNK * kRedLd + 32 * kWtLd + 32 * 8 + 2 * kK) * sizeof(float);
+  switch (c / 128) {
+    case 1: return sizeof(Smem<1>);
+    case 2: return sizeof(Smem<2>);
+    case 4: return sizeof(Smem<4>);
+    default: return sizeof(Smem<8>);
+  }
 }
 
-int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int S, const float* ctr, const float* coef, const float* beta,
-                            const float* fg, const float* bg, long long mask_stride, int N, int c, int hw, int chunks, int ntiles,
-                            float* dfts, long long d_ep, float* part, cudaStream_t st) {
-  const size_t smem = pemp_mpa_bwd_mma_smem(c);
-#define PEMP_BWD_MMA(MBV)                                                                                                        \
-  do {                                                                                                                           \
-    cudaError_t e = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
-                                         static_cast<int>(smem));                                                               \
-    if (e != cudaSuccess) return static_cast<int>(e);                                                                            \
-    mpa_bwd_mma_kernel<MBV><<<dim3(chunks, N), kT, smem, st>>>(fts, ep, S, ctr, coef, beta, fg, bg, mask_stride, hw, ntiles,    \
-                                                               dfts, d_ep, part);                                               \
-  } while (0)
+// Returns PEMP_E_ALIGN (nothing launched) when the operand cannot be described by a tensor map; the caller then uses the
+// CUDA-core kernel.
+int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
+                            const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
+                            float* dfts, long long d_ep, float* part, float* img_part, int* done, cudaStream_t st) {
+  CUtensorMap map;
+  // no L2 promotion beyond the 128-byte row piece: a CTA comes back for the neighbouring piece ~10 us later, by which time the
+  // write stream has pushed it out of L2 (with 256-byte promotion the kernel read 1.6 x its algorithmic bytes from DRAM, ncu)
+  if (!make_rows4_map(&map, fts, B, S, c, hw, ep, c >= 256 ? c / 16 : c / 8, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return PEMP_E_ALIGN;
+  const int N = B * S;
+  cudaError_t err = cudaMemsetAsync(done, 0, static_cast<size_t>(N) * sizeof(int), st);
+  if (err != cudaSuccess) return static_cast<int>(err);
+  mpa_bwd_mma_table_kernel<<<dim3((c * kTLd + 255) / 256, N), 256, 0, st>>>(coef, ctr, c, tabg);
   switch (c / 128) {
-    case 1: PEMP_BWD_MMA(1); break;
-    case 2: PEMP_BWD_MMA(2); break;
-    case 4: PEMP_BWD_MMA(4); break;
-    case 8: PEMP_BWD_MMA(8); break;
+    case 1: return launch<1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
+    case 2: return launch<2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
+    case 4: return launch<4>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
+    case 8: return launch<8>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
     default: return PEMP_E_SHAPE;
   }
-#undef PEMP_BWD_MMA
-  return PEMP_OK;
 }
+size_t pemp_mpa_bwd_mma_table_bytes(int N, int c) { return static_cast<size_t>(N) * c * kTLd * sizeof(float); }
