@@ -35,7 +35,7 @@ int pemp_mpa_bwd_mma_tiles(int hw);
 size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
-                            float* dfts, long long d_ep, float* part, float* img_part, int* done, cudaStream_t st);
+                            float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st);
 static int g_bwd_path = 0;   // diagnostic switch, see pemp_debug_bwd_path
 
 namespace {
@@ -885,7 +885,7 @@ namespace {
 // workspace of the K2 backward: coef [N][c][K] | beta [N][2K] | partials [N][chunks][(c + 1) K] | image tables of the tensor-path
 // kernel.  `chunks` is the larger of the two kernels' splits (the diagnostic switch picks the kernel at launch time).
 struct MpaBwdWs {
-  size_t off_beta, off_part, off_tab, off_img, off_done, total;
+  size_t off_beta, off_part, off_tab, off_img, total;
 };
 MpaBwdWs mpa_bwd_ws(int N, int c, int hw, int p) {
   const size_t n = static_cast<size_t>(N), K = 2 * p;
@@ -900,8 +900,7 @@ MpaBwdWs mpa_bwd_ws(int N, int c, int hw, int p) {
   w.off_part = w.off_beta + align_up(n * 2 * K * 4, 256);
   w.off_tab = w.off_part + align_up(n * chunks * (c + 1) * K * 4, 256);
   w.off_img = w.off_tab + (mma ? align_up(pemp_mpa_bwd_mma_table_bytes(N, c), 256) : 0);      // per-image sums of the partials
-  w.off_done = w.off_img + (mma ? align_up(n * (c + 1) * K * 4, 256) : 0);                     // per-image arrival counters
-  w.total = w.off_done + (mma ? align_up(n * sizeof(int), 256) : 0);
+  w.total = w.off_img + (mma ? align_up(n * (c + 1) * K * 4, 256) : 0);
   return w;
 }
 }  // namespace
@@ -939,8 +938,8 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
     float* tabg = reinterpret_cast<float*>(ws + wl.off_tab);
     float* img_part = reinterpret_cast<float*>(ws + wl.off_img);
     rc = pemp_mpa_bwd_mma_launch(fts, ep, B, S, ctr, coef, beta, fg, bg, mask_stride, c, hw, pm.chunks, tabg, d_fts, d_ep, part,
-                                 img_part, reinterpret_cast<int*>(ws + wl.off_done), st);
-    if (rc == PEMP_OK) {                         // the main kernel has already added the partials of an image
+                                 img_part, st);
+    if (rc == PEMP_OK) {                         // the partials of an image have already been added
       nparts = N;
       part = img_part;
     }

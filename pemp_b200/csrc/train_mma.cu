@@ -36,7 +36,7 @@ int pemp_mpa_bwd_mma_tiles(int hw);
 size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
-                            float* dfts, long long d_ep, float* part, float* img_part, int* done, cudaStream_t st);
+                            float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st);
 
 namespace {
 
@@ -86,11 +86,10 @@ struct Smem {
   alignas(1024) float tile[kW][CW * 32];         // warp w: rows [CW half, CW half + CW) of the class-e box, e = w & 3, half = w >> 2
   alignas(16) float tab[c * kTLd];               // row R = w CW + r  <->  channel 4 (CW half + r) + e
   alignas(16) float red[kW][kNK * kRedLd];       // partial dots of the warps: [k][pixel of the tile]
-  alignas(16) float wt[32 * kWtLd];              // [pixel]{ a_k (6) | 2 dl_k of the non-first prototypes (4) | 0 0 }
+  alignas(16) float wt[2][32 * kWtLd];           // [tile parity][pixel]{ a_k (6) | 2 dl_k of the non-first prototypes (4) | 0 0 }
   alignas(16) float dv[kDvRows * 8];             // [pixel + 3]{ 2 dl_k (6) | 0 0 }
-  alignas(16) float stage[kW][8 * kStgLd];       // per warp: one 8-row block of the gradient tile on its way out
+  alignas(16) float stage[kW - 2][8 * kStgLd];   // per B1 warp (2..7): one 8-row block of the gradient tile on its way out
   float konst[2 * kK];                           // |ctr_k|^2 - |ctr_g0|^2, beta
-  int last;                                      // this CTA finished its image last
   alignas(8) uint64_t full[kW];
 };
 
@@ -99,7 +98,7 @@ __global__ void __launch_bounds__(kT, MB <= 4 ? 2 : 1)
 mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* __restrict__ tabg,
                    const float* __restrict__ beta, const float* __restrict__ fg, const float* __restrict__ bg,
                    long long mask_stride, int hw, int ntiles, float* __restrict__ dfts, long long d_ep_stride,
-                   float* __restrict__ part, float* __restrict__ img_part, int* __restrict__ done) {
+                   float* __restrict__ part) {
   constexpr int c = 128 * MB, CW = 16 * MB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem<MB>& sm = *reinterpret_cast<Smem<MB>*>(smem_raw);
@@ -142,7 +141,7 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     for (int i = 0; i < (c * kTLd / 4 + kT - 1) / kT; ++i)
       if (tid + i * kT < c * kTLd / 4) tdst[tid + i * kT] = __ldg(tsrc + tid + i * kT);
   }
-  for (int i = tid; i < 32 * kWtLd; i += kT) sm.wt[i] = 0.f;
+  for (int i = tid; i < 2 * 32 * kWtLd; i += kT) (&sm.wt[0][0])[i] = 0.f;
   for (int i = tid; i < kDvRows * 8; i += kT) sm.dv[i] = 0.f;
   if (tid < kK) {
     sm.konst[tid] = __ldg(beta + n * 2 * kK + kK + tid);
@@ -153,6 +152,74 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   for (int i = 0; i < MB; ++i) accB[i][0] = accB[i][1] = accB[i][2] = accB[i][3] = 0.f;
   float dsum[kP] = {0.f, 0.f, 0.f};              // lane 0 of warps 0 / 1: sum_x 2 dl_k of its group
   __syncthreads();
+
+  // ---- phase B1: df^T [pixel 16] x [row 8] per block, contraction over the 10 columns (8 + 2) ----
+  // W fragments of a tile (A operand: pixel 16 mb + g (+8), column tg (+4) / 8 + tg; columns 10, 11 hold zeros)
+  auto load_w = [&](const float* wt, FragA (&w0)[2], FragA (&w1)[2]) {
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const float* p0 = wt + (mb * 16 + g) * kWtLd + tg;
+      const float* p1 = p0 + 8 * kWtLd;
+      split_tf32(p0[0], w0[mb].hi[0], w0[mb].lo[0]);
+      split_tf32(p1[0], w0[mb].hi[1], w0[mb].lo[1]);
+      split_tf32(p0[4], w0[mb].hi[2], w0[mb].lo[2]);
+      split_tf32(p1[4], w0[mb].hi[3], w0[mb].lo[3]);
+      split_tf32(p0[8], w1[mb].hi[0], w1[mb].lo[0]);
+      split_tf32(p1[8], w1[mb].hi[1], w1[mb].lo[1]);
+      w1[mb].hi[2] = w1[mb].hi[3] = w1[mb].lo[2] = w1[mb].lo[3] = 0u;
+    }
+  };
+  // One block of 8 table rows (tb8 = its first row) x 32 pixels.  C fragment: (pixel 16 mb + g (+8), rows 2 tg / 2 tg + 1 of the
+  // block).  Stored straight from the fragments a warp instruction wrote 4 channel rows x 32 bytes (4-8 L1 requests, and the
+  // next block's MMAs waited on the stores' data registers: 14 % of all stall samples, ncu); the block goes through 1 KB of
+  // shared memory instead and leaves as 8 rows of 112 contiguous bytes.  orow = row 0 of the block at this lane's pixel; the
+  // rows of a block are channels 4 apart.
+  float* stg = sm.stage[warp >= 2 ? warp - 2 : 0];
+  auto b1_block = [&](const FragA (&w0)[2], const FragA (&w1)[2], const float* tb8, float* orow, int rem) {
+    const float* tb0 = tb8 + g * kTLd + tg;
+    FragB b0, b1;
+    split_tf32(tb0[0], b0.hi[0], b0.lo[0]);
+    split_tf32(tb0[4], b0.hi[1], b0.lo[1]);
+    split_tf32(tb0[8], b1.hi[0], b1.lo[0]);               // columns 8 + tg: 10, 11 hold zeros
+    b1.hi[1] = b1.lo[1] = 0u;
+    float d[2][4];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) d[mb][0] = d[mb][1] = d[mb][2] = d[mb][3] = 0.f;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w1[mb], b1);
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w0[mb], b0);
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      float* sp = stg + 2 * tg * kStgLd + mb * 16 + g;
+      sp[0] = d[mb][0];
+      sp[kStgLd] = d[mb][1];
+      sp[8] = d[mb][2];
+      sp[kStgLd + 8] = d[mb][3];
+    }
+    __syncwarp();
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = stg[j * kStgLd + lane];
+    __syncwarp();
+    if (lane < rem) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) orow[4LL * j * hw] = v[j];
+    }
+  };
+  // The rows of warps 0 / 1 (classes 0 / 1, first half) of tile tp, shared out over warps 2..7: they run while warps 0 / 1 do
+  // the pixel step of the NEXT tile (every other warp used to sit at the barrier for that long: 9 % of all stall samples), so
+  // the weights are double buffered by tile parity.
+  auto b1_foreign = [&](int tp) {
+    if (warp < 2) return;
+    FragA w0[2], w1[2];
+    load_w(sm.wt[(tp - tb) & 1], w0, w1);
+    const int xp = tp * kStep, rem = min(kStep, hw - xp);
+    for (int q = warp - 2; q < 2 * (CW / 8); q += kW - 2) {
+      const int wf = q / (CW / 8), nb = q - wf * (CW / 8);      // owner warp (= class, half 0) and block
+      b1_block(w0, w1, sm.tab + (wf * CW + nb * 8) * kTLd, dst + static_cast<long long>(4 * (nb * 8) + wf) * hw + xp + lane, rem);
+    }
+  };
 
   for (int t = tb; t < te; ++t) {
     const int x0 = t * kStep;
@@ -247,13 +314,16 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
       for (int k = 0; k < kP; ++k) {
         const float d2 = live ? 2.0f * l[k] * (ds[k] - dot) : 0.f;
         if (lane < kStep) {
-          sm.wt[lane * kWtLd + grp * kP + k] = m * l[k];
+          float* wtp = sm.wt[(t - tb) & 1];
+          wtp[lane * kWtLd + grp * kP + k] = m * l[k];
           sm.dv[(lane + 3) * 8 + grp * kP + k] = d2;
-          if (k > 0) sm.wt[lane * kWtLd + kK + grp * (kP - 1) + k - 1] = d2;
+          if (k > 0) wtp[lane * kWtLd + kK + grp * (kP - 1) + k - 1] = d2;
         }
         const float tot = warp_sum(d2);
         if (lane == 0) dsum[k] += tot;
       }
+    } else if (t > tb) {
+      b1_foreign(t - 1);
     }
     __syncthreads();
     // ---------------- phase B2: dctr [row 16] x [k 8 (6 used)] per row block, contraction over the 32 box columns
@@ -299,64 +369,17 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     }
     __syncwarp();
     if (t + 1 < te) fill(t + 1, NH - 1);
-    // ---------------- phase B1: df^T [pixel 16] x [row 8] per block, contraction over the 10 columns (8 + 2)
-    {
+    // ---------------- phase B1 of this tile: the warp's own rows (warps 0 / 1 leave theirs to the others, see b1_foreign)
+    if (warp >= 2) {
       FragA w0[2], w1[2];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const float* p0 = sm.wt + (mb * 16 + g) * kWtLd + tg;
-        const float* p1 = p0 + 8 * kWtLd;
-        split_tf32(p0[0], w0[mb].hi[0], w0[mb].lo[0]);
-        split_tf32(p1[0], w0[mb].hi[1], w0[mb].lo[1]);
-        split_tf32(p0[4], w0[mb].hi[2], w0[mb].lo[2]);
-        split_tf32(p1[4], w0[mb].hi[3], w0[mb].lo[3]);
-        split_tf32(p0[8], w1[mb].hi[0], w1[mb].lo[0]);      // columns 8 + tg: 10, 11 hold zeros
-        split_tf32(p1[8], w1[mb].hi[1], w1[mb].lo[1]);
-        w1[mb].hi[2] = w1[mb].hi[3] = w1[mb].lo[2] = w1[mb].lo[3] = 0u;
-      }
-      const int rem = min(kStep, hw - x0);        // valid pixels of this tile
-      // C fragment: (pixel 16 mb + g (+8), rows 2 tg / 2 tg + 1 of the block).  Stored straight from the fragments a warp
-      // instruction wrote 4 channel rows x 32 bytes (4-8 L1 requests, and the next block's MMAs waited on the stores' data
-      // registers: 14 % of all stall samples, ncu); the block goes through 1 KB of shared memory instead and leaves as 8 rows
-      // of 112 contiguous bytes.
-      float* stg = sm.stage[warp];
-      float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + x0 + lane;   // row j of a block: + 4 j hw
+      load_w(sm.wt[(t - tb) & 1], w0, w1);
+      const int rem = min(kStep, hw - x0);
+      float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + x0 + lane;
 #pragma unroll 2
-      for (int nb = 0; nb < CW / 8; ++nb) {
-        const float* tb0 = trow + (nb * 8 + g) * kTLd + tg;
-        FragB b0, b1;
-        split_tf32(tb0[0], b0.hi[0], b0.lo[0]);
-        split_tf32(tb0[4], b0.hi[1], b0.lo[1]);
-        split_tf32(tb0[8], b1.hi[0], b1.lo[0]);             // columns 8 + tg: 10, 11 hold zeros
-        b1.hi[1] = b1.lo[1] = 0u;
-        float d[2][4];
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) d[mb][0] = d[mb][1] = d[mb][2] = d[mb][3] = 0.f;
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w1[mb], b1);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w0[mb], b0);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          float* sp = stg + 2 * tg * kStgLd + mb * 16 + g;
-          sp[0] = d[mb][0];
-          sp[kStgLd] = d[mb][1];
-          sp[8] = d[mb][2];
-          sp[kStgLd + 8] = d[mb][3];
-        }
-        __syncwarp();
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = stg[j * kStgLd + lane];
-        __syncwarp();
-        if (lane < rem) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) orow[4LL * j * hw] = v[j];
-        }
-        orow += 32LL * hw;                        // 8 rows of the box = channels 4 apart
-      }
+      for (int nb = 0; nb < CW / 8; ++nb) b1_block(w0, w1, trow + nb * 8 * kTLd, orow + 32LL * nb * hw, rem);
     }
   }
+  if (tb < te) b1_foreign(te - 1);                 // the rows of warps 0 / 1 for the last tile
   float* dstp = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * (c + 1) * kK;
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
@@ -370,22 +393,21 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
 #pragma unroll
     for (int k = 0; k < kP; ++k) dstp[c * kK + warp * kP + k] = dsum[k];
   }
-  // The CTA that finishes an image last adds the image's partials in chunk order (the order is fixed, whoever does it): the
-  // finalize kernel then reads one partial per image instead of one per CTA (880 x 12 KB = 22 us at 80 images before).
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) sm.last = atomicAdd(done + n, 1) == static_cast<int>(gridDim.x) - 1;
-  __syncthreads();
-  if (sm.last) {
-    __threadfence();
-    const float* pp = part + static_cast<long long>(n) * gridDim.x * (c + 1) * kK;
-    float* ip = img_part + static_cast<long long>(n) * (c + 1) * kK;
-    for (int i = tid; i < (c + 1) * kK; i += kT) {
-      double sum = 0.0;
-      for (unsigned ch = 0; ch < gridDim.x; ++ch) sum += static_cast<double>(__ldcg(pp + static_cast<long long>(ch) * (c + 1) * kK + i));
-      ip[i] = static_cast<float>(sum);
-    }
-  }
+}
+
+// img_part[n] = sum of the image's per-CTA partials, in chunk order: the finalize kernel then reads one partial per image
+// instead of one per CTA (880 x 12 KB took it 22 us at 80 images).  A separate launch: letting the last CTA of an image do
+// it inside the main kernel needs a __threadfence per CTA, which waits for all of the CTA's gradient stores (9 % of the
+// kernel's stall samples, ncu).
+__global__ void __launch_bounds__(256)
+mpa_bwd_image_sum_kernel(const float* __restrict__ part, int chunks, int M, float* __restrict__ img_part) {
+  const int n = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= M) return;
+  const float* pp = part + static_cast<long long>(n) * chunks * M + i;
+  double sum = 0.0;
+#pragma unroll 4
+  for (int ch = 0; ch < chunks; ++ch) sum += static_cast<double>(__ldg(pp + static_cast<long long>(ch) * M));
+  img_part[static_cast<long long>(n) * M + i] = static_cast<float>(sum);
 }
 
 // tabg [N][c][kTLd] in the row order of the main kernel (row R = w CW + r <-> channel 4 (CW (w >> 2) + r) + (w & 3)):
@@ -409,13 +431,15 @@ mpa_bwd_mma_table_kernel(const float* __restrict__ coef, const float* __restrict
 
 template <int MB>
 int launch(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
-           long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part, int* done,
+           long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
            cudaStream_t st) {
   const size_t smem = sizeof(Smem<MB>);
   cudaError_t err = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return static_cast<int>(err);
   mpa_bwd_mma_kernel<MB><<<dim3(chunks, N), kT, smem, st>>>(map, S, tabg, beta, fg, bg, mask_stride, hw,
-                                                           pemp_mpa_bwd_mma_tiles(hw), dfts, d_ep, part, img_part, done);
+                                                           pemp_mpa_bwd_mma_tiles(hw), dfts, d_ep, part);
+  const int M = (128 * MB + 1) * kK;
+  mpa_bwd_image_sum_kernel<<<dim3((M + 255) / 256, N), 256, 0, st>>>(part, chunks, M, img_part);
   return PEMP_OK;
 }
 
@@ -437,20 +461,18 @@ size_t pemp_mpa_bwd_mma_smem(int c) {
 // CUDA-core kernel.
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
-                            float* dfts, long long d_ep, float* part, float* img_part, int* done, cudaStream_t st) {
+                            float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st) {
   CUtensorMap map;
   // no L2 promotion beyond the 128-byte row piece: a CTA comes back for the neighbouring piece ~10 us later, by which time the
   // write stream has pushed it out of L2 (with 256-byte promotion the kernel read 1.6 x its algorithmic bytes from DRAM, ncu)
   if (!make_rows4_map(&map, fts, B, S, c, hw, ep, c >= 256 ? c / 16 : c / 8, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return PEMP_E_ALIGN;
   const int N = B * S;
-  cudaError_t err = cudaMemsetAsync(done, 0, static_cast<size_t>(N) * sizeof(int), st);
-  if (err != cudaSuccess) return static_cast<int>(err);
   mpa_bwd_mma_table_kernel<<<dim3((c * kTLd + 255) / 256, N), 256, 0, st>>>(coef, ctr, c, tabg);
   switch (c / 128) {
-    case 1: return launch<1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
-    case 2: return launch<2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
-    case 4: return launch<4>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
-    case 8: return launch<8>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, done, st);
+    case 1: return launch<1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+    case 2: return launch<2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+    case 4: return launch<4>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+    case 8: return launch<8>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
     default: return PEMP_E_SHAPE;
   }
 }
