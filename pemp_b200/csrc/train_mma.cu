@@ -48,7 +48,7 @@ constexpr int kND = 2 * (kP - 1);                // centre-difference columns (t
 constexpr int kNK = kK + kND;                    // 10 table columns: [0, 6) coef, [6, 8) fg differences, [8, 10) bg differences
 constexpr int kTLd = 12;                         // table row pitch: conflict-free for the fragments of phase A and of B1
 constexpr int kStep = 28;                        // pixels a tile advances (32 box columns cover them for every class)
-constexpr int kRedLd = 40;                       // pixel pitch of a dot row in `red`
+constexpr int kRedLd = 36;                       // pixel pitch of a dot row in `red` (two CTAs per SM need every KB)
 constexpr int kWtLd = 12;                        // W[x][0..10) + two zero columns (conflict-free fragment reads)
 constexpr int kStgLd = 36;                       // pixel pitch of a staged gradient row (conflict-free fragment stores)
 constexpr int kDvRows = 32 + 3;                  // dv rows for pixels -3 .. 31 of a tile (rows outside [0, 28) stay zero)
@@ -88,10 +88,12 @@ struct Smem {
   alignas(16) float red[kW][kNK * kRedLd];       // partial dots of the warps: [k][pixel of the tile]
   alignas(16) float wt[2][32 * kWtLd];           // [tile parity][pixel]{ a_k (6) | 2 dl_k of the non-first prototypes (4) | 0 0 }
   alignas(16) float dv[kDvRows * 8];             // [pixel + 3]{ 2 dl_k (6) | 0 0 }
-  alignas(16) float stage[kW - 2][8 * kStgLd];   // per B1 warp (2..7): one 8-row block of the gradient tile on its way out
+  alignas(16) float stage[kW][8 * kStgLd];       // per warp: one 8-row block of the gradient tile on its way out
   float konst[2 * kK];                           // |ctr_k|^2 - |ctr_g0|^2, beta
   alignas(8) uint64_t full[kW];
 };
+
+static_assert(2 * (sizeof(Smem<4>) + 1024) <= 228 * 1024, "two CTAs per SM at c = 512");
 
 template <int MB>
 __global__ void __launch_bounds__(kT, MB <= 4 ? 2 : 1)
@@ -174,7 +176,7 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   // next block's MMAs waited on the stores' data registers: 14 % of all stall samples, ncu); the block goes through 1 KB of
   // shared memory instead and leaves as 8 rows of 112 contiguous bytes.  orow = row 0 of the block at this lane's pixel; the
   // rows of a block are channels 4 apart.
-  float* stg = sm.stage[warp >= 2 ? warp - 2 : 0];
+  float* stg = sm.stage[warp];
   auto b1_block = [&](const FragA (&w0)[2], const FragA (&w1)[2], const float* tb8, float* orow, int rem) {
     const float* tb0 = tb8 + g * kTLd + tg;
     FragB b0, b1;
@@ -207,16 +209,18 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
       for (int j = 0; j < 8; ++j) orow[4LL * j * hw] = v[j];
     }
   };
-  // The rows of warps 0 / 1 (classes 0 / 1, first half) of tile tp, shared out over warps 2..7: they run while warps 0 / 1 do
-  // the pixel step of the NEXT tile (every other warp used to sit at the barrier for that long: 9 % of all stall samples), so
-  // the weights are double buffered by tile parity.
+  // The last kF row blocks of warps 0 / 1 (classes 0 / 1, first half) of tile tp, shared out over warps 2..7: they run while
+  // warps 0 / 1 do the pixel step of the NEXT tile (every other warp used to sit at the barrier for that long: 9 % of all stall
+  // samples), so the weights are double buffered by tile parity.  kF balances the two kinds of warps: pixel step + 5 blocks
+  // against 8 + 1 blocks at c = 512.
+  constexpr int kF = (3 * (CW / 8)) / 8 > 0 ? (3 * (CW / 8)) / 8 : 1;
   auto b1_foreign = [&](int tp) {
     if (warp < 2) return;
     FragA w0[2], w1[2];
     load_w(sm.wt[(tp - tb) & 1], w0, w1);
     const int xp = tp * kStep, rem = min(kStep, hw - xp);
-    for (int q = warp - 2; q < 2 * (CW / 8); q += kW - 2) {
-      const int wf = q / (CW / 8), nb = q - wf * (CW / 8);      // owner warp (= class, half 0) and block
+    for (int q = warp - 2; q < 2 * kF; q += kW - 2) {
+      const int wf = q / kF, nb = CW / 8 - kF + (q - wf * kF);  // owner warp (= class, half 0) and block
       b1_block(w0, w1, sm.tab + (wf * CW + nb * 8) * kTLd, dst + static_cast<long long>(4 * (nb * 8) + wf) * hw + xp + lane, rem);
     }
   };
@@ -369,14 +373,14 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     }
     __syncwarp();
     if (t + 1 < te) fill(t + 1, NH - 1);
-    // ---------------- phase B1 of this tile: the warp's own rows (warps 0 / 1 leave theirs to the others, see b1_foreign)
-    if (warp >= 2) {
+    // ---------------- phase B1 of this tile: the warp's own rows (warps 0 / 1 leave their last kF blocks to the others)
+    {
       FragA w0[2], w1[2];
       load_w(sm.wt[(t - tb) & 1], w0, w1);
-      const int rem = min(kStep, hw - x0);
+      const int rem = min(kStep, hw - x0), nown = warp < 2 ? CW / 8 - kF : CW / 8;
       float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + x0 + lane;
 #pragma unroll 2
-      for (int nb = 0; nb < CW / 8; ++nb) b1_block(w0, w1, trow + nb * 8 * kTLd, orow + 32LL * nb * hw, rem);
+      for (int nb = 0; nb < nown; ++nb) b1_block(w0, w1, trow + nb * 8 * kTLd, orow + 32LL * nb * hw, rem);
     }
   }
   if (tb < te) b1_foreign(te - 1);                 // the rows of warps 0 / 1 for the last tile
