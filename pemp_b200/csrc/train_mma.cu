@@ -34,6 +34,7 @@ size_t pemp_mpa_bwd_mma_smem(int c);
 bool pemp_mpa_bwd_mma_shape(int c, int p, int hw);
 int pemp_mpa_bwd_mma_tiles(int hw);
 size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
+int pemp_mpa_bwd_mma_table_ld();
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
                             float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st);
@@ -134,7 +135,7 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     for (int h = 0; h < NH; ++h) fill(tb, h);
   }
 
-  // table of this image, laid out by mpa_bwd_mma_table_kernel: a straight 16-byte copy (the first tile is on its way meanwhile;
+  // table of this image, laid out by mpa_bwd_prepare_kernel (train.cu): a straight 16-byte copy (the first tile is on its way meanwhile;
   // when every CTA built its table from coef / ctr itself the prologue was 15 % of all stall samples at ~8 tiles per CTA)
   {
     const float4* tsrc = reinterpret_cast<const float4*>(tabg + static_cast<long long>(n) * c * kTLd);
@@ -414,25 +415,6 @@ mpa_bwd_image_sum_kernel(const float* __restrict__ part, int chunks, int M, floa
   img_part[static_cast<long long>(n) * M + i] = static_cast<float>(sum);
 }
 
-// tabg [N][c][kTLd] in the row order of the main kernel (row R = w CW + r <-> channel 4 (CW (w >> 2) + r) + (w & 3)):
-// { coef[ch][0..6) | ctr_k - ctr_g0 of the non-first prototypes (exact in double, one rounding; see train.cu) | 0 0 }
-__global__ void __launch_bounds__(256)
-mpa_bwd_mma_table_kernel(const float* __restrict__ coef, const float* __restrict__ ctr, int c, float* __restrict__ tabg) {
-  const int n = blockIdx.y, CW = c / kW;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= c * kTLd) return;
-  const int R = i / kTLd, k = i - R * kTLd;
-  const int w = R / CW, r = R - w * CW, ch = 4 * (CW * (w >> 2) + r) + (w & 3);
-  float v = 0.f;
-  if (k < kK) {
-    v = __ldg(coef + (static_cast<long long>(n) * c + ch) * kK + k);
-  } else if (k < kNK) {
-    const int j = k - kK, grp = j / (kP - 1), kk = grp * kP + 1 + (j - grp * (kP - 1));
-    v = static_cast<float>(static_cast<double>(__ldg(ctr + ch * kK + kk)) - static_cast<double>(__ldg(ctr + ch * kK + grp * kP)));
-  }
-  tabg[static_cast<long long>(n) * c * kTLd + i] = v;
-}
-
 template <int MB>
 int launch(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
            long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
@@ -471,7 +453,6 @@ int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const 
   // write stream has pushed it out of L2 (with 256-byte promotion the kernel read 1.6 x its algorithmic bytes from DRAM, ncu)
   if (!make_rows4_map(&map, fts, B, S, c, hw, ep, c >= 256 ? c / 16 : c / 8, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return PEMP_E_ALIGN;
   const int N = B * S;
-  mpa_bwd_mma_table_kernel<<<dim3((c * kTLd + 255) / 256, N), 256, 0, st>>>(coef, ctr, c, tabg);
   switch (c / 128) {
     case 1: return launch<1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
     case 2: return launch<2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
@@ -480,4 +461,6 @@ int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const 
     default: return PEMP_E_SHAPE;
   }
 }
+// tabg [N][c][kTLd], written by mpa_bwd_prepare_kernel (train.cu) in the row order of the main kernel
 size_t pemp_mpa_bwd_mma_table_bytes(int N, int c) { return static_cast<size_t>(N) * c * kTLd * sizeof(float); }
+int pemp_mpa_bwd_mma_table_ld() { return kTLd; }
