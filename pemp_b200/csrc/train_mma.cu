@@ -19,13 +19,18 @@
 // 3 x TF32: x = hi + lo with hi = x & 0xffffe000 (what the tensor core reads of an fp32 register) and lo = x - hi (exact);
 // a.b ~ lo_a hi_b + hi_a lo_b + hi_a hi_b, small products first (see K9), error ~2^-21 per product.
 //
-// Structure: 256 threads, two CTAs per SM; a CTA owns a run of 28-pixel tiles of one image.  The features come through the
-// "four rows per group" tensor map of the forward kernels (tma_common.cuh): warp w = e + 4 half owns rows [CW half, CW half +
-// CW) of the class-e box of a tile (channels 4 g + e; CW = c/8), i.e. its own 128-byte-swizzled half box with its own mbarrier -
-// the tile buffer is warp-private in every phase, one lane issues ONE bulk-tensor load per warp and tile (the first version
-// filled it with 64 four-byte cp.async per thread: a third of all stall samples sat in that loop, ncu), the load of tile t+1 is
-// issued after B2(t) and runs under B1(t), which needs no features, and only two block barriers per tile remain (dots -> pixel
-// step -> weights).  Box column i of class e is pixel x_nom + i - o_e, o_e = (e hw + x_nom) & 3 (aligned box origins).
+// Structure: two CTAs per SM, each eight product warps + two pixel-step warps (96 registers); a CTA owns a run of 28-pixel
+// tiles of one image.  The features come through the "four rows per group" tensor map of the forward kernels (tma_common.cuh):
+// product warp w = e + 4 half owns rows [CW half, CW half + CW) of the class-e box of a tile (channels 4 g + e; CW = c/8), i.e.
+// its own 128-byte-swizzled half box with its own mbarrier - the tile buffer is warp-private in every phase and is refilled in
+// two pieces, each as soon as B2 is done with its rows (the first version filled it with 64 four-byte cp.async per thread: a
+// third of all stall samples sat in that loop, ncu).  Box column i of class e is pixel x_nom + i - o_e, o_e = (e hw + x_nom) & 3
+// (aligned box origins).  Per tile a product warp runs
+//     wait box(t) | A(t) -> dots -> arrive | second half of B1(t-1) | wait weights(t) | B2(t) + refills | first half of B1(t)
+// and the pixel-step warps (one per class group, lane = pixel) turn the eight partial dot sets into the weights of the tile
+// (double buffered by tile parity) behind two mbarriers: B1 needs no features, so one half of it hides the pixel step and the
+// other the TMA latency, and no warp ever waits at a block barrier (when two of the product warps did the pixel step between
+// two __syncthreads, those were 16 % of all stall samples).
 #include <math_constants.h>
 
 #include "tma_common.cuh"
@@ -43,7 +48,8 @@ namespace {
 
 using namespace pemp_tma;
 
-constexpr int kT = 256, kW = 8;                  // threads / warps per CTA
+constexpr int kW = 8;                            // product warps: warp w = e + 4 half owns a half box of class e
+constexpr int kT = (kW + 2) * 32;                // + two pixel-step warps (one per class group)
 constexpr int kP = 3, kK = 2 * kP;               // prototypes per group, coefficient columns
 constexpr int kND = 2 * (kP - 1);                // centre-difference columns (the first prototype of a group has none)
 constexpr int kNK = kK + kND;                    // 10 table columns: [0, 6) coef, [6, 8) fg differences, [8, 10) bg differences
@@ -91,7 +97,9 @@ struct Smem {
   alignas(16) float dv[kDvRows * 8];             // [pixel + 3]{ 2 dl_k (6) | 0 0 }
   alignas(16) float stage[kW][8 * kStgLd];       // per warp: one 8-row block of the gradient tile on its way out
   float konst[2 * kK];                           // |ctr_k|^2 - |ctr_g0|^2, beta
-  alignas(8) uint64_t full[kW];
+  alignas(8) uint64_t full[kW];                  // per product warp: its half box of the next tile has landed
+  alignas(8) uint64_t part_bar;                  // all product warps have written their dots of a tile
+  alignas(8) uint64_t wts_bar;                   // both pixel-step warps have written the weights of a tile
 };
 
 static_assert(2 * (sizeof(Smem<4>) + 1024) <= 228 * 1024, "two CTAs per SM at c = 512");
@@ -112,12 +120,15 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   float* dst = dfts + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(si) * c * hw;
   const int tb = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
   const int te = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
-  float* box = sm.tile[warp];
-  const float* trow = sm.tab + warp * CW * kTLd;  // this warp's table rows
+  const bool pixel_warp = warp >= kW;            // warps 8 / 9: pixel step of the foreground / background group
+  float* box = sm.tile[pixel_warp ? 0 : warp];
+  const float* trow = sm.tab + (pixel_warp ? 0 : warp) * CW * kTLd;  // this warp's table rows
 
   constexpr int NH = MB >= 2 ? 2 : 1;            // the half box is refilled in NH pieces, each as soon as B2 is done with its rows
   if (tid == 0) {
     for (int w = 0; w < kW; ++w) mbar_init(&sm.full[w], NH);
+    mbar_init(&sm.part_bar, kW);
+    mbar_init(&sm.wts_bar, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -130,7 +141,7 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
                   si * (c / 4) + CW * half + h * (CW / NH), b);
     }
   };
-  if (tb < te) {
+  if (tb < te && !pixel_warp) {
 #pragma unroll
     for (int h = 0; h < NH; ++h) fill(tb, h);
   }
@@ -153,8 +164,80 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   float accB[MB][4];                             // dctr partial: (row 16 mb + g (+8) of the warp, k = 2 tg (+1))
 #pragma unroll
   for (int i = 0; i < MB; ++i) accB[i][0] = accB[i][1] = accB[i][2] = accB[i][3] = 0.f;
-  float dsum[kP] = {0.f, 0.f, 0.f};              // lane 0 of warps 0 / 1: sum_x 2 dl_k of its group
   __syncthreads();
+  float* dstp = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * (c + 1) * kK;
+
+  if (pixel_warp) {
+    // ============================ pixel-step warps: lane = pixel of the tile ============================
+    // wait for the eight partial dot sets of a tile, add them in a fixed order, soft-max and its derivative -> the weights of
+    // the tile (double buffered by tile parity: the product warps use them for one and a half tiles) and dv; they own the
+    // sums of 2 dl_k.  The product warps never wait at a block barrier: as warps of the same CTA did this step, everybody
+    // else sat at two barriers per tile (16 % of all stall samples, ncu).
+    const int grp = warp - kW;
+    float dsum[kP] = {0.f, 0.f, 0.f};
+    for (int t = tb; t < te; ++t) {
+      const int x0 = t * kStep, par = (t - tb) & 1;
+      const bool live = lane < kStep && x0 + lane < hw;
+      const int pl = lane < kStep ? lane : kStep - 1;
+      const float m = live ? __ldg((grp == 0 ? fg : bg) + static_cast<long long>(n) * mask_stride + x0 + lane) : 0.f;
+      mbar_wait(&sm.part_bar, par);
+      float sa[kP], sc[kP];
+#pragma unroll
+      for (int k = 0; k < kP; ++k) {
+        float u = 0.f, v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {            // fixed order
+          u += sm.red[w][(grp * kP + k) * kRedLd + pl];
+          if (k > 0) v += sm.red[w][(kK + grp * (kP - 1) + k - 1) * kRedLd + pl];
+        }
+        sa[k] = u;
+        sc[k] = v;
+      }
+      float l[kP], mx = -CUDART_INF_F;
+#pragma unroll
+      for (int k = 0; k < kP; ++k) {
+        l[k] = fmaf(2.0f, sc[k], -sm.konst[grp * kP + k]);
+        mx = fmaxf(mx, l[k]);
+      }
+      float z = 0.f;
+#pragma unroll
+      for (int k = 0; k < kP; ++k) {
+        l[k] = expf(l[k] - mx);
+        z += l[k];
+      }
+      const float iz = 1.0f / z;
+      float ds[kP], dot = 0.f, d2[kP];
+#pragma unroll
+      for (int k = 0; k < kP; ++k) {
+        l[k] *= iz;                                                              // sigma_k
+        ds[k] = m * (sa[k] + sm.konst[kK + grp * kP + k]);                      // d sigma_k
+        dot = fmaf(l[k], ds[k], dot);
+      }
+      float* wtp = sm.wt[par];
+#pragma unroll
+      for (int k = 0; k < kP; ++k) {
+        d2[k] = live ? 2.0f * l[k] * (ds[k] - dot) : 0.f;
+        if (lane < kStep) {
+          wtp[lane * kWtLd + grp * kP + k] = m * l[k];
+          sm.dv[(lane + 3) * 8 + grp * kP + k] = d2[k];
+          if (k > 0) wtp[lane * kWtLd + kK + grp * (kP - 1) + k - 1] = d2[k];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.wts_bar);
+#pragma unroll
+      for (int k = 0; k < kP; ++k) {               // off the critical path: after the hand-over
+        const float tot = warp_sum(d2[k]);
+        if (lane == 0) dsum[k] += tot;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < kP; ++k) dstp[c * kK + grp * kP + k] = dsum[k];
+    }
+    return;
+  }
+  // ============================ product warps ============================
 
   // ---- phase B1: df^T [pixel 16] x [row 8] per block, contraction over the 10 columns (8 + 2) ----
   // W fragments of a tile (A operand: pixel 16 mb + g (+8), column tg (+4) / 8 + tg; columns 10, 11 hold zeros)
@@ -210,29 +293,21 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
       for (int j = 0; j < 8; ++j) orow[4LL * j * hw] = v[j];
     }
   };
-  // The last kF row blocks of warps 0 / 1 (classes 0 / 1, first half) of tile tp, shared out over warps 2..7: they run while
-  // warps 0 / 1 do the pixel step of the NEXT tile (every other warp used to sit at the barrier for that long: 9 % of all stall
-  // samples), so the weights are double buffered by tile parity.  kF balances the two kinds of warps: pixel step + 5 blocks
-  // against 8 + 1 blocks at c = 512.
-  constexpr int kF = (3 * (CW / 8)) / 8 > 0 ? (3 * (CW / 8)) / 8 : 1;
-  auto b1_foreign = [&](int tp) {
-    if (warp < 2) return;
+  // B1 of a tile in two halves of the warp's row blocks: the first one right after the refill (covers the TMA latency), the
+  // second one after the dots of the NEXT tile are handed over (covers the pixel step) - hence the double-buffered weights
+  auto b1_range = [&](int tp, int nb0, int nb1) {
     FragA w0[2], w1[2];
     load_w(sm.wt[(tp - tb) & 1], w0, w1);
     const int xp = tp * kStep, rem = min(kStep, hw - xp);
-    for (int q = warp - 2; q < 2 * kF; q += kW - 2) {
-      const int wf = q / kF, nb = CW / 8 - kF + (q - wf * kF);  // owner warp (= class, half 0) and block
-      b1_block(w0, w1, sm.tab + (wf * CW + nb * 8) * kTLd, dst + static_cast<long long>(4 * (nb * 8) + wf) * hw + xp + lane, rem);
-    }
+    float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + xp + lane;
+#pragma unroll 2
+    for (int nb = nb0; nb < nb1; ++nb) b1_block(w0, w1, trow + nb * 8 * kTLd, orow + 32LL * nb * hw, rem);
   };
+  constexpr int kH = CW / 16;                    // row blocks in the first half
 
   for (int t = tb; t < te; ++t) {
     const int x0 = t * kStep;
     const int o = (e * hw + x0) & 3;              // box column i is pixel x0 + i - o
-    // the pixel-step warps fetch their mask value now: its latency used to sit between the two barriers of the tile
-    float m_px = 0.f;
-    if (warp < 2 && lane < kStep && x0 + lane < hw)
-      m_px = __ldg((warp == 0 ? fg : bg) + static_cast<long long>(n) * mask_stride + x0 + lane);
     mbar_wait(&sm.full[warp], (t - tb) & 1);
     // ---------------- phase A: dots^T [k 16 (10 used)] x [column 8] per column block, contraction over the warp's rows
     // (contraction slots tg / tg + 4 of a block are its rows 2 tg / 2 tg + 1: conflict-free against the box swizzle)
@@ -276,61 +351,10 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
         }
       }
     }
-    __syncthreads();
-    // ---------------- pixel step: warp 0 = foreground group, warp 1 = background group, lane = pixel of the tile
-    if (warp < 2) {
-      const int grp = warp, x = x0 + lane;
-      const bool live = lane < kStep && x < hw;
-      const int pl = lane < kStep ? lane : kStep - 1;
-      const float m = m_px;
-      float sa[kP], sc[kP];
-#pragma unroll
-      for (int k = 0; k < kP; ++k) {
-        float u = 0.f, v = 0.f;
-#pragma unroll
-        for (int w = 0; w < kW; ++w) {            // fixed order
-          u += sm.red[w][(grp * kP + k) * kRedLd + pl];
-          if (k > 0) v += sm.red[w][(kK + grp * (kP - 1) + k - 1) * kRedLd + pl];
-        }
-        sa[k] = u;
-        sc[k] = v;
-      }
-      float l[kP], mx = -CUDART_INF_F;
-#pragma unroll
-      for (int k = 0; k < kP; ++k) {
-        l[k] = fmaf(2.0f, sc[k], -sm.konst[grp * kP + k]);
-        mx = fmaxf(mx, l[k]);
-      }
-      float z = 0.f;
-#pragma unroll
-      for (int k = 0; k < kP; ++k) {
-        l[k] = expf(l[k] - mx);
-        z += l[k];
-      }
-      const float iz = 1.0f / z;
-      float ds[kP], dot = 0.f;
-#pragma unroll
-      for (int k = 0; k < kP; ++k) {
-        l[k] *= iz;                                                              // sigma_k
-        ds[k] = m * (sa[k] + sm.konst[kK + grp * kP + k]);                      // d sigma_k
-        dot = fmaf(l[k], ds[k], dot);
-      }
-#pragma unroll
-      for (int k = 0; k < kP; ++k) {
-        const float d2 = live ? 2.0f * l[k] * (ds[k] - dot) : 0.f;
-        if (lane < kStep) {
-          float* wtp = sm.wt[(t - tb) & 1];
-          wtp[lane * kWtLd + grp * kP + k] = m * l[k];
-          sm.dv[(lane + 3) * 8 + grp * kP + k] = d2;
-          if (k > 0) wtp[lane * kWtLd + kK + grp * (kP - 1) + k - 1] = d2;
-        }
-        const float tot = warp_sum(d2);
-        if (lane == 0) dsum[k] += tot;
-      }
-    } else if (t > tb) {
-      b1_foreign(t - 1);
-    }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.part_bar);     // dots of tile t handed to the pixel-step warps
+    if (t > tb) b1_range(t - 1, kH, CW / 8);      // second half of the previous tile's gradient rows meanwhile
+    mbar_wait(&sm.wts_bar, (t - tb) & 1);         // weights / dv of tile t
     // ---------------- phase B2: dctr [row 16] x [k 8 (6 used)] per row block, contraction over the 32 box columns
     {
       FragB d[4];
@@ -374,18 +398,10 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     }
     __syncwarp();
     if (t + 1 < te) fill(t + 1, NH - 1);
-    // ---------------- phase B1 of this tile: the warp's own rows (warps 0 / 1 leave their last kF blocks to the others)
-    {
-      FragA w0[2], w1[2];
-      load_w(sm.wt[(t - tb) & 1], w0, w1);
-      const int rem = min(kStep, hw - x0), nown = warp < 2 ? CW / 8 - kF : CW / 8;
-      float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + x0 + lane;
-#pragma unroll 2
-      for (int nb = 0; nb < nown; ++nb) b1_block(w0, w1, trow + nb * 8 * kTLd, orow + 32LL * nb * hw, rem);
-    }
+    // ---------------- phase B1 of this tile, first half of the warp's row blocks (under the refill)
+    b1_range(t, 0, kH);
   }
-  if (tb < te) b1_foreign(te - 1);                 // the rows of warps 0 / 1 for the last tile
-  float* dstp = part + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * (c + 1) * kK;
+  if (tb < te) b1_range(te - 1, kH, CW / 8);
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
     if (tg < kK / 2) {
@@ -393,10 +409,6 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
       *reinterpret_cast<float2*>(dstp + ch * kK + 2 * tg) = make_float2(accB[mb][0], accB[mb][1]);
       *reinterpret_cast<float2*>(dstp + (ch + 32) * kK + 2 * tg) = make_float2(accB[mb][2], accB[mb][3]);
     }
-  }
-  if (warp < 2 && lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kP; ++k) dstp[c * kK + warp * kP + k] = dsum[k];
   }
 }
 
