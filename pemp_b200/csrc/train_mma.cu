@@ -55,7 +55,7 @@ constexpr int kND = 2 * (kP - 1);                // centre-difference columns (t
 constexpr int kNK = kK + kND;                    // 10 table columns: [0, 6) coef, [6, 8) fg differences, [8, 10) bg differences
 constexpr int kTLd = 12;                         // table row pitch: conflict-free for the fragments of phase A and of B1
 constexpr int kStep = 28;                        // pixels a tile advances (32 box columns cover them for every class)
-constexpr int kRedLd = 36;                       // pixel pitch of a dot row in `red` (two CTAs per SM need every KB)
+constexpr int kRedLd = 33;                       // pixel pitch of a dot row in `red`: a fragment store touches banks g + 8 tg
 constexpr int kWtLd = 12;                        // W[x][0..10) + two zero columns (conflict-free fragment reads)
 constexpr int kStgLd = 36;                       // pixel pitch of a staged gradient row (conflict-free fragment stores)
 constexpr int kDvRows = 32 + 3;                  // dv rows for pixels -3 .. 31 of a tile (rows outside [0, 28) stay zero)
@@ -84,8 +84,7 @@ __device__ __forceinline__ void mma3(float (&d)[4], const FragA& a, const FragB&
   mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], b.lo[0], b.lo[1]);
   mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], b.hi[0], b.hi[1]);
 }
-// element (row, col) of a 128-byte-swizzled box whose rows are 32 floats: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
-__device__ __forceinline__ int box_at(int row, int col) { return row * 32 + ((((col >> 2) ^ row) & 7) << 2) + (col & 3); }
+// (a 128-byte-swizzled box: 16-byte chunk j of row r sits at chunk j ^ (r & 7); rows are 32 floats)
 
 template <int MB>                                // 16-row blocks per warp: c = 128 MB
 struct Smem {
@@ -104,13 +103,17 @@ struct Smem {
 
 static_assert(2 * (sizeof(Smem<4>) + 1024) <= 228 * 1024, "two CTAs per SM at c = 512");
 
-template <int MB>
+// HW: the map size as a compile-time constant (0 = take the argument).  The gradient rows of a block are channels 4 apart, i.e.
+// 16 hw bytes: with hw known the eight stores of a block use immediate offsets instead of a 64-bit pointer bump each (the
+// bumps and the block addressing were 11 % of all instructions, ncu); instantiated for the PEMP map, 51 x 51.
+template <int MB, int HW>
 __global__ void __launch_bounds__(kT, MB <= 4 ? 2 : 1)
 mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* __restrict__ tabg,
                    const float* __restrict__ beta, const float* __restrict__ fg, const float* __restrict__ bg,
-                   long long mask_stride, int hw, int ntiles, float* __restrict__ dfts, long long d_ep_stride,
+                   long long mask_stride, int hw_arg, int ntiles, float* __restrict__ dfts, long long d_ep_stride,
                    float* __restrict__ part) {
   constexpr int c = 128 * MB, CW = 16 * MB;
+  const int hw = HW > 0 ? HW : hw_arg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem<MB>& sm = *reinterpret_cast<Smem<MB>*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -261,6 +264,7 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   // shared memory instead and leaves as 8 rows of 112 contiguous bytes.  orow = row 0 of the block at this lane's pixel; the
   // rows of a block are channels 4 apart.
   float* stg = sm.stage[warp];
+  const long long row_step = 4LL * hw;             // the rows of a block are channels 4 apart
   auto b1_block = [&](const FragA (&w0)[2], const FragA (&w1)[2], const float* tb8, float* orow, int rem) {
     const float* tb0 = tb8 + g * kTLd + tg;
     FragB b0, b1;
@@ -289,8 +293,12 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     for (int j = 0; j < 8; ++j) v[j] = stg[j * kStgLd + lane];
     __syncwarp();
     if (lane < rem) {
+      float* op = orow;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) orow[4LL * j * hw] = v[j];
+      for (int j = 0; j < 8; ++j) {
+        *op = v[j];
+        op += row_step;
+      }
     }
   };
   // B1 of a tile in two halves of the warp's row blocks: the first one right after the refill (covers the TMA latency), the
@@ -309,41 +317,54 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     const int x0 = t * kStep;
     const int o = (e * hw + x0) & 3;              // box column i is pixel x0 + i - o
     mbar_wait(&sm.full[warp], (t - tb) & 1);
-    // ---------------- phase A: dots^T [k 16 (10 used)] x [column 8] per column block, contraction over the warp's rows
-    // (contraction slots tg / tg + 4 of a block are its rows 2 tg / 2 tg + 1: conflict-free against the box swizzle)
+    // ---------------- phase A: dots^T [k 16 (10 used)] x [column 8] per column block, contraction over the warp's rows.
+    // Contraction slots tg / tg + 4 of a row block are its rows 2 tg / 2 tg + 1, and column slot n of column block j is box
+    // column 4 n + j: a lane's four B elements of a row are then ONE 16-byte chunk (chunk g of the row, conflict-free
+    // against the box swizzle) instead of four 4-byte loads with their own swizzled addresses.
     float dacc[4][4];
 #pragma unroll
     for (int pb = 0; pb < 4; ++pb) dacc[pb][0] = dacc[pb][1] = dacc[pb][2] = dacc[pb][3] = 0.f;
+    {
+      const float* fa = box + (2 * tg) * 32 + ((g ^ (2 * tg)) << 2);          // row 2 tg of a block, chunk g
+      const float* fb = box + (2 * tg + 1) * 32 + ((g ^ (2 * tg + 1)) << 2);  // row 2 tg + 1
+      const float* ta = trow + (2 * tg) * kTLd + g;
 #pragma unroll 2
-    for (int cb = 0; cb < CW / 8; ++cb) {
-      const int r0 = cb * 8 + 2 * tg;
-      const float* ta = trow + r0 * kTLd + g;
-      FragA a;
-      split_tf32(ta[0], a.hi[0], a.lo[0]);
-      split_tf32(g < kNK - 8 ? ta[8] : 0.f, a.hi[1], a.lo[1]);
-      split_tf32(ta[kTLd], a.hi[2], a.lo[2]);
-      split_tf32(g < kNK - 8 ? ta[kTLd + 8] : 0.f, a.hi[3], a.lo[3]);
-      FragB f[4];
+      for (int cb = 0; cb < CW / 8; ++cb) {
+        FragA a;
+        split_tf32(ta[0], a.hi[0], a.lo[0]);
+        split_tf32(g < kNK - 8 ? ta[8] : 0.f, a.hi[1], a.lo[1]);
+        split_tf32(ta[kTLd], a.hi[2], a.lo[2]);
+        split_tf32(g < kNK - 8 ? ta[kTLd + 8] : 0.f, a.hi[3], a.lo[3]);
+        const float4 va = *reinterpret_cast<const float4*>(fa), vb = *reinterpret_cast<const float4*>(fb);
+        FragB f[4];
+        split_tf32(va.x, f[0].hi[0], f[0].lo[0]);
+        split_tf32(va.y, f[1].hi[0], f[1].lo[0]);
+        split_tf32(va.z, f[2].hi[0], f[2].lo[0]);
+        split_tf32(va.w, f[3].hi[0], f[3].lo[0]);
+        split_tf32(vb.x, f[0].hi[1], f[0].lo[1]);
+        split_tf32(vb.y, f[1].hi[1], f[1].lo[1]);
+        split_tf32(vb.z, f[2].hi[1], f[2].lo[1]);
+        split_tf32(vb.w, f[3].hi[1], f[3].lo[1]);
+        // the three products of a block as three rounds over the four independent accumulators (no back-to-back dependence)
 #pragma unroll
-      for (int pb = 0; pb < 4; ++pb) {
-        split_tf32(box[box_at(r0, pb * 8 + g)], f[pb].hi[0], f[pb].lo[0]);
-        split_tf32(box[box_at(r0 + 1, pb * 8 + g)], f[pb].hi[1], f[pb].lo[1]);
+        for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.lo[0], a.lo[1], a.lo[2], a.lo[3], f[pb].hi[0], f[pb].hi[1]);
+#pragma unroll
+        for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.hi[0], a.hi[1], a.hi[2], a.hi[3], f[pb].lo[0], f[pb].lo[1]);
+#pragma unroll
+        for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.hi[0], a.hi[1], a.hi[2], a.hi[3], f[pb].hi[0], f[pb].hi[1]);
+        fa += 8 * 32;
+        fb += 8 * 32;
+        ta += 8 * kTLd;
       }
-      // the three products of a block as three rounds over the four independent accumulators (no back-to-back dependence)
-#pragma unroll
-      for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.lo[0], a.lo[1], a.lo[2], a.lo[3], f[pb].hi[0], f[pb].hi[1]);
-#pragma unroll
-      for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.hi[0], a.hi[1], a.hi[2], a.hi[3], f[pb].lo[0], f[pb].lo[1]);
-#pragma unroll
-      for (int pb = 0; pb < 4; ++pb) mma_tf32(dacc[pb], a.hi[0], a.hi[1], a.hi[2], a.hi[3], f[pb].hi[0], f[pb].hi[1]);
     }
     {
+      // C fragment of column block j: (k = g (+8), column slots 2 tg / 2 tg + 1) = box columns 8 tg + j / 8 tg + 4 + j
       float* rw = sm.red[warp];
 #pragma unroll
       for (int pb = 0; pb < 4; ++pb) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int p = pb * 8 + 2 * tg + j - o;
+          const int p = 8 * tg + 4 * j + pb - o;
           if (p >= 0 && p < kStep) {
             rw[g * kRedLd + p] = dacc[pb][j];
             if (g < kNK - 8) rw[(g + 8) * kRedLd + p] = dacc[pb][2 + j];
@@ -355,29 +376,44 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
     if (lane == 0) mbar_arrive(&sm.part_bar);     // dots of tile t handed to the pixel-step warps
     if (t > tb) b1_range(t - 1, kH, CW / 8);      // second half of the previous tile's gradient rows meanwhile
     mbar_wait(&sm.wts_bar, (t - tb) & 1);         // weights / dv of tile t
-    // ---------------- phase B2: dctr [row 16] x [k 8 (6 used)] per row block, contraction over the 32 box columns
+    // ---------------- phase B2: dctr [row 16] x [k 8 (6 used)] per row block, contraction over the 32 box columns.
+    // Contraction slots tg / tg + 4 of column block kb are the box columns 8 tg + 2 kb / 8 tg + 2 kb + 1: a lane's eight A
+    // elements of a row (all four column blocks) are the two chunks 2 tg, 2 tg + 1 of the row.
     {
       FragB d[4];
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        const float* dp = sm.dv + (kb * 8 + tg - o + 3) * 8 + g;
+        const float* dp = sm.dv + (8 * tg + 2 * kb - o + 3) * 8 + g;
         split_tf32(dp[0], d[kb].hi[0], d[kb].lo[0]);
-        split_tf32(dp[4 * 8], d[kb].hi[1], d[kb].lo[1]);
+        split_tf32(dp[8], d[kb].hi[1], d[kb].lo[1]);
       }
-      constexpr int MG = MB / NH < 4 ? MB / NH : 4;   // row blocks in flight: independent accumulators, products in rounds
+      const float* fr = box + g * 32;                      // row g of a 16-row block; its swizzle phase is g
+      const int c0 = ((2 * tg) ^ g) << 2, c1 = ((2 * tg + 1) ^ g) << 2;
+      constexpr int MG = MB / NH < 2 ? MB / NH : 2;        // row blocks in flight: independent accumulators, products in rounds
 #pragma unroll
       for (int m0 = 0; m0 < MB; m0 += MG) {
+        float4 u[MG][4];                                   // [block]{row g: chunks 2 tg, 2 tg + 1; row g + 8: the same}
+#pragma unroll
+        for (int j = 0; j < MG; ++j) {
+          const float* r = fr + (m0 + j) * 16 * 32;
+          u[j][0] = *reinterpret_cast<const float4*>(r + c0);
+          u[j][1] = *reinterpret_cast<const float4*>(r + c1);
+          u[j][2] = *reinterpret_cast<const float4*>(r + 8 * 32 + c0);
+          u[j][3] = *reinterpret_cast<const float4*>(r + 8 * 32 + c1);
+        }
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          const int px = kb * 8 + tg;
           FragA a[MG];
 #pragma unroll
           for (int j = 0; j < MG; ++j) {
-            const int r0 = (m0 + j) * 16 + g;
-            split_tf32(box[box_at(r0, px)], a[j].hi[0], a[j].lo[0]);
-            split_tf32(box[box_at(r0 + 8, px)], a[j].hi[1], a[j].lo[1]);
-            split_tf32(box[box_at(r0, px + 4)], a[j].hi[2], a[j].lo[2]);
-            split_tf32(box[box_at(r0 + 8, px + 4)], a[j].hi[3], a[j].lo[3]);
+            // columns 8 tg + 2 kb, + 1: elements (2 kb, 2 kb + 1) of the 8-column run = chunk kb >> 1, halves x y / z w
+            const float4 lo4 = u[j][kb >> 1], hi4 = u[j][2 + (kb >> 1)];
+            const float e0 = (kb & 1) ? lo4.z : lo4.x, e1 = (kb & 1) ? lo4.w : lo4.y;
+            const float e2 = (kb & 1) ? hi4.z : hi4.x, e3 = (kb & 1) ? hi4.w : hi4.y;
+            split_tf32(e0, a[j].hi[0], a[j].lo[0]);       // (row g, slot tg)
+            split_tf32(e2, a[j].hi[1], a[j].lo[1]);       // (row g + 8, slot tg)
+            split_tf32(e1, a[j].hi[2], a[j].lo[2]);       // (row g, slot tg + 4)
+            split_tf32(e3, a[j].hi[3], a[j].lo[3]);       // (row g + 8, slot tg + 4)
           }
 #pragma unroll
           for (int j = 0; j < MG; ++j)
@@ -427,18 +463,27 @@ mpa_bwd_image_sum_kernel(const float* __restrict__ part, int chunks, int M, floa
   img_part[static_cast<long long>(n) * M + i] = static_cast<float>(sum);
 }
 
-template <int MB>
-int launch(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
+template <int MB, int HW>
+int launch_hw(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
            long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
            cudaStream_t st) {
   const size_t smem = sizeof(Smem<MB>);
-  cudaError_t err = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t err = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MB, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return static_cast<int>(err);
-  mpa_bwd_mma_kernel<MB><<<dim3(chunks, N), kT, smem, st>>>(map, S, tabg, beta, fg, bg, mask_stride, hw,
+  mpa_bwd_mma_kernel<MB, HW><<<dim3(chunks, N), kT, smem, st>>>(map, S, tabg, beta, fg, bg, mask_stride, hw,
                                                            pemp_mpa_bwd_mma_tiles(hw), dfts, d_ep, part);
   const int M = (128 * MB + 1) * kK;
   mpa_bwd_image_sum_kernel<<<dim3((M + 255) / 256, N), 256, 0, st>>>(part, chunks, M, img_part);
   return PEMP_OK;
+}
+
+constexpr int kHwPemp = 51 * 51;                 // the PEMP feature map (417 x 417 crops at stride 8)
+template <int MB>
+int launch(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
+           long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
+           cudaStream_t st) {
+  if (hw == kHwPemp) return launch_hw<MB, kHwPemp>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+  return launch_hw<MB, 0>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
 }
 
 }  // namespace
