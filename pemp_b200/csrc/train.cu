@@ -34,6 +34,7 @@ bool pemp_mpa_bwd_mma_shape(int c, int p, int hw);
 int pemp_mpa_bwd_mma_tiles(int hw);
 size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
 int pemp_mpa_bwd_mma_table_ld();
+int pemp_mpa_bwd_mma_rows_per_warp(int c);
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
                             float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st);
@@ -363,7 +364,7 @@ cosine_bwd_finalize_kernel(const float* __restrict__ part, const float* __restri
 __global__ void __launch_bounds__(kBT)
 mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__ g_bg, const float* __restrict__ shot_centre,
                        const float* __restrict__ shot_den, const float* __restrict__ ctr, int N, int S, int c, int P,
-                       float* __restrict__ coef, float* __restrict__ beta, float* __restrict__ tabg, int tab_ld) {
+                       float* __restrict__ coef, float* __restrict__ beta, float* __restrict__ tabg, int tab_ld, int CW) {
   // One pass over the channels with all 2P columns at once and ONE block reduction (the first version ran 2P block sums in a
   // row and had 2P threads of EVERY CTA add the c squared-norm terms serially in double: 49 us of a 430-us backward at 80
   // images).  Block N computes the squared-norm differences, which do not depend on the image, once for the launch.
@@ -399,9 +400,9 @@ mpa_bwd_prepare_kernel(const float* __restrict__ g_fg, const float* __restrict__
       }
       if (tabg) {
         // the image's table for the tensor-path kernel (train_mma.cu), in its row order: row R = w CW + r <-> channel
-        // 4 (CW half + r) + e with w = e + 4 half, CW = c / 8:  { coef[ch][0..K) | ctr_k - ctr_g0 of the non-first prototypes
-        // (exact in double, one rounding) | 0 .. }
-        const int CW = c / 8, g4 = ch >> 2, R = ((ch & 3) + 4 * (g4 / CW)) * CW + g4 % CW;
+        // 4 (CW q + r) + e with w = e + 4 q, CW = rows per product warp:  { coef[ch][0..K) | ctr_k - ctr_g0 of the non-first
+        // prototypes (exact in double, one rounding) | 0 .. }
+        const int g4 = ch >> 2, R = ((ch & 3) + 4 * (g4 / CW)) * CW + g4 % CW;
         float* row = tabg + (static_cast<long long>(n) * c + R) * tab_ld;
         int col = 0;
         for (int k = 0; k < K; ++k) row[col++] = coef[(static_cast<long long>(n) * c + ch) * K + k];
@@ -947,7 +948,7 @@ extern "C" int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_
   const long long d_ep = d_fts_episode_stride ? d_fts_episode_stride : static_cast<long long>(S) * c * hw;
   float* tabg = mma ? reinterpret_cast<float*>(ws + wl.off_tab) : nullptr;
   mpa_bwd_prepare_kernel<<<N + 1, kBT, 0, st>>>(g_fg, g_bg, shot_centre, shot_den, ctr, N, S, c, p, coef, beta, tabg,
-                                                pemp_mpa_bwd_mma_table_ld());
+                                                pemp_mpa_bwd_mma_table_ld(), pemp_mpa_bwd_mma_rows_per_warp(c));
   int rc = PEMP_E_ALIGN;
   long long nparts = static_cast<long long>(N) * pl.chunks;
   if (mma) {                                     // PEMP_E_ALIGN: the operand has no tensor map - the CUDA-core kernel takes it

@@ -40,6 +40,7 @@ bool pemp_mpa_bwd_mma_shape(int c, int p, int hw);
 int pemp_mpa_bwd_mma_tiles(int hw);
 size_t pemp_mpa_bwd_mma_table_bytes(int N, int c);
 int pemp_mpa_bwd_mma_table_ld();
+int pemp_mpa_bwd_mma_rows_per_warp(int c);
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
                             float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st);
@@ -48,8 +49,10 @@ namespace {
 
 using namespace pemp_tma;
 
-constexpr int kW = 8;                            // product warps: warp w = e + 4 half owns a half box of class e
-constexpr int kT = (kW + 2) * 32;                // + two pixel-step warps (one per class group)
+// A configuration is (MB, KW, NBUF): KW product warps (+ two pixel-step warps, one per class group), warp w = e + 4 q owns rows
+// [CW q, CW q + CW) of the class-e box with CW = 16 MB = c / KW, in NBUF buffers:
+//   c = 512 / 256: KW = 16, NBUF = 2, one CTA per SM: the box of tile t+1 is requested before tile t is touched
+//   c = 128 / 1024: KW = 8, NBUF = 1 (two CTAs per SM at c = 128): the box is refilled piecewise as soon as B2 is done with it
 constexpr int kP = 3, kK = 2 * kP;               // prototypes per group, coefficient columns
 constexpr int kND = 2 * (kP - 1);                // centre-difference columns (the first prototype of a group has none)
 constexpr int kNK = kK + kND;                    // 10 table columns: [0, 6) coef, [6, 8) fg differences, [8, 10) bg differences
@@ -86,36 +89,36 @@ __device__ __forceinline__ void mma3(float (&d)[4], const FragA& a, const FragB&
 }
 // (a 128-byte-swizzled box: 16-byte chunk j of row r sits at chunk j ^ (r & 7); rows are 32 floats)
 
-template <int MB>                                // 16-row blocks per warp: c = 128 MB
+template <int MB, int KW, int NBUF>              // MB: 16-row blocks per warp
 struct Smem {
-  static constexpr int c = 128 * MB, CW = 16 * MB;
-  alignas(1024) float tile[kW][CW * 32];         // warp w: rows [CW half, CW half + CW) of the class-e box, e = w & 3, half = w >> 2
+  static constexpr int CW = 16 * MB, c = CW * KW;
+  alignas(1024) float tile[NBUF][KW][CW * 32];   // warp w: rows [CW q, CW q + CW) of the class-e box, e = w & 3, q = w >> 2
   alignas(16) float tab[c * kTLd];               // row R = w CW + r  <->  channel 4 (CW half + r) + e
-  alignas(16) float red[kW][kNK * kRedLd];       // partial dots of the warps: [k][pixel of the tile]
+  alignas(16) float red[KW][kNK * kRedLd];       // partial dots of the warps: [k][pixel of the tile]
   alignas(16) float wt[2][32 * kWtLd];           // [tile parity][pixel]{ a_k (6) | 2 dl_k of the non-first prototypes (4) | 0 0 }
   alignas(16) float dv[kDvRows * 8];             // [pixel + 3]{ 2 dl_k (6) | 0 0 }
-  alignas(16) float stage[kW][8 * kStgLd];       // per warp: one 8-row block of the gradient tile on its way out
+  alignas(16) float stage[KW][8 * kStgLd];       // per warp: one 8-row block of the gradient tile on its way out
   float konst[2 * kK];                           // |ctr_k|^2 - |ctr_g0|^2, beta
-  alignas(8) uint64_t full[kW];                  // per product warp: its half box of the next tile has landed
+  alignas(8) uint64_t full[NBUF][KW];            // per product warp and buffer: the box has landed
   alignas(8) uint64_t part_bar;                  // all product warps have written their dots of a tile
   alignas(8) uint64_t wts_bar;                   // both pixel-step warps have written the weights of a tile
 };
 
-static_assert(2 * (sizeof(Smem<4>) + 1024) <= 228 * 1024, "two CTAs per SM at c = 512");
+static_assert(sizeof(Smem<2, 16, 2>) <= 227 * 1024, "c = 512, double buffered, one CTA per SM");
 
 // HW: the map size as a compile-time constant (0 = take the argument).  The gradient rows of a block are channels 4 apart, i.e.
 // 16 hw bytes: with hw known the eight stores of a block use immediate offsets instead of a 64-bit pointer bump each (the
 // bumps and the block addressing were 11 % of all instructions, ncu); instantiated for the PEMP map, 51 x 51.
-template <int MB, int HW>
-__global__ void __launch_bounds__(kT, MB <= 4 ? 2 : 1)
+template <int MB, int KW, int NBUF, int HW>
+__global__ void __launch_bounds__((KW + 2) * 32, (MB == 1 && KW == 8) ? 2 : 1)
 mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* __restrict__ tabg,
                    const float* __restrict__ beta, const float* __restrict__ fg, const float* __restrict__ bg,
                    long long mask_stride, int hw_arg, int ntiles, float* __restrict__ dfts, long long d_ep_stride,
                    float* __restrict__ part) {
-  constexpr int c = 128 * MB, CW = 16 * MB;
+  constexpr int CW = 16 * MB, c = CW * KW, kW = KW, kT = (KW + 2) * 32;
   const int hw = HW > 0 ? HW : hw_arg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem<MB>& sm = *reinterpret_cast<Smem<MB>*>(smem_raw);
+  Smem<MB, KW, NBUF>& sm = *reinterpret_cast<Smem<MB, KW, NBUF>*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
   const int e = warp & 3, half = warp >> 2;
@@ -124,29 +127,30 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   const int tb = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
   const int te = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
   const bool pixel_warp = warp >= kW;            // warps 8 / 9: pixel step of the foreground / background group
-  float* box = sm.tile[pixel_warp ? 0 : warp];
+  float* box = sm.tile[0][pixel_warp ? 0 : warp];
   const float* trow = sm.tab + (pixel_warp ? 0 : warp) * CW * kTLd;  // this warp's table rows
 
-  constexpr int NH = MB >= 2 ? 2 : 1;            // the half box is refilled in NH pieces, each as soon as B2 is done with its rows
+  // NBUF = 1: the box is refilled in NH pieces, each as soon as B2 is done with its rows
+  constexpr int NH = (NBUF == 1 && MB >= 2) ? 2 : 1;
   if (tid == 0) {
-    for (int w = 0; w < kW; ++w) mbar_init(&sm.full[w], NH);
+    for (int w = 0; w < NBUF * kW; ++w) mbar_init(&sm.full[0][0] + w, NH);
     mbar_init(&sm.part_bar, kW);
     mbar_init(&sm.wts_bar, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  // NH bulk-tensor loads per warp and tile: CW / NH rows x 32 floats of class e each
-  auto fill = [&](int t, int h) {
+  // NH bulk-tensor loads per warp and tile: CW / NH rows x 32 floats of class e each, into buffer `buf`
+  auto fill = [&](int t, int buf, int h) {
     if (lane == 0) {
-      mbar_expect_tx(&sm.full[warp], CW / NH * 32 * 4);
-      tma_load_3d(&map, &sm.full[warp], box + h * (CW / NH) * 32, (e * hw + t * kStep) & ~3,
+      mbar_expect_tx(&sm.full[buf][warp], CW / NH * 32 * 4);
+      tma_load_3d(&map, &sm.full[buf][warp], sm.tile[buf][warp] + h * (CW / NH) * 32, (e * hw + t * kStep) & ~3,
                   si * (c / 4) + CW * half + h * (CW / NH), b);
     }
   };
   if (tb < te && !pixel_warp) {
 #pragma unroll
-    for (int h = 0; h < NH; ++h) fill(tb, h);
+    for (int h = 0; h < NH; ++h) fill(tb, 0, h);
   }
 
   // table of this image, laid out by mpa_bwd_prepare_kernel (train.cu): a straight 16-byte copy (the first tile is on its way meanwhile;
@@ -187,14 +191,18 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
       float sa[kP], sc[kP];
 #pragma unroll
       for (int k = 0; k < kP; ++k) {
-        float u = 0.f, v = 0.f;
+        float u0 = 0.f, u1 = 0.f, v0 = 0.f, v1 = 0.f;   // fixed order, two chains (this sum is on the tile's critical path)
 #pragma unroll
-        for (int w = 0; w < kW; ++w) {            // fixed order
-          u += sm.red[w][(grp * kP + k) * kRedLd + pl];
-          if (k > 0) v += sm.red[w][(kK + grp * (kP - 1) + k - 1) * kRedLd + pl];
+        for (int w = 0; w < kW; w += 2) {
+          u0 += sm.red[w][(grp * kP + k) * kRedLd + pl];
+          u1 += sm.red[w + 1][(grp * kP + k) * kRedLd + pl];
+          if (k > 0) {
+            v0 += sm.red[w][(kK + grp * (kP - 1) + k - 1) * kRedLd + pl];
+            v1 += sm.red[w + 1][(kK + grp * (kP - 1) + k - 1) * kRedLd + pl];
+          }
         }
-        sa[k] = u;
-        sc[k] = v;
+        sa[k] = u0 + u1;
+        sc[k] = v0 + v1;
       }
       float l[kP], mx = -CUDART_INF_F;
 #pragma unroll
@@ -311,12 +319,17 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
 #pragma unroll 2
     for (int nb = nb0; nb < nb1; ++nb) b1_block(w0, w1, trow + nb * 8 * kTLd, orow + 32LL * nb * hw, rem);
   };
-  constexpr int kH = CW / 16;                    // row blocks in the first half
+  // row blocks in the first half.  Two buffers: the next box is already on its way, so all of B1 goes under the pixel step
+  constexpr int kH = NBUF == 2 ? 0 : CW / 16;
 
   for (int t = tb; t < te; ++t) {
     const int x0 = t * kStep;
     const int o = (e * hw + x0) & 3;              // box column i is pixel x0 + i - o
-    mbar_wait(&sm.full[warp], (t - tb) & 1);
+    const int buf = NBUF == 2 ? (t - tb) & 1 : 0;
+    // two buffers: the other one was last read by B2(t-1), so the box of tile t+1 is requested a whole tile ahead
+    if (NBUF == 2 && t + 1 < te) fill(t + 1, buf ^ 1, 0);
+    box = sm.tile[buf][warp];
+    mbar_wait(&sm.full[buf][warp], NBUF == 2 ? ((t - tb) >> 1) & 1 : (t - tb) & 1);
     // ---------------- phase A: dots^T [k 16 (10 used)] x [column 8] per column block, contraction over the warp's rows.
     // Contraction slots tg / tg + 4 of a row block are its rows 2 tg / 2 tg + 1, and column slot n of column block j is box
     // column 4 n + j: a lane's four B elements of a row are then ONE 16-byte chunk (chunk g of the row, conflict-free
@@ -428,14 +441,14 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
         // the warp is done with these rows of its half box: fetch them for the next tile (under the rest of B2 and B1)
         if (NH > 1 && m0 + MG == MB / NH) {
           __syncwarp();
-          if (t + 1 < te) fill(t + 1, 0);
+          if (t + 1 < te) fill(t + 1, 0, 0);
         }
       }
     }
     __syncwarp();
-    if (t + 1 < te) fill(t + 1, NH - 1);
+    if (NBUF == 1 && t + 1 < te) fill(t + 1, 0, NH - 1);
     // ---------------- phase B1 of this tile, first half of the warp's row blocks (under the refill)
-    b1_range(t, 0, kH);
+    if (kH > 0) b1_range(t, 0, kH);
   }
   if (tb < te) b1_range(te - 1, kH, CW / 8);
 #pragma unroll
@@ -463,40 +476,44 @@ mpa_bwd_image_sum_kernel(const float* __restrict__ part, int chunks, int M, floa
   img_part[static_cast<long long>(n) * M + i] = static_cast<float>(sum);
 }
 
-template <int MB, int HW>
+template <int MB, int KW, int NBUF, int HW>
 int launch_hw(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
-           long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
-           cudaStream_t st) {
-  const size_t smem = sizeof(Smem<MB>);
-  cudaError_t err = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MB, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+              long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
+              cudaStream_t st) {
+  const size_t smem = sizeof(Smem<MB, KW, NBUF>);
+  cudaError_t err = cudaFuncSetAttribute(mpa_bwd_mma_kernel<MB, KW, NBUF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
   if (err != cudaSuccess) return static_cast<int>(err);
-  mpa_bwd_mma_kernel<MB, HW><<<dim3(chunks, N), kT, smem, st>>>(map, S, tabg, beta, fg, bg, mask_stride, hw,
-                                                           pemp_mpa_bwd_mma_tiles(hw), dfts, d_ep, part);
-  const int M = (128 * MB + 1) * kK;
+  mpa_bwd_mma_kernel<MB, KW, NBUF, HW><<<dim3(chunks, N), (KW + 2) * 32, smem, st>>>(
+      map, S, tabg, beta, fg, bg, mask_stride, hw, pemp_mpa_bwd_mma_tiles(hw), dfts, d_ep, part);
+  const int M = (16 * MB * KW + 1) * kK;
   mpa_bwd_image_sum_kernel<<<dim3((M + 255) / 256, N), 256, 0, st>>>(part, chunks, M, img_part);
   return PEMP_OK;
 }
 
 constexpr int kHwPemp = 51 * 51;                 // the PEMP feature map (417 x 417 crops at stride 8)
-template <int MB>
+template <int MB, int KW, int NBUF>
 int launch(const CUtensorMap& map, int S, const float* tabg, const float* beta, const float* fg, const float* bg,
            long long mask_stride, int N, int hw, int chunks, float* dfts, long long d_ep, float* part, float* img_part,
            cudaStream_t st) {
-  if (hw == kHwPemp) return launch_hw<MB, kHwPemp>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
-  return launch_hw<MB, 0>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+  if (hw == kHwPemp)
+    return launch_hw<MB, KW, NBUF, kHwPemp>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+  return launch_hw<MB, KW, NBUF, 0>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
 }
 
 }  // namespace
 
 bool pemp_mpa_bwd_mma_shape(int c, int p, int hw) { return p == kP && (c == 128 || c == 256 || c == 512 || c == 1024) && hw >= 32; }
 int pemp_mpa_bwd_mma_tiles(int hw) { return (hw + kStep - 1) / kStep; }
+// rows of a class box per product warp (the table of an image is laid out in that order by mpa_bwd_prepare_kernel)
+int pemp_mpa_bwd_mma_rows_per_warp(int c) { return c == 512 ? 32 : c == 1024 ? 128 : 16; }
 
 size_t pemp_mpa_bwd_mma_smem(int c) {
-  switch (c / 128) {
-    case 1: return sizeof(Smem<1>);
-    case 2: return sizeof(Smem<2>);
-    case 4: return sizeof(Smem<4>);
-    default: return sizeof(Smem<8>);
+  switch (c) {
+    case 128: return sizeof(Smem<1, 8, 1>);
+    case 256: return sizeof(Smem<1, 16, 2>);
+    case 512: return sizeof(Smem<2, 16, 2>);
+    default: return sizeof(Smem<8, 8, 1>);
   }
 }
 
@@ -508,13 +525,14 @@ int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const 
   CUtensorMap map;
   // no L2 promotion beyond the 128-byte row piece: a CTA comes back for the neighbouring piece ~10 us later, by which time the
   // write stream has pushed it out of L2 (with 256-byte promotion the kernel read 1.6 x its algorithmic bytes from DRAM, ncu)
-  if (!make_rows4_map(&map, fts, B, S, c, hw, ep, c >= 256 ? c / 16 : c / 8, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return PEMP_E_ALIGN;
+  const int box_rows = c == 1024 ? 64 : pemp_mpa_bwd_mma_rows_per_warp(c);      // c = 1024: two pieces per box
+  if (!make_rows4_map(&map, fts, B, S, c, hw, ep, box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return PEMP_E_ALIGN;
   const int N = B * S;
-  switch (c / 128) {
-    case 1: return launch<1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
-    case 2: return launch<2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
-    case 4: return launch<4>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
-    case 8: return launch<8>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+  switch (c) {
+    case 128: return launch<1, 8, 1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+    case 256: return launch<1, 16, 2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+    case 512: return launch<2, 16, 2>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
+    case 1024: return launch<8, 8, 1>(map, S, tabg, beta, fg, bg, mask_stride, N, hw, chunks, dfts, d_ep, part, img_part, st);
     default: return PEMP_E_SHAPE;
   }
 }
