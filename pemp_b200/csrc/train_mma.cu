@@ -251,8 +251,14 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   // ============================ product warps ============================
 
   // ---- phase B1: df^T [pixel 16] x [row 8] per block, contraction over the 10 columns (8 + 2) ----
-  // W fragments of a tile (A operand: pixel 16 mb + g (+8), column tg (+4) / 8 + tg; columns 10, 11 hold zeros)
-  auto load_w = [&](const float* wt, FragA (&w0)[2], FragA (&w1)[2]) {
+  // The columns 0..7 take the three products of the split as three MMAs; the columns 8, 9 would need three more that are
+  // three quarters zeros, so their three products are stacked along the contraction axis of ONE MMA instead: slot t < 2 holds
+  // (W_hi, T_hi) of column 8 + t, slot t >= 2 (W_lo, T_hi) and slot t + 4 < 6 (W_hi, T_lo) - 4 MMAs per block instead of 6.
+  // W fragments of a tile (A operand: pixel 16 mb + g (+8), column tg (+4) for w0; the stacked columns 8 + (tg & 1) for w1)
+  struct FragS {
+    uint32_t a[4];
+  };
+  auto load_w = [&](const float* wt, FragA (&w0)[2], FragS (&w1)[2]) {
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
       const float* p0 = wt + (mb * 16 + g) * kWtLd + tg;
@@ -261,9 +267,13 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
       split_tf32(p1[0], w0[mb].hi[1], w0[mb].lo[1]);
       split_tf32(p0[4], w0[mb].hi[2], w0[mb].lo[2]);
       split_tf32(p1[4], w0[mb].hi[3], w0[mb].lo[3]);
-      split_tf32(p0[8], w1[mb].hi[0], w1[mb].lo[0]);
-      split_tf32(p1[8], w1[mb].hi[1], w1[mb].lo[1]);
-      w1[mb].hi[2] = w1[mb].hi[3] = w1[mb].lo[2] = w1[mb].lo[3] = 0u;
+      uint32_t h0, l0, h1, l1;
+      split_tf32(p0[8 - tg + (tg & 1)], h0, l0);
+      split_tf32(p1[8 - tg + (tg & 1)], h1, l1);
+      w1[mb].a[0] = tg < 2 ? h0 : l0;
+      w1[mb].a[1] = tg < 2 ? h1 : l1;
+      w1[mb].a[2] = tg < 2 ? h0 : 0u;
+      w1[mb].a[3] = tg < 2 ? h1 : 0u;
     }
   };
   // One block of 8 table rows (tb8 = its first row) x 32 pixels.  C fragment: (pixel 16 mb + g (+8), rows 2 tg / 2 tg + 1 of the
@@ -273,18 +283,19 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   // rows of a block are channels 4 apart.
   float* stg = sm.stage[warp];
   const long long row_step = 4LL * hw;             // the rows of a block are channels 4 apart
-  auto b1_block = [&](const FragA (&w0)[2], const FragA (&w1)[2], const float* tb8, float* orow, int rem) {
+  auto b1_block = [&](const FragA (&w0)[2], const FragS (&w1)[2], const float* tb8, float* orow, int rem) {
     const float* tb0 = tb8 + g * kTLd + tg;
-    FragB b0, b1;
+    FragB b0;
     split_tf32(tb0[0], b0.hi[0], b0.lo[0]);
     split_tf32(tb0[4], b0.hi[1], b0.lo[1]);
-    split_tf32(tb0[8], b1.hi[0], b1.lo[0]);               // columns 8 + tg: 10, 11 hold zeros
-    b1.hi[1] = b1.lo[1] = 0u;
+    uint32_t th, tl;
+    split_tf32(tb0[8 - tg + (tg & 1)], th, tl);           // stacked columns 8 + (tg & 1): slot tg = T_hi, slot tg + 4 = T_lo (tg < 2)
+    tl = tg < 2 ? tl : 0u;
     float d[2][4];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) d[mb][0] = d[mb][1] = d[mb][2] = d[mb][3] = 0.f;
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w1[mb], b1);
+    for (int mb = 0; mb < 2; ++mb) mma_tf32(d[mb], w1[mb].a[0], w1[mb].a[1], w1[mb].a[2], w1[mb].a[3], th, tl);
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) mma3(d[mb], w0[mb], b0);
 #pragma unroll
@@ -312,7 +323,8 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   // B1 of a tile in two halves of the warp's row blocks: the first one right after the refill (covers the TMA latency), the
   // second one after the dots of the NEXT tile are handed over (covers the pixel step) - hence the double-buffered weights
   auto b1_range = [&](int tp, int nb0, int nb1) {
-    FragA w0[2], w1[2];
+    FragA w0[2];
+    FragS w1[2];
     load_w(sm.wt[(tp - tb) & 1], w0, w1);
     const int xp = tp * kStep, rem = min(kStep, hw - xp);
     float* orow = dst + static_cast<long long>(4 * (CW * half) + e) * hw + xp + lane;
