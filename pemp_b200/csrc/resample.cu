@@ -155,6 +155,7 @@ upsample_argmax_kernel(const float* __restrict__ pred, float* __restrict__ logit
 #define PEMP_K4_BAND 16
 #endif
 constexpr int kBandRows = PEMP_K4_BAND, kBandMaxSrc = 8;
+__host__ __device__ inline int band_pitch(int W) { return W + (W >> 4) + 1; }   // float2 elements per staged source row
 // kHist: the FewShotMetric counts of K10 (core/metrics.py:9-23) are taken from the mask bytes while they are still in
 // registers - one launch and one read of the mask fewer (pemp_upsample_argmax_hist).
 template <bool kHist>
@@ -162,7 +163,15 @@ __global__ void __launch_bounds__(256)
 upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict__ mask8, int h, int w, int H, int W,
                             float sy, float sx, int bands, const uint8_t* __restrict__ ref, const int64_t* __restrict__ cls,
                             int num_classes, unsigned long long* __restrict__ stat) {
-  extern __shared__ float hrow[];                    // [nsrc][2][W]
+  // hrow [nsrc][Wp]{ch 0, ch 1}: the two classes of a pixel side by side, so a sample is two 8-byte loads (top and bottom
+  // source row) instead of four 4-byte ones; pixel X sits at X + (X >> 4) (Wp = band_pitch(W)): the lanes of a warp read
+  // pixels 4 apart (a lane owns a quad), which is a 4-way bank conflict in a dense row and conflict-free with one pad element
+  // per 16.  vrow [kBandRows]: the vertical coefficients of the band's output rows, computed once.  (Round 2: ncu counted
+  // 18.6 thread instructions per pixel, most of them index arithmetic - a 64-bit division per quad, the row coefficients
+  // per quad, bounds and wrap tests per pixel - and 3.7 M of 5.1 M shared wavefronts were conflicts of the quad reads.)
+  extern __shared__ float hrow[];
+  __shared__ float4 vrow[kBandRows];                 // { (i0 - src0) * Wp, (i1 - src0) * Wp (as int bits), l0, l1 }
+  const int Wp = band_pitch(W);
   const int n = blockIdx.x / bands, band = blockIdx.x - n * bands;
   const int Y0 = band * kBandRows, Y1 = min(H, Y0 + kBandRows);
   const int src0 = lerp_coeff(Y0, sy, h).i0, nsrc = lerp_coeff(Y1 - 1, sy, h).i1 - src0 + 1;
@@ -170,52 +179,77 @@ upsample_argmax_band_kernel(const float* __restrict__ pred, uint8_t* __restrict_
   const float* p0 = pred + static_cast<long long>(n) * 2 * hw + src0 * w;
   for (int X = threadIdx.x; X < W; X += blockDim.x) {
     const Lerp lx = lerp_coeff(X, sx, w);
-    for (int r = 0; r < nsrc; ++r)
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const float* row = p0 + ch * hw + r * w;
-        hrow[(r * 2 + ch) * W + X] = lerp2(lx.l0, __ldg(row + lx.i0), lx.l1, __ldg(row + lx.i1));
-      }
+    for (int r = 0; r < nsrc; ++r) {
+      const float* row = p0 + r * w;
+      const float a = lerp2(lx.l0, __ldg(row + lx.i0), lx.l1, __ldg(row + lx.i1));
+      const float c = lerp2(lx.l0, __ldg(row + hw + lx.i0), lx.l1, __ldg(row + hw + lx.i1));
+      reinterpret_cast<float2*>(hrow)[r * Wp + X + (X >> 4)] = make_float2(a, c);
+    }
+  }
+  if (threadIdx.x < kBandRows) {
+    const Lerp ly = lerp_coeff(min(Y0 + static_cast<int>(threadIdx.x), H - 1), sy, h);
+    vrow[threadIdx.x] = make_float4(__int_as_float((ly.i0 - src0) * Wp), __int_as_float((ly.i1 - src0) * Wp), ly.l0, ly.l1);
   }
   __syncthreads();
   const long long HW = static_cast<long long>(H) * W;
   const long long base0 = n * HW + static_cast<long long>(Y0) * W, base1 = n * HW + static_cast<long long>(Y1) * W;
+  const float2* hr = reinterpret_cast<const float2*>(hrow);
   PempCounts cnt = {0, 0, 0, 0, 0, 0};
-  for (long long q = (base0 >> 2) + threadIdx.x; (q << 2) < base1; q += blockDim.x) {
-    const long long i0 = q << 2;
-    const long long first = i0 < base0 ? base0 : i0;          // first element of the quad inside the band
-    const int r0 = static_cast<int>(first - n * HW);
-    int Y = r0 / W, X = r0 - Y * W;
-    Lerp ly = lerp_coeff(Y, sy, h);
-    const float* rt = hrow + (ly.i0 - src0) * 2 * W;
-    const float* rb = hrow + (ly.i1 - src0) * 2 * W;
+  // one sample: v_c = fma(l0, top_c, l1 * bottom_c) for the two classes, class 1 wins only if strictly larger
+  auto sample = [&](const float4 vy, int X) -> uint32_t {
+    const int xp = X + (X >> 4);
+    const float2 t = hr[__float_as_int(vy.x) + xp], bt = hr[__float_as_int(vy.y) + xp];
+    const float v0 = lerp2(vy.z, t.x, vy.w, bt.x);
+    const float v1 = lerp2(vy.z, t.y, vy.w, bt.y);
+    return v1 > v0 ? 1u : 0u;
+  };
+  // quads of the flattened output (aligned 32-bit stores although W is odd); a thread's quads are 4 * blockDim apart, so
+  // its (row, column) advances by constants instead of being re-derived with a division
+  const long long q0 = (base0 >> 2) + threadIdx.x;
+  const int stepY = static_cast<int>(4 * blockDim.x) / W, stepX = static_cast<int>(4 * blockDim.x) - stepY * W;
+  int rel = static_cast<int>((q0 << 2) - base0);     // offset of the quad's first element in the band (may be < 0 for the first quad)
+  int Y = rel >= 0 ? rel / W : 0, X = rel >= 0 ? rel - Y * W : rel;
+  const int band_len = static_cast<int>(base1 - base0);
+  for (long long q = q0; rel < band_len; q += blockDim.x, rel += 4 * blockDim.x) {
     uint32_t packed = 0;
+    if (rel >= 0 && rel + 3 < band_len && X + 3 < W) {         // whole quad inside the band and inside one row
+      const float4 vy = vrow[Y];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const long long i = i0 + e;
-      if (i >= first && i < base1) {
-        const float v0 = lerp2(ly.l0, rt[X], ly.l1, rb[X]);
-        const float v1 = lerp2(ly.l0, rt[W + X], ly.l1, rb[W + X]);
-        packed |= (v1 > v0 ? 1u : 0u) << (8 * e);   // first index wins ties => background
-        if (++X == W) {
-          X = 0;
-          ++Y;
-          ly = lerp_coeff(min(Y, H - 1), sy, h);
-          rt = hrow + (ly.i0 - src0) * 2 * W;
-          rb = hrow + (ly.i1 - src0) * 2 * W;
-        }
-      }
-    }
-    if (i0 >= base0 && i0 + 3 < base1) {
+      for (int e = 0; e < 4; ++e) packed |= sample(vy, X + e) << (8 * e);
       reinterpret_cast<uint32_t*>(mask8)[q] = packed;
       if (kHist) pemp_count_word(packed, __ldg(reinterpret_cast<const uint32_t*>(ref) + q), cnt);
-    } else {
+    } else {                                                   // band boundary or a quad that wraps to the next row
+      int yy = Y, xx = rel < 0 ? 0 : X;
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (i0 + e >= base0 && i0 + e < base1) {
-          mask8[i0 + e] = static_cast<uint8_t>(packed >> (8 * e));
-          if (kHist) pemp_count_byte(static_cast<uint8_t>(packed >> (8 * e)), __ldg(ref + i0 + e), cnt);
+      for (int e = 0; e < 4; ++e) {
+        const int r = rel + e;
+        if (r >= 0 && r < band_len) packed |= sample(vrow[yy], xx) << (8 * e);
+        if (r >= 0 && ++xx == W) {
+          xx = 0;
+          ++yy;
         }
+      }
+      if (rel >= 0 && rel + 3 < band_len) {
+        reinterpret_cast<uint32_t*>(mask8)[q] = packed;
+        if (kHist) pemp_count_word(packed, __ldg(reinterpret_cast<const uint32_t*>(ref) + q), cnt);
+      } else {
+        const long long i0 = q << 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (rel + e >= 0 && rel + e < band_len) {
+            mask8[i0 + e] = static_cast<uint8_t>(packed >> (8 * e));
+            if (kHist) pemp_count_byte(static_cast<uint8_t>(packed >> (8 * e)), __ldg(ref + i0 + e), cnt);
+          }
+      }
+    }
+    X += stepX;
+    Y += stepY;
+    if (X >= W) {
+      X -= W;
+      ++Y;
+    } else if (X < 0) {                                        // (only after a first quad that starts before the band)
+      X += W;
+      --Y;
     }
   }
   if (kHist) {   // block reduction, then six integer atomics (order independent => exact)
@@ -257,7 +291,7 @@ extern "C" int pemp_upsample_argmax(const float* pred, int N, int h, int w, int 
   if (mask8 && !logits && !mask64) {
     // source rows one band can touch: floor((kBandRows - 1) * sy) + 3 (top row, its partner, rounding)
     const int nsrc_max = static_cast<int>((kBandRows - 1) * sy) + 3;
-    const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
+    const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * band_pitch(W) * sizeof(float);
     if (nsrc_max <= kBandMaxSrc && smem <= 48 * 1024) {
       const int bands = (H + kBandRows - 1) / kBandRows;
       upsample_argmax_band_kernel<false><<<static_cast<unsigned>(N) * bands, 256, smem, st>>>(pred, mask8, h, w, H, W, sy, sx, bands,
@@ -291,7 +325,7 @@ extern "C" int pemp_upsample_argmax_hist(const float* pred, int N, int h, int w,
   PEMP_REQUIRE((reinterpret_cast<uintptr_t>(mask8) & 3) == 0 && (reinterpret_cast<uintptr_t>(ref) & 3) == 0, PEMP_E_ALIGN);
   const float sy = lerp_scale(h, H), sx = lerp_scale(w, W);
   const int nsrc_max = static_cast<int>((kBandRows - 1) * sy) + 3;
-  const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * W * sizeof(float);
+  const size_t smem = static_cast<size_t>(nsrc_max < h ? nsrc_max : h) * 2 * band_pitch(W) * sizeof(float);
   if (nsrc_max <= kBandMaxSrc && smem <= 48 * 1024) {
     const int bands = (H + kBandRows - 1) / kBandRows;
     upsample_argmax_band_kernel<true><<<static_cast<unsigned>(N) * bands, 256, smem, as_stream(stream)>>>(
