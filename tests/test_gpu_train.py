@@ -81,6 +81,34 @@ def test_meta_proto_attn_backward_tensor_path_vs_cuda_core_kernel_full_size():
     assert ef < 5e-5 and ec < 5e-5
 
 
+def test_meta_proto_attn_backward_falls_back_when_the_operand_has_no_tensor_map():
+    """The tensor-path kernel reads the features through a TMA tensor map (16-byte aligned base); a support map that starts
+    4 bytes into an allocation cannot be encoded, and the entry point must take the CUDA-core kernel for it - bit for bit what
+    `pemp_debug_bwd_path(1)` gives on an aligned copy of the same values."""
+    from pemp_b200 import _cabi, ops
+    B, S, c, h, P = 1, 2, 256, 13, 3
+    feats, ctr, fg, bg = _case(B, S, 1, c, h, h, P, seed=5)
+    g = torch.Generator().manual_seed(9)
+    gf, gb = torch.randn(B, c, P, generator=g).cuda(), torch.randn(B, c, P, generator=g).cuda()
+    sup = feats[:, :S].reshape(B * S, c, h * h).cuda().contiguous()
+    store = torch.empty(sup.numel() + 1, dtype=torch.float32, device="cuda")
+    off = store[1:].view_as(sup)                                   # same values, base pointer 4 bytes off a 16-byte boundary
+    off.copy_(sup)
+    assert off.data_ptr() % 16 != 0 and sup.data_ptr() % 16 == 0
+    ctr_cu, fg_cu, bg_cu = ctr.cuda(), fg.cuda(), bg.cuda()
+    _, _, saved_a = ops.meta_proto_attn_train(sup, ctr_cu, fg_cu, bg_cu, B, S)
+    _, _, saved_o = ops.meta_proto_attn_train(off, ctr_cu, fg_cu, bg_cu, B, S)
+    d_o, c_o = ops.meta_proto_attn_bwd(saved_o, gf, gb, B, S)      # automatic choice: must fall back
+    _cabi.lib().pemp_debug_bwd_path(1)
+    try:
+        d_a, c_a = ops.meta_proto_attn_bwd(saved_a, gf, gb, B, S)  # CUDA-core kernel on the aligned copy
+    finally:
+        _cabi.lib().pemp_debug_bwd_path(0)
+    d_t, c_t = ops.meta_proto_attn_bwd(saved_a, gf, gb, B, S)      # tensor path on the aligned copy: close, not identical
+    assert nrel(d_o.cpu(), d_a.cpu()) < 2e-5 and nrel(c_o.cpu(), c_a.cpu()) < 2e-5
+    assert nrel(d_t.cpu(), d_a.cpu()) < 5e-5 and nrel(c_t.cpu(), c_a.cpu()) < 5e-5
+
+
 @pytest.mark.parametrize("B,Q,c,h,w,P", [(2, 1, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (2, 2, 512, 13, 13, 3),
                                           (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (2, 1, 1024, 6, 7, 2)])
 def test_cosine_match_backward_matches_autograd_of_the_oracle(B, Q, c, h, w, P):
