@@ -13,24 +13,27 @@
 // at 0.31-0.33 of the HBM peak with the shared pipe 63 % busy.  With register fragments a table / weight value is read once per
 // 8 x 8 block (~3 000 crossbar cycles per tile).  tcgen05 is not an option here: its operands live in shared memory behind
 // descriptors (T as hi + lo K-major panels = 48-64 KB next to the 64-KB tile, twice per SM) and the three products contract
-// over three different axes of the same tile; 240 m16n8k8 per warp and tile keep the legacy pipe (measured 2.0 clk per
-// instruction and SM, tools/probes/mma_sync_probe.cu) a quarter busy.
+// over three different axes of the same tile; ~1 700 m16n8k8 per tile keep the legacy pipe (measured 2.0 clk per instruction
+// and SM, tools/probes/mma_sync_probe.cu) a third busy.
 //
 // 3 x TF32: x = hi + lo with hi = x & 0xffffe000 (what the tensor core reads of an fp32 register) and lo = x - hi (exact);
 // a.b ~ lo_a hi_b + hi_a lo_b + hi_a hi_b, small products first (see K9), error ~2^-21 per product.
 //
-// Structure: two CTAs per SM, each eight product warps + two pixel-step warps (96 registers); a CTA owns a run of 28-pixel
-// tiles of one image.  The features come through the "four rows per group" tensor map of the forward kernels (tma_common.cuh):
-// product warp w = e + 4 half owns rows [CW half, CW half + CW) of the class-e box of a tile (channels 4 g + e; CW = c/8), i.e.
-// its own 128-byte-swizzled half box with its own mbarrier - the tile buffer is warp-private in every phase and is refilled in
-// two pieces, each as soon as B2 is done with its rows (the first version filled it with 64 four-byte cp.async per thread: a
-// third of all stall samples sat in that loop, ncu).  Box column i of class e is pixel x_nom + i - o_e, o_e = (e hw + x_nom) & 3
+// Structure (c = 512, the PEMP shape; the configurations are listed below): ONE CTA per SM with sixteen product warps + two
+// pixel-step warps (96 registers); a CTA owns a run of 28-pixel tiles of one image (grid = images x chunks, train.cu plans the
+// split).  The features come through the "four rows per group" tensor map of the forward kernels (tma_common.cuh): product
+// warp w = e + 4 q owns rows [CW q, CW q + CW) of the class-e box of a tile (channels 4 g + e; CW = c / 16), i.e. its own
+// 128-byte-swizzled quarter box, double buffered, each buffer with its own mbarrier - the tile is warp-private in every phase
+// and the box of tile t+1 is requested before tile t is touched (the first version filled a single buffer with 64 four-byte
+// cp.async per thread: a third of all stall samples sat in that loop; single-buffered TMA boxes still left the product warps
+// waiting for the refill a quarter of the time).  Box column i of class e is pixel x_nom + i - o_e, o_e = (e hw + x_nom) & 3
 // (aligned box origins).  Per tile a product warp runs
-//     wait box(t) | A(t) -> dots -> arrive | second half of B1(t-1) | wait weights(t) | B2(t) + refills | first half of B1(t)
-// and the pixel-step warps (one per class group, lane = pixel) turn the eight partial dot sets into the weights of the tile
-// (double buffered by tile parity) behind two mbarriers: B1 needs no features, so one half of it hides the pixel step and the
-// other the TMA latency, and no warp ever waits at a block barrier (when two of the product warps did the pixel step between
-// two __syncthreads, those were 16 % of all stall samples).
+//     request box(t+1) | wait box(t) | A(t) -> dots -> arrive | B1(t-1) | wait weights(t) | B2(t)
+// and the pixel-step warps (one per class group, lane = pixel) turn the sixteen partial dot sets into the weights of the tile
+// (double buffered by tile parity) behind two mbarriers: B1 needs no features, so it hides the pixel step, and no warp ever
+// waits at a block barrier in the tile loop (when two of the product warps did the pixel step between two __syncthreads,
+// those were 16 % of all stall samples).  The single-buffered configurations split B1 in two halves around B2 instead: one
+// hides the pixel step, the other the refill.
 #include <math_constants.h>
 
 #include "tma_common.cuh"
@@ -121,12 +124,12 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
   Smem<MB, KW, NBUF>& sm = *reinterpret_cast<Smem<MB, KW, NBUF>*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
-  const int e = warp & 3, half = warp >> 2;
+  const int e = warp & 3, half = warp >> 2;      // channel class and row range (q in the comments) of this product warp
   const int n = blockIdx.y, b = n / S, si = n - b * S;
   float* dst = dfts + static_cast<long long>(b) * d_ep_stride + static_cast<long long>(si) * c * hw;
   const int tb = static_cast<int>(static_cast<long long>(ntiles) * blockIdx.x / gridDim.x);
   const int te = static_cast<int>(static_cast<long long>(ntiles) * (blockIdx.x + 1) / gridDim.x);
-  const bool pixel_warp = warp >= kW;            // warps 8 / 9: pixel step of the foreground / background group
+  const bool pixel_warp = warp >= kW;            // the last two warps: pixel step of the foreground / background group
   float* box = sm.tile[0][pixel_warp ? 0 : warp];
   const float* trow = sm.tab + (pixel_warp ? 0 : warp) * CW * kTLd;  // this warp's table rows
 
@@ -176,8 +179,8 @@ mpa_bwd_mma_kernel(const __grid_constant__ CUtensorMap map, int S, const float* 
 
   if (pixel_warp) {
     // ============================ pixel-step warps: lane = pixel of the tile ============================
-    // wait for the eight partial dot sets of a tile, add them in a fixed order, soft-max and its derivative -> the weights of
-    // the tile (double buffered by tile parity: the product warps use them for one and a half tiles) and dv; they own the
+    // wait for the KW partial dot sets of a tile, add them in a fixed order, soft-max and its derivative -> the weights of
+    // the tile (double buffered by tile parity: the product warps use them into the next tile) and dv; they own the
     // sums of 2 dl_k.  The product warps never wait at a block barrier: as warps of the same CTA did this step, everybody
     // else sat at two barriers per tile (16 % of all stall samples, ncu).
     const int grp = warp - kW;
