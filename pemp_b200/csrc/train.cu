@@ -325,24 +325,39 @@ cosine_bwd_kernel(const float* __restrict__ qry, long long ep_stride, int Q, con
   }
 }
 
-// one CTA per prototype set: add the partials of its Q query maps, then the backward of the normalisation
+// one CTA per prototype set: add the partials of its Q query maps, then the backward of the normalisation.  A thread reads the
+// whole K-float row of its channel from every partial in ONE pass with several loads in flight (the first version made a pass
+// per column with a single 4-byte load in flight: 20 us for 16 query maps, a fifth of the whole backward).
 __global__ void __launch_bounds__(kBT)
 cosine_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ pn, const float* __restrict__ nrm, int Q,
                            int chunks, int c, int P, float* __restrict__ d_fg, float* __restrict__ d_bg) {
   __shared__ float scratch[kBW];
   const int b = blockIdx.x, K = 2 * P;
-  for (int k = 0; k < K; ++k) {
-    float d[kMaxCPT];
+  float d[kMaxCPT][8];
+#pragma unroll
+  for (int i = 0; i < kMaxCPT; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[i][k] = 0.f;
+    const int ch = threadIdx.x + i * kBT;
+    if (ch < c) {
+      const float* row = part + (static_cast<long long>(b) * Q * chunks * c + ch) * K;
+#pragma unroll 4
+      for (int j = 0; j < Q * chunks; ++j) {       // in index order: the same sums as before, bit for bit
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < K) d[i][k] += __ldg(row + k);
+        row += static_cast<long long>(c) * K;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k >= K) break;
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxCPT; ++i) {
       const int ch = threadIdx.x + i * kBT;
-      d[i] = 0.f;
-      if (ch < c) {
-        for (int j = 0; j < Q * chunks; ++j)
-          d[i] += part[((static_cast<long long>(b) * Q * chunks + j) * c + ch) * K + k];
-        dot = fmaf(pn[(static_cast<long long>(b) * c + ch) * K + k], d[i], dot);
-      }
+      if (ch < c) dot = fmaf(pn[(static_cast<long long>(b) * c + ch) * K + k], d[i][k], dot);
     }
     dot = block_sum(dot, scratch);
     const float nv = nrm[b * K + k];
@@ -352,7 +367,7 @@ cosine_bwd_finalize_kernel(const float* __restrict__ part, const float* __restri
       const int ch = threadIdx.x + i * kBT;
       if (ch < c) {
         const float pv = pn[(static_cast<long long>(b) * c + ch) * K + k];
-        out[static_cast<long long>(ch) * P] = (nv < kCosEps) ? d[i] / kCosEps : (d[i] - pv * dot) / nv;
+        out[static_cast<long long>(ch) * P] = (nv < kCosEps) ? d[i][k] / kCosEps : (d[i][k] - pv * dot) / nv;
       }
     }
   }
