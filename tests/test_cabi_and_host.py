@@ -73,6 +73,15 @@ def test_training_path_has_no_cpu_fallback_and_plans_on_the_host():
     per_image_few = few - 512 * 6 * 4            # minus the coefficient table: partials of one image
     assert per_image_few > (many / 320) * 2      # one image alone is split over more CTAs than each of 320 images
     assert lib.pemp_meta_proto_attn_bwd_workspace_bytes(1, 1, 512, 2601, 5) == 0
+    # tensor-path shapes (p = 3, c in {128, 256, 512, 1024}, hw >= 32) also carry the image tables [N, c, 12] and the per-image
+    # partial sums [N, (c + 1) 6]; any other shape plans the CUDA-core kernel only
+    N, c, hw = 10, 512, 2601
+    with_tables = lib.pemp_meta_proto_attn_bwd_workspace_bytes(2, 5, c, hw, 3)
+    assert with_tables >= N * c * 12 * 4 + N * (c + 1) * 6 * 4 + N * c * 6 * 4
+    small_map = lib.pemp_meta_proto_attn_bwd_workspace_bytes(2, 5, c, 25, 3)       # hw < 32: no tensor map
+    other_p = lib.pemp_meta_proto_attn_bwd_workspace_bytes(2, 5, c, hw, 2)
+    assert 0 < small_map < N * c * 12 * 4 + lib.pemp_meta_proto_attn_bwd_workspace_bytes(2, 5, c, 25, 3) and other_p > 0
+    assert lib.pemp_debug_bwd_path(0) in (0, 1)                                     # the switch exists and reports its previous value
     assert lib.pemp_cosine_match_bwd_workspace_bytes(64, 64, 512, 2601, 3) > 0
     assert lib.pemp_upsample_ce_workspace_bytes(64, 51, 51, 401, 401) >= 64 * 401 * 401 * 4
     assert lib.pemp_boundary_weight_workspace_bytes(64, 401, 401) >= 64 * 401 * 401 * 5
