@@ -81,6 +81,38 @@ def test_meta_proto_attn_backward_tensor_path_vs_cuda_core_kernel_full_size():
     assert ef < 5e-5 and ec < 5e-5
 
 
+def test_meta_proto_attn_backward_survives_many_launches_at_bench_size():
+    """The tensor-path K2 backward hands work between warps through mbarriers (boxes, dots, weights) with parity waits; a
+    hazard in such a protocol shows up as a launch failure or a changed bit only under timing variation.  200 launches at
+    the training-bench size (64 episodes: 320 images, 1 CTA per SM, ~12 waves), a competing stream writing memory
+    meanwhile, every 50th result compared bit for bit with the first."""
+    from pemp_b200 import ops
+    B, S, c, h, P = 64, 5, 512, 51, 3
+    g = torch.Generator(device="cuda").manual_seed(4)
+    feats = torch.randn(B, S, c, h, h, device="cuda", generator=g) * 0.5
+    ctr = torch.randn(c, 2 * P, device="cuda", generator=g) * 0.5
+    fg = (torch.rand(B * S, h * h, device="cuda", generator=g) > 0.6).float()
+    bg = 1 - fg
+    gf, gb = torch.randn(B, c, P, device="cuda", generator=g), torch.randn(B, c, P, device="cuda", generator=g)
+    _, _, saved = ops.meta_proto_attn_train(feats, ctr, fg, bg, B, S)
+    side = torch.cuda.Stream()
+    noise = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    ref = None
+    for it in range(200):
+        if it % 4 == 0:
+            with torch.cuda.stream(side):
+                noise.fill_(float(it))                       # 256 MB of competing writes: shifts the kernel's timing
+        d, dc = ops.meta_proto_attn_bwd(saved, gf, gb, B, S)
+        if it % 50 == 49:
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = (d.clone(), dc.clone())
+            else:
+                assert torch.equal(ref[0], d) and torch.equal(ref[1], dc), f"launch {it} differs"
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(ref[0]).all()) and bool(torch.isfinite(ref[1]).all())
+
+
 def test_meta_proto_attn_backward_falls_back_when_the_operand_has_no_tensor_map():
     """The tensor-path kernel reads the features through a TMA tensor map (16-byte aligned base); a support map that starts
     4 bytes into an allocation cannot be encoded, and the entry point must take the CUDA-core kernel for it - bit for bit what
