@@ -733,7 +733,7 @@ def run_ours(args):
         del wl.batch
         torch.cuda.empty_cache()
         from tools import kernel_bench
-        extra = kernel_bench.run(only="K1 ,K3,K6,K7,K8,K9,K11")
+        extra = kernel_bench.run(only="K1 ,K3,K6,K7,K8,K9,K11,K12")
 
     if rank == 0:
         hbm_eps = peaks["hbm_gbs"] * 1e3 / (wl.alg_bytes_per_episode / 1e6)

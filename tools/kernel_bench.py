@@ -2,7 +2,7 @@
     python tools/kernel_bench.py [--B 64] [--S 5]
 prints one JSON line per kernel: ms, algorithmic GB (or GFLOP), GB/s (TFLOP/s), fraction of the measured peak.
 `run(...)` returns the same rows as dicts: `bench.py` attaches them to its JSON line as `roofline_extra`, so the kernels that
-are not on the headline workload (K1, K6, K7, K8, K9, K11, K15) are measured in the driver's own run as well."""
+are not on the headline workload (K1, K6, K7, K8, K9, K11, K12, K15) are measured in the driver's own run as well."""
 import argparse
 import json
 import os
@@ -64,7 +64,15 @@ def run(B=64, S=5, c=512, h=51, H=401, only="", k9_batch=2, emit=None):
     cls = torch.randint(1, 6, (B,), device=dev)
     stat = torch.zeros(21, 3, dtype=torch.int64, device=dev)
     feats_all = torch.cat((sup.view(B, S, c, h, h), qry.view(B, 1, c, h, h)), dim=1).view(B * (S + 1), c, h, h).contiguous()
+    # training path (K12): the forward-for-training state, upstream gradients of the prototypes / of the prediction
+    _, _, saved = ops.meta_proto_attn_train(sup, ctr, low[:, 0], low[:, 1], B, S)
+    gfp, gbp = torch.randn(B, c, 3, device=dev, generator=g), torch.randn(B, c, 3, device=dev, generator=g)
+    gpred = torch.randn(B, 2, hw, device=dev, generator=g)
     rows = [
+        # backward kernels: read the feature map once, write its gradient once
+        ("K12 meta_proto_attn_bwd (TMA + 3xTF32 mma.sync)", lambda: ops.meta_proto_attn_bwd(saved, gfp, gbp, B, S),
+         B * S * (2 * c * hw + 2 * hw) * 4),
+        ("K12 cosine_match_bwd", lambda: ops.cosine_match_bwd(qry, fgp, bgp, gpred), B * (2 * c * hw + 2 * hw) * 4),
         ("K0 mask_nearest", lambda: ops.mask_nearest(sup_mask, h, h), B * S * 2 * hw * 4 * 2),
         ("K2 meta_proto_attn", lambda: ops.meta_proto_attn(sup, ctr, low[:, 0], low[:, 1], B, S),
          B * (S * (c * hw + 2 * hw) * 4 + 2 * c * 6 * 4)),
