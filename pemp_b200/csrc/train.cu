@@ -38,6 +38,13 @@ int pemp_mpa_bwd_mma_rows_per_warp(int c);
 int pemp_mpa_bwd_mma_launch(const float* fts, long long ep, int B, int S, const float* ctr, const float* coef, const float* beta,
                             const float* fg, const float* bg, long long mask_stride, int c, int hw, int chunks, float* tabg,
                             float* dfts, long long d_ep, float* part, float* img_part, cudaStream_t st);
+// train_mma_cos.cu: K3 backward on the same structure (P = 3, c in {256, 512})
+bool pemp_cos_bwd_mma_shape(int c, int P, int hw);
+size_t pemp_cos_bwd_mma_smem(int c);
+size_t pemp_cos_bwd_mma_table_bytes(int Bp, int c);
+int pemp_cos_bwd_mma_tiles(int hw);
+int pemp_cos_bwd_mma_launch(bool dense, const float* qry, long long ep, int Bp, int Q, const float* pn, const float* g, int c, int hw,
+                            int chunks, float scalar, float* tabg, float* dq, long long d_ep, float* part, cudaStream_t st);
 static int g_bwd_path = 0;   // diagnostic switch, see pemp_debug_bwd_path
 
 namespace {
@@ -847,12 +854,32 @@ extern "C" int pemp_map_pool_lowres_bwd(const float* fg, const float* bg, long l
   return launch_status();
 }
 
+namespace {
+// workspace of the K3 backward: pn [Bp][c][K] | nrm [Bp][K] | partials [N][chunks][c][K] | tables of the tensor-path kernel.
+// `chunks` is the larger of the two kernels' splits (the diagnostic switch picks the kernel at launch time).
+struct CosBwdWs {
+  size_t off_nrm, off_part, off_tab, total;
+};
+CosBwdWs cos_bwd_ws(int N, int Bp, int c, int hw, int P) {
+  const size_t K = 2 * P;
+  const bool mma = pemp_cos_bwd_mma_shape(c, P, hw);
+  int chunks = bwd_plan(N, hw, cos_smem(c, 2 * P)).chunks;
+  if (mma) {
+    const int m = bwd_plan(N, hw, pemp_cos_bwd_mma_smem(c), pemp_cos_bwd_mma_tiles(hw)).chunks;
+    if (m > chunks) chunks = m;
+  }
+  CosBwdWs w;
+  w.off_nrm = align_up(static_cast<size_t>(Bp) * c * K * 4, 256);
+  w.off_part = w.off_nrm + align_up(static_cast<size_t>(Bp) * K * 4, 256);
+  w.off_tab = w.off_part + align_up(static_cast<size_t>(N) * chunks * c * K * 4, 256);
+  w.total = w.off_tab + (mma ? align_up(pemp_cos_bwd_mma_table_bytes(Bp, c), 256) : 0);
+  return w;
+}
+}  // namespace
+
 extern "C" size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P) {
   if (N <= 0 || Bp <= 0 || c <= 0 || hw <= 0 || P < 1 || P > 4) return 0;
-  const BwdPlan pl = bwd_plan(N, hw, cos_smem(c, 2 * P));
-  const size_t K = 2 * P;
-  return align_up(static_cast<size_t>(Bp) * c * K * 4, 256) + align_up(static_cast<size_t>(Bp) * K * 4, 256) +
-         align_up(static_cast<size_t>(N) * pl.chunks * c * K * 4, 256);
+  return cos_bwd_ws(N, Bp, c, hw, P).total;
 }
 
 namespace {
@@ -865,15 +892,23 @@ int cosine_bwd_common(bool dense, const float* qry, long long qry_episode_stride
   PEMP_REQUIRE(workspace && workspace_bytes >= pemp_cosine_match_bwd_workspace_bytes(N, Bp, c, hw, P), PEMP_E_WORKSPACE);
   cudaStream_t st = as_stream(stream);
   const BwdPlan pl = bwd_plan(N, hw, cos_smem(c, 2 * P));
-  const int K = 2 * P, Q = N / Bp;
+  const int Q = N / Bp;
   char* ws = static_cast<char*>(workspace);
+  const CosBwdWs wl = cos_bwd_ws(N, Bp, c, hw, P);
   float* pn = reinterpret_cast<float*>(ws);
-  float* nrm = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(Bp) * c * K * 4, 256));
-  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(nrm) + align_up(static_cast<size_t>(Bp) * K * 4, 256));
+  float* nrm = reinterpret_cast<float*>(ws + wl.off_nrm);
+  float* part = reinterpret_cast<float*>(ws + wl.off_part);
   const long long ep = qry_episode_stride ? qry_episode_stride : static_cast<long long>(Q) * c * hw;
   const long long d_ep = d_qry_episode_stride ? d_qry_episode_stride : static_cast<long long>(Q) * c * hw;
   proto_norm_kernel<<<Bp, kBT, 0, st>>>(fg_proto, bg_proto, c, P, pn, nrm);
-  int rc;
+  int rc = PEMP_E_ALIGN, chunks = pl.chunks;
+  if (g_bwd_path == 0 && pemp_cos_bwd_mma_shape(c, P, hw)) {   // PEMP_E_ALIGN: no tensor map - the CUDA-core kernel takes it
+    const int m = bwd_plan(N, hw, pemp_cos_bwd_mma_smem(c), pemp_cos_bwd_mma_tiles(hw)).chunks;
+    rc = pemp_cos_bwd_mma_launch(dense, qry, ep, Bp, Q, pn, g, c, hw, m, scalar, reinterpret_cast<float*>(ws + wl.off_tab), d_qry,
+                                 d_ep, part, st);
+    if (rc == PEMP_OK) chunks = m;
+  }
+  if (rc == PEMP_E_ALIGN) {
 #define PEMP_COS_BWD(KK)                                                                                                        \
   rc = dense ? launch_cos_bwd<KK, true>(qry, ep, Q, pn, g, N, c, hw, pl, scalar, d_qry, d_ep, part, st)                        \
              : launch_cos_bwd<KK, false>(qry, ep, Q, pn, g, N, c, hw, pl, scalar, d_qry, d_ep, part, st)
@@ -884,8 +919,9 @@ int cosine_bwd_common(bool dense, const float* qry, long long qry_episode_stride
     default: PEMP_COS_BWD(8); break;
   }
 #undef PEMP_COS_BWD
+  }
   if (rc != PEMP_OK) return rc;
-  cosine_bwd_finalize_kernel<<<Bp, kBT, 0, st>>>(part, pn, nrm, Q, pl.chunks, c, P, d_fg, d_bg);
+  cosine_bwd_finalize_kernel<<<Bp, kBT, 0, st>>>(part, pn, nrm, Q, chunks, c, P, d_fg, d_bg);
   return launch_status();
 }
 }  // namespace

@@ -142,7 +142,9 @@ def test_meta_proto_attn_backward_falls_back_when_the_operand_has_no_tensor_map(
 
 
 @pytest.mark.parametrize("B,Q,c,h,w,P", [(2, 1, 64, 9, 11, 3), (1, 1, 512, 51, 51, 3), (2, 2, 512, 13, 13, 3),
-                                          (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (2, 1, 1024, 6, 7, 2)])
+                                          (3, 1, 32, 7, 5, 1), (1, 2, 128, 8, 9, 4), (2, 1, 1024, 6, 7, 2),
+                                          # the tensor-path kernel (P = 3, c in {256, 512}), ragged last tiles, Q > 1
+                                          (2, 1, 256, 9, 11, 3), (1, 3, 256, 13, 7, 3), (2, 2, 512, 7, 9, 3)])
 def test_cosine_match_backward_matches_autograd_of_the_oracle(B, Q, c, h, w, P):
     from pemp_b200 import autograd as A
     g = torch.Generator().manual_seed(c + w)
@@ -162,6 +164,29 @@ def test_cosine_match_backward_matches_autograd_of_the_oracle(B, Q, c, h, w, P):
     assert nrel(q_cu.grad.cpu().view(B * Q, c, h * w), q64.grad.float()) < GTOL
     assert nrel(f_cu.grad.cpu(), f64.grad.float()) < GTOL
     assert nrel(b_cu.grad.cpu(), b64.grad.float()) < GTOL
+
+
+def test_cosine_match_backward_tensor_path_vs_cuda_core_kernel_full_size():
+    """The two implementations of the K3 backward (train_mma_cos.cu / train.cu) on the same full-size input, arg-max and dense
+    form, through `pemp_debug_bwd_path`; the arg-max is recomputed by both, so the inputs avoid near-ties (random features)."""
+    from pemp_b200 import _cabi, ops
+    B, Q, c, h, P = 4, 1, 512, 51, 3
+    g = torch.Generator().manual_seed(17)
+    qry = torch.randn(B * Q, c, h * h, generator=g).cuda()
+    fgp, bgp = torch.randn(B, c, P, generator=g).cuda(), torch.randn(B, c, P, generator=g).cuda()
+    for dense in (False, True):
+        gp = (torch.randn(B * Q, 2, P, h * h, generator=g) if dense else torch.randn(B * Q, 2, h * h, generator=g)).cuda()
+        new = ops.cosine_match_bwd(qry, fgp, bgp, gp, dense=dense)
+        again = ops.cosine_match_bwd(qry, fgp, bgp, gp, dense=dense)
+        assert all(torch.equal(a, b) for a, b in zip(new, again))             # deterministic
+        _cabi.lib().pemp_debug_bwd_path(1)
+        try:
+            old = ops.cosine_match_bwd(qry, fgp, bgp, gp, dense=dense)
+        finally:
+            _cabi.lib().pemp_debug_bwd_path(0)
+        errs = [nrel(a.cpu(), b.cpu()) for a, b in zip(new, old)]
+        print({"case": "K3 backward tensor path vs CUDA cores", "dense": dense, "d_qry": errs[0], "d_fg": errs[1], "d_bg": errs[2]})
+        assert max(errs) < 2e-5
 
 
 def test_cosine_match_backward_with_tiny_vectors_uses_the_clamped_branch():
