@@ -514,7 +514,9 @@ def test_bench_size_properties_of_the_training_step():
     lh, _ = A.pemp_head_loss(fh, low[: B // 2 * S].contiguous(), ch, B // 2, S, Q, tgt_h)
     lh.backward()
     assert abs(float(lh.detach()) - loss1) < 1e-6 * max(1.0, abs(loss1))
-    assert nrel((2.0 * gf1[: B // 2]).cpu(), fh.grad.view(B // 2, S + Q, c, h, w).cpu()) < 1e-6
+    # (not bit for bit: how an image's tiles are split over CTAs depends on the number of images in the launch, so the
+    # prototype gradients of the half batch are summed in another grouping - 1.5e-6 observed)
+    assert nrel((2.0 * gf1[: B // 2]).cpu(), fh.grad.view(B // 2, S + Q, c, h, w).cpu()) < 5e-6
     assert nrel(gc1.cpu(), ch.grad.cpu()) < 1e-5
     # (3) a support image whose masks are all zero contributes no gradient to its features
     low0 = low.clone()
