@@ -231,9 +231,10 @@ int pemp_meta_proto_attn_bwd(const float* fts, long long fts_episode_stride, con
                              const float* g_fg, const float* g_bg, int B, int S, int c, int hw, int p, float* d_fts,
                              long long d_fts_episode_stride, float* d_ctr, void* workspace, size_t workspace_bytes,
                              pemp_stream_t stream);
-/* Diagnostic (tests only), as pemp_debug_mpa_path: the backward of K2 has a kernel that runs the three per-tile products on the
- * warp-level tensor path (3 x TF32, fp32-grade) for p = 3, c in {128, 256, 512, 1024} and a CUDA-core kernel for every other
- * shape; mode 1 forces the latter, mode 0 restores the automatic choice.  Returns the previous mode.                   */
+/* Diagnostic (tests only), as pemp_debug_mpa_path: the backward of K2 (p = 3, c in {128, 256, 512, 1024}) and of K3 (P = 3,
+ * c in {256, 512}) have kernels that run the three per-tile products on the warp-level tensor path (3 x TF32, fp32-grade) and
+ * CUDA-core kernels for every other shape; mode 1 forces the latter, mode 0 restores the automatic choice.  Returns the
+ * previous mode.                                                                                                        */
 int pemp_debug_bwd_path(int mode);
 size_t pemp_cosine_match_bwd_workspace_bytes(int N, int Bp, int c, int hw, int P);
 int pemp_cosine_match_bwd(const float* qry, long long qry_episode_stride, const float* fg_proto, const float* bg_proto,
