@@ -106,6 +106,19 @@ def test_dot_rows_and_stage_rows_are_conflict_free():
     assert conflict_degree([3 * 36 + lane for lane in range(32)], 1) == 1
 
 
+def test_k3_backward_norm_row_and_feature_term():
+    # train_mma_cos.cu: the squared norm of box column 4 g + j ends up in the lanes tg = 0 (after two shuffles over tg) and goes to
+    # row 6 of the warp's dot rows; the eight lanes that store a column block's norms hit eight different banks
+    for j, o in itertools.product(range(4), range(4)):
+        words = [6 * 33 + 4 * g + j - o + 3 for g in range(8)]
+        assert len({w % 32 for w in words}) == 8
+    cols = sorted(4 * g + j for g in range(8) for j in range(4))
+    assert cols == list(range(32))
+    # B1 reads the feature of (row, this lane's pixel) back from the swizzled box: consecutive columns of one row
+    for row, o in itertools.product(range(8), range(4)):
+        assert conflict_degree([box_word(row, min(lane + o, 31)) for lane in range(28)] + [0, 1, 2, 3], 1) <= 2
+
+
 def test_tile_geometry_28_of_32_columns_cover_every_pixel_once():
     # box column i of class e holds pixel x_nom + i - o_e with o_e = (e hw + x_nom) & 3; tiles advance by 28 pixels
     hw = 51 * 51
